@@ -1,0 +1,132 @@
+/* shud_b200.h - C ABI of the B200-native SHUD hot path.
+ *
+ * Drop-in boundary for the reference's CVODE right-hand side and the N_Vector
+ * arithmetic CVODE/SPGMR runs on the same state vectors.
+ * Plain pointers and sizes only; the library behind it is hand-written sm_100a
+ * CUDA (shud_up_b200/csrc).  There is NO CPU fallback: every entry point returns
+ * SHUD_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * State vector layout (reference src/Model/Macros.hpp:21-25, blocked):
+ *     y = [ Ysurf[Ne] | Yunsat[Ne] | Ygw[Ne] | Yriv[Nr] | Ylake[Nl] ],  NY = 3 Ne + Nr + Nl
+ * Units: metres, minutes (reference src/ModelData/MD_readin.cpp:290-349).
+ * Indices in nabr/lakenabr/iLake/down/iEle/iRiv are 1-BASED exactly as the reference
+ * holds them (0 = none, negative = special); [3][Ne] arrays are edge-major:
+ * a[j*Ne + i] is edge j of cell i.
+ */
+#ifndef SHUD_B200_H
+#define SHUD_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHUD_OK 0
+#define SHUD_ERR_NO_DEVICE (-1) /* no CUDA device / extension unusable: never falls back to the CPU */
+#define SHUD_ERR_ARG (-2)
+#define SHUD_ERR_CUDA (-3)
+/* device-side checks mirror the reference's myexit() codes (src/Model/Macros.hpp:77-82) */
+#define SHUD_ERRNAN 10    /* CheckNANi / CheckNonNegative, src/Equations/functions.cpp:90-103,148-154 */
+#define SHUD_ERRDATAIN 13 /* effKH out of range, src/Equations/Equations.cpp:129-132 */
+#define SHUD_ERRRIVBC 1   /* unknown river 'down' code, src/ModelData/MD_RiverFlux.cpp:55-57 (exit(1)) */
+
+/* ---- static model data: what Model_Data::initialize() leaves behind, flattened
+ * AoS -> SoA once after initialize()+LoadIC() (reference src/Model/shud.cpp:50-67).
+ * Field names are the reference's (src/classes/Element.hpp, River.hpp, Lake.hpp). ---- */
+typedef struct shud_mesh {
+    int32_t Ne, Nr, Ns, Nl;
+    int32_t close_boundary; /* Control_Data::CloseBoundary, src/classes/Model_Control.hpp:164 */
+    int32_t lakeon;         /* global lakeon, src/Model/shud.cpp:30 */
+    /* per cell [Ne] */
+    const double *area, *z_surf, *z_bottom, *depression, *AquiferDepth, *Sy;
+    const double *infD, *infKsatV, *macKsatV, *hAreaF, *ThetaS, *ThetaR, *ThetaFC, *Beta;
+    const double *KsatH, *KsatV, *macKsatH, *macD, *geo_vAreaF;
+    const double *VegFrac, *ImpAF, *WetlandLevel, *RootReachLevel, *Rough, *QSS;
+    /* per cell and edge [3][Ne] */
+    const double *edge, *Dist2Nabor, *Dist2Edge, *avgRough;
+    const int32_t *nabr, *lakenabr;
+    /* per cell [Ne] */
+    const int32_t *iLake, *iBC, *iSS;
+    /* per reach [Nr] */
+    const double *riv_Length, *riv_BedSlope, *riv_depth, *riv_BottomWidth, *riv_bankslope;
+    const double *riv_avgRough, *riv_Dist2DownStream, *riv_KsatH, *riv_BedThick, *riv_zbank;
+    const int32_t *riv_down, *riv_BC, *riv_toLake;
+    /* per river-element segment [Ns] */
+    const int32_t *seg_iEle, *seg_iRiv;
+    const double *seg_length, *seg_Cwr;
+    /* per lake [Nl]; bathymetry table of lake l is rows lake_bathy_ptr[l] .. lake_bathy_ptr[l+1]-1 */
+    const double *lake_zmin;
+    const int32_t *lake_NumEleLake;
+    const int32_t *lake_bathy_ptr; /* [Nl+1] */
+    const double *lake_bathy_yi, *lake_bathy_ai;
+} shud_mesh;
+
+/* ---- values that change only between CVode() calls (after updateforcing()+ET(),
+ * reference src/Model/shud.cpp:106-109): one upload per forcing step. ---- */
+typedef struct shud_forcing {
+    const double *qEleNetPrep, *qPotEvap, *qPotTran, *t_lai, *fu_Surf, *fu_Sub, *qElePrep; /* [Ne] */
+    const double *qEleE_IC; /* [Ne] read AND rewritten by the RHS (src/ModelData/MD_ET.cpp:370,381) */
+    /* boundary-condition values already looked up (tsd_*BC.getX is a step function of the
+     * ring pointer, src/classes/TimeSeriesData.cpp:270-273).  NULL = no such BC anywhere. */
+    const double *ele_yBC, *ele_QBC; /* [Ne] */
+    const double *riv_yBC, *riv_qBC; /* [Nr] */
+} shud_forcing;
+
+/* ---- flux arrays the reference's Print_Ctrl reads (src/ModelData/MD_initialize.cpp:258-342);
+ * filled by the *_diag RHS variant.  Any pointer may be NULL (skipped). ---- */
+typedef struct shud_diag {
+    double *qEleInfil, *qEleExfil, *qEleRecharge;            /* [Ne] */
+    double *qEs, *qEu, *qEg, *qTu, *qTg;                     /* [Ne] */
+    double *qEleTrans, *qEleEvapo, *qEleETA, *iBeta;         /* [Ne] */
+    double *u_effKH, *u_satn;                                /* [Ne] */
+    double *QeleSurf, *QeleSub;                              /* [3][Ne] */
+    double *QeleSurfTot, *QeleSubTot, *Qe2r_Surf, *Qe2r_Sub; /* [Ne] */
+    double *QsegSurf, *QsegSub;                              /* [Ns] */
+    double *QrivSurf, *QrivSub, *QrivUp, *QrivDown;          /* [Nr] */
+    double *y2LakeArea, *QLakeSurf, *QLakeSub, *QLakeRivIn, *QLakeRivOut, *qLakeEvap, *qLakePrcp; /* [Nl] */
+} shud_diag;
+
+typedef struct shud_ctx shud_ctx;
+
+/* Build the device-resident SoA mirror (cells reordered for locality, CSR gathers for
+ * segment->cell, segment->reach, reach->downstream, bank-edge->lake) and the CUDA graph.
+ * `device` is the CUDA ordinal.  Replaces: nothing in the reference - it is the one-time
+ * export after Model_Data::initialize() (src/Model/shud.cpp:51). */
+int shud_b200_create(const shud_mesh *mesh, int device, shud_ctx **out);
+void shud_b200_destroy(shud_ctx *ctx);
+int64_t shud_b200_ny(const shud_ctx *ctx);
+/* the CUDA stream (cudaStream_t) every call of this context is ordered on */
+void *shud_b200_stream(shud_ctx *ctx);
+
+/* Upload one forcing step (host pointers).  Replaces the implicit hand-over of
+ * qEleNetPrep.. after Model_Data::updateforcing()+ET() (src/Model/shud.cpp:106-109). */
+int shud_b200_set_forcing(shud_ctx *ctx, const shud_forcing *f);
+/* Carried state: Ele[i].u_satn left by the previous call.
+ * shud_b200_prime computes it from y the way Model_Data::updateforcing does through
+ * _Element::updateElement (src/ModelData/MD_ET.cpp:14-19, src/classes/Element.cpp:347-373). */
+int shud_b200_prime(shud_ctx *ctx, const double *y_host);
+int shud_b200_set_carried(shud_ctx *ctx, const double *u_satn_host);
+int shud_b200_get_carried(shud_ctx *ctx, double *u_satn_host, double *qEleE_IC_host);
+
+/* The RHS.  Replaces int f(double t, N_Vector y, N_Vector ydot, void *MD)
+ * (src/Model/f.hpp:12, src/Model/f.cpp:2-32) = f_update + f_loop + f_applyDY
+ * (src/ModelData/MD_update.cpp:102-189, MD_f.cpp:9-50, MD_f.cpp:52-215).
+ * _dev: y/ydot are device pointers, asynchronous on shud_b200_stream().
+ * plain: y/ydot are host pointers; copies in, runs, copies out, synchronises and
+ * returns the device error word (0, or SHUD_ERRNAN / SHUD_ERRDATAIN / SHUD_ERRRIVBC). */
+int shud_b200_rhs_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+int shud_b200_rhs(shud_ctx *ctx, double t, const double *y_host, double *ydot_host);
+/* Same arithmetic, and additionally stores every flux array of shud_diag on the device. */
+int shud_b200_rhs_diag_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+/* Download the flux arrays left by the last shud_b200_rhs_diag_dev (host pointers). */
+int shud_b200_get_diag(shud_ctx *ctx, const shud_diag *out);
+/* Synchronise and read the device error word: code in the return value, offending
+ * 1-based cell/reach id in *where (may be NULL).  Mirrors myexit(code)
+ * (src/Equations/functions.cpp:10-36) without killing the process. */
+int shud_b200_check(shud_ctx *ctx, int32_t *where);
+/* number of kernels one shud_b200_rhs_dev launches (for bench.py's gpu_launches) */
+int shud_b200_launches_per_rhs(const shud_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHUD_B200_H */

@@ -1,0 +1,70 @@
+"""Loader for the CPU oracle (oracle/shud_oracle.c).  TEST INFRASTRUCTURE: importable from
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+_LIB = None
+
+from shud_up_b200 import abi, snapshot  # noqa: E402
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(ROOT, "oracle", "_ref", "liboracle.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        L = C.CDLL(so)
+        PD = C.POINTER(C.c_double)
+        L.shud_oracle_rhs.restype = C.c_int
+        L.shud_oracle_rhs.argtypes = [C.POINTER(abi.ShudMesh), C.POINTER(abi.ShudForcing), PD, PD, PD, PD,
+                                      C.POINTER(abi.ShudDiag), C.c_int]
+        L.shud_oracle_prime.restype = None
+        L.shud_oracle_prime.argtypes = [C.POINTER(abi.ShudMesh), PD, PD]
+        _LIB = L
+    return _LIB
+
+
+def load_case(basin, case):
+    """static mesh of the basin overlaid with the case's arrays (mutations override)."""
+    snap = snapshot.load(os.path.join(GOLDEN, f"{basin}.mesh.npz"))
+    snap.update(snapshot.load(os.path.join(GOLDEN, f"{basin}.{case}.npz")))
+    return snap
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def oracle_rhs(snap, y=None, u_satn=None, qEleE_IC=None, nthreads=1, want_diag=True):
+    """one reference-equivalent f() call; returns dict(ydot, u_satn, qEleE_IC, err, diag arrays)."""
+    mesh, keep = abi.make_mesh(snap)
+    Ne, Nr, Ns, Nl = mesh.Ne, mesh.Nr, mesh.Ns, mesh.Nl
+    y = np.ascontiguousarray(snap["y"] if y is None else y, dtype=np.float64)
+    satn = np.array(snap["ele_u_satn"] if u_satn is None else u_satn, dtype=np.float64, copy=True)
+    eic = np.array(snap["qEleE_IC_in"] if qEleE_IC is None else qEleE_IC, dtype=np.float64, copy=True)
+    forc, keep2 = abi.make_forcing(snap, qEleE_IC=eic)
+    ydot = np.empty_like(y)
+    out = {}
+    if want_diag:
+        diag, arrs = abi.make_diag(Ne, Nr, Ns, Nl)
+        dp = C.byref(diag)
+    else:
+        arrs, dp = {}, None
+    err = lib().shud_oracle_rhs(C.byref(mesh), C.byref(forc), _pd(satn), _pd(eic), _pd(y), _pd(ydot), dp, nthreads)
+    out.update(arrs)
+    out.update(ydot=ydot, u_satn_out=satn, qEleE_IC_out=eic, err=err)
+    return out
+
+
+def oracle_prime(snap, y):
+    mesh, keep = abi.make_mesh(snap)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    satn = np.empty(mesh.Ne, dtype=np.float64)
+    lib().shud_oracle_prime(C.byref(mesh), _pd(y), _pd(satn))
+    return satn
