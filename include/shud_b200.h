@@ -46,6 +46,9 @@ typedef struct shud_mesh {
     const int32_t *nabr, *lakenabr;
     /* per cell [Ne] */
     const int32_t *iLake, *iBC, *iSS;
+    /* cell centroids (Triangle::x,y, src/classes/Element.hpp:32-33): used ONLY to order cells along a
+     * Hilbert curve for memory locality; may be NULL (then the given order is kept) */
+    const double *x, *y;
     /* per reach [Nr] */
     const double *riv_Length, *riv_BedSlope, *riv_depth, *riv_BottomWidth, *riv_bankslope;
     const double *riv_avgRough, *riv_Dist2DownStream, *riv_KsatH, *riv_BedThick, *riv_zbank;
@@ -106,6 +109,14 @@ int shud_b200_set_forcing(shud_ctx *ctx, const shud_forcing *f);
 int shud_b200_prime(shud_ctx *ctx, const double *y_host);
 int shud_b200_set_carried(shud_ctx *ctx, const double *u_satn_host);
 int shud_b200_get_carried(shud_ctx *ctx, double *u_satn_host, double *qEleE_IC_host);
+
+/* Device vectors handed to the *_dev entry points and to the N_Vector ops are in DEVICE ORDER:
+ * same blocked layout, cells and reaches renumbered for locality.  These two kernels convert a
+ * device-resident vector between the reference order and the device order (both pointers on the
+ * device, src != dst); shud_b200_perm() exposes the maps (device id -> 0-based reference id). */
+int shud_b200_to_device_order(shud_ctx *ctx, const double *ref_order_dev, double *dev_order_dev);
+int shud_b200_from_device_order(shud_ctx *ctx, const double *dev_order_dev, double *ref_order_dev);
+int shud_b200_perm(const shud_ctx *ctx, int32_t *cell_perm /*[Ne]*/, int32_t *reach_perm /*[Nr]*/);
 
 /* The RHS.  Replaces int f(double t, N_Vector y, N_Vector ydot, void *MD)
  * (src/Model/f.hpp:12, src/Model/f.cpp:2-32) = f_update + f_loop + f_applyDY

@@ -290,6 +290,7 @@ int main(int argc, char **argv) {
     put1i("close_boundary", MD->CS.CloseBoundary);
     put1i("lakeon", lakeon);
     put1d("t", t);
+    ELE_D(x) ELE_D(y)
     ELE_D(area) ELE_D(z_surf) ELE_D(z_bottom) ELE_D(depression)
     ELE_D(AquiferDepth) ELE_D(Sy) ELE_D(infD) ELE_D(infKsatV) ELE_D(macKsatV) ELE_D(hAreaF)
     ELE_D(ThetaS) ELE_D(ThetaR) ELE_D(ThetaFC) ELE_D(Alpha) ELE_D(Beta)

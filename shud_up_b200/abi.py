@@ -32,6 +32,7 @@ class ShudMesh(C.Structure):
                 + [(n, _PD) for n in MESH_EDGE_D]
                 + [(n, _PI) for n in MESH_EDGE_I]
                 + [(n, _PI) for n in MESH_CELL_I]
+                + [("x", _PD), ("y", _PD)]
                 + [(n, _PD) for n in MESH_RIV_D]
                 + [(n, _PI) for n in MESH_RIV_I]
                 + [(n, _PI) for n in MESH_SEG_I]
@@ -93,6 +94,12 @@ def make_mesh(snap):
                          + ["lake_NumEleLake", "lake_bathy_ptr"], _i)):
         for n in names:
             a, p = conv(snap[_key(snap, n)])
+            keep.append(a)
+            setattr(m, n, p)
+    for n in ("x", "y"):  # optional centroids
+        src = snap.get(n, snap.get("ele_" + n))
+        if src is not None:
+            a, p = _d(src)
             keep.append(a)
             setattr(m, n, p)
     return m, keep

@@ -1,0 +1,174 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI
+(include/shud_b200.h -> shud_up_b200/libshud_b200.so).
+
+    rhs = ShudRHS(mesh_dict)            # after Model_Data::initialize()  (src/Model/shud.cpp:51)
+    rhs.set_forcing(forcing_dict)       # after updateforcing()+ET()      (src/Model/shud.cpp:106-109)
+    rhs.f(t, y, ydot)                   # int f(t, N_Vector y, N_Vector ydot, void*)  (src/Model/f.hpp:12)
+
+The CUDA library is the only implementation: if it cannot be loaded, or there is no CUDA
+device, construction raises - nothing here computes on the CPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshud_b200.so")
+_lib = None
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int32)
+
+
+class ShudError(RuntimeError):
+    pass
+
+
+# myexit() codes of the reference (src/Equations/functions.cpp:10-36, src/Model/Macros.hpp:77-82)
+ERR_TEXT = {10: "NAN/INF VALUE (ERRNAN)", 13: "Data validation (ERRDATAIN)", 1: "River Routing Boundary Condition Type Is Wrong",
+            -1: "no CUDA device", -2: "bad argument", -3: "CUDA runtime error"}
+
+
+def lib():
+    """Load libshud_b200.so (built in-tree by shud_up_b200/build.py).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ShudError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    sig = {
+        "shud_b200_create": (C.c_int, [C.POINTER(abi.ShudMesh), C.c_int, C.POINTER(vp)]),
+        "shud_b200_destroy": (None, [vp]),
+        "shud_b200_ny": (C.c_int64, [vp]),
+        "shud_b200_stream": (vp, [vp]),
+        "shud_b200_set_forcing": (C.c_int, [vp, C.POINTER(abi.ShudForcing)]),
+        "shud_b200_prime": (C.c_int, [vp, _PD]),
+        "shud_b200_set_carried": (C.c_int, [vp, _PD]),
+        "shud_b200_get_carried": (C.c_int, [vp, _PD, _PD]),
+        "shud_b200_to_device_order": (C.c_int, [vp, vp, vp]),
+        "shud_b200_from_device_order": (C.c_int, [vp, vp, vp]),
+        "shud_b200_perm": (C.c_int, [vp, _PI, _PI]),
+        "shud_b200_rhs_dev": (C.c_int, [vp, C.c_double, vp, vp]),
+        "shud_b200_rhs": (C.c_int, [vp, C.c_double, vp, vp]),
+        "shud_b200_rhs_diag_dev": (C.c_int, [vp, C.c_double, vp, vp]),
+        "shud_b200_get_diag": (C.c_int, [vp, C.POINTER(abi.ShudDiag)]),
+        "shud_b200_check": (C.c_int, [vp, _PI]),
+        "shud_b200_launches_per_rhs": (C.c_int, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise ShudError(f"{what} failed: code {rc} ({ERR_TEXT.get(rc, '?')})")
+
+
+def _ptr(a):
+    """device/host pointer of a torch tensor or numpy array (float64, contiguous)."""
+    if hasattr(a, "data_ptr"):
+        assert a.dtype.is_floating_point and a.element_size() == 8 and a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return C.c_void_p(a.ctypes.data)
+
+
+class ShudRHS:
+    """One GPU's copy of the model: static SoA mirror + forcing-step arrays + carried state."""
+
+    def __init__(self, mesh, device=0):
+        L = lib()
+        self._mesh_struct, self._keep = abi.make_mesh(mesh)
+        self.Ne, self.Nr, self.Ns, self.Nl = (self._mesh_struct.Ne, self._mesh_struct.Nr, self._mesh_struct.Ns,
+                                              self._mesh_struct.Nl)
+        h = C.c_void_p()
+        rc = L.shud_b200_create(C.byref(self._mesh_struct), int(device), C.byref(h))
+        _chk(rc, "shud_b200_create")
+        self._h = h
+        self.device = int(device)
+        self.NY = int(L.shud_b200_ny(h))
+        self.launches_per_rhs = int(L.shud_b200_launches_per_rhs(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().shud_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    @property
+    def stream_ptr(self):
+        return lib().shud_b200_stream(self._h)
+
+    def torch_stream(self):
+        import torch
+        return torch.cuda.ExternalStream(self.stream_ptr, device=f"cuda:{self.device}")
+
+    def perm(self):
+        cp = np.empty(self.Ne, dtype=np.int32)
+        rp = np.empty(max(self.Nr, 1), dtype=np.int32)
+        _chk(lib().shud_b200_perm(self._h, cp.ctypes.data_as(_PI), rp.ctypes.data_as(_PI)), "perm")
+        return cp, rp[:self.Nr]
+
+    def to_device_order(self, ref_dev, out_dev):
+        _chk(lib().shud_b200_to_device_order(self._h, _ptr(ref_dev), _ptr(out_dev)), "to_device_order")
+
+    def from_device_order(self, dev_dev, out_ref):
+        _chk(lib().shud_b200_from_device_order(self._h, _ptr(dev_dev), _ptr(out_ref)), "from_device_order")
+
+    # ---- forcing step / carried state ----
+    def set_forcing(self, forcing, qEleE_IC=None):
+        f, keep = abi.make_forcing(forcing, qEleE_IC=qEleE_IC)
+        _chk(lib().shud_b200_set_forcing(self._h, C.byref(f)), "shud_b200_set_forcing")
+
+    def prime(self, y_host):
+        y = np.ascontiguousarray(y_host, dtype=np.float64)
+        _chk(lib().shud_b200_prime(self._h, y.ctypes.data_as(_PD)), "shud_b200_prime")
+
+    def set_carried(self, u_satn):
+        a = np.ascontiguousarray(u_satn, dtype=np.float64)
+        _chk(lib().shud_b200_set_carried(self._h, a.ctypes.data_as(_PD)), "shud_b200_set_carried")
+
+    def get_carried(self):
+        s = np.empty(self.Ne)
+        e = np.empty(self.Ne)
+        _chk(lib().shud_b200_get_carried(self._h, s.ctypes.data_as(_PD), e.ctypes.data_as(_PD)), "get_carried")
+        return s, e
+
+    # ---- the RHS ----
+    def f(self, t, y, ydot):
+        """CVRhsFn on host vectors in reference order (numpy, or pinned torch CPU tensors).
+        Raises ShudError with the reference's exit code where the reference would myexit()."""
+        rc = lib().shud_b200_rhs(self._h, float(t), _ptr(y), _ptr(ydot))
+        if rc != 0:
+            raise ShudError(f"f(): reference would exit with code {rc} ({ERR_TEXT.get(rc, '?')})")
+        return 0
+
+    def f_dev(self, t, y_dev, ydot_dev, diag=False):
+        """asynchronous RHS on device vectors in device order (torch cuda float64 tensors)."""
+        fn = lib().shud_b200_rhs_diag_dev if diag else lib().shud_b200_rhs_dev
+        _chk(fn(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "shud_b200_rhs_dev")
+
+    def check(self):
+        where = C.c_int32(0)
+        code = lib().shud_b200_check(self._h, C.byref(where))
+        return code, where.value
+
+    def get_diag(self):
+        d, arrs = abi.make_diag(self.Ne, self.Nr, self.Ns, self.Nl)
+        _chk(lib().shud_b200_get_diag(self._h, C.byref(d)), "shud_b200_get_diag")
+        return arrs

@@ -1,0 +1,958 @@
+// shud_rhs.cu - the SHUD right-hand side f(t,y,ydot) on one B200 (sm_100a), FP64, SoA.
+//
+// Replaces the reference's f() = f_update + f_loop + f_applyDY
+// (src/Model/f.cpp:2-32, src/ModelData/MD_update.cpp:102-189, MD_f.cpp:9-215) behind the C ABI
+// of include/shud_b200.h.  Layout and kernels are described in DESIGN.md; in short:
+//   * cells are renumbered along a Hilbert curve (locality of the 3 neighbour gathers), reaches
+//     follow the cells their segments touch, segments are grouped by reach;
+//   * every flux is evaluated owner-computes (cell i computes its own 3 edges and its own
+//     river segments; a reach re-evaluates its upstream reaches' Manning flux) - no atomics,
+//     every sum runs in a fixed order, so ydot is run-to-run reproducible;
+//   * launches per RHS: effKH pre-pass, cell kernel, river+lake kernel.
+// Device vectors are in DEVICE ORDER (permuted); shud_b200_rhs() (host pointers, reference
+// order) permutes on the way in and out.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "shud_b200.h"
+#include "shud_phys.cuh"
+
+namespace {
+
+using namespace shud;
+
+constexpr unsigned F_LAKE = 1u, F_HEADBC = 2u, F_FLUXBC = 4u, F_SS_SURF = 8u, F_SS_GW = 16u;
+constexpr int NSEG_SHIFT = 8;
+
+struct DevMesh {
+    int Ne, Nr, Ns, Nl, close_boundary, has_headbc, nbank;
+    // static per cell
+    const double *area, *z_surf, *z_bottom, *depression, *aqd, *sy, *infD, *infKsatV, *macKsatV, *hAreaF, *thetaS,
+        *thetaR, *thetaFC, *beta, *ksatH, *ksatV, *macKsatH, *macD, *vAreaF, *vegFrac, *impAF, *wetland, *rootReach,
+        *rough, *qss;
+    const double *edge, *dist, *dist2edge, *avgRough;  // [3][Ne]
+    const int *nbr;                                    // [3][Ne]: >=0 cell, -1 boundary, <=-2 bank slot (-2-v)
+    const unsigned *flags;
+    const int *cell_seg_first;  // valid where nseg>0: first entry in cell_seg_idx
+    const int *cell_seg_idx;    // segment (device order) ids, ascending reference id per cell
+    // forcing step
+    double *netPrep, *potEvap, *potTran, *lai, *fuSurf, *fuSub, *eic, *satn, *ele_yBC, *ele_QBC;
+    // work
+    double *effKH, *QsegSurf, *QsegSub;
+    // reaches
+    const double *r_len, *r_slope, *r_depth, *r_w0, *r_bank, *r_rough, *r_dist, *r_ksatH, *r_bed, *r_zbank;
+    const int *r_down, *r_bc, *r_toLake, *r_up_ptr, *r_up_idx, *r_seg_ptr;
+    double *r_yBC, *r_qBC;
+    // segments (device order = grouped by reach)
+    const int *s_riv;
+    const double *s_len, *s_cwr;
+    // lakes
+    const double *l_zmin, *l_yi0, *l_by, *l_ba;
+    const int *l_bptr, *l_bank_ptr, *l_rin_ptr, *l_rin_idx;
+    const int *bank_cell, *bank_j, *bank_lake;
+    const double *bank_kh;
+    double *l_evap_raw, *l_prcp;
+    int *err;  // [0] code, [1] where (1-based reference id)
+};
+
+struct DevDiag {
+    double *qEleInfil, *qEleExfil, *qEleRecharge, *qEs, *qEu, *qEg, *qTu, *qTg, *qEleTrans, *qEleEvapo, *qEleETA,
+        *iBeta, *QeleSurf, *QeleSub, *QeleSurfTot, *QeleSubTot, *Qe2r_Surf, *Qe2r_Sub, *QrivSurf, *QrivSub, *QrivUp,
+        *QrivDown, *y2LakeArea, *QLakeSurf, *QLakeSub, *QLakeRivIn, *QLakeRivOut, *qLakeEvap, *qLakePrcp;
+};
+
+__device__ __forceinline__ void raise_err(int *err, int code, int where) {
+    if (atomicMax(&err[0], code) < code) err[1] = where;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: horizontal effective conductivity of every cell (neighbours need it before any edge flux)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restrict__ Y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.Ne) return;
+    const unsigned fl = m.flags[i];
+    double kh;
+    if (fl & F_LAKE) {
+        kh = m.ksatH[i];  // _Element::updateLakeElement, src/classes/Element.cpp:336-337
+    } else {
+        const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : Y[2 * (size_t)m.Ne + i];
+        int e = 0;
+        kh = eff_kh(ygw, m.aqd[i], m.macD[i], m.macKsatH[i], m.vAreaF[i], m.ksatH[i], &e);
+        if (e) raise_err(m.err, e, i + 1);
+    }
+    m.effKH[i] = kh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: everything a cell owns: ET partition, infiltration, recharge, its 3 overland and 3
+// groundwater edge fluxes, its river segments, and the three balance equations.
+// ---------------------------------------------------------------------------------------------
+template <bool DIAG>
+__global__ void __launch_bounds__(128) k_cell(DevMesh m, DevDiag d, const double *__restrict__ Y,
+                                              double *__restrict__ DY) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Ne = m.Ne;
+    if (i >= Ne) return;
+    const size_t NE = (size_t)Ne;
+    const unsigned fl = m.flags[i];
+    const double ysf = Y[i], yus = Y[NE + i];
+    const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : Y[2 * NE + i];
+    const double zs = m.z_surf[i], zb = m.z_bottom[i], depression = m.depression[i];
+    const double fuSub = m.fuSub[i];
+    const double kh = m.effKH[i];
+    int err = 0;
+
+    CellVert v;
+    double netPrep = m.netPrep[i];
+    double Qs[3], Qg[3];
+    if (fl & F_LAKE) {
+        // fun_Ele_lakeVertical / fun_Ele_lakeHorizon, src/ModelData/MD_ElementFlux.cpp:2-23
+        v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
+        v.satn = 1.; v.infil = v.exfil = v.rech = 0.; v.err = 0;
+        Qs[0] = Qs[1] = Qs[2] = 0.; Qg[0] = Qg[1] = Qg[2] = 0.;
+        if (DIAG) {
+            const double pe = m.potEvap[i];
+            d.qEleTrans[i] = 0.; d.qEleEvapo[i] = pe; d.qEleETA[i] = 0. + pe + 0.;
+        }
+    } else {
+        CellParams p;
+        p.aqd = m.aqd[i]; p.sy = 0.; p.infD = m.infD[i]; p.infKsatV = m.infKsatV[i]; p.macKsatV = m.macKsatV[i];
+        p.hAreaF = m.hAreaF[i]; p.thetaS = m.thetaS[i]; p.thetaR = m.thetaR[i]; p.thetaFC = m.thetaFC[i];
+        p.beta = m.beta[i]; p.ksatV = m.ksatV[i]; p.vegFrac = m.vegFrac[i]; p.impAF = m.impAF[i];
+        p.wetland = m.wetland[i]; p.rootReach = m.rootReach[i];
+        CellForc f;
+        f.netPrep = netPrep; f.potEvap = m.potEvap[i]; f.potTran = m.potTran[i]; f.lai = m.lai[i];
+        f.fuSurf = m.fuSurf[i]; f.fuSub = fuSub;
+        v = cell_vertical(p, f, ysf, yus, ygw, m.satn[i], m.eic[i]);
+        if (v.err) err = v.err;
+        if (DIAG) {
+            const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
+            d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
+            d.iBeta[i] = v.iBeta;
+        }
+        // ---- lateral fluxes through the 3 edges ----
+        const double isf = ysf < 0. ? 0. : ysf;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int nb = m.nbr[j * NE + i];
+            const double B = m.edge[j * NE + i];
+            double qs = 0., qg = 0.;
+            if (nb >= 0) {
+                double nsf = Y[nb];
+                nsf = nsf < 0. ? 0. : nsf;
+                double ygw_n = Y[2 * NE + nb];
+                if (m.has_headbc && (m.flags[nb] & F_HEADBC)) ygw_n = m.ele_yBC[nb];
+                const double dist = m.dist[j * NE + i];
+                qs = edge_surface(isf, zs, nsf, m.z_surf[nb], depression, dist, B, m.avgRough[j * NE + i]);
+                qg = edge_sub(ygw, zb, ygw_n, m.z_bottom[nb], kh, m.effKH[nb], dist, B);
+            } else if (nb <= -2) {
+                // bank of a lake: weir over the shore + Darcy against the lake stage (MD_ElementFlux.cpp:46-53,107-121)
+                const int slot = -2 - nb, l = m.bank_lake[slot];
+                const double yl = Y[3 * NE + m.Nr + l];
+                const double nsf = yl < 0. ? 0. : yl;
+                qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, B, 0.01);
+                qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], m.dist[j * NE + i], B);
+            } else if (!m.close_boundary) {
+                // open boundary (MD_ElementFlux.cpp:81-92,139-151)
+                const double d2e = m.dist2edge[j * NE + i];
+                if (isf > depression) {
+                    const double s = isf / d2e * 0.5;
+                    if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B / m.rough[i];
+                }
+                if (ygw > depression * 10.) {
+                    const double grad = ygw / d2e * 0.5;
+                    if (grad > 0.) qg = kh * grad;
+                }
+            }
+            Qs[j] = qs;
+            Qg[j] = qg * fuSub;
+        }
+    }
+    m.eic[i] = v.eic;
+    m.satn[i] = v.satn;
+
+    // ---- river segments touching this cell (fun_Seg_surface / fun_Seg_sub, MD_RiverFlux.cpp:100-126;
+    //      PassValue's element side, MD_f.cpp:228-235) ----
+    double e2rS = 0., e2rG = 0.;
+    const int nseg = (int)(fl >> NSEG_SHIFT);
+    if (nseg) {
+        const int k0 = m.cell_seg_first[i];
+        double isf2 = ysf - v.infil + v.exfil;
+        isf2 = dmax(0., isf2);
+        for (int k = 0; k < nseg; k++) {
+            const int s = m.cell_seg_idx[k0 + k], r = m.s_riv[s];
+            const double yr = (m.r_bc[r] > 0) ? m.r_yBC[r] : Y[3 * NE + r];
+            const double zr = zs - m.r_depth[r], len = m.s_len[s];
+            const double qs = weir_jtoi(zs, isf2, zr, yr, zs + m.r_zbank[r], m.s_cwr[s], len, depression);
+            const double qg = flux_r2e_gw(yr, zr, ygw, zb, kh, m.r_ksatH[r], len, m.r_bed[r]) * fuSub;
+            m.QsegSurf[s] = qs;
+            m.QsegSub[s] = qg;
+            e2rS += -qs;
+            e2rG += -qg;
+        }
+    }
+
+    // ---- f_applyDY, cell part (MD_f.cpp:65-156) ----
+    const double area = m.area[i];
+    double surfTot = e2rS, subTot = e2rG;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        surfTot += Qs[j];
+        subTot += Qg[j];
+        if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
+    }
+    double dsf = netPrep - v.infil + v.exfil - surfTot / area - v.Es;
+    double dus = v.infil - v.rech - v.Eu - v.Tu;
+    double dgw = v.rech - v.exfil - subTot / area - v.Eg - v.Tg;
+    if (fl & F_HEADBC) dgw = 0;
+    else if (fl & F_FLUXBC) dgw += m.ele_QBC[i] / area;
+    if (fl & F_SS_SURF) dsf += m.qss[i] / area;
+    else if (fl & F_SS_GW) dgw += m.qss[i] / area;
+    const double sy = m.sy[i];
+    dus /= sy;
+    dgw /= sy;
+    if (fl & F_LAKE) { dsf = 0.; dus = 0.; dgw = 0.; }
+    DY[i] = dsf;
+    DY[NE + i] = dus;
+    DY[2 * NE + i] = dgw;
+    if (err) raise_err(m.err, err, i + 1);
+    if (DIAG) {
+        d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech;
+        d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
+        d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
+    }
+}
+
+// Manning flux of reach r towards its downstream end, everything gathered from global memory
+__device__ __forceinline__ double reach_down_flux(const DevMesh &m, const double *__restrict__ Yr, int r, int *err) {
+    const double yraw = Yr[r];
+    const double ystg = (m.r_bc[r] > 0) ? m.r_yBC[r] : yraw;
+    const int down = m.r_down[r];
+    double y_dn = 0., depth_dn = 0., slope_dn = 0.;
+    if (down >= 0) {
+        y_dn = (m.r_bc[down] > 0) ? m.r_yBC[down] : Yr[down];
+        depth_dn = m.r_depth[down];
+        slope_dn = m.r_slope[down];
+    }
+    // r_down device coding: >=0 downstream reach (device id); <0 the reference's outlet code
+    return river_down(yraw, ystg, m.r_w0[r], m.r_bank[r], m.r_len[r], m.r_slope[r], m.r_depth[r], m.r_rough[r],
+                      m.r_dist[r], down >= 0 ? 1 : down, m.r_toLake[r], y_dn, depth_dn, slope_dn, err);
+}
+
+// fixed-shape block sum (deterministic): warp shuffle tree, then warp 0 over the warp partials
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *sm) {
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < NT / 32) ? sm[threadIdx.x] : 0.;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    }
+    return t;  // valid in thread 0
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: blocks [0, nb_riv) - one thread per reach: routing, river side of PassValue, stage equation
+//     (Flux_RiverDown MD_RiverFlux.cpp:5-63, PassValue MD_f.cpp:228-240, f_applyDY MD_f.cpp:157-179);
+//     blocks [nb_riv, nb_riv+Nl) - one block per lake (MD_f.cpp:16-17,44-47,180-191).
+// ---------------------------------------------------------------------------------------------
+template <bool DIAG>
+__global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const double *__restrict__ Y,
+                                                    double *__restrict__ DY, int nb_riv) {
+    const size_t NE = (size_t)m.Ne;
+    const double *Yr = Y + 3 * NE;
+    if ((int)blockIdx.x < nb_riv) {
+        const int r = blockIdx.x * blockDim.x + threadIdx.x;
+        if (r >= m.Nr) return;
+        int err = 0;
+        const double qdown = reach_down_flux(m, Yr, r, &err);
+        double up = 0.;
+        for (int k = m.r_up_ptr[r]; k < m.r_up_ptr[r + 1]; k++) up += -reach_down_flux(m, Yr, m.r_up_idx[k], &err);
+        double surf = 0., sub = 0.;
+        for (int s = m.r_seg_ptr[r]; s < m.r_seg_ptr[r + 1]; s++) {
+            surf += m.QsegSurf[s];
+            sub += m.QsegSub[s];
+        }
+        const int bc = m.r_bc[r];
+        double dy;
+        if (bc > 0) {
+            dy = 0.;
+        } else {
+            const double qbc = (bc < 0) ? m.r_qBC[r] : 0.;
+            const RivGeom g = riv_geom(Yr[r], m.r_w0[r], m.r_bank[r]);
+            dy = (-up - surf - sub - qdown + qbc) / m.r_len[r];
+            if (dy < -1. * g.csArea) dy = -1. * g.csArea;
+            dy = dA_to_dY(dy, g.topWidth, m.r_bank[r]);
+        }
+        DY[3 * NE + r] = dy;
+        if (err) raise_err(m.err, err, r + 1);
+        if (DIAG) { d.QrivSurf[r] = surf; d.QrivSub[r] = sub; d.QrivUp[r] = up; d.QrivDown[r] = qdown; }
+        return;
+    }
+    // ---- lake l ----
+    __shared__ double sm[8];
+    const int l = blockIdx.x - nb_riv;
+    const double yl = Y[3 * NE + m.Nr + l];
+    double qs = 0., qg = 0., qin = 0.;
+    for (int k = m.l_bank_ptr[l] + threadIdx.x; k < m.l_bank_ptr[l + 1]; k += blockDim.x) {
+        const int i = m.bank_cell[k], j = m.bank_j[k];
+        const unsigned fl = m.flags[i];
+        double ysf = Y[i];
+        const double isf = ysf < 0. ? 0. : ysf, zs = m.z_surf[i];
+        const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : Y[2 * NE + i];
+        const double B = m.edge[j * NE + i];
+        qs += weir_jtoi(m.l_zmin[l], yl < 0. ? 0. : yl, zs, isf, zs, 0.6, B, 0.01);
+        // QLakeSub takes Q before the fu_Sub factor (MD_ElementFlux.cpp:121 precedes :153)
+        qg += edge_sub(ygw, m.z_bottom[i], yl, m.l_yi0[l], m.effKH[i], m.bank_kh[k], m.dist[j * NE + i], B);
+    }
+    int err = 0;
+    for (int k = m.l_rin_ptr[l] + threadIdx.x; k < m.l_rin_ptr[l + 1]; k += blockDim.x)
+        qin += reach_down_flux(m, Yr, m.l_rin_idx[k], &err);
+    qs = block_sum<128>(qs, sm);
+    qg = block_sum<128>(qg, sm);
+    qin = block_sum<128>(qin, sm);
+    if (threadIdx.x == 0) {
+        const int b0 = m.l_bptr[l], b1 = m.l_bptr[l + 1];
+        const double area = lake_toparea(m.l_by + b0, m.l_ba + b0, b1 - b0, yl + m.l_zmin[l]);
+        const double prcp = m.l_prcp[l];
+        double evap = dmin(m.l_evap_raw[l], prcp + yl);
+        evap = dmax(0., evap);
+        const double qout = 0.;  // QLakeRivOut is never fed in the reference (MD_update.cpp:184)
+        DY[3 * NE + m.Nr + l] = prcp - evap + (qin - qout + qg + qs) / area;
+        if (DIAG) {
+            d.y2LakeArea[l] = area; d.QLakeSurf[l] = qs; d.QLakeSub[l] = qg; d.QLakeRivIn[l] = qin;
+            d.QLakeRivOut[l] = qout; d.qLakeEvap[l] = evap; d.qLakePrcp[l] = prcp;
+        }
+    }
+}
+
+// carried state from y (Model_Data::updateforcing -> updateElement for every cell, MD_ET.cpp:14-19)
+__global__ void k_prime(DevMesh m, const double *__restrict__ Y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.Ne) return;
+    m.satn[i] = cell_satn(m.aqd[i], m.thetaS[i], m.thetaR[i], Y[(size_t)m.Ne + i], Y[2 * (size_t)m.Ne + i]);
+}
+
+// reference order <-> device order (cells x3 blocks, reaches; lakes keep their order)
+__global__ void k_to_dev(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ cperm,
+                         const int *__restrict__ rperm, int Ne, int Nr, int Nl) {
+    const size_t n = 3 * (size_t)Ne + Nr + Nl;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        size_t s;
+        if (k < 3 * (size_t)Ne) {
+            const size_t b = k / Ne, i = k - b * Ne;
+            s = b * Ne + cperm[i];
+        } else if (k < 3 * (size_t)Ne + Nr) {
+            s = 3 * (size_t)Ne + rperm[k - 3 * (size_t)Ne];
+        } else {
+            s = k;
+        }
+        dst[k] = src[s];
+    }
+}
+__global__ void k_from_dev(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ cperm,
+                           const int *__restrict__ rperm, int Ne, int Nr, int Nl) {
+    const size_t n = 3 * (size_t)Ne + Nr + Nl;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        size_t s;
+        if (k < 3 * (size_t)Ne) {
+            const size_t b = k / Ne, i = k - b * Ne;
+            s = b * Ne + cperm[i];
+        } else if (k < 3 * (size_t)Ne + Nr) {
+            s = 3 * (size_t)Ne + rperm[k - 3 * (size_t)Ne];
+        } else {
+            s = k;
+        }
+        dst[s] = src[k];
+    }
+}
+
+// Hilbert index of (x,y) on a 2^16 x 2^16 grid
+uint64_t hilbert_d(uint32_t x, uint32_t y) {
+    uint64_t dd = 0;
+    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+        dd += (uint64_t)s * s * ((3 * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
+            std::swap(x, y);
+        }
+    }
+    return dd;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side: context
+// ---------------------------------------------------------------------------------------------
+struct shud_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int Ne = 0, Nr = 0, Ns = 0, Nl = 0;
+    int64_t NY = 0;
+    DevMesh m{};
+    DevDiag diag{};
+    bool diag_alloc = false;
+    std::vector<void *> allocs;
+    std::vector<int> cperm, rperm, sperm;  // device id -> reference id (0-based)
+    std::vector<int> cinv, rinv;           // reference id -> device id
+    int *d_cperm = nullptr, *d_rperm = nullptr;
+    double *y_stage = nullptr, *y_dev = nullptr, *ydot_dev = nullptr;  // for the host-pointer entry point
+    std::vector<int> lake_cells;  // reference ids of lake cells, ascending
+    std::vector<int> lake_of_cell;
+    std::vector<int> lake_nele;
+    double *h_pinned = nullptr;  // staging for forcing uploads (pinned)
+    size_t h_pinned_n = 0;
+    bool has_ebc_arrays = false;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            fprintf(stderr, "[shud_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return SHUD_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+namespace {
+
+template <class T>
+T *dev_alloc(shud_ctx *c, size_t n) {
+    void *p = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+    c->allocs.push_back(p);
+    return (T *)p;
+}
+template <class T>
+T *dev_upload(shud_ctx *c, const std::vector<T> &h) {
+    T *p = dev_alloc<T>(c, h.size());
+    if (p && !h.empty()) cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return p;
+}
+// gather a per-cell host array into device order and upload
+const double *up_cell(shud_ctx *c, const double *src) {
+    std::vector<double> h(c->Ne);
+    for (int i = 0; i < c->Ne; i++) h[i] = src[c->cperm[i]];
+    return dev_upload(c, h);
+}
+const double *up_edge(shud_ctx *c, const double *src) {
+    std::vector<double> h(3 * (size_t)c->Ne);
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < c->Ne; i++) h[(size_t)j * c->Ne + i] = src[(size_t)j * c->Ne + c->cperm[i]];
+    return dev_upload(c, h);
+}
+const double *up_riv(shud_ctx *c, const double *src) {
+    std::vector<double> h(c->Nr);
+    for (int i = 0; i < c->Nr; i++) h[i] = src[c->rperm[i]];
+    return dev_upload(c, h);
+}
+
+}  // namespace
+
+extern "C" {
+
+int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
+    if (!M || !out || M->Ne <= 0) return SHUD_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) return SHUD_ERR_NO_DEVICE;
+    CK(cudaSetDevice(device));
+    shud_ctx *c = new shud_ctx();
+    c->device = device;
+    const int Ne = c->Ne = M->Ne, Nr = c->Nr = M->Nr, Ns = c->Ns = M->Ns, Nl = c->Nl = M->Nl;
+    c->NY = 3 * (int64_t)Ne + Nr + Nl;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    // ---- cell order: Hilbert curve over centroids (if given) ----
+    c->cperm.resize(Ne);
+    std::iota(c->cperm.begin(), c->cperm.end(), 0);
+    if (M->x && M->y && Ne > 1) {
+        double x0 = M->x[0], x1 = x0, y0 = M->y[0], y1 = y0;
+        for (int i = 1; i < Ne; i++) {
+            x0 = std::min(x0, M->x[i]); x1 = std::max(x1, M->x[i]);
+            y0 = std::min(y0, M->y[i]); y1 = std::max(y1, M->y[i]);
+        }
+        const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-30);
+        std::vector<uint64_t> key(Ne);
+        for (int i = 0; i < Ne; i++) {
+            const uint32_t hx = (uint32_t)std::min(65535.0, (M->x[i] - x0) / span * 65535.0);
+            const uint32_t hy = (uint32_t)std::min(65535.0, (M->y[i] - y0) / span * 65535.0);
+            key[i] = hilbert_d(hx, hy);
+        }
+        std::stable_sort(c->cperm.begin(), c->cperm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    }
+    c->cinv.resize(Ne);
+    for (int i = 0; i < Ne; i++) c->cinv[c->cperm[i]] = i;
+
+    // ---- reach order: follow the cells their segments touch ----
+    c->rperm.resize(Nr);
+    std::iota(c->rperm.begin(), c->rperm.end(), 0);
+    {
+        std::vector<int64_t> key(Nr, INT64_MAX / 2);
+        for (int s = 0; s < Ns; s++) {
+            const int r = M->seg_iRiv[s] - 1, e = M->seg_iEle[s] - 1;
+            if (r < 0 || r >= Nr || e < 0 || e >= Ne) { delete c; return SHUD_ERR_ARG; }
+            key[r] = std::min<int64_t>(key[r], c->cinv[e]);
+        }
+        std::stable_sort(c->rperm.begin(), c->rperm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    }
+    c->rinv.resize(Nr);
+    for (int i = 0; i < Nr; i++) c->rinv[c->rperm[i]] = i;
+
+    // ---- segment order: grouped by reach (device id), ascending reference id inside ----
+    c->sperm.resize(Ns);
+    std::iota(c->sperm.begin(), c->sperm.end(), 0);
+    std::stable_sort(c->sperm.begin(), c->sperm.end(),
+                     [&](int a, int b) { return c->rinv[M->seg_iRiv[a] - 1] < c->rinv[M->seg_iRiv[b] - 1]; });
+    std::vector<int> sinv(Ns);
+    for (int s = 0; s < Ns; s++) sinv[c->sperm[s]] = s;
+
+    DevMesh &m = c->m;
+    m.Ne = Ne; m.Nr = Nr; m.Ns = Ns; m.Nl = Nl;
+    m.close_boundary = M->close_boundary;
+
+    // ---- static per-cell arrays ----
+    m.area = up_cell(c, M->area); m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom);
+    m.depression = up_cell(c, M->depression); m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy);
+    m.infD = up_cell(c, M->infD); m.infKsatV = up_cell(c, M->infKsatV); m.macKsatV = up_cell(c, M->macKsatV);
+    m.hAreaF = up_cell(c, M->hAreaF); m.thetaS = up_cell(c, M->ThetaS); m.thetaR = up_cell(c, M->ThetaR);
+    m.thetaFC = up_cell(c, M->ThetaFC); m.beta = up_cell(c, M->Beta); m.ksatH = up_cell(c, M->KsatH);
+    m.ksatV = up_cell(c, M->KsatV); m.macKsatH = up_cell(c, M->macKsatH); m.macD = up_cell(c, M->macD);
+    m.vAreaF = up_cell(c, M->geo_vAreaF); m.vegFrac = up_cell(c, M->VegFrac); m.impAF = up_cell(c, M->ImpAF);
+    m.wetland = up_cell(c, M->WetlandLevel); m.rootReach = up_cell(c, M->RootReachLevel);
+    m.rough = up_cell(c, M->Rough); m.qss = up_cell(c, M->QSS);
+    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor); m.dist2edge = up_edge(c, M->Dist2Edge);
+    m.avgRough = up_edge(c, M->avgRough);
+
+    // ---- topology, flags, bank edges ----
+    const bool lakeon = M->lakeon != 0 && Nl > 0;
+    std::vector<unsigned> flags(Ne, 0u);
+    std::vector<int> nbr(3 * (size_t)Ne, -1);
+    std::vector<int> bank_cell, bank_j, bank_lake;
+    std::vector<double> bank_kh;
+    // bank edges in ascending reference (cell, edge) order, grouped by lake afterwards
+    struct Bank { int lake, ref_cell, j; double kh; };
+    std::vector<Bank> banks;
+    int has_headbc = 0;
+    c->lake_of_cell.assign(Ne, -1);
+    for (int o = 0; o < Ne; o++) {  // o = reference id
+        const int i = c->cinv[o];
+        unsigned f = 0;
+        const bool is_lake = lakeon && M->iLake[o] > 0;
+        if (M->iLake[o] > 0) f |= F_LAKE;  // f_applyDY tests iLake alone (MD_f.cpp:146)
+        if (is_lake) { c->lake_cells.push_back(o); c->lake_of_cell[o] = M->iLake[o] - 1; }
+        if (M->iBC[o] > 0) { f |= F_HEADBC; has_headbc = 1; }
+        else if (M->iBC[o] < 0) f |= F_FLUXBC;
+        if (M->iSS[o] > 0) f |= F_SS_SURF;
+        else if (M->iSS[o] < 0) f |= F_SS_GW;
+        flags[i] = f;
+        for (int j = 0; j < 3; j++) {
+            const int nb = M->nabr[(size_t)j * Ne + o] - 1;
+            const int lk = M->lakenabr ? M->lakenabr[(size_t)j * Ne + o] - 1 : -1;
+            int v = -1;
+            if (lk >= 0 && lk < Nl && !is_lake) {
+                // effKH of the lake-side cell is its KsatH (updateLakeElement)
+                banks.push_back({lk, o, j, (nb >= 0 && nb < Ne) ? M->KsatH[nb] : 0.0});
+                v = -2;  // slot patched below
+            } else if (nb >= 0 && nb < Ne) {
+                v = c->cinv[nb];
+            }
+            nbr[(size_t)j * Ne + i] = v;
+        }
+    }
+    if (M->iLake && !lakeon)
+        for (int o = 0; o < Ne; o++)
+            if (M->iLake[o] > 0) { /* lake module off but cell tagged: treated as land in f_loop */ }
+    // group banks by lake (stable: keeps ascending (cell, edge) inside a lake)
+    std::stable_sort(banks.begin(), banks.end(), [](const Bank &a, const Bank &b) { return a.lake < b.lake; });
+    std::vector<int> l_bank_ptr(Nl + 1, 0);
+    for (size_t k = 0; k < banks.size(); k++) {
+        const Bank &b = banks[k];
+        const int i = c->cinv[b.ref_cell];
+        nbr[(size_t)b.j * Ne + i] = -2 - (int)k;
+        bank_cell.push_back(i); bank_j.push_back(b.j); bank_lake.push_back(b.lake); bank_kh.push_back(b.kh);
+        l_bank_ptr[b.lake + 1]++;
+    }
+    for (int l = 0; l < Nl; l++) l_bank_ptr[l + 1] += l_bank_ptr[l];
+    m.nbank = (int)banks.size();
+    m.has_headbc = has_headbc;
+
+    // ---- cell -> segments (ascending reference segment id) ----
+    std::vector<int> nseg(Ne, 0), cell_seg_first(Ne, 0), cell_seg_idx(Ns);
+    for (int s = 0; s < Ns; s++) nseg[c->cinv[M->seg_iEle[s] - 1]]++;
+    {
+        int acc = 0;
+        for (int i = 0; i < Ne; i++) { cell_seg_first[i] = acc; acc += nseg[i]; }
+        std::vector<int> fill(Ne, 0);
+        for (int s = 0; s < Ns; s++) {  // ascending reference id
+            const int i = c->cinv[M->seg_iEle[s] - 1];
+            cell_seg_idx[cell_seg_first[i] + fill[i]++] = sinv[s];
+        }
+        for (int i = 0; i < Ne; i++) {
+            if (nseg[i] > 0xFFFFFF) { delete c; return SHUD_ERR_ARG; }
+            flags[i] |= (unsigned)nseg[i] << NSEG_SHIFT;
+        }
+    }
+    m.flags = dev_upload(c, flags); m.nbr = dev_upload(c, nbr);
+    m.cell_seg_first = dev_upload(c, cell_seg_first); m.cell_seg_idx = dev_upload(c, cell_seg_idx);
+    m.bank_cell = dev_upload(c, bank_cell); m.bank_j = dev_upload(c, bank_j); m.bank_lake = dev_upload(c, bank_lake);
+    m.bank_kh = dev_upload(c, bank_kh);
+
+    // ---- reaches ----
+    m.r_len = up_riv(c, M->riv_Length); m.r_slope = up_riv(c, M->riv_BedSlope); m.r_depth = up_riv(c, M->riv_depth);
+    m.r_w0 = up_riv(c, M->riv_BottomWidth); m.r_bank = up_riv(c, M->riv_bankslope);
+    m.r_rough = up_riv(c, M->riv_avgRough); m.r_dist = up_riv(c, M->riv_Dist2DownStream);
+    m.r_ksatH = up_riv(c, M->riv_KsatH); m.r_bed = up_riv(c, M->riv_BedThick); m.r_zbank = up_riv(c, M->riv_zbank);
+    {
+        std::vector<int> down(Nr), bc(Nr), toLake(Nr), up_ptr(Nr + 1, 0), up_idx, seg_ptr(Nr + 1, 0);
+        std::vector<std::vector<int>> ups(Nr);
+        for (int o = 0; o < Nr; o++) {  // ascending reference id => upstream lists come out ascending
+            const int r = c->rinv[o];
+            const int dn = M->riv_down[o];
+            const int tl = (lakeon && M->riv_toLake) ? M->riv_toLake[o] : -9999;
+            bc[r] = M->riv_BC[o];
+            toLake[r] = (tl >= 0 && tl < Nl) ? tl : -1;
+            if (dn > 0 && dn <= Nr) {
+                down[r] = c->rinv[dn - 1];
+                // PassValue: iDownStrm >= 0 && toLake <= 0 (MD_f.cpp:237)
+                if (tl <= 0) ups[c->rinv[dn - 1]].push_back(r);
+            } else {
+                down[r] = (dn > 0) ? -99 : (dn == 0 ? -99 : dn);  // outlet codes stay negative; 0 / bad -> error code
+                if (dn == 0) down[r] = -99;
+            }
+        }
+        for (int r = 0; r < Nr; r++) {
+            up_ptr[r + 1] = up_ptr[r] + (int)ups[r].size();
+            for (int u : ups[r]) up_idx.push_back(u);
+        }
+        for (int s = 0; s < Ns; s++) seg_ptr[c->rinv[M->seg_iRiv[c->sperm[s]] - 1] + 1]++;
+        for (int r = 0; r < Nr; r++) seg_ptr[r + 1] += seg_ptr[r];
+        m.r_down = dev_upload(c, down); m.r_bc = dev_upload(c, bc); m.r_toLake = dev_upload(c, toLake);
+        m.r_up_ptr = dev_upload(c, up_ptr); m.r_up_idx = dev_upload(c, up_idx); m.r_seg_ptr = dev_upload(c, seg_ptr);
+        // lakes: inflowing reaches, ascending reference id
+        std::vector<int> rin_ptr(Nl + 1, 0), rin_idx;
+        for (int l = 0; l < Nl; l++) {
+            for (int o = 0; o < Nr; o++)
+                if (toLake[c->rinv[o]] == l) rin_idx.push_back(c->rinv[o]);
+            rin_ptr[l + 1] = (int)rin_idx.size();
+        }
+        m.l_rin_ptr = dev_upload(c, rin_ptr); m.l_rin_idx = dev_upload(c, rin_idx);
+    }
+    // ---- segments ----
+    {
+        std::vector<int> s_riv(Ns);
+        std::vector<double> s_len(Ns), s_cwr(Ns);
+        for (int s = 0; s < Ns; s++) {
+            const int o = c->sperm[s];
+            s_riv[s] = c->rinv[M->seg_iRiv[o] - 1]; s_len[s] = M->seg_length[o]; s_cwr[s] = M->seg_Cwr[o];
+        }
+        m.s_riv = dev_upload(c, s_riv); m.s_len = dev_upload(c, s_len); m.s_cwr = dev_upload(c, s_cwr);
+    }
+    // ---- lakes ----
+    {
+        std::vector<double> zmin(Nl), yi0(Nl), by, ba;
+        std::vector<int> bptr(Nl + 1, 0);
+        c->lake_nele.assign(Nl, 1);
+        for (int l = 0; l < Nl; l++) {
+            zmin[l] = M->lake_zmin[l];
+            yi0[l] = M->lake_bathy_yi[M->lake_bathy_ptr[l]];
+            c->lake_nele[l] = M->lake_NumEleLake[l];
+        }
+        if (Nl > 0) {
+            const int nb = M->lake_bathy_ptr[Nl];
+            by.assign(M->lake_bathy_yi, M->lake_bathy_yi + nb);
+            ba.assign(M->lake_bathy_ai, M->lake_bathy_ai + nb);
+            bptr.assign(M->lake_bathy_ptr, M->lake_bathy_ptr + Nl + 1);
+        }
+        m.l_zmin = dev_upload(c, zmin); m.l_yi0 = dev_upload(c, yi0); m.l_by = dev_upload(c, by);
+        m.l_ba = dev_upload(c, ba); m.l_bptr = dev_upload(c, bptr); m.l_bank_ptr = dev_upload(c, l_bank_ptr);
+        m.l_evap_raw = dev_alloc<double>(c, Nl); m.l_prcp = dev_alloc<double>(c, Nl);
+        CK(cudaMemset(m.l_evap_raw, 0, sizeof(double) * std::max(Nl, 1)));
+        CK(cudaMemset(m.l_prcp, 0, sizeof(double) * std::max(Nl, 1)));
+    }
+    // ---- dynamic arrays ----
+    m.netPrep = dev_alloc<double>(c, Ne); m.potEvap = dev_alloc<double>(c, Ne); m.potTran = dev_alloc<double>(c, Ne);
+    m.lai = dev_alloc<double>(c, Ne); m.fuSurf = dev_alloc<double>(c, Ne); m.fuSub = dev_alloc<double>(c, Ne);
+    m.eic = dev_alloc<double>(c, Ne); m.satn = dev_alloc<double>(c, Ne);
+    m.ele_yBC = dev_alloc<double>(c, Ne); m.ele_QBC = dev_alloc<double>(c, Ne);
+    m.r_yBC = dev_alloc<double>(c, Nr); m.r_qBC = dev_alloc<double>(c, Nr);
+    m.effKH = dev_alloc<double>(c, Ne); m.QsegSurf = dev_alloc<double>(c, Ns); m.QsegSub = dev_alloc<double>(c, Ns);
+    m.err = dev_alloc<int>(c, 2);
+    for (double *p : {m.netPrep, m.potEvap, m.potTran, m.lai, m.fuSurf, m.fuSub, m.eic, m.satn, m.ele_yBC, m.ele_QBC,
+                      m.effKH})
+        CK(cudaMemset(p, 0, sizeof(double) * Ne));
+    CK(cudaMemset(m.r_yBC, 0, sizeof(double) * std::max(Nr, 1)));
+    CK(cudaMemset(m.r_qBC, 0, sizeof(double) * std::max(Nr, 1)));
+    CK(cudaMemset(m.err, 0, sizeof(int) * 2));
+    c->d_cperm = dev_upload(c, c->cperm); c->d_rperm = dev_upload(c, c->rperm);
+    c->y_stage = dev_alloc<double>(c, c->NY); c->y_dev = dev_alloc<double>(c, c->NY);
+    c->ydot_dev = dev_alloc<double>(c, c->NY);
+    c->h_pinned_n = (size_t)std::max(Ne, Nr);
+    CK(cudaMallocHost(&c->h_pinned, sizeof(double) * c->h_pinned_n));
+    CK(cudaDeviceSynchronize());
+    *out = c;
+    return SHUD_OK;
+}
+
+void shud_b200_destroy(shud_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void *p : c->allocs) cudaFree(p);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int64_t shud_b200_ny(const shud_ctx *c) { return c ? c->NY : 0; }
+void *shud_b200_stream(shud_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int shud_b200_launches_per_rhs(const shud_ctx *c) { return (c && (c->Nr > 0 || c->Nl > 0)) ? 3 : 2; }
+
+static int upload_perm(shud_ctx *c, double *dst, const double *src, const std::vector<int> &perm) {
+    // gather on the host into pinned memory, then one async copy (stream-ordered)
+    CK(cudaStreamSynchronize(c->stream));  // h_pinned is reused
+    const size_t n = perm.size();
+    for (size_t i = 0; i < n; i++) c->h_pinned[i] = src[perm[i]];
+    CK(cudaMemcpyAsync(dst, c->h_pinned, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return SHUD_OK;
+}
+
+int shud_b200_set_forcing(shud_ctx *c, const shud_forcing *f) {
+    if (!c || !f) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    DevMesh &m = c->m;
+    const double *src[] = {f->qEleNetPrep, f->qPotEvap, f->qPotTran, f->t_lai, f->fu_Surf, f->fu_Sub, f->qEleE_IC};
+    double *dst[] = {m.netPrep, m.potEvap, m.potTran, m.lai, m.fuSurf, m.fuSub, m.eic};
+    for (int k = 0; k < 7; k++) {
+        if (!src[k]) return SHUD_ERR_ARG;
+        int rc = upload_perm(c, dst[k], src[k], c->cperm);
+        if (rc) return rc;
+    }
+    if (f->ele_yBC) { int rc = upload_perm(c, m.ele_yBC, f->ele_yBC, c->cperm); if (rc) return rc; }
+    if (f->ele_QBC) { int rc = upload_perm(c, m.ele_QBC, f->ele_QBC, c->cperm); if (rc) return rc; }
+    if (f->riv_yBC && c->Nr) { int rc = upload_perm(c, m.r_yBC, f->riv_yBC, c->rperm); if (rc) return rc; }
+    if (f->riv_qBC && c->Nr) { int rc = upload_perm(c, m.r_qBC, f->riv_qBC, c->rperm); if (rc) return rc; }
+    // lake-cell evaporation / precipitation means, ascending reference cell order (MD_f.cpp:16-17):
+    // they depend on the forcing step only (qEleEvapo of a lake cell is qPotEvap, MD_ElementFlux.cpp:15)
+    if (c->Nl > 0) {
+        if (!f->qElePrep) return SHUD_ERR_ARG;
+        std::vector<double> ev(c->Nl, 0.), pr(c->Nl, 0.);
+        for (int o : c->lake_cells) {
+            const int l = c->lake_of_cell[o];
+            ev[l] += f->qPotEvap[o] / c->lake_nele[l];
+            pr[l] += f->qElePrep[o] / c->lake_nele[l];
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(m.l_evap_raw, ev.data(), sizeof(double) * c->Nl, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(m.l_prcp, pr.data(), sizeof(double) * c->Nl, cudaMemcpyHostToDevice));
+    }
+    return SHUD_OK;
+}
+
+int shud_b200_set_carried(shud_ctx *c, const double *satn) {
+    if (!c || !satn) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    return upload_perm(c, c->m.satn, satn, c->cperm);
+}
+
+int shud_b200_get_carried(shud_ctx *c, double *satn, double *eic) {
+    if (!c) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    std::vector<double> h(c->Ne);
+    CK(cudaStreamSynchronize(c->stream));
+    if (satn) {
+        CK(cudaMemcpy(h.data(), c->m.satn, sizeof(double) * c->Ne, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c->Ne; i++) satn[c->cperm[i]] = h[i];
+    }
+    if (eic) {
+        CK(cudaMemcpy(h.data(), c->m.eic, sizeof(double) * c->Ne, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c->Ne; i++) eic[c->cperm[i]] = h[i];
+    }
+    return SHUD_OK;
+}
+
+int shud_b200_to_device_order(shud_ctx *c, const double *ref_dev, double *dev_dev) {
+    if (!c) return SHUD_ERR_ARG;
+    k_to_dev<<<296, 256, 0, c->stream>>>(ref_dev, dev_dev, c->d_cperm, c->d_rperm, c->Ne, c->Nr, c->Nl);
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+int shud_b200_from_device_order(shud_ctx *c, const double *dev_dev, double *ref_dev) {
+    if (!c) return SHUD_ERR_ARG;
+    k_from_dev<<<296, 256, 0, c->stream>>>(dev_dev, ref_dev, c->d_cperm, c->d_rperm, c->Ne, c->Nr, c->Nl);
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+
+int shud_b200_perm(const shud_ctx *c, int32_t *cp, int32_t *rp) {
+    if (!c) return SHUD_ERR_ARG;
+    if (cp) std::copy(c->cperm.begin(), c->cperm.end(), cp);
+    if (rp) std::copy(c->rperm.begin(), c->rperm.end(), rp);
+    return SHUD_OK;
+}
+
+int shud_b200_prime(shud_ctx *c, const double *y_host) {
+    if (!c || !y_host) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->y_stage, y_host, sizeof(double) * c->NY, cudaMemcpyHostToDevice, c->stream));
+    int rc = shud_b200_to_device_order(c, c->y_stage, c->y_dev);
+    if (rc) return rc;
+    k_prime<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, c->y_dev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return SHUD_OK;
+}
+
+static int ensure_diag(shud_ctx *c) {
+    if (c->diag_alloc) return SHUD_OK;
+    DevDiag &d = c->diag;
+    const int Ne = c->Ne, Nr = c->Nr, Nl = c->Nl;
+    double **cell[] = {&d.qEleInfil, &d.qEleExfil, &d.qEleRecharge, &d.qEs, &d.qEu, &d.qEg, &d.qTu, &d.qTg,
+                       &d.qEleTrans, &d.qEleEvapo, &d.qEleETA, &d.iBeta, &d.QeleSurfTot, &d.QeleSubTot, &d.Qe2r_Surf,
+                       &d.Qe2r_Sub};
+    for (double **p : cell) {
+        *p = dev_alloc<double>(c, Ne);
+        if (!*p) return SHUD_ERR_CUDA;
+        cudaMemset(*p, 0, sizeof(double) * Ne);
+    }
+    d.QeleSurf = dev_alloc<double>(c, 3 * (size_t)Ne); d.QeleSub = dev_alloc<double>(c, 3 * (size_t)Ne);
+    double **riv[] = {&d.QrivSurf, &d.QrivSub, &d.QrivUp, &d.QrivDown};
+    for (double **p : riv) *p = dev_alloc<double>(c, Nr);
+    double **lake[] = {&d.y2LakeArea, &d.QLakeSurf, &d.QLakeSub, &d.QLakeRivIn, &d.QLakeRivOut, &d.qLakeEvap,
+                       &d.qLakePrcp};
+    for (double **p : lake) *p = dev_alloc<double>(c, Nl);
+    c->diag_alloc = true;
+    return SHUD_OK;
+}
+
+}  // extern "C"
+template <bool DIAG>
+static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
+    const int Ne = c->Ne;
+    k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+    k_cell<DIAG><<<(Ne + 127) / 128, 128, 0, c->stream>>>(c->m, c->diag, y, ydot);
+    const int nb_riv = (c->Nr + 127) / 128;
+    if (nb_riv + c->Nl > 0)
+        k_river_lake<DIAG><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+extern "C" {
+
+int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
+    (void)t;  // f() depends on t only through values uploaded by shud_b200_set_forcing
+    if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    return launch_rhs<false>(c, y, ydot);
+}
+
+int shud_b200_rhs_diag_dev(shud_ctx *c, double t, const double *y, double *ydot) {
+    (void)t;
+    if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    int rc = ensure_diag(c);
+    if (rc) return rc;
+    return launch_rhs<true>(c, y, ydot);
+}
+
+int shud_b200_check(shud_ctx *c, int32_t *where) {
+    if (!c) return SHUD_ERR_ARG;
+    int h[2] = {0, 0};
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(h, c->m.err, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[0]) {
+        CK(cudaMemset(c->m.err, 0, sizeof(h)));
+        // device ids -> reference ids (code 1 is raised by reaches, the others by cells)
+        if (where) {
+            const int k = h[1] - 1;
+            if (h[0] == SHUD_ERRRIVBC) *where = (k >= 0 && k < c->Nr) ? c->rperm[k] + 1 : 0;
+            else *where = (k >= 0 && k < c->Ne) ? c->cperm[k] + 1 : 0;
+        }
+    } else if (where) {
+        *where = 0;
+    }
+    return h[0];
+}
+
+int shud_b200_rhs(shud_ctx *c, double t, const double *y_host, double *ydot_host) {
+    if (!c || !y_host || !ydot_host) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->y_stage, y_host, sizeof(double) * c->NY, cudaMemcpyHostToDevice, c->stream));
+    int rc = shud_b200_to_device_order(c, c->y_stage, c->y_dev);
+    if (rc) return rc;
+    rc = shud_b200_rhs_dev(c, t, c->y_dev, c->ydot_dev);
+    if (rc) return rc;
+    rc = shud_b200_from_device_order(c, c->ydot_dev, c->y_stage);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ydot_host, c->y_stage, sizeof(double) * c->NY, cudaMemcpyDeviceToHost, c->stream));
+    return shud_b200_check(c, nullptr);
+}
+
+int shud_b200_get_diag(shud_ctx *c, const shud_diag *o) {
+    if (!c || !o || !c->diag_alloc) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int Ne = c->Ne, Nr = c->Nr, Ns = c->Ns, Nl = c->Nl;
+    std::vector<double> h;
+    auto cell = [&](const double *dsrc, double *dst, int nblk) -> int {
+        if (!dst) return 0;
+        h.resize((size_t)nblk * Ne);
+        if (cudaMemcpy(h.data(), dsrc, sizeof(double) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+        for (int b = 0; b < nblk; b++)
+            for (int i = 0; i < Ne; i++) dst[(size_t)b * Ne + c->cperm[i]] = h[(size_t)b * Ne + i];
+        return 0;
+    };
+    auto riv = [&](const double *dsrc, double *dst) -> int {
+        if (!dst || Nr == 0) return 0;
+        h.resize(Nr);
+        if (cudaMemcpy(h.data(), dsrc, sizeof(double) * Nr, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+        for (int i = 0; i < Nr; i++) dst[c->rperm[i]] = h[i];
+        return 0;
+    };
+    auto seg = [&](const double *dsrc, double *dst) -> int {
+        if (!dst || Ns == 0) return 0;
+        h.resize(Ns);
+        if (cudaMemcpy(h.data(), dsrc, sizeof(double) * Ns, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+        for (int i = 0; i < Ns; i++) dst[c->sperm[i]] = h[i];
+        return 0;
+    };
+    auto lake = [&](const double *dsrc, double *dst) -> int {
+        if (!dst || Nl == 0) return 0;
+        return cudaMemcpy(dst, dsrc, sizeof(double) * Nl, cudaMemcpyDeviceToHost) != cudaSuccess;
+    };
+    const DevDiag &d = c->diag;
+    int bad = 0;
+    bad |= cell(d.qEleInfil, o->qEleInfil, 1); bad |= cell(d.qEleExfil, o->qEleExfil, 1);
+    bad |= cell(d.qEleRecharge, o->qEleRecharge, 1); bad |= cell(d.qEs, o->qEs, 1); bad |= cell(d.qEu, o->qEu, 1);
+    bad |= cell(d.qEg, o->qEg, 1); bad |= cell(d.qTu, o->qTu, 1); bad |= cell(d.qTg, o->qTg, 1);
+    bad |= cell(d.qEleTrans, o->qEleTrans, 1); bad |= cell(d.qEleEvapo, o->qEleEvapo, 1);
+    bad |= cell(d.qEleETA, o->qEleETA, 1); bad |= cell(d.iBeta, o->iBeta, 1);
+    bad |= cell(c->m.effKH, o->u_effKH, 1); bad |= cell(c->m.satn, o->u_satn, 1);
+    bad |= cell(d.QeleSurf, o->QeleSurf, 3); bad |= cell(d.QeleSub, o->QeleSub, 3);
+    bad |= cell(d.QeleSurfTot, o->QeleSurfTot, 1); bad |= cell(d.QeleSubTot, o->QeleSubTot, 1);
+    bad |= cell(d.Qe2r_Surf, o->Qe2r_Surf, 1); bad |= cell(d.Qe2r_Sub, o->Qe2r_Sub, 1);
+    bad |= seg(c->m.QsegSurf, o->QsegSurf); bad |= seg(c->m.QsegSub, o->QsegSub);
+    bad |= riv(d.QrivSurf, o->QrivSurf); bad |= riv(d.QrivSub, o->QrivSub); bad |= riv(d.QrivUp, o->QrivUp);
+    bad |= riv(d.QrivDown, o->QrivDown);
+    bad |= lake(d.y2LakeArea, o->y2LakeArea); bad |= lake(d.QLakeSurf, o->QLakeSurf);
+    bad |= lake(d.QLakeSub, o->QLakeSub); bad |= lake(d.QLakeRivIn, o->QLakeRivIn);
+    bad |= lake(d.QLakeRivOut, o->QLakeRivOut); bad |= lake(d.qLakeEvap, o->qLakeEvap);
+    bad |= lake(d.qLakePrcp, o->qLakePrcp);
+    return bad ? SHUD_ERR_CUDA : SHUD_OK;
+}
+
+}  // extern "C"

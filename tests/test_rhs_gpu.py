@@ -1,0 +1,139 @@
+"""GPU parity of the CUDA RHS (through the C ABI) against the CPU oracle and the golden
+snapshots of the unmodified reference f().  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import parity
+from shud_up_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("ccw", "ic"), ("ccw", "rand1"), ("ccw", "mut2"), ("heihe", "ic"), ("heihe", "rand3"),
+         ("qhh", "ic"), ("qhh", "rand4"), ("qhh", "mut5")]
+# flux arrays compared at 1e-12 relative on their own (no cancellation inside them)
+FLUX = ["qEleInfil", "qEleExfil", "qEleRecharge", "qEs", "qEu", "qEg", "qTu", "qTg", "qEleTrans", "qEleEvapo",
+        "qEleETA", "u_effKH", "u_satn", "QeleSurf", "QeleSub", "QsegSurf", "QsegSub", "QrivDown", "y2LakeArea",
+        "qLakeEvap", "qLakePrcp", "QLakeRivIn"]
+# sums of the above: compared relative to the sum of |addends|
+SUMS = ["QeleSurfTot", "QeleSubTot", "Qe2r_Surf", "Qe2r_Sub", "QrivSurf", "QrivSub", "QrivUp", "QLakeSurf", "QLakeSub"]
+
+
+def _run_gpu(snap, diag=True):
+    import torch
+    from shud_up_b200.api import ShudRHS
+    rhs = ShudRHS(snap)
+    rhs.set_forcing(snap, qEleE_IC=snap["qEleE_IC_in"])
+    rhs.set_carried(snap["ele_u_satn"])
+    dev = torch.device("cuda:0")
+    with torch.cuda.stream(rhs.torch_stream()):
+        y_ref = torch.from_numpy(np.ascontiguousarray(snap["y"])).to(dev)
+        y_dev = torch.empty_like(y_ref)
+        yd_dev = torch.full_like(y_ref, float("nan"))
+        yd_ref = torch.empty_like(y_ref)
+        rhs.to_device_order(y_ref, y_dev)
+        rhs.f_dev(0.0, y_dev, yd_dev, diag=diag)
+        rhs.from_device_order(yd_dev, yd_ref)
+    code, where = rhs.check()
+    out = {"ydot": yd_ref.cpu().numpy(), "code": code, "where": where}
+    if diag:
+        out.update(rhs.get_diag())
+    s, e = rhs.get_carried()
+    out["u_satn_out"], out["qEleE_IC_out"] = s, e
+    return rhs, out
+
+
+@pytest.mark.parametrize("basin,case", CASES)
+def test_ydot_and_fluxes_match_oracle(basin, case):
+    snap = oracle_lib.load_case(basin, case)
+    ref = oracle_lib.oracle_rhs(snap)
+    assert ref["err"] == 0
+    rhs, got = _run_gpu(snap)
+    assert got["code"] == 0, got
+    Ne = rhs.Ne
+    scale = parity.ydot_scale(snap, ref)
+    bad = parity.mismatches(got["ydot"], ref["ydot"], scale)
+    # the golden file holds the reference's own ydot; the oracle equals it bit for bit (test_oracle_golden)
+    assert np.array_equal(ref["ydot"], snap["ydot"])
+    assert bad.size == 0, (f"{basin}.{case}: {bad.size} ydot components outside 1e-12*max(|ydot|,sum|terms|); "
+                           f"first {bad[:5]} got {got['ydot'][bad[:5]]} ref {ref['ydot'][bad[:5]]}")
+    lake = snap["ele_iLake"] > 0
+    problems = []
+    for name in FLUX:
+        if ref[name].size == 0:
+            continue
+        b = parity.mismatches(got[name], ref[name])
+        if b.size:
+            problems.append((name, b.size, b[:3].tolist()))
+    sums = {"QeleSurfTot": np.abs(ref["QeleSurf"]).reshape(3, Ne).sum(0) + np.abs(ref["Qe2r_Surf"]),
+            "QeleSubTot": np.abs(ref["QeleSub"]).reshape(3, Ne).sum(0) + np.abs(ref["Qe2r_Sub"])}
+    for name in SUMS:
+        if ref[name].size == 0:
+            continue
+        sc = sums.get(name)
+        if sc is None:  # sums over segments / reaches / bank edges: scale by the largest addend-sum available
+            sc = np.full(ref[name].shape, 0.0)
+            if name.startswith("Qe2r") or name.startswith("Qriv") or name.startswith("QLake"):
+                sc = np.full(ref[name].shape, np.abs(ref[name]).max() if ref[name].size else 0.0)
+        b = parity.mismatches(got[name], ref[name], sc)
+        if b.size:
+            problems.append((name, b.size, b[:3].tolist()))
+    b = parity.mismatches(got["iBeta"][~lake], ref["iBeta"][~lake])
+    if b.size:
+        problems.append(("iBeta", b.size, b[:3].tolist()))
+    for name in ("u_satn_out", "qEleE_IC_out"):
+        b = parity.mismatches(got[name], ref[name])
+        if b.size:
+            problems.append((name, b.size, b[:3].tolist()))
+    assert not problems, f"{basin}.{case}: {problems}"
+
+
+@pytest.mark.parametrize("basin,case", [("ccw", "rand1"), ("qhh", "mut5")])
+def test_host_entry_point_f(basin, case):
+    """shud_b200_rhs: host vectors in reference order (the CVRhsFn shape), solver mode (no diag)."""
+    from shud_up_b200.api import ShudRHS
+    snap = oracle_lib.load_case(basin, case)
+    ref = oracle_lib.oracle_rhs(snap)
+    rhs = ShudRHS(snap)
+    rhs.set_forcing(snap, qEleE_IC=snap["qEleE_IC_in"])
+    rhs.set_carried(snap["ele_u_satn"])
+    y = np.ascontiguousarray(snap["y"])
+    ydot = np.full_like(y, np.nan)
+    assert rhs.f(0.0, y, ydot) == 0
+    bad = parity.mismatches(ydot, ref["ydot"], parity.ydot_scale(snap, ref))
+    assert bad.size == 0
+    # carried state moved on exactly as the reference's did
+    s, e = rhs.get_carried()
+    assert parity.mismatches(s, ref["u_satn_out"]).size == 0
+    assert parity.mismatches(e, ref["qEleE_IC_out"]).size == 0
+    # a second call on the same y reproduces the first bit for bit (deterministic sums, no atomics)
+    ydot2 = np.empty_like(y)
+    rhs.set_forcing(snap, qEleE_IC=snap["qEleE_IC_in"])
+    rhs.set_carried(snap["ele_u_satn"])
+    rhs.f(0.0, y, ydot2)
+    assert np.array_equal(ydot, ydot2)
+
+
+def test_prime_matches_oracle():
+    from shud_up_b200.api import ShudRHS
+    snap = oracle_lib.load_case("qhh", "rand4")
+    rhs = ShudRHS(snap)
+    rhs.prime(snap["y"])
+    s, _ = rhs.get_carried()
+    assert np.array_equal(s, oracle_lib.oracle_prime(snap, snap["y"]))
+
+
+def test_device_error_word_mirrors_reference_exit_codes():
+    """NaN in y -> the reference aborts with ERRNAN (10) from CheckNonNegative/CheckNANij
+    (src/ModelData/MD_ET.cpp:394-401, MD_f.cpp:73-74); the replacement reports the same code."""
+    from shud_up_b200.api import ShudRHS, ShudError
+    snap = oracle_lib.load_case("ccw", "rand1")
+    y = snap["y"].copy()
+    y[5] = np.nan
+    ref = oracle_lib.oracle_rhs(snap, y=y)
+    assert ref["err"] == 10
+    rhs = ShudRHS(snap)
+    rhs.set_forcing(snap, qEleE_IC=snap["qEleE_IC_in"])
+    rhs.set_carried(snap["ele_u_satn"])
+    with pytest.raises(ShudError, match="code 10"):
+        rhs.f(0.0, y, np.empty_like(y))
