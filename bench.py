@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py - RHS cell-updates/s of the SHUD hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  the reference's algorithm on the host cores
+
+One "step" = one complete f(t,y,ydot) over the synthetic mesh (every cell, segment, reach, lake).
+N=1 workload: BASELINE.json configs[3], the synthetic 1M-triangle mesh + 50k reaches + 150k segments
+(seed 20240611).  N>1: weak scaling, one 1M-cell horizontal stripe of the N x 1M-cell
+mesh per rank (configs[4] at N=8 is the 8M-cell mesh); stripes follow the river-tree bands, so only
+cell states cross the cut.
+Inputs are 400 MB per rank (> the 126 MB L2), so no L2 flush is needed between timed steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rhs_cell_updates_per_sec"
+UNIT = "cell-updates/s"
+B_CELL, B_RIV, B_SEG = 392, 124, 72  # algorithmic bytes per unit and f() call
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def stripe_mesh(world, rank):
+    """the rank's share of the N x 1M-cell mesh: N=1 -> 1000x500 quads; N>1 -> the same width, 500 rows per rank"""
+    from shud_up_b200 import synth
+    cfg = synth.named("1M")
+    return synth.make(cfg["nx"], cfg["ny"], ntree=cfg["ntree"], reaches_per_tree=cfg["reaches_per_tree"],
+                      seed=synth.SEED + rank)
+
+
+def cpu_oracle_time(mesh, nthreads, budget_s=15.0, max_calls=50):
+    """time the CPU restatement of the reference f() (oracle/, the checker) on the host cores"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+    import oracle_lib
+    from shud_up_b200 import abi
+    L = oracle_lib.lib()
+    ms, keep = abi.make_mesh(mesh)
+    satn = oracle_lib.oracle_prime(mesh, mesh["y"])
+    eic = np.array(mesh["qEleE_IC_in"], dtype=np.float64, copy=True)
+    fs, keep2 = abi.make_forcing(mesh, qEleE_IC=eic)
+    y = np.ascontiguousarray(mesh["y"], dtype=np.float64)
+    ydot = np.empty_like(y)
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    call = lambda: L.shud_oracle_rhs(C.byref(ms), C.byref(fs), pd(satn), pd(eic), pd(y), pd(ydot), None, nthreads)
+    call()  # warm-up (first touch of the workspace)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        rc = call()
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= max_calls:
+            break
+    assert rc == 0
+    return el / n, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warm = a.steps, max(a.warmup, 3)
+    ncpu = os.cpu_count() or 1
+
+    if a.impl == "reference":
+        # the reference's own algorithm for this path on the host cores: the serial f() physics with
+        # `omp parallel for` on its cell / segment / reach loops (oracle port; the as-shipped OpenMP build
+        # drops ET and lakes - SURVEY.md 2.1 - and needs the basin text inputs, which do not exist on this box)
+        if rank != 0:
+            return
+        mesh = stripe_mesh(1, 0)
+        Ne = int(mesh["Ne"][0])
+        per, n = cpu_oracle_time(mesh, ncpu, budget_s=max(5.0, min(60.0, 0.1 * steps)), max_calls=max(steps, 3))
+        v = Ne / per
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
+                          "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "synthetic-1M: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
+                                     "seed": 20240611},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncpu, "kind": "port",
+                                           "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP"},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from shud_up_b200.api import ShudRHS
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    mesh = stripe_mesh(world, rank)
+    Ne, Nr, Ns, Nl = (int(mesh[k][0]) for k in ("Ne", "Nr", "Ns", "Nl"))
+    rhs = ShudRHS(mesh, device=local_rank)
+    rhs.set_forcing(mesh, qEleE_IC=mesh["qEleE_IC_in"])
+    rhs.prime(mesh["y"])
+    st = rhs.torch_stream()
+    dev = torch.device(f"cuda:{local_rank}")
+    with torch.cuda.stream(st):
+        y_ref = torch.from_numpy(np.ascontiguousarray(mesh["y"])).to(dev)
+        y = torch.empty_like(y_ref)
+        ydot = torch.empty_like(y_ref)
+        rhs.to_device_order(y_ref, y)
+    st.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value) ----------------
+    for _ in range(warm):
+        rhs.f_dev(0.0, y, ydot)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record(st)
+        for _ in range(steps):
+            rhs.f_dev(0.0, y, ydot)
+        ev1.record(st)
+        barrier()
+        ms_dev = ev0.elapsed_time(ev1)
+        if ms_dev < 1500:  # keep the region long enough for a few clock samples
+            reps = int(1500 / max(ms_dev, 1e-3)) + 1
+            for _ in range(reps):
+                for _ in range(steps):
+                    rhs.f_dev(0.0, y, ydot)
+            torch.cuda.synchronize()
+    code, where = rhs.check()
+    assert code == 0, (code, where)
+    clocks = clk.summary()
+
+    # ---------------- per-kernel timing (roofline of the dominant kernel) ----------------
+    nst = rhs.launches_per_rhs
+    kt = []
+    for s in range(nst):
+        for _ in range(3):
+            rhs.f_stage_dev(s, y, ydot)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            rhs.f_stage_dev(s, y, ydot)
+        e1.record(st)
+        st.synchronize()
+        kt.append(e0.elapsed_time(e1) / steps)
+
+    # ---------------- end to end through the CVRhsFn-shaped entry point (host vectors) ----------------
+    yh = torch.from_numpy(np.ascontiguousarray(mesh["y"])).pin_memory()
+    ydh = torch.empty_like(yh).pin_memory()
+    for _ in range(3):
+        rhs.f(0.0, yh, ydh)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(steps, 50))
+    for _ in range(n_e2e):
+        rhs.f(0.0, yh, ydh)  # H2D y, permute, 3 kernels, permute, D2H ydot, sync, error word
+    torch.cuda.synchronize()
+    s_e2e = (time.perf_counter() - t0) / n_e2e
+
+    # ---------------- reduce over ranks: max time ----------------
+    tt = torch.tensor([ms_dev, s_e2e * 1e3], dtype=torch.float64, device=dev)
+    cells = torch.tensor([float(Ne)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cells, op=dist.ReduceOp.SUM)
+    ms_dev_max, ms_e2e_max = float(tt[0]), float(tt[1])
+    total_cells = float(cells[0])
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        ms_step = ms_dev_max / steps
+        value = total_cells * steps / (ms_dev_max * 1e-3)
+        b_rhs = B_CELL * Ne + B_RIV * Nr + B_SEG * Ns
+        dom = int(np.argmax(kt))
+        names = ["k_effkh", "k_cell", "k_river_lake"]
+        # bytes of the dominant (cell) kernel: everything per cell and per segment except what the effKH
+        # pre-pass alone touches (its 4 parameters + its effKH store: 40 B/cell), DESIGN.md section 4
+        b_dom = {0: 60 * Ne, 1: (B_CELL - 40) * Ne + B_SEG * Ns, 2: B_RIV * Nr + 16 * Ns}[dom]
+        ach = b_dom / (kt[dom] * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": "synthetic-1M per GPU: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
+                          "seed": 20240611, "l2": "inputs 400 MB per rank > 126 MB L2, no flush needed",
+                          "multi_gpu": "replicated stripes (no halo exchange yet)" if world > 1 else "single GPU"},
+               "gpu_launches": nst * steps,
+               "clocks": clocks,
+               "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": b_dom, "kernel_ms": kt[dom],
+                            "all_kernels_ms": dict(zip(names, kt)),
+                            "rhs_bytes": b_rhs, "rhs_achieved_gbs": b_rhs / (ms_step * 1e-3) / 1e9,
+                            "rhs_frac": b_rhs / (ms_step * 1e-3) / 1e9 / peak},
+               "e2e": {"value": total_cells / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * rhs.NY * world,
+                       "d2h_bytes_per_step": 8 * rhs.NY * world, "ms_per_step": ms_e2e_max}}
+        if world == 1:
+            per, n = cpu_oracle_time(mesh, ncpu, budget_s=a.cpu_budget)
+            out["cpu_baseline"] = {"value": Ne / per, "unit": UNIT, "cores": ncpu, "kind": "port",
+                                   "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP on {ncpu} threads",
+                                   "ms_per_step": per * 1e3}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,9 @@ int shud_b200_perm(const shud_ctx *ctx, int32_t *cell_perm /*[Ne]*/, int32_t *re
  * returns the device error word (0, or SHUD_ERRNAN / SHUD_ERRDATAIN / SHUD_ERRRIVBC). */
 int shud_b200_rhs_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
 int shud_b200_rhs(shud_ctx *ctx, double t, const double *y_host, double *ydot_host);
+/* One launch of the RHS sequence alone (stage 0 effKH pre-pass, 1 cell kernel, 2 river+lake kernel):
+ * for per-kernel CUDA-event timing and ncu; shud_b200_rhs_dev == stages 0,1,2 in order. */
+int shud_b200_rhs_stage_dev(shud_ctx *ctx, int stage, const double *y_dev, double *ydot_dev);
 /* Same arithmetic, and additionally stores every flux array of shud_diag on the device. */
 int shud_b200_rhs_diag_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
 /* Download the flux arrays left by the last shud_b200_rhs_diag_dev (host pointers). */

@@ -263,6 +263,11 @@ int main(int argc, char **argv) {
             Y[3 * Ne + i] = (r < 0.1) ? 0. : (r < 0.15 ? -1e-3 * urand() : (r < 0.25 ? d * (1.0 + 0.3 * urand()) : 0.5 * d * urand()));
         }
         for (int i = 0; i < Nl; i++) Y[3 * Ne + Nr + i] *= (0.5 + urand());
+        /* interception evaporation: ET() leaves 0 when the canopy store is empty (it is, at the
+         * initial condition); give f_etFlux both of its branches (qEleE_IC >= / < qPotTran,
+         * src/ModelData/MD_ET.cpp:368-379) */
+        for (int i = 0; i < Ne; i++)
+            MD->qEleE_IC[i] = (urand() < 0.3) ? 0. : 1.5 * urand() * MD->qPotTran[i];
     }
     /* the reference never refreshes uYgw of flux-BC cells (iBC<0,
      * src/ModelData/MD_update.cpp:114-124) - a stale read; the replacement uses

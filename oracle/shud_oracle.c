@@ -40,6 +40,11 @@
 #define MIN(a, b) ((a) > (b) ? (b) : (a))
 #define MAX(a, b) ((a) < (b) ? (b) : (a))
 
+#include <stdio.h>
+#include <time.h>
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+static int g_prof = -1;
+#define PROF(tag) do { if (g_prof > 0) { double t_ = now_s(); fprintf(stderr, "[oracle] %-10s %.1f ms\n", tag, (t_ - t_prof) * 1e3); t_prof = t_; } } while (0)
 const char *shud_oracle_version(void) { return "shud_oracle r1 (serial f(), SoA)"; }
 
 /* src/Equations/functions.cpp:90-103 */
@@ -288,10 +293,21 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
 #ifndef _OPENMP
     nthreads = 1;
 #endif
-    /* ---- scratch: the reference's global/Model_Data work arrays ---- */
-    size_t nd = 24 * NE + 12 * (size_t)Nr + 2 * (size_t)Ns + 9 * (size_t)Nl + 16;
-    double *W = (double *)calloc(nd, sizeof(double));
-    if (!W) return SHUD_ERR_ARG;
+    if (g_prof < 0) g_prof = getenv("SHUD_ORACLE_PROF") ? 1 : 0;
+    double t_prof = now_s();
+    /* ---- scratch: the reference's global/Model_Data work arrays.  Like the reference's, they
+     * persist between calls (one cached workspace per process; not thread-safe - neither is f()). ---- */
+    size_t nd = 26 * NE + 12 * (size_t)Nr + 2 * (size_t)Ns + 9 * (size_t)Nl + 16;
+    static double *W = NULL;
+    static size_t Wn = 0;
+    if (Wn < nd) {
+        free(W);
+        W = (double *)malloc(nd * sizeof(double));
+        Wn = W ? nd : 0;
+        if (!W) return SHUD_ERR_ARG;
+#pragma omp parallel for num_threads(nthreads) if (nthreads > 1) schedule(static)
+        for (long k = 0; k < (long)nd; k++) W[k] = 0.; /* first touch spread over the threads */
+    }
     double *p = W;
 #define TAKE(n) (p += (n), p - (n))
     double *uYsf = TAKE(NE), *uYus = TAKE(NE), *uYgw = TAKE(NE), *QBC = TAKE(NE);
@@ -302,15 +318,23 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
     c.effKH = TAKE(NE); c.deficit = TAKE(NE); c.Kmax = TAKE(NE); c.theta = TAKE(NE); c.satKr = TAKE(NE);
     c.satn = u_satn_io;
     double *QeleSurf = TAKE(3 * NE), *QeleSub = TAKE(3 * NE);
+    double *Qe2rS = TAKE(NE), *Qe2rG = TAKE(NE);
     double *uYriv = TAKE(Nr), *qBC = TAKE(Nr), *topWidth = TAKE(Nr), *CSarea = TAKE(Nr), *CSperem = TAKE(Nr);
     double *QrivSurf = TAKE(Nr), *QrivSub = TAKE(Nr), *QrivUp = TAKE(Nr), *QrivDown = TAKE(Nr);
     double *QsegSurf = TAKE(Ns), *QsegSub = TAKE(Ns);
     double *yLakeStg = TAKE(Nl), *y2LakeArea = TAKE(Nl), *QLakeSurf = TAKE(Nl), *QLakeSub = TAKE(Nl);
     double *QLakeRivIn = TAKE(Nl), *QLakeRivOut = TAKE(Nl), *qLakeEvap = TAKE(Nl), *qLakePrcp = TAKE(Nl);
-    double *Qe2rS = (double *)calloc(2 * NE + 1, sizeof(double)), *Qe2rG = Qe2rS + NE;
-    if (!Qe2rS) { free(W); return SHUD_ERR_ARG; }
+    /* the accumulators f_update resets every call (MD_update.cpp:165-185) */
+#pragma omp parallel for num_threads(nthreads) if (nthreads > 1) schedule(static)
+    for (int i = 0; i < Ne; i++) { Qe2rS[i] = 0.; Qe2rG[i] = 0.; }
+    for (int i = 0; i < Nr; i++) { QrivSurf[i] = 0.; QrivSub[i] = 0.; QrivUp[i] = 0.; }
+    for (int l = 0; l < Nl; l++) {
+        QLakeSurf[l] = 0.; QLakeSub[l] = 0.; qLakeEvap[l] = 0.; qLakePrcp[l] = 0.; QLakeRivIn[l] = 0.; QLakeRivOut[l] = 0.;
+    }
 
+    PROF("alloc");
     /* ================= f_update, src/ModelData/MD_update.cpp:102-189 ================= */
+#pragma omp parallel for num_threads(nthreads) if (nthreads > 1) schedule(static)
     for (int i = 0; i < Ne; i++) {
         uYsf[i] = Y[i];
         uYus[i] = Y[i + NE];
@@ -346,6 +370,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
         y2LakeArea[l] = lake_toparea(m->lake_bathy_yi + b0, m->lake_bathy_ai + b0, b1 - b0, yLakeStg[l] + m->lake_zmin[l]);
     }
 
+    PROF("f_update");
     /* ================= f_loop, src/ModelData/MD_f.cpp:9-50 ================= */
     /* ---- LOOP A (MD_f.cpp:11-26) ---- */
 #pragma omp parallel for num_threads(nthreads) if (nthreads > 1) reduction(max : err) schedule(static)
@@ -471,6 +496,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
         }
         if (e > err) err = e;
     }
+    PROF("loopA");
     /* lake-cell accumulations of LOOP A, ascending cell order (MD_f.cpp:16-17) */
     if (m->lakeon)
         for (int i = 0; i < Ne; i++)
@@ -571,6 +597,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
             QeleSub[j * NE + i] = Q * F->fu_Sub[i];
         }
     }
+    PROF("loopB");
     /* bank-edge accumulations of LOOP B, ascending (cell, edge) order (MD_ElementFlux.cpp:52,121).
      * QLakeSub accumulates Q BEFORE the fu_Sub factor (line 121 precedes line 153). */
     if (m->lakeon && Nl > 0)
@@ -600,6 +627,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
             }
         }
 
+    PROF("loopC_pre");
     /* ---- LOOP C (MD_f.cpp:37-40): fun_Seg_surface / fun_Seg_sub, MD_RiverFlux.cpp:100-126 ---- */
 #pragma omp parallel for num_threads(nthreads) if (nthreads > 1) schedule(static)
     for (int s = 0; s < Ns; s++) {
@@ -612,6 +640,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
                                  m->riv_KsatH[ir], m->seg_length[s], m->riv_BedThick[ir]);
         QsegSub[s] *= F->fu_Sub[ie];
     }
+    PROF("loopC");
     /* ---- LOOP D (MD_f.cpp:41-43): Flux_RiverDown, MD_RiverFlux.cpp:5-63 ---- */
 #pragma omp parallel for num_threads(nthreads) if (nthreads > 1) reduction(max : err) schedule(static)
     for (int i = 0; i < Nr; i++) {
@@ -659,6 +688,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
         qLakeEvap[l] = MIN(qLakeEvap[l], qLakePrcp[l] + yLakeStg[l]);
         qLakeEvap[l] = MAX(0, qLakeEvap[l]);
     }
+    PROF("loopD");
     /* ---- PassValue, MD_f.cpp:217-240: ordered scatter-add, ascending source index ---- */
     for (int s = 0; s < Ns; s++) {
         const int ie = m->seg_iEle[s] - 1, ir = m->seg_iRiv[s] - 1;
@@ -672,6 +702,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
         if (iDown >= 0 && m->riv_toLake[i] <= 0) QrivUp[iDown] += -QrivDown[i];
     }
 
+    PROF("PassValue");
     /* ================= f_applyDY, src/ModelData/MD_f.cpp:52-191 ================= */
 #pragma omp parallel for num_threads(nthreads) if (nthreads > 1) reduction(max : err) schedule(static)
     for (int i = 0; i < Ne; i++) {
@@ -721,6 +752,7 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
                               (QLakeRivIn[l] - QLakeRivOut[l] + QLakeSub[l] + QLakeSurf[l]) / y2LakeArea[l];
     }
 
+    PROF("applyDY");
     /* ---- diagnostics ---- */
     if (diag) {
 #define COPY(dst, src, n) do { if (diag->dst) memcpy(diag->dst, src, sizeof(double) * (size_t)(n)); } while (0)
@@ -735,7 +767,5 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
         COPY(QLakeRivIn, QLakeRivIn, Nl); COPY(QLakeRivOut, QLakeRivOut, Nl);
         COPY(qLakeEvap, qLakeEvap, Nl); COPY(qLakePrcp, qLakePrcp, Nl);
     }
-    free(Qe2rS);
-    free(W);
     return err;
 }

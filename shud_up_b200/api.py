@@ -55,6 +55,7 @@ def lib():
         "shud_b200_perm": (C.c_int, [vp, _PI, _PI]),
         "shud_b200_rhs_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs": (C.c_int, [vp, C.c_double, vp, vp]),
+        "shud_b200_rhs_stage_dev": (C.c_int, [vp, C.c_int, vp, vp]),
         "shud_b200_rhs_diag_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_get_diag": (C.c_int, [vp, C.POINTER(abi.ShudDiag)]),
         "shud_b200_check": (C.c_int, [vp, _PI]),
@@ -162,6 +163,9 @@ class ShudRHS:
         """asynchronous RHS on device vectors in device order (torch cuda float64 tensors)."""
         fn = lib().shud_b200_rhs_diag_dev if diag else lib().shud_b200_rhs_dev
         _chk(fn(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "shud_b200_rhs_dev")
+
+    def f_stage_dev(self, stage, y_dev, ydot_dev):
+        _chk(lib().shud_b200_rhs_stage_dev(self._h, int(stage), _ptr(y_dev), _ptr(ydot_dev)), "rhs_stage_dev")
 
     def check(self):
         where = C.c_int32(0)

@@ -861,6 +861,19 @@ int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     return launch_rhs<false>(c, y, ydot);
 }
 
+// one launch of the sequence on its own (profiling / per-kernel CUDA-event timing in bench.py)
+int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydot) {
+    if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
+    if (stage == 0) k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+    else if (stage == 1) k_cell<false><<<(Ne + 127) / 128, 128, 0, c->stream>>>(c->m, c->diag, y, ydot);
+    else if (stage == 2 && nb_riv + c->Nl > 0)
+        k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    else return SHUD_ERR_ARG;
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+
 int shud_b200_rhs_diag_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     (void)t;
     if (!c || !y || !ydot) return SHUD_ERR_ARG;

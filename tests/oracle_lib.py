@@ -3,12 +3,15 @@ tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference l
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 _LIB = None
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 from shud_up_b200 import abi, snapshot  # noqa: E402
 

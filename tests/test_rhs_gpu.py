@@ -129,7 +129,7 @@ def test_device_error_word_mirrors_reference_exit_codes():
     from shud_up_b200.api import ShudRHS, ShudError
     snap = oracle_lib.load_case("ccw", "rand1")
     y = snap["y"].copy()
-    y[5] = np.nan
+    y[2 * int(snap["Ne"][0]) + 5] = np.nan  # a NaN groundwater head -> NaN edge flux -> CheckNANij
     ref = oracle_lib.oracle_rhs(snap, y=y)
     assert ref["err"] == 10
     rhs = ShudRHS(snap)

@@ -34,7 +34,7 @@ DYNAMIC_ELE = ("ele_yBC", "ele_QBC", "ele_u_satn", "riv_yBC", "riv_qBC")
 def rainy_minute(basin, start_min):
     a = np.loadtxt(os.path.join(REF, "input", basin, "forcing.csv"), skiprows=2)
     ok = np.where((a[:, 1] > 0.5) & (a[:, 2] > 3.0) & (a[:, 5] > 100.0) & (a[:, 0] * 1440 > start_min + 1440))[0]
-    return float(round(a[ok[0], 0] * 1440.0))
+    return float(round(a[ok[0], 0] * 1440.0)) + 5.0  # inside the rainy record, not on its edge
 
 
 CASES = [
