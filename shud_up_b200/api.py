@@ -16,7 +16,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshud_b200.so")
+LIB_PATH = os.environ.get("SHUD_B200_LIB", os.path.join(_HERE, "libshud_b200.so"))  # env override: A/B builds
 _lib = None
 _PD = C.POINTER(C.c_double)
 _PI = C.POINTER(C.c_int32)

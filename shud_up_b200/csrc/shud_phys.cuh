@@ -28,12 +28,28 @@ __device__ __forceinline__ bool bad_nonneg(double x) {
     return x < 0.0 || not_finite(x) || fabs(x - kNA_VALUE) < kZERO;
 }
 
+// Division by a STATIC quantity.  Default: the IEEE division the reference performs.  With SHUD_RCP the
+// host stores the reciprocal of that static array instead and the kernel multiplies (<= 1.5 ulp away
+// from the quotient; inside the 1e-12 parity tolerance, not bit-identical).
+#ifdef SHUD_RCP
+#define SHUD_DIVS(x, d_or_rcp) ((x) * (d_or_rcp))
+#else
+#define SHUD_DIVS(x, d_or_rcp) ((x) / (d_or_rcp))
+#endif
+
 // ManningEquation, src/Equations/Equations.hpp:54-63 (pow23 = cbrt^2, :36-39)
 __device__ __forceinline__ double manning(double area, double rough, double R, double S) {
     const double c = cbrt(R);
     const double p23 = c * c;
     if (S > 0) return sqrt(S) * area * p23 / rough;
     return -1.0 * sqrt(-S) * area * p23 / rough;
+}
+// same, for a cell edge: `rough` is the static avgRough[j] (or its reciprocal under SHUD_RCP)
+__device__ __forceinline__ double manning_edge(double area, double rough, double R, double S) {
+    const double c = cbrt(R);
+    const double p23 = c * c;
+    if (S > 0) return SHUD_DIVS(sqrt(S) * area * p23, rough);
+    return SHUD_DIVS(-1.0 * sqrt(-S) * area * p23, rough);
 }
 
 // effKH, src/Equations/Equations.cpp:116-134.  Range violation -> *err = 13 (myexit(ERRDATAIN)).
@@ -53,8 +69,17 @@ __device__ __forceinline__ double eff_kh(double ygw, double aqd, double macD, do
 }
 
 // van Genuchten-Mualem relative conductivity, satKfun, src/Equations/Equations.cpp:136-141
+// x^a for 0 < x < 1.  SHUD_POW_EXPLOG: exp(a log x) - |a log x| ulp-level error (<= ~2e-14 relative for the
+// exponents here) instead of pow()'s <= 2 ulp, at well under half the instructions.
+__device__ __forceinline__ double pow01(double x, double a) {
+#ifdef SHUD_POW_EXPLOG
+    return exp(a * log(x));
+#else
+    return pow(x, a);
+#endif
+}
 __device__ __forceinline__ double sat_kr(double s, double n) {
-    const double t = -1. + pow(1. - pow(s, n / (n - 1.)), (n - 1.) / n);
+    const double t = -1. + pow01(1. - pow01(s, n / (n - 1.)), (n - 1.) / n);
     return sqrt(s) * t * t;
 }
 
@@ -298,9 +323,9 @@ __device__ __forceinline__ double edge_surface(double isf, double zs, double nsf
     double ym = (h1 > h2) ? ((isf > depression) ? isf : 0.) : ((nsf > depression) ? nsf : 0.);
     ym = dmin(ym, kMAXYSURF);
     if (ym <= 0.) return 0.;
-    const double s = dh / dist;
+    const double s = SHUD_DIVS(dh, dist);
     if ((s > 0 && isf <= 0) || (s < 0 && nsf <= 0)) return 0.;
-    return manning(ym * B, rough, ym, s);
+    return manning_edge(ym * B, rough, ym, s);
 }
 
 // groundwater flux through one edge, fun_Ele_sub, src/ModelData/MD_ElementFlux.cpp:107-138 (before fu_Sub).
@@ -310,7 +335,7 @@ __device__ __forceinline__ double edge_sub(double ygw, double zb, double y_n, do
     const double dh = (ygw + zb) - (y_n + z_n);
     if ((dh > 0. && ygw <= 0.02) || (dh < 0. && y_n <= 0.02)) return 0.;
     const double ym = (dmax(ygw, 0.) + dmax(y_n, 0.)) * .5;  // avgY_gw, Equations.cpp:52-56
-    const double grad = dh / dist;
+    const double grad = SHUD_DIVS(dh, dist);
     const double km = 0.5 * (kh + kh_n);
     return km * grad * ym * B;
 }

@@ -8,7 +8,7 @@
 //   * every flux is evaluated owner-computes (cell i computes its own 3 edges and its own
 //     river segments; a reach re-evaluates its upstream reaches' Manning flux) - no atomics,
 //     every sum runs in a fixed order, so ydot is run-to-run reproducible;
-//   * launches per RHS: effKH pre-pass, cell kernel, river+lake kernel.
+//   * launches per RHS: effKH pre-pass, warp-specialised fused cell kernel, river+lake kernel.
 // Device vectors are in DEVICE ORDER (permuted); shud_b200_rhs() (host pointers, reference
 // order) permutes on the way in and out.
 #include <cuda_runtime.h>
@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -39,8 +40,12 @@ struct DevMesh {
     const double *edge, *dist, *dist2edge, *avgRough;  // [3][Ne]
     const int *nbr;                                    // [3][Ne]: >=0 cell, -1 boundary, <=-2 bank slot (-2-v)
     const unsigned *flags;
-    const int *cell_seg_first;  // valid where nseg>0: first entry in cell_seg_idx
-    const int *cell_seg_idx;    // segment (device order) ids, ascending reference id per cell
+    const int *cell_seg_first;  // first slot of the cell in the cell-ordered segment table below
+    // cell-ordered segment table (slot = cell_seg_first[i] + k, ascending reference segment id per cell):
+    // everything static the cell side of a segment needs, copied next to each other so that the only
+    // dependent gather left is the reach stage
+    const int *cs_seg, *cs_riv, *cs_bc;  // segment id (device order), reach id (device order), reach BC code
+    const double *cs_len, *cs_cwr, *cs_depth, *cs_zbank, *cs_ksatH, *cs_bed;
     // forcing step
     double *netPrep, *potEvap, *potTran, *lai, *fuSurf, *fuSub, *eic, *satn, *ele_yBC, *ele_QBC;
     // work
@@ -94,77 +99,104 @@ __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restri
 // K1: everything a cell owns: ET partition, infiltration, recharge, its 3 overland and 3
 // groundwater edge fluxes, its river segments, and the three balance equations.
 // ---------------------------------------------------------------------------------------------
-template <bool DIAG>
-__global__ void __launch_bounds__(128) k_cell(DevMesh m, DevDiag d, const double *__restrict__ Y,
-                                              double *__restrict__ DY) {
+template <bool DIAG, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const double *__restrict__ Y,
+                                                    double *__restrict__ DY) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int Ne = m.Ne;
-    if (i >= Ne) return;
     const size_t NE = (size_t)Ne;
-    const unsigned fl = m.flags[i];
-    const double ysf = Y[i], yus = Y[NE + i];
-    const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : Y[2 * NE + i];
-    const double zs = m.z_surf[i], zb = m.z_bottom[i], depression = m.depression[i];
-    const double fuSub = m.fuSub[i];
+    if (i >= Ne) return;
+    // ---- phase 0: every load this cell owns is issued before anything is consumed, so one warp keeps
+    //      ~45 coalesced 256-byte requests in flight (the kernel is latency-bound otherwise) ----
+    const unsigned fl = __ldg(m.flags + i);
+    const int seg0 = __ldg(m.cell_seg_first + i);
+    const int nb0 = __ldg(m.nbr + i), nb1 = __ldg(m.nbr + NE + i), nb2 = __ldg(m.nbr + 2 * NE + i);
+    const double ysf = Y[i], yus = Y[NE + i], ygw_raw = Y[2 * NE + i];
     const double kh = m.effKH[i];
+    const double satn_prev = m.satn[i], eic_in = m.eic[i];
+    CellForc f;
+    f.netPrep = __ldg(m.netPrep + i); f.potEvap = __ldg(m.potEvap + i); f.potTran = __ldg(m.potTran + i);
+    f.lai = __ldg(m.lai + i); f.fuSurf = __ldg(m.fuSurf + i); f.fuSub = __ldg(m.fuSub + i);
+    CellParams p;
+    p.aqd = __ldg(m.aqd + i); p.sy = __ldg(m.sy + i); p.infD = __ldg(m.infD + i); p.infKsatV = __ldg(m.infKsatV + i);
+    p.macKsatV = __ldg(m.macKsatV + i); p.hAreaF = __ldg(m.hAreaF + i); p.thetaS = __ldg(m.thetaS + i);
+    p.thetaR = __ldg(m.thetaR + i); p.thetaFC = __ldg(m.thetaFC + i); p.beta = __ldg(m.beta + i);
+    p.ksatV = __ldg(m.ksatV + i); p.vegFrac = __ldg(m.vegFrac + i); p.impAF = __ldg(m.impAF + i);
+    p.wetland = __ldg(m.wetland + i); p.rootReach = __ldg(m.rootReach + i);
+    const double zs = __ldg(m.z_surf + i), zb = __ldg(m.z_bottom + i), depression = __ldg(m.depression + i);
+    const double area = __ldg(m.area + i);
+    double B[3], dist[3], arough[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        B[j] = __ldg(m.edge + j * NE + i);
+        dist[j] = __ldg(m.dist + j * NE + i);
+        arough[j] = __ldg(m.avgRough + j * NE + i);
+    }
+    // ---- phase 1: neighbour gathers, unconditional (index clamped to the cell itself where there is no
+    //      neighbour cell) so that all 15 go out together as soon as the indices land ----
+    const int nb[3] = {nb0, nb1, nb2};
+    double n_ysf[3], n_ygw[3], n_zs[3], n_zb[3], n_kh[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int k = nb[j] >= 0 ? nb[j] : i;
+        n_ysf[j] = Y[k];
+        n_ygw[j] = Y[2 * NE + k];
+        n_zs[j] = __ldg(m.z_surf + k);
+        n_zb[j] = __ldg(m.z_bottom + k);
+        n_kh[j] = m.effKH[k];
+    }
+    const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : ygw_raw;
+    const double fuSub = f.fuSub;
     int err = 0;
 
+    // ---- phase 2: vertical processes (own data only; the gathers are still in flight) ----
     CellVert v;
-    double netPrep = m.netPrep[i];
-    double Qs[3], Qg[3];
     if (fl & F_LAKE) {
-        // fun_Ele_lakeVertical / fun_Ele_lakeHorizon, src/ModelData/MD_ElementFlux.cpp:2-23
+        // fun_Ele_lakeVertical, src/ModelData/MD_ElementFlux.cpp:2-17
         v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
         v.satn = 1.; v.infil = v.exfil = v.rech = 0.; v.err = 0;
-        Qs[0] = Qs[1] = Qs[2] = 0.; Qg[0] = Qg[1] = Qg[2] = 0.;
-        if (DIAG) {
-            const double pe = m.potEvap[i];
-            d.qEleTrans[i] = 0.; d.qEleEvapo[i] = pe; d.qEleETA[i] = 0. + pe + 0.;
-        }
     } else {
-        CellParams p;
-        p.aqd = m.aqd[i]; p.sy = 0.; p.infD = m.infD[i]; p.infKsatV = m.infKsatV[i]; p.macKsatV = m.macKsatV[i];
-        p.hAreaF = m.hAreaF[i]; p.thetaS = m.thetaS[i]; p.thetaR = m.thetaR[i]; p.thetaFC = m.thetaFC[i];
-        p.beta = m.beta[i]; p.ksatV = m.ksatV[i]; p.vegFrac = m.vegFrac[i]; p.impAF = m.impAF[i];
-        p.wetland = m.wetland[i]; p.rootReach = m.rootReach[i];
-        CellForc f;
-        f.netPrep = netPrep; f.potEvap = m.potEvap[i]; f.potTran = m.potTran[i]; f.lai = m.lai[i];
-        f.fuSurf = m.fuSurf[i]; f.fuSub = fuSub;
-        v = cell_vertical(p, f, ysf, yus, ygw, m.satn[i], m.eic[i]);
+        v = cell_vertical(p, f, ysf, yus, ygw, satn_prev, eic_in);
         if (v.err) err = v.err;
-        if (DIAG) {
+    }
+    m.eic[i] = v.eic;
+    m.satn[i] = v.satn;
+    if (DIAG) {
+        if (fl & F_LAKE) {
+            d.qEleTrans[i] = 0.; d.qEleEvapo[i] = f.potEvap; d.qEleETA[i] = 0. + f.potEvap + 0.;
+        } else {
             const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
             d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
             d.iBeta[i] = v.iBeta;
         }
-        // ---- lateral fluxes through the 3 edges ----
+    }
+
+    // ---- phase 3: lateral fluxes through the 3 edges (fun_Ele_surface / fun_Ele_sub) ----
+    double Qs[3] = {0., 0., 0.}, Qg[3] = {0., 0., 0.};
+    if (!(fl & F_LAKE)) {  // fun_Ele_lakeHorizon: a lake cell has no lateral flux of its own
         const double isf = ysf < 0. ? 0. : ysf;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const int nb = m.nbr[j * NE + i];
-            const double B = m.edge[j * NE + i];
             double qs = 0., qg = 0.;
-            if (nb >= 0) {
-                double nsf = Y[nb];
-                nsf = nsf < 0. ? 0. : nsf;
-                double ygw_n = Y[2 * NE + nb];
-                if (m.has_headbc && (m.flags[nb] & F_HEADBC)) ygw_n = m.ele_yBC[nb];
-                const double dist = m.dist[j * NE + i];
-                qs = edge_surface(isf, zs, nsf, m.z_surf[nb], depression, dist, B, m.avgRough[j * NE + i]);
-                qg = edge_sub(ygw, zb, ygw_n, m.z_bottom[nb], kh, m.effKH[nb], dist, B);
-            } else if (nb <= -2) {
+            if (nb[j] >= 0) {
+                const double nsf = n_ysf[j] < 0. ? 0. : n_ysf[j];
+                double ygw_n = n_ygw[j];
+                if (m.has_headbc && (m.flags[nb[j]] & F_HEADBC)) ygw_n = m.ele_yBC[nb[j]];
+                qs = edge_surface(isf, zs, nsf, n_zs[j], depression, dist[j], B[j], arough[j]);
+                qg = edge_sub(ygw, zb, ygw_n, n_zb[j], kh, n_kh[j], dist[j], B[j]);
+            } else if (nb[j] <= -2) {
                 // bank of a lake: weir over the shore + Darcy against the lake stage (MD_ElementFlux.cpp:46-53,107-121)
-                const int slot = -2 - nb, l = m.bank_lake[slot];
+                const int slot = -2 - nb[j], l = m.bank_lake[slot];
                 const double yl = Y[3 * NE + m.Nr + l];
                 const double nsf = yl < 0. ? 0. : yl;
-                qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, B, 0.01);
-                qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], m.dist[j * NE + i], B);
+                qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, B[j], 0.01);
+                qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], dist[j], B[j]);
             } else if (!m.close_boundary) {
                 // open boundary (MD_ElementFlux.cpp:81-92,139-151)
                 const double d2e = m.dist2edge[j * NE + i];
                 if (isf > depression) {
                     const double s = isf / d2e * 0.5;
-                    if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B / m.rough[i];
+                    if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B[j] / m.rough[i];
                 }
                 if (ygw > depression * 10.) {
                     const double grad = ygw / d2e * 0.5;
@@ -175,23 +207,21 @@ __global__ void __launch_bounds__(128) k_cell(DevMesh m, DevDiag d, const double
             Qg[j] = qg * fuSub;
         }
     }
-    m.eic[i] = v.eic;
-    m.satn[i] = v.satn;
 
     // ---- river segments touching this cell (fun_Seg_surface / fun_Seg_sub, MD_RiverFlux.cpp:100-126;
     //      PassValue's element side, MD_f.cpp:228-235) ----
     double e2rS = 0., e2rG = 0.;
     const int nseg = (int)(fl >> NSEG_SHIFT);
     if (nseg) {
-        const int k0 = m.cell_seg_first[i];
         double isf2 = ysf - v.infil + v.exfil;
         isf2 = dmax(0., isf2);
         for (int k = 0; k < nseg; k++) {
-            const int s = m.cell_seg_idx[k0 + k], r = m.s_riv[s];
-            const double yr = (m.r_bc[r] > 0) ? m.r_yBC[r] : Y[3 * NE + r];
-            const double zr = zs - m.r_depth[r], len = m.s_len[s];
-            const double qs = weir_jtoi(zs, isf2, zr, yr, zs + m.r_zbank[r], m.s_cwr[s], len, depression);
-            const double qg = flux_r2e_gw(yr, zr, ygw, zb, kh, m.r_ksatH[r], len, m.r_bed[r]) * fuSub;
+            const int q = seg0 + k;
+            const int s = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
+            const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
+            const double zr = zs - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
+            const double qs = weir_jtoi(zs, isf2, zr, yr, zs + __ldg(m.cs_zbank + q), __ldg(m.cs_cwr + q), len, depression);
+            const double qg = flux_r2e_gw(yr, zr, ygw, zb, kh, __ldg(m.cs_ksatH + q), len, __ldg(m.cs_bed + q)) * fuSub;
             m.QsegSurf[s] = qs;
             m.QsegSub[s] = qg;
             e2rS += -qs;
@@ -200,7 +230,6 @@ __global__ void __launch_bounds__(128) k_cell(DevMesh m, DevDiag d, const double
     }
 
     // ---- f_applyDY, cell part (MD_f.cpp:65-156) ----
-    const double area = m.area[i];
     double surfTot = e2rS, subTot = e2rG;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -208,16 +237,15 @@ __global__ void __launch_bounds__(128) k_cell(DevMesh m, DevDiag d, const double
         subTot += Qg[j];
         if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
     }
-    double dsf = netPrep - v.infil + v.exfil - surfTot / area - v.Es;
+    double dsf = f.netPrep - v.infil + v.exfil - SHUD_DIVS(surfTot, area) - v.Es;
     double dus = v.infil - v.rech - v.Eu - v.Tu;
-    double dgw = v.rech - v.exfil - subTot / area - v.Eg - v.Tg;
+    double dgw = v.rech - v.exfil - SHUD_DIVS(subTot, area) - v.Eg - v.Tg;
     if (fl & F_HEADBC) dgw = 0;
-    else if (fl & F_FLUXBC) dgw += m.ele_QBC[i] / area;
-    if (fl & F_SS_SURF) dsf += m.qss[i] / area;
-    else if (fl & F_SS_GW) dgw += m.qss[i] / area;
-    const double sy = m.sy[i];
-    dus /= sy;
-    dgw /= sy;
+    else if (fl & F_FLUXBC) dgw += SHUD_DIVS(m.ele_QBC[i], area);
+    if (fl & F_SS_SURF) dsf += SHUD_DIVS(m.qss[i], area);
+    else if (fl & F_SS_GW) dgw += SHUD_DIVS(m.qss[i], area);
+    dus = SHUD_DIVS(dus, p.sy);
+    dgw = SHUD_DIVS(dgw, p.sy);
     if (fl & F_LAKE) { dsf = 0.; dus = 0.; dgw = 0.; }
     DY[i] = dsf;
     DY[NE + i] = dus;
@@ -226,6 +254,195 @@ __global__ void __launch_bounds__(128) k_cell(DevMesh m, DevDiag d, const double
     if (DIAG) {
         d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech;
         d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
+        d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised fused cell kernel.  A 256-thread block owns a tile of 128 consecutive cells
+// (consecutive along the Hilbert curve, so a compact patch of the mesh):
+//   warps 0-3 ("lateral" role, one thread per cell): stage the tile's Ysurf, Ygw, z_surf, z_bottom and
+//       effKH in shared memory, take the neighbour values of the 3 edges from there (global memory only
+//       for the ~10 % of neighbours outside the tile), compute the 3 overland + 3 groundwater edge
+//       fluxes, then - once the vertical role has handed over - the river segments and the surface and
+//       groundwater balance equations;
+//   warps 4-7 ("vertical" role, one thread per cell): ET partition, updateElement, infiltration,
+//       recharge; store the carried state and ydot[unsat]; hand P1, Es, G1, Eg, Tg and the ponding left
+//       for the river weir to the lateral role through shared memory.
+// Each role keeps about half of the cell's ~45 inputs live, so twice as many warps are resident as in
+// the one-thread-per-cell form, with no extra HBM traffic.  No atomics; every sum in a fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int TILE = 128;
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <bool DIAG, int MINB>
+__global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, const double *__restrict__ Y,
+                                                          double *__restrict__ DY) {
+    __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE];
+    __shared__ double x_P1[TILE], x_Es[TILE], x_G1[TILE], x_Eg[TILE], x_Tg[TILE], x_isf2[TILE];
+    const int Ne = m.Ne;
+    const size_t NE = (size_t)Ne;
+    const int lane_cell = threadIdx.x & (TILE - 1);
+    const int i0 = blockIdx.x * TILE;
+    const int i = i0 + lane_cell;
+    const bool valid = i < Ne;
+    const int ic = valid ? i : Ne - 1;  // clamped index: tail threads load something harmless
+    const unsigned fl = __ldg(m.flags + ic);
+
+    if (threadIdx.x >= TILE) {
+        // =============================== vertical role ===============================
+        const double ysf = Y[ic], yus = Y[NE + ic], ygw_raw = Y[2 * NE + ic];
+        const double satn_prev = m.satn[ic], eic_in = m.eic[ic];
+        CellForc f;
+        f.netPrep = __ldg(m.netPrep + ic); f.potEvap = __ldg(m.potEvap + ic); f.potTran = __ldg(m.potTran + ic);
+        f.lai = __ldg(m.lai + ic); f.fuSurf = __ldg(m.fuSurf + ic); f.fuSub = __ldg(m.fuSub + ic);
+        CellParams p;
+        p.aqd = __ldg(m.aqd + ic); p.sy = __ldg(m.sy + ic); p.infD = __ldg(m.infD + ic);
+        p.infKsatV = __ldg(m.infKsatV + ic); p.macKsatV = __ldg(m.macKsatV + ic); p.hAreaF = __ldg(m.hAreaF + ic);
+        p.thetaS = __ldg(m.thetaS + ic); p.thetaR = __ldg(m.thetaR + ic); p.thetaFC = __ldg(m.thetaFC + ic);
+        p.beta = __ldg(m.beta + ic); p.ksatV = __ldg(m.ksatV + ic); p.vegFrac = __ldg(m.vegFrac + ic);
+        p.impAF = __ldg(m.impAF + ic); p.wetland = __ldg(m.wetland + ic); p.rootReach = __ldg(m.rootReach + ic);
+        const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
+        CellVert v;
+        if (fl & F_LAKE) {
+            v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
+            v.satn = 1.; v.infil = v.exfil = v.rech = 0.; v.err = 0;
+        } else {
+            v = cell_vertical(p, f, ysf, yus, ygw, satn_prev, eic_in);
+        }
+        double isf2 = ysf - v.infil + v.exfil;
+        x_P1[lane_cell] = f.netPrep - v.infil + v.exfil;
+        x_Es[lane_cell] = v.Es;
+        x_G1[lane_cell] = v.rech - v.exfil;
+        x_Eg[lane_cell] = v.Eg;
+        x_Tg[lane_cell] = v.Tg;
+        x_isf2[lane_cell] = dmax(0., isf2);
+        bar_arrive(2, 2 * TILE);  // hand-over: the lateral warps wait on barrier 2
+        if (valid) {
+            m.eic[i] = v.eic;
+            m.satn[i] = v.satn;
+            double dus = v.infil - v.rech - v.Eu - v.Tu;
+            dus = SHUD_DIVS(dus, p.sy);
+            if (fl & F_LAKE) dus = 0.;
+            DY[NE + i] = dus;
+            if (v.err) raise_err(m.err, v.err, i + 1);
+            if (DIAG) {
+                if (fl & F_LAKE) {
+                    d.qEleTrans[i] = 0.; d.qEleEvapo[i] = f.potEvap; d.qEleETA[i] = 0. + f.potEvap + 0.;
+                } else {
+                    const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
+                    d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
+                    d.iBeta[i] = v.iBeta;
+                }
+                d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech;
+                d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
+            }
+        }
+        return;
+    }
+    // =============================== lateral role ===============================
+    const int seg0 = __ldg(m.cell_seg_first + ic);
+    const int nb[3] = {__ldg(m.nbr + ic), __ldg(m.nbr + NE + ic), __ldg(m.nbr + 2 * NE + ic)};
+    const double ysf = Y[ic], ygw_raw = Y[2 * NE + ic];
+    const double kh = m.effKH[ic];
+    const double zs = __ldg(m.z_surf + ic), zb = __ldg(m.z_bottom + ic);
+    const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
+    t_sf[lane_cell] = ysf; t_gw[lane_cell] = ygw; t_zs[lane_cell] = zs; t_zb[lane_cell] = zb; t_kh[lane_cell] = kh;
+    const double fuSub = __ldg(m.fuSub + ic), depression = __ldg(m.depression + ic);
+    const double area = __ldg(m.area + ic), sy = __ldg(m.sy + ic);
+    double B[3], dist[3], arough[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        B[j] = __ldg(m.edge + j * NE + ic);
+        dist[j] = __ldg(m.dist + j * NE + ic);
+        arough[j] = __ldg(m.avgRough + j * NE + ic);
+    }
+    bar_sync(1, TILE);  // the tile's own values are in shared memory (lateral warps only)
+    int err = 0;
+    double Qs[3] = {0., 0., 0.}, Qg[3] = {0., 0., 0.};
+    if (!(fl & F_LAKE)) {
+        const double isf = ysf < 0. ? 0. : ysf;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double qs = 0., qg = 0.;
+            const int k = nb[j];
+            if (k >= 0) {
+                double nsf, ygw_n, zs_n, zb_n, kh_n;
+                const unsigned r = (unsigned)(k - i0);
+                if (r < (unsigned)TILE) {  // neighbour inside the tile: shared memory
+                    nsf = t_sf[r]; ygw_n = t_gw[r]; zs_n = t_zs[r]; zb_n = t_zb[r]; kh_n = t_kh[r];
+                } else {
+                    nsf = Y[k]; ygw_n = Y[2 * NE + k]; zs_n = __ldg(m.z_surf + k); zb_n = __ldg(m.z_bottom + k);
+                    kh_n = m.effKH[k];
+                    if (m.has_headbc && (m.flags[k] & F_HEADBC)) ygw_n = m.ele_yBC[k];
+                }
+                nsf = nsf < 0. ? 0. : nsf;
+                qs = edge_surface(isf, zs, nsf, zs_n, depression, dist[j], B[j], arough[j]);
+                qg = edge_sub(ygw, zb, ygw_n, zb_n, kh, kh_n, dist[j], B[j]);
+            } else if (k <= -2) {
+                const int slot = -2 - k, l = m.bank_lake[slot];
+                const double yl = Y[3 * NE + m.Nr + l];
+                const double nsf = yl < 0. ? 0. : yl;
+                qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, B[j], 0.01);
+                qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], dist[j], B[j]);
+            } else if (!m.close_boundary) {
+                const double d2e = m.dist2edge[j * NE + ic];
+                if (isf > depression) {
+                    const double s = isf / d2e * 0.5;
+                    if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B[j] / m.rough[ic];
+                }
+                if (ygw > depression * 10.) {
+                    const double grad = ygw / d2e * 0.5;
+                    if (grad > 0.) qg = kh * grad;
+                }
+            }
+            Qs[j] = qs;
+            Qg[j] = qg * fuSub;
+        }
+    }
+    bar_sync(2, 2 * TILE);  // vertical role has handed over
+    const double P1 = x_P1[lane_cell], Es = x_Es[lane_cell], G1 = x_G1[lane_cell], Eg = x_Eg[lane_cell],
+                 Tg = x_Tg[lane_cell];
+    if (!valid) return;
+    double e2rS = 0., e2rG = 0.;
+    const int nseg = (int)(fl >> NSEG_SHIFT);
+    if (nseg) {
+        const double isf2 = x_isf2[lane_cell];
+        for (int k = 0; k < nseg; k++) {
+            const int q = seg0 + k;
+            const int s = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
+            const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
+            const double zr = zs - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
+            const double qs = weir_jtoi(zs, isf2, zr, yr, zs + __ldg(m.cs_zbank + q), __ldg(m.cs_cwr + q), len, depression);
+            const double qg = flux_r2e_gw(yr, zr, ygw, zb, kh, __ldg(m.cs_ksatH + q), len, __ldg(m.cs_bed + q)) * fuSub;
+            m.QsegSurf[s] = qs;
+            m.QsegSub[s] = qg;
+            e2rS += -qs;
+            e2rG += -qg;
+        }
+    }
+    double surfTot = e2rS, subTot = e2rG;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        surfTot += Qs[j];
+        subTot += Qg[j];
+        if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
+    }
+    double dsf = P1 - SHUD_DIVS(surfTot, area) - Es;
+    double dgw = G1 - SHUD_DIVS(subTot, area) - Eg - Tg;
+    if (fl & F_HEADBC) dgw = 0;
+    else if (fl & F_FLUXBC) dgw += SHUD_DIVS(m.ele_QBC[i], area);
+    if (fl & F_SS_SURF) dsf += SHUD_DIVS(m.qss[i], area);
+    else if (fl & F_SS_GW) dgw += SHUD_DIVS(m.qss[i], area);
+    dgw = SHUD_DIVS(dgw, sy);
+    if (fl & F_LAKE) { dsf = 0.; dgw = 0.; }
+    DY[i] = dsf;
+    DY[2 * NE + i] = dgw;
+    if (err) raise_err(m.err, err, i + 1);
+    if (DIAG) {
 #pragma unroll
         for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
         d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
@@ -419,6 +636,9 @@ struct shud_ctx {
     double *h_pinned = nullptr;  // staging for forcing uploads (pinned)
     size_t h_pinned_n = 0;
     bool has_ebc_arrays = false;
+    int fused_minb = 4;
+    int split = 2;      // 2: warp-specialised fused cell kernel (default); 0: one-thread-per-cell k_cell (SHUD_SPLIT, A/B only)
+    int cell_minb = 4;  // resident blocks per SM the cell kernel is compiled for (tuning knob)
 };
 
 #define CK(call)                                                                                         \
@@ -447,15 +667,24 @@ T *dev_upload(shud_ctx *c, const std::vector<T> &h) {
     return p;
 }
 // gather a per-cell host array into device order and upload
-const double *up_cell(shud_ctx *c, const double *src) {
+// static divisors are stored as reciprocals under SHUD_RCP (see shud_phys.cuh)
+#ifdef SHUD_RCP
+inline double divisor(double x) { return 1.0 / x; }
+#else
+inline double divisor(double x) { return x; }
+#endif
+const double *up_cell(shud_ctx *c, const double *src, bool as_divisor = false) {
     std::vector<double> h(c->Ne);
-    for (int i = 0; i < c->Ne; i++) h[i] = src[c->cperm[i]];
+    for (int i = 0; i < c->Ne; i++) h[i] = as_divisor ? divisor(src[c->cperm[i]]) : src[c->cperm[i]];
     return dev_upload(c, h);
 }
-const double *up_edge(shud_ctx *c, const double *src) {
+const double *up_edge(shud_ctx *c, const double *src, bool as_divisor = false) {
     std::vector<double> h(3 * (size_t)c->Ne);
     for (int j = 0; j < 3; j++)
-        for (int i = 0; i < c->Ne; i++) h[(size_t)j * c->Ne + i] = src[(size_t)j * c->Ne + c->cperm[i]];
+        for (int i = 0; i < c->Ne; i++) {
+            const double x = src[(size_t)j * c->Ne + c->cperm[i]];
+            h[(size_t)j * c->Ne + i] = as_divisor ? divisor(x) : x;
+        }
     return dev_upload(c, h);
 }
 const double *up_riv(shud_ctx *c, const double *src) {
@@ -526,10 +755,16 @@ int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
     DevMesh &m = c->m;
     m.Ne = Ne; m.Nr = Nr; m.Ns = Ns; m.Nl = Nl;
     m.close_boundary = M->close_boundary;
+    {
+        const char *e1 = getenv("SHUD_CELL_MINB");
+        if (e1) c->cell_minb = atoi(e1);
+        if (getenv("SHUD_SPLIT")) c->split = atoi(getenv("SHUD_SPLIT"));
+        if (getenv("SHUD_FUSED_MINB")) c->fused_minb = atoi(getenv("SHUD_FUSED_MINB"));
+    }
 
     // ---- static per-cell arrays ----
-    m.area = up_cell(c, M->area); m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom);
-    m.depression = up_cell(c, M->depression); m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy);
+    m.area = up_cell(c, M->area, true); m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom);
+    m.depression = up_cell(c, M->depression); m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy, true);
     m.infD = up_cell(c, M->infD); m.infKsatV = up_cell(c, M->infKsatV); m.macKsatV = up_cell(c, M->macKsatV);
     m.hAreaF = up_cell(c, M->hAreaF); m.thetaS = up_cell(c, M->ThetaS); m.thetaR = up_cell(c, M->ThetaR);
     m.thetaFC = up_cell(c, M->ThetaFC); m.beta = up_cell(c, M->Beta); m.ksatH = up_cell(c, M->KsatH);
@@ -537,8 +772,8 @@ int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
     m.vAreaF = up_cell(c, M->geo_vAreaF); m.vegFrac = up_cell(c, M->VegFrac); m.impAF = up_cell(c, M->ImpAF);
     m.wetland = up_cell(c, M->WetlandLevel); m.rootReach = up_cell(c, M->RootReachLevel);
     m.rough = up_cell(c, M->Rough); m.qss = up_cell(c, M->QSS);
-    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor); m.dist2edge = up_edge(c, M->Dist2Edge);
-    m.avgRough = up_edge(c, M->avgRough);
+    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor, true); m.dist2edge = up_edge(c, M->Dist2Edge);
+    m.avgRough = up_edge(c, M->avgRough, true);
 
     // ---- topology, flags, bank edges ----
     const bool lakeon = M->lakeon != 0 && Nl > 0;
@@ -610,7 +845,22 @@ int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
         }
     }
     m.flags = dev_upload(c, flags); m.nbr = dev_upload(c, nbr);
-    m.cell_seg_first = dev_upload(c, cell_seg_first); m.cell_seg_idx = dev_upload(c, cell_seg_idx);
+    m.cell_seg_first = dev_upload(c, cell_seg_first);
+    {
+        std::vector<int> cs_seg(Ns), cs_riv(Ns), cs_bc(Ns);
+        std::vector<double> cs_len(Ns), cs_cwr(Ns), cs_depth(Ns), cs_zbank(Ns), cs_ksatH(Ns), cs_bed(Ns);
+        for (int q = 0; q < Ns; q++) {
+            const int sd = cell_seg_idx[q];   // segment, device order
+            const int so = c->sperm[sd];      // segment, reference id
+            const int ro = M->seg_iRiv[so] - 1;
+            cs_seg[q] = sd; cs_riv[q] = c->rinv[ro]; cs_bc[q] = M->riv_BC[ro];
+            cs_len[q] = M->seg_length[so]; cs_cwr[q] = M->seg_Cwr[so]; cs_depth[q] = M->riv_depth[ro];
+            cs_zbank[q] = M->riv_zbank[ro]; cs_ksatH[q] = M->riv_KsatH[ro]; cs_bed[q] = M->riv_BedThick[ro];
+        }
+        m.cs_seg = dev_upload(c, cs_seg); m.cs_riv = dev_upload(c, cs_riv); m.cs_bc = dev_upload(c, cs_bc);
+        m.cs_len = dev_upload(c, cs_len); m.cs_cwr = dev_upload(c, cs_cwr); m.cs_depth = dev_upload(c, cs_depth);
+        m.cs_zbank = dev_upload(c, cs_zbank); m.cs_ksatH = dev_upload(c, cs_ksatH); m.cs_bed = dev_upload(c, cs_bed);
+    }
     m.bank_cell = dev_upload(c, bank_cell); m.bank_j = dev_upload(c, bank_j); m.bank_lake = dev_upload(c, bank_lake);
     m.bank_kh = dev_upload(c, bank_kh);
 
@@ -843,10 +1093,35 @@ static int ensure_diag(shud_ctx *c) {
 
 }  // extern "C"
 template <bool DIAG>
+static void launch_cell(shud_ctx *c, const double *y, double *ydot) {
+    const int nb = (c->Ne + 127) / 128;
+    switch (c->cell_minb) {
+        case 3: k_cell<DIAG, 3><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+        case 5: k_cell<DIAG, 5><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+        case 6: k_cell<DIAG, 6><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+        case 8: k_cell<DIAG, 8><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+        default: k_cell<DIAG, 4><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+    }
+}
+template <bool DIAG>
+static void launch_fused(shud_ctx *c, const double *y, double *ydot) {
+    const int nb = (c->Ne + TILE - 1) / TILE;
+    switch (c->fused_minb) {
+        case 2: k_fused<DIAG, 2><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+        case 3: k_fused<DIAG, 3><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+        default: k_fused<DIAG, 4><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+    }
+}
+template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     const int Ne = c->Ne;
-    k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
-    k_cell<DIAG><<<(Ne + 127) / 128, 128, 0, c->stream>>>(c->m, c->diag, y, ydot);
+    if (c->split == 2) {
+        k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        launch_fused<DIAG>(c, y, ydot);
+    } else {
+        k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        launch_cell<DIAG>(c, y, ydot);
+    }
     const int nb_riv = (c->Nr + 127) / 128;
     if (nb_riv + c->Nl > 0)
         k_river_lake<DIAG><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
@@ -865,8 +1140,9 @@ int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
 int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydot) {
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
-    if (stage == 0) k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
-    else if (stage == 1) k_cell<false><<<(Ne + 127) / 128, 128, 0, c->stream>>>(c->m, c->diag, y, ydot);
+    if (c->split == 2 && stage == 1) launch_fused<false>(c, y, ydot);
+    else if (stage == 0) k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+    else if (stage == 1) launch_cell<false>(c, y, ydot);
     else if (stage == 2 && nb_riv + c->Nl > 0)
         k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
     else return SHUD_ERR_ARG;
