@@ -1,0 +1,72 @@
+/* shud_nvector.h - C ABI of the device N_Vector arithmetic CVODE(BDF/Newton) + CVLS + SPGMR run on
+ * the SHUD state vectors (SURVEY.md section 8(a) row a22, 8(b) "N_Vector ops table").
+ *
+ * The reference takes these from SUNDIALS' nvector_serial / nvector_openmp (linked at reference
+ * Makefile:87-88, vectors created at src/Model/shud.cpp:59-64, cloned by CVODE and SPGMR through
+ * src/Equations/cvode_config.cpp:169,176).  SUNDIALS is not vendored in the reference; the semantics
+ * below are those of the SUNDIALS 6 N_Vector documentation (the version the reference pins:
+ * configure:17-21, README.md:18).  Each function names the ops-table member it replaces.
+ *
+ * All vector arguments are DEVICE pointers to `n` contiguous doubles.  Streaming operations are
+ * asynchronous on the workspace's stream; reductions return their value through a host pointer and
+ * synchronise the stream (CVODE consumes every norm / dot product on the host).  Reductions use a
+ * fixed grid and a fixed-shape warp-shuffle tree: deterministic run to run.  There is no CPU fallback.
+ */
+#ifndef SHUD_NVECTOR_H
+#define SHUD_NVECTOR_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHUD_NV_MAXVEC 8 /* vectors per fused call (CVODE: q+1 <= 6 Nordsieck rows; SPGMR: maxl+1 = 6) */
+
+typedef struct shud_nvws shud_nvws; /* reduction workspace bound to one device + stream */
+
+/* `stream` is a cudaStream_t (e.g. shud_b200_stream()); NULL = the legacy default stream */
+int shud_nv_ws_create(int device, void *stream, shud_nvws **out);
+void shud_nv_ws_destroy(shud_nvws *ws);
+
+/* ---- streaming operations (return 0 or a negative SHUD_ERR_* code) ---- */
+int shud_nv_linearsum(shud_nvws *ws, int64_t n, double a, const double *x, double b, const double *y, double *z); /* nvlinearsum  z = a x + b y */
+int shud_nv_const(shud_nvws *ws, int64_t n, double c, double *z);                                                /* nvconst      z = c */
+int shud_nv_prod(shud_nvws *ws, int64_t n, const double *x, const double *y, double *z);                        /* nvprod       z = x .* y */
+int shud_nv_div(shud_nvws *ws, int64_t n, const double *x, const double *y, double *z);                         /* nvdiv        z = x ./ y */
+int shud_nv_scale(shud_nvws *ws, int64_t n, double c, const double *x, double *z);                              /* nvscale      z = c x */
+int shud_nv_abs(shud_nvws *ws, int64_t n, const double *x, double *z);                                          /* nvabs        z = |x| */
+int shud_nv_inv(shud_nvws *ws, int64_t n, const double *x, double *z);                                          /* nvinv        z = 1 ./ x */
+int shud_nv_addconst(shud_nvws *ws, int64_t n, const double *x, double b, double *z);                           /* nvaddconst   z = x + b */
+int shud_nv_compare(shud_nvws *ws, int64_t n, double c, const double *x, double *z);                            /* nvcompare    z = |x| >= c ? 1 : 0 */
+
+/* ---- reductions (value in *out on the host; the call synchronises the stream) ---- */
+int shud_nv_dotprod(shud_nvws *ws, int64_t n, const double *x, const double *y, double *out);    /* nvdotprod (+ nvdotprodlocal) */
+int shud_nv_maxnorm(shud_nvws *ws, int64_t n, const double *x, double *out);                     /* nvmaxnorm (+ nvmaxnormlocal) */
+int shud_nv_min(shud_nvws *ws, int64_t n, const double *x, double *out);                         /* nvmin     (+ nvminlocal)     */
+int shud_nv_l1norm(shud_nvws *ws, int64_t n, const double *x, double *out);                      /* nvl1norm  */
+int shud_nv_wsqrsum(shud_nvws *ws, int64_t n, const double *x, const double *w, double *out);    /* nvwsqrsumlocal  sum (x w)^2 */
+int shud_nv_wsqrsum_mask(shud_nvws *ws, int64_t n, const double *x, const double *w, const double *id, double *out); /* nvwsqrsummasklocal */
+/* nvwrmsnorm = sqrt(wsqrsum / n_global); nvwl2norm = sqrt(wsqrsum).  n_global is the length of the whole
+ * (possibly distributed) vector: a single-GPU caller passes n. */
+int shud_nv_wrmsnorm(shud_nvws *ws, int64_t n, const double *x, const double *w, int64_t n_global, double *out);
+int shud_nv_wrmsnorm_mask(shud_nvws *ws, int64_t n, const double *x, const double *w, const double *id, int64_t n_global, double *out);
+int shud_nv_wl2norm(shud_nvws *ws, int64_t n, const double *x, const double *w, double *out);
+/* nvinvtest: z = 1./x where x != 0; *all_nonzero = 1 if no zero was met.  nvconstrmask: SUNDIALS' constraint
+ * test (c = +-1: x c >= 0 ... , +-2: x c > 0), m = 1 where violated; *all_ok = 1 if none.
+ * nvminquotient: min over denom != 0 of num/denom (DBL_MAX if none). */
+int shud_nv_invtest(shud_nvws *ws, int64_t n, const double *x, double *z, int *all_nonzero);
+int shud_nv_constrmask(shud_nvws *ws, int64_t n, const double *c, const double *x, double *m, int *all_ok);
+int shud_nv_minquotient(shud_nvws *ws, int64_t n, const double *num, const double *denom, double *out);
+
+/* ---- fused operations (pointer arrays are HOST arrays of device pointers, nvec <= SHUD_NV_MAXVEC) ---- */
+int shud_nv_linearcombination(shud_nvws *ws, int64_t n, int nvec, const double *c, const double *const *X, double *z);         /* nvlinearcombination  z = sum c_k X_k */
+int shud_nv_scaleaddmulti(shud_nvws *ws, int64_t n, int nvec, const double *a, const double *x, const double *const *Y, double *const *Z); /* nvscaleaddmulti  Z_k = a_k x + Y_k */
+int shud_nv_dotprodmulti(shud_nvws *ws, int64_t n, int nvec, const double *x, const double *const *Y, double *out);            /* nvdotprodmulti  out_k = x . Y_k */
+int shud_nv_linearsumvectorarray(shud_nvws *ws, int64_t n, int nvec, double a, const double *const *X, double b, const double *const *Y, double *const *Z);
+int shud_nv_scalevectorarray(shud_nvws *ws, int64_t n, int nvec, const double *c, const double *const *X, double *const *Z);
+int shud_nv_constvectorarray(shud_nvws *ws, int64_t n, int nvec, double c, double *const *Z);
+int shud_nv_wrmsnormvectorarray(shud_nvws *ws, int64_t n, int nvec, const double *const *X, const double *const *W, int64_t n_global, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

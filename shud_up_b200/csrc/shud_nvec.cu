@@ -1,1 +1,396 @@
-// placeholder translation unit: the device N_Vector lands here
+// shud_nvec.cu - device N_Vector arithmetic for CVODE(BDF, Newton) + CVLS + SPGMR on the SHUD state
+// vectors (include/shud_nvector.h).  Pure HBM streaming: grid-stride kernels with 4 independent 8-byte
+// loads per thread and array in flight, grid sized as a multiple of the 148 SMs.  Reductions: per-thread
+// partial -> fixed-shape warp-shuffle tree -> one partial per block -> the last block to finish sums the
+// block partials in index order (no floating-point atomics: the result is run-to-run reproducible) and
+// stores the scalar(s) straight into mapped pinned host memory, so the host needs one stream
+// synchronisation and no extra copy.
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+
+#include "shud_b200.h"
+#include "shud_nvector.h"
+
+namespace {
+
+constexpr int NT = 256;          // threads per block
+constexpr int MAXB = 148 * 8;    // blocks: 8 per SM
+constexpr int UNROLL = 4;
+
+struct Ptrs {
+    const double *p[SHUD_NV_MAXVEC];
+};
+struct MPtrs {
+    double *p[SHUD_NV_MAXVEC];
+};
+struct Coef {
+    double c[SHUD_NV_MAXVEC];
+};
+
+inline int grid_for(int64_t n) {
+    int64_t b = (n + (int64_t)NT * UNROLL - 1) / ((int64_t)NT * UNROLL);
+    if (b < 1) b = 1;
+    if (b > MAXB) b = MAXB;
+    return (int)b;
+}
+
+// ---------------- streaming ----------------
+template <class F>
+__global__ void __launch_bounds__(NT) k_map(int64_t n, F f) {
+    const int64_t stride = (int64_t)gridDim.x * NT;
+    int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) f(i + u * stride);
+    }
+    for (; i < n; i += stride) f(i);
+}
+
+struct FLinearSum {
+    double a, b; const double *x, *y; double *z;
+    __device__ void operator()(int64_t i) const { z[i] = a * x[i] + b * y[i]; }
+};
+struct FAxpy {  // y += a x  (in-place form CVODE uses most: one stream fewer)
+    double a; const double *x; double *y;
+    __device__ void operator()(int64_t i) const { y[i] = a * x[i] + y[i]; }
+};
+struct FConst { double c; double *z; __device__ void operator()(int64_t i) const { z[i] = c; } };
+struct FProd { const double *x, *y; double *z; __device__ void operator()(int64_t i) const { z[i] = x[i] * y[i]; } };
+struct FDiv { const double *x, *y; double *z; __device__ void operator()(int64_t i) const { z[i] = x[i] / y[i]; } };
+struct FScale { double c; const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = c * x[i]; } };
+struct FAbs { const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = fabs(x[i]); } };
+struct FInv { const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = 1.0 / x[i]; } };
+struct FAddConst { const double *x; double b; double *z; __device__ void operator()(int64_t i) const { z[i] = x[i] + b; } };
+struct FCompare { double c; const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = (fabs(x[i]) >= c) ? 1.0 : 0.0; } };
+struct FLinComb {
+    int nv; Coef c; Ptrs X; double *z;
+    __device__ void operator()(int64_t i) const {
+        double s = c.c[0] * X.p[0][i];
+        for (int k = 1; k < nv; k++) s += c.c[k] * X.p[k][i];
+        z[i] = s;
+    }
+};
+struct FScaleAddMulti {
+    int nv; Coef a; const double *x; Ptrs Y; MPtrs Z;
+    __device__ void operator()(int64_t i) const {
+        const double xi = x[i];
+        for (int k = 0; k < nv; k++) Z.p[k][i] = a.c[k] * xi + Y.p[k][i];
+    }
+};
+struct FLinSumVA {
+    int nv; double a, b; Ptrs X, Y; MPtrs Z;
+    __device__ void operator()(int64_t i) const { for (int k = 0; k < nv; k++) Z.p[k][i] = a * X.p[k][i] + b * Y.p[k][i]; }
+};
+struct FScaleVA {
+    int nv; Coef c; Ptrs X; MPtrs Z;
+    __device__ void operator()(int64_t i) const { for (int k = 0; k < nv; k++) Z.p[k][i] = c.c[k] * X.p[k][i]; }
+};
+struct FConstVA {
+    int nv; double c; MPtrs Z;
+    __device__ void operator()(int64_t i) const { for (int k = 0; k < nv; k++) Z.p[k][i] = c; }
+};
+
+// ---------------- reductions ----------------
+enum { R_SUM = 0, R_MAX = 1, R_MIN = 2 };
+template <int KIND>
+__device__ __forceinline__ double comb(double a, double b) {
+    if (KIND == R_SUM) return a + b;
+    if (KIND == R_MAX) return a < b ? b : a;
+    return a > b ? b : a;
+}
+template <int KIND>
+__device__ __forceinline__ double ident() { return KIND == R_SUM ? 0.0 : (KIND == R_MAX ? 0.0 : DBL_MAX); }
+
+template <int KIND>
+__device__ __forceinline__ double block_reduce(double v, double *sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = comb<KIND>(v, __shfl_down_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = ident<KIND>();
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < NT / 32) ? sm[threadIdx.x] : ident<KIND>();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = comb<KIND>(t, __shfl_down_sync(0xffffffffu, t, o));
+    }
+    __syncthreads();
+    return t;  // valid in thread 0
+}
+
+// NV accumulators per thread (1 for plain reductions, up to SHUD_NV_MAXVEC for the multi forms);
+// F::term(k, i) is the value element i contributes to accumulator k.
+// post: 0 none, 1 sqrt(v / nglob), 2 sqrt(v)
+template <int KIND, int NV, class F>
+__global__ void __launch_bounds__(NT) k_reduce(int64_t n, F f, int nv, double *partial, unsigned *counter,
+                                               double *d_out, volatile double *h_out, int post, double nglob) {
+    __shared__ double sm[NT / 32];
+    __shared__ bool last;
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = ident<KIND>();
+    const int64_t stride = (int64_t)gridDim.x * NT;
+    int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int k = 0; k < NV; k++)
+                if (k < nv) acc[k] = comb<KIND>(acc[k], f.term(k, i + u * stride));
+    }
+    for (; i < n; i += stride)
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+            if (k < nv) acc[k] = comb<KIND>(acc[k], f.term(k, i));
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        if (k < nv) {
+            const double b = block_reduce<KIND>(acc[k], sm);
+            if (threadIdx.x == 0) partial[(size_t)k * MAXB + blockIdx.x] = b;
+        }
+    }
+    __threadfence();
+    if (threadIdx.x == 0) last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int k = 0; k < nv; k++) {
+        double v = ident<KIND>();
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += NT) v = comb<KIND>(v, partial[(size_t)k * MAXB + b]);
+        v = block_reduce<KIND>(v, sm);
+        if (threadIdx.x == 0) {
+            if (post == 1) v = sqrt(v / nglob);
+            else if (post == 2) v = sqrt(v);
+            d_out[k] = v;
+            h_out[k] = v;
+        }
+    }
+}
+
+struct TDot { const double *x, *y; __device__ double term(int, int64_t i) const { return x[i] * y[i]; } };
+struct TAbs { const double *x; __device__ double term(int, int64_t i) const { return fabs(x[i]); } };
+struct TVal { const double *x; __device__ double term(int, int64_t i) const { return x[i]; } };
+struct TWSqr { const double *x, *w; __device__ double term(int, int64_t i) const { const double t = x[i] * w[i]; return t * t; } };
+struct TWSqrMask {
+    const double *x, *w, *id;
+    __device__ double term(int, int64_t i) const { const double t = x[i] * w[i]; return id[i] > 0.0 ? t * t : 0.0; }
+};
+struct TMinQuot {
+    const double *num, *den;
+    __device__ double term(int, int64_t i) const { return den[i] != 0.0 ? num[i] / den[i] : DBL_MAX; }
+};
+struct TDotMulti { const double *x; Ptrs Y; __device__ double term(int k, int64_t i) const { return x[i] * Y.p[k][i]; } };
+struct TWSqrMulti {
+    Ptrs X, W;
+    __device__ double term(int k, int64_t i) const { const double t = X.p[k][i] * W.p[k][i]; return t * t; }
+};
+// map + flag reductions (z written as a side effect; term = 1 where the test fails)
+struct TInvTest {
+    const double *x; double *z;
+    __device__ double term(int, int64_t i) const {
+        const double v = x[i];
+        if (v == 0.0) return 1.0;
+        z[i] = 1.0 / v;
+        return 0.0;
+    }
+};
+struct TConstrMask {
+    const double *c, *x; double *m;
+    __device__ double term(int, int64_t i) const {
+        const double ci = c[i], xi = x[i];
+        m[i] = 0.0;
+        if (ci == 0.0) return 0.0;
+        // |c| = 2: strict sign; |c| = 1: non-strict (SUNDIALS N_VConstrMask)
+        const bool bad = (fabs(ci) > 1.5) ? (xi * ci <= 0.0) : (xi * ci < 0.0);
+        if (bad) { m[i] = 1.0; return 1.0; }
+        return 0.0;
+    }
+};
+
+}  // namespace
+
+struct shud_nvws {
+    int device;
+    cudaStream_t stream;
+    double *partial;       // [SHUD_NV_MAXVEC][MAXB]
+    unsigned *counter;
+    double *d_out;         // [SHUD_NV_MAXVEC]
+    double *h_out;         // mapped pinned, [SHUD_NV_MAXVEC]
+    double *h_out_dev;     // device alias of h_out
+};
+
+#define CKN(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            fprintf(stderr, "[shud_nvec] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return SHUD_ERR_CUDA;                                                                          \
+        }                                                                                                  \
+    } while (0)
+
+namespace {
+template <class F>
+int run_map(shud_nvws *ws, int64_t n, F f) {
+    if (!ws) return SHUD_ERR_ARG;
+    if (n <= 0) return SHUD_OK;
+    k_map<<<grid_for(n), NT, 0, ws->stream>>>(n, f);
+    CKN(cudaGetLastError());
+    return SHUD_OK;
+}
+template <int KIND, int NV, class F>
+int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, double *out) {
+    if (!ws || !out || nv < 1 || nv > NV) return SHUD_ERR_ARG;
+    if (n <= 0) {
+        for (int k = 0; k < nv; k++) out[k] = (KIND == R_MIN) ? DBL_MAX : 0.0;
+        return SHUD_OK;
+    }
+    k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
+                                                              ws->h_out_dev, post, nglob);
+    CKN(cudaGetLastError());
+    CKN(cudaStreamSynchronize(ws->stream));
+    for (int k = 0; k < nv; k++) out[k] = ws->h_out[k];
+    return SHUD_OK;
+}
+bool fill(Ptrs &P, const double *const *X, int nv) {
+    if (!X || nv < 1 || nv > SHUD_NV_MAXVEC) return false;
+    for (int k = 0; k < nv; k++) P.p[k] = X[k];
+    return true;
+}
+bool fill(MPtrs &P, double *const *X, int nv) {
+    if (!X || nv < 1 || nv > SHUD_NV_MAXVEC) return false;
+    for (int k = 0; k < nv; k++) P.p[k] = X[k];
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+int shud_nv_ws_create(int device, void *stream, shud_nvws **out) {
+    if (!out) return SHUD_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) return SHUD_ERR_NO_DEVICE;
+    CKN(cudaSetDevice(device));
+    shud_nvws *ws = new shud_nvws();
+    ws->device = device;
+    ws->stream = (cudaStream_t)stream;
+    CKN(cudaMalloc(&ws->partial, sizeof(double) * SHUD_NV_MAXVEC * MAXB));
+    CKN(cudaMalloc(&ws->counter, sizeof(unsigned)));
+    CKN(cudaMemset(ws->counter, 0, sizeof(unsigned)));
+    CKN(cudaMalloc(&ws->d_out, sizeof(double) * SHUD_NV_MAXVEC));
+    CKN(cudaHostAlloc(&ws->h_out, sizeof(double) * SHUD_NV_MAXVEC, cudaHostAllocMapped));
+    CKN(cudaHostGetDevicePointer((void **)&ws->h_out_dev, ws->h_out, 0));
+    *out = ws;
+    return SHUD_OK;
+}
+void shud_nv_ws_destroy(shud_nvws *ws) {
+    if (!ws) return;
+    cudaSetDevice(ws->device);
+    cudaStreamSynchronize(ws->stream);
+    cudaFree(ws->partial); cudaFree(ws->counter); cudaFree(ws->d_out); cudaFreeHost(ws->h_out);
+    delete ws;
+}
+
+int shud_nv_linearsum(shud_nvws *ws, int64_t n, double a, const double *x, double b, const double *y, double *z) {
+    if (b == 1.0 && z == y) return run_map(ws, n, FAxpy{a, x, z});   // y += a x
+    if (a == 1.0 && z == x) return run_map(ws, n, FAxpy{b, y, z});   // x += b y
+    return run_map(ws, n, FLinearSum{a, b, x, y, z});
+}
+int shud_nv_const(shud_nvws *ws, int64_t n, double c, double *z) { return run_map(ws, n, FConst{c, z}); }
+int shud_nv_prod(shud_nvws *ws, int64_t n, const double *x, const double *y, double *z) { return run_map(ws, n, FProd{x, y, z}); }
+int shud_nv_div(shud_nvws *ws, int64_t n, const double *x, const double *y, double *z) { return run_map(ws, n, FDiv{x, y, z}); }
+int shud_nv_scale(shud_nvws *ws, int64_t n, double c, const double *x, double *z) { return run_map(ws, n, FScale{c, x, z}); }
+int shud_nv_abs(shud_nvws *ws, int64_t n, const double *x, double *z) { return run_map(ws, n, FAbs{x, z}); }
+int shud_nv_inv(shud_nvws *ws, int64_t n, const double *x, double *z) { return run_map(ws, n, FInv{x, z}); }
+int shud_nv_addconst(shud_nvws *ws, int64_t n, const double *x, double b, double *z) { return run_map(ws, n, FAddConst{x, b, z}); }
+int shud_nv_compare(shud_nvws *ws, int64_t n, double c, const double *x, double *z) { return run_map(ws, n, FCompare{c, x, z}); }
+
+int shud_nv_dotprod(shud_nvws *ws, int64_t n, const double *x, const double *y, double *out) {
+    return run_reduce<R_SUM, 1>(ws, n, TDot{x, y}, 1, 0, 1.0, out);
+}
+int shud_nv_maxnorm(shud_nvws *ws, int64_t n, const double *x, double *out) {
+    return run_reduce<R_MAX, 1>(ws, n, TAbs{x}, 1, 0, 1.0, out);
+}
+int shud_nv_min(shud_nvws *ws, int64_t n, const double *x, double *out) {
+    return run_reduce<R_MIN, 1>(ws, n, TVal{x}, 1, 0, 1.0, out);
+}
+int shud_nv_l1norm(shud_nvws *ws, int64_t n, const double *x, double *out) {
+    return run_reduce<R_SUM, 1>(ws, n, TAbs{x}, 1, 0, 1.0, out);
+}
+int shud_nv_wsqrsum(shud_nvws *ws, int64_t n, const double *x, const double *w, double *out) {
+    return run_reduce<R_SUM, 1>(ws, n, TWSqr{x, w}, 1, 0, 1.0, out);
+}
+int shud_nv_wsqrsum_mask(shud_nvws *ws, int64_t n, const double *x, const double *w, const double *id, double *out) {
+    return run_reduce<R_SUM, 1>(ws, n, TWSqrMask{x, w, id}, 1, 0, 1.0, out);
+}
+int shud_nv_wrmsnorm(shud_nvws *ws, int64_t n, const double *x, const double *w, int64_t ng, double *out) {
+    return run_reduce<R_SUM, 1>(ws, n, TWSqr{x, w}, 1, 1, (double)(ng > 0 ? ng : n), out);
+}
+int shud_nv_wrmsnorm_mask(shud_nvws *ws, int64_t n, const double *x, const double *w, const double *id, int64_t ng,
+                          double *out) {
+    return run_reduce<R_SUM, 1>(ws, n, TWSqrMask{x, w, id}, 1, 1, (double)(ng > 0 ? ng : n), out);
+}
+int shud_nv_wl2norm(shud_nvws *ws, int64_t n, const double *x, const double *w, double *out) {
+    return run_reduce<R_SUM, 1>(ws, n, TWSqr{x, w}, 1, 2, 1.0, out);
+}
+int shud_nv_invtest(shud_nvws *ws, int64_t n, const double *x, double *z, int *ok) {
+    double bad = 0.;
+    int rc = run_reduce<R_SUM, 1>(ws, n, TInvTest{x, z}, 1, 0, 1.0, &bad);
+    if (ok) *ok = (bad == 0.0);
+    return rc;
+}
+int shud_nv_constrmask(shud_nvws *ws, int64_t n, const double *c, const double *x, double *m, int *ok) {
+    double bad = 0.;
+    int rc = run_reduce<R_SUM, 1>(ws, n, TConstrMask{c, x, m}, 1, 0, 1.0, &bad);
+    if (ok) *ok = (bad == 0.0);
+    return rc;
+}
+int shud_nv_minquotient(shud_nvws *ws, int64_t n, const double *num, const double *den, double *out) {
+    return run_reduce<R_MIN, 1>(ws, n, TMinQuot{num, den}, 1, 0, 1.0, out);
+}
+
+int shud_nv_linearcombination(shud_nvws *ws, int64_t n, int nv, const double *c, const double *const *X, double *z) {
+    FLinComb f; f.nv = nv; f.z = z;
+    if (!c || !fill(f.X, X, nv)) return SHUD_ERR_ARG;
+    for (int k = 0; k < nv; k++) f.c.c[k] = c[k];
+    return run_map(ws, n, f);
+}
+int shud_nv_scaleaddmulti(shud_nvws *ws, int64_t n, int nv, const double *a, const double *x, const double *const *Y,
+                          double *const *Z) {
+    FScaleAddMulti f; f.nv = nv; f.x = x;
+    if (!a || !fill(f.Y, Y, nv) || !fill(f.Z, Z, nv)) return SHUD_ERR_ARG;
+    for (int k = 0; k < nv; k++) f.a.c[k] = a[k];
+    return run_map(ws, n, f);
+}
+int shud_nv_dotprodmulti(shud_nvws *ws, int64_t n, int nv, const double *x, const double *const *Y, double *out) {
+    TDotMulti f; f.x = x;
+    if (!fill(f.Y, Y, nv)) return SHUD_ERR_ARG;
+    return run_reduce<R_SUM, SHUD_NV_MAXVEC>(ws, n, f, nv, 0, 1.0, out);
+}
+int shud_nv_linearsumvectorarray(shud_nvws *ws, int64_t n, int nv, double a, const double *const *X, double b,
+                                 const double *const *Y, double *const *Z) {
+    FLinSumVA f; f.nv = nv; f.a = a; f.b = b;
+    if (!fill(f.X, X, nv) || !fill(f.Y, Y, nv) || !fill(f.Z, Z, nv)) return SHUD_ERR_ARG;
+    return run_map(ws, n, f);
+}
+int shud_nv_scalevectorarray(shud_nvws *ws, int64_t n, int nv, const double *c, const double *const *X,
+                             double *const *Z) {
+    FScaleVA f; f.nv = nv;
+    if (!c || !fill(f.X, X, nv) || !fill(f.Z, Z, nv)) return SHUD_ERR_ARG;
+    for (int k = 0; k < nv; k++) f.c.c[k] = c[k];
+    return run_map(ws, n, f);
+}
+int shud_nv_constvectorarray(shud_nvws *ws, int64_t n, int nv, double c, double *const *Z) {
+    FConstVA f; f.nv = nv; f.c = c;
+    if (!fill(f.Z, Z, nv)) return SHUD_ERR_ARG;
+    return run_map(ws, n, f);
+}
+int shud_nv_wrmsnormvectorarray(shud_nvws *ws, int64_t n, int nv, const double *const *X, const double *const *W,
+                                int64_t ng, double *out) {
+    TWSqrMulti f;
+    if (!fill(f.X, X, nv) || !fill(f.W, W, nv)) return SHUD_ERR_ARG;
+    return run_reduce<R_SUM, SHUD_NV_MAXVEC>(ws, n, f, nv, 1, (double)(ng > 0 ? ng : n), out);
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every
+entry point include/*.h declares; the product path never touches the oracle and fails loudly
+(no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = []
+    for h in ("shud_b200.h", "shud_nvector.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names += re.findall(r"\b(shud_(?:b200|nv)_\w+)\s*\(", txt)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from shud_up_b200 import build
+    return ctypes.CDLL(build.build())
+
+
+def test_every_declared_entry_point_is_exported(lib):
+    names = _declared()
+    assert len(names) > 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_library_is_sm100a_only(lib):
+    from shud_up_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from shud_up_b200.api import ShudRHS, ShudError
+    snap = oracle_lib.load_case("ccw", "ic")
+    with pytest.raises(ShudError, match="no CUDA device"):
+        ShudRHS(snap)
+    from shud_up_b200.nvector import NVectorOps
+    with pytest.raises(ShudError, match="no CUDA device"):
+        NVectorOps(0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "shud_up_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "shud_oracle" not in txt, f
+
+
+def test_abi_struct_layout_matches_header():
+    """field order of the ctypes mirrors == declaration order in the header"""
+    from shud_up_b200 import abi
+    txt = open(os.path.join(ROOT, "include", "shud_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    for cname, cls in (("shud_mesh", abi.ShudMesh), ("shud_forcing", abi.ShudForcing), ("shud_diag", abi.ShudDiag)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), txt, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(double|int32_t)\s*", "", decl)
+            fields += [x.strip().lstrip("*").strip() for x in decl.split(",")]
+        assert fields == [f[0] for f in cls._fields_], cname
