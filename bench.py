@@ -74,11 +74,16 @@ class ClockSampler:
 
 
 def stripe_mesh(world, rank):
-    """the rank's share of the N x 1M-cell mesh: N=1 -> 1000x500 quads; N>1 -> the same width, 500 rows per rank"""
+    """the rank's share of the N x 1M-cell mesh.  N=1: synthetic-1M (1000 x 500 quads).  N>1: the mesh of
+    1000 x 500N quads (N=8: 8,000,000 cells / 400,000 reaches / 1,200,000 segments, configs[4]) cut into N
+    horizontal stripes of 500 quad rows = 1M cells each; a rank builds only its own stripe plus its halo."""
     from shud_up_b200 import synth
     cfg = synth.named("1M")
-    return synth.make(cfg["nx"], cfg["ny"], ntree=cfg["ntree"], reaches_per_tree=cfg["reaches_per_tree"],
-                      seed=synth.SEED + rank)
+    if world == 1:
+        return synth.make(cfg["nx"], cfg["ny"], ntree=cfg["ntree"], reaches_per_tree=cfg["reaches_per_tree"])
+    rows = cfg["ny"]
+    return synth.make(cfg["nx"], rows * world, ntree=cfg["ntree"] * world, reaches_per_tree=cfg["reaches_per_tree"],
+                      rows=(rank * rows, (rank + 1) * rows), stripe_rows=rows)
 
 
 def cpu_oracle_time(mesh, nthreads, budget_s=15.0, max_calls=50):
@@ -163,6 +168,20 @@ def main():
         ydot = torch.empty_like(y_ref)
         rhs.to_device_order(y_ref, y)
     st.synchronize()
+    hx = None
+    if world > 1:
+        from shud_up_b200 import partition
+        with torch.cuda.stream(st):
+            hx = partition.HaloExchange(mesh, dist, dev, cell_perm=rhs.perm()[0], pack_fn=rhs.pack_halo)
+            rhs.set_halo_state(hx.halo_state)
+        st.synchronize()
+
+    def step():
+        # one f(): halo exchange of the boundary cells' (Ysurf, Ygw) over NCCL, then the 3 kernels
+        if hx is not None:
+            with torch.cuda.stream(st):
+                hx.exchange(y)
+        rhs.f_dev(0.0, y, ydot)
 
     def barrier():
         if world > 1:
@@ -171,13 +190,13 @@ def main():
 
     # ---------------- device-resident timing (value) ----------------
     for _ in range(warm):
-        rhs.f_dev(0.0, y, ydot)
+        step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         ev0.record(st)
         for _ in range(steps):
-            rhs.f_dev(0.0, y, ydot)
+            step()
         ev1.record(st)
         barrier()
         ms_dev = ev0.elapsed_time(ev1)
@@ -185,7 +204,7 @@ def main():
             reps = int(1500 / max(ms_dev, 1e-3)) + 1
             for _ in range(reps):
                 for _ in range(steps):
-                    rhs.f_dev(0.0, y, ydot)
+                    step()
             torch.cuda.synchronize()
     code, where = rhs.check()
     assert code == 0, (code, where)
@@ -208,15 +227,32 @@ def main():
     # ---------------- end to end through the CVRhsFn-shaped entry point (host vectors) ----------------
     yh = torch.from_numpy(np.ascontiguousarray(mesh["y"])).pin_memory()
     ydh = torch.empty_like(yh).pin_memory()
+    def e2e_step():
+        if hx is None:
+            rhs.f(0.0, yh, ydh)  # H2D y, permute, 3 kernels, permute, D2H ydot, sync, error word
+        else:                    # same sequence with the halo exchange between the upload and the kernels
+            with torch.cuda.stream(st):
+                y_ref.copy_(yh, non_blocking=True)
+                rhs.to_device_order(y_ref, y)
+                hx.exchange(y)
+                rhs.f_dev(0.0, y, ydot)
+                rhs.from_device_order(ydot, y_ref)
+                ydh.copy_(y_ref, non_blocking=True)
+            st.synchronize()
+            assert rhs.check()[0] == 0
     for _ in range(3):
-        rhs.f(0.0, yh, ydh)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     n_e2e = max(3, min(steps, 50))
     for _ in range(n_e2e):
-        rhs.f(0.0, yh, ydh)  # H2D y, permute, 3 kernels, permute, D2H ydot, sync, error word
+        e2e_step()
     torch.cuda.synchronize()
     s_e2e = (time.perf_counter() - t0) / n_e2e
+    if hx is not None:  # restore the device-order state for anything that follows
+        with torch.cuda.stream(st):
+            y_ref.copy_(yh); rhs.to_device_order(y_ref, y)
+        st.synchronize()
 
     # ---------------- reduce over ranks: max time ----------------
     tt = torch.tensor([ms_dev, s_e2e * 1e3], dtype=torch.float64, device=dev)
@@ -242,7 +278,8 @@ def main():
                "data": "synthetic",
                "config": {"workload": "synthetic-1M per GPU: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
                           "seed": 20240611, "l2": "inputs 400 MB per rank > 126 MB L2, no flush needed",
-                          "multi_gpu": "replicated stripes (no halo exchange yet)" if world > 1 else "single GPU"},
+                          "multi_gpu": (f"{world} stripes of 1M cells of the {world}M-cell mesh, NCCL all_to_all halo exchange of "
+                                        f"{hx.bytes_per_exchange} B per rank and f()") if world > 1 else "single GPU"},
                "gpu_launches": nst * steps,
                "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -88,6 +88,17 @@ typedef struct shud_diag {
     double *y2LakeArea, *QLakeSurf, *QLakeSub, *QLakeRivIn, *QLakeRivOut, *qLakeEvap, *qLakePrcp; /* [Nl] */
 } shud_diag;
 
+/* ---- one partition of a larger mesh (multi-GPU).  The shud_mesh of a partition
+ * holds its OWNED cells, reaches, segments and lakes; a neighbour index nabr in Ne+1 .. Ne+Nhalo names halo
+ * cell (nabr-Ne-1): a cell owned by another partition whose state arrives by halo exchange before each RHS.
+ * Only what an edge flux needs from the far side is kept for a halo cell.  Restrictions of this version:
+ * halo cells are plain land cells (no head BC, not lake), and reaches / lakes are not cut by the partition. ---- */
+typedef struct shud_halo {
+    int32_t Nhalo;
+    const double *z_surf, *z_bottom;                               /* [Nhalo] geometry of the far cell */
+    const double *AquiferDepth, *macD, *macKsatH, *geo_vAreaF, *KsatH; /* [Nhalo] its effKH parameters */
+} shud_halo;
+
 typedef struct shud_ctx shud_ctx;
 
 /* Build the device-resident SoA mirror (cells reordered for locality, CSR gathers for
@@ -95,6 +106,14 @@ typedef struct shud_ctx shud_ctx;
  * `device` is the CUDA ordinal.  Replaces: nothing in the reference - it is the one-time
  * export after Model_Data::initialize() (src/Model/shud.cpp:51). */
 int shud_b200_create(const shud_mesh *mesh, int device, shud_ctx **out);
+/* Same, for one partition with halo cells (halo may be NULL = shud_b200_create). */
+int shud_b200_create_partition(const shud_mesh *mesh, const shud_halo *halo, int device, shud_ctx **out);
+/* Device buffer [Nhalo][2] = (Ysurf, Ygw) of every halo cell: the receive buffer of the halo exchange,
+ * registered once and read by the kernels of every following RHS. */
+int shud_b200_set_halo_state_dev(shud_ctx *ctx, const double *halo_state_dev);
+/* Pack (Ysurf, Ygw) of `n` owned cells (device-order ids in idx_dev) into out_dev[2k], out_dev[2k+1]:
+ * the send side of the halo exchange (same pair layout, so a peer's message lands in place). */
+int shud_b200_pack_halo_dev(shud_ctx *ctx, const double *y_dev, const int32_t *idx_dev, int32_t n, double *out_dev);
 void shud_b200_destroy(shud_ctx *ctx);
 int64_t shud_b200_ny(const shud_ctx *ctx);
 /* the CUDA stream (cudaStream_t) every call of this context is ordered on */

@@ -41,6 +41,27 @@ class ShudMesh(C.Structure):
                    ("lake_bathy_yi", _PD), ("lake_bathy_ai", _PD)])
 
 
+HALO_D = ["z_surf", "z_bottom", "AquiferDepth", "macD", "macKsatH", "geo_vAreaF", "KsatH"]
+
+
+class ShudHalo(C.Structure):
+    _fields_ = [("Nhalo", C.c_int32)] + [(n, _PD) for n in HALO_D]
+
+
+def make_halo(halo):
+    """dict with keys halo_<name> [Nhalo] -> (ShudHalo, keepalive)"""
+    h = ShudHalo()
+    keep = []
+    n = int(np.asarray(halo["halo_z_surf"]).shape[0])
+    h.Nhalo = n
+    for name in HALO_D:
+        a, p = _d(halo["halo_" + name])
+        assert a.shape[0] == n
+        keep.append(a)
+        setattr(h, name, p)
+    return h, keep
+
+
 FORCING_D = ["qEleNetPrep", "qPotEvap", "qPotTran", "t_lai", "fu_Surf", "fu_Sub", "qElePrep",
              "qEleE_IC", "ele_yBC", "ele_QBC", "riv_yBC", "riv_qBC"]
 

@@ -43,6 +43,9 @@ def lib():
     vp = C.c_void_p
     sig = {
         "shud_b200_create": (C.c_int, [C.POINTER(abi.ShudMesh), C.c_int, C.POINTER(vp)]),
+        "shud_b200_create_partition": (C.c_int, [C.POINTER(abi.ShudMesh), C.POINTER(abi.ShudHalo), C.c_int, C.POINTER(vp)]),
+        "shud_b200_set_halo_state_dev": (C.c_int, [vp, vp]),
+        "shud_b200_pack_halo_dev": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
         "shud_b200_destroy": (None, [vp]),
         "shud_b200_ny": (C.c_int64, [vp]),
         "shud_b200_stream": (vp, [vp]),
@@ -87,12 +90,21 @@ class ShudRHS:
     """One GPU's copy of the model: static SoA mirror + forcing-step arrays + carried state."""
 
     def __init__(self, mesh, device=0):
+        """mesh: dict of the static SoA arrays; if it carries halo_* arrays it is one partition of a
+        larger mesh (shud_up_b200/partition.py) and nabr may name halo cells Ne+1..Ne+Nhalo."""
         L = lib()
         self._mesh_struct, self._keep = abi.make_mesh(mesh)
         self.Ne, self.Nr, self.Ns, self.Nl = (self._mesh_struct.Ne, self._mesh_struct.Nr, self._mesh_struct.Ns,
                                               self._mesh_struct.Nl)
         h = C.c_void_p()
-        rc = L.shud_b200_create(C.byref(self._mesh_struct), int(device), C.byref(h))
+        self.Nhalo = 0
+        if "halo_z_surf" in mesh and len(mesh["halo_z_surf"]) > 0:
+            hs, keep = abi.make_halo(mesh)
+            self._keep += keep
+            self.Nhalo = hs.Nhalo
+            rc = L.shud_b200_create_partition(C.byref(self._mesh_struct), C.byref(hs), int(device), C.byref(h))
+        else:
+            rc = L.shud_b200_create(C.byref(self._mesh_struct), int(device), C.byref(h))
         _chk(rc, "shud_b200_create")
         self._h = h
         self.device = int(device)
@@ -130,6 +142,18 @@ class ShudRHS:
 
     def from_device_order(self, dev_dev, out_ref):
         _chk(lib().shud_b200_from_device_order(self._h, _ptr(dev_dev), _ptr(out_ref)), "from_device_order")
+
+    # ---- halo exchange plumbing (multi-GPU) ----
+    def set_halo_state(self, halo_state_dev):
+        """register the device buffer [Nhalo][2] = (Ysurf, Ygw) the exchange fills before each RHS"""
+        self._halo_buf = halo_state_dev
+        _chk(lib().shud_b200_set_halo_state_dev(self._h, _ptr(halo_state_dev)), "set_halo_state")
+
+    def pack_halo(self, y_dev, idx_dev, out_dev):
+        """out[2k] = Ysurf[idx[k]], out[2k+1] = Ygw[idx[k]]  (idx: int32 device-order cell ids, on the device)"""
+        n = int(idx_dev.numel())
+        _chk(lib().shud_b200_pack_halo_dev(self._h, _ptr(y_dev), C.c_void_p(idx_dev.data_ptr()), n, _ptr(out_dev)),
+             "pack_halo")
 
     # ---- forcing step / carried state ----
     def set_forcing(self, forcing, qEleE_IC=None):

@@ -63,6 +63,11 @@ struct DevMesh {
     const int *bank_cell, *bank_j, *bank_lake;
     const double *bank_kh;
     double *l_evap_raw, *l_prcp;
+    // halo cells of a partition (ids Ne .. Ne+Nhalo-1 in nbr)
+    int Nhalo;
+    const double *h_zs, *h_zb, *h_aqd, *h_macD, *h_macKsatH, *h_vAreaF, *h_ksatH;
+    const double *h_state;        // [Nhalo][2] = (Ysurf, Ygw) of each halo cell, filled by the halo exchange
+    double *h_kh;                 // effKH of halo cells (k_effkh)
     int *err;  // [0] code, [1] where (1-based reference id)
 };
 
@@ -81,7 +86,14 @@ __device__ __forceinline__ void raise_err(int *err, int code, int where) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restrict__ Y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.Ne) return;
+    if (i >= m.Ne) {
+        const int h = i - m.Ne;  // halo cell: same formula on the exchanged groundwater head
+        if (h < m.Nhalo) {
+            int e = 0;
+            m.h_kh[h] = eff_kh(m.h_state[2 * h + 1], m.h_aqd[h], m.h_macD[h], m.h_macKsatH[h], m.h_vAreaF[h], m.h_ksatH[h], &e);
+        }
+        return;
+    }
     const unsigned fl = m.flags[i];
     double kh;
     if (fl & F_LAKE) {
@@ -138,12 +150,16 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
     double n_ysf[3], n_ygw[3], n_zs[3], n_zb[3], n_kh[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const int k = nb[j] >= 0 ? nb[j] : i;
+        const int k = (nb[j] >= 0 && nb[j] < Ne) ? nb[j] : i;
         n_ysf[j] = Y[k];
         n_ygw[j] = Y[2 * NE + k];
         n_zs[j] = __ldg(m.z_surf + k);
         n_zb[j] = __ldg(m.z_bottom + k);
         n_kh[j] = m.effKH[k];
+        if (nb[j] >= Ne) {  // halo cell of a partition
+            const int h = nb[j] - Ne;
+            n_ysf[j] = m.h_state[2 * h]; n_ygw[j] = m.h_state[2 * h + 1]; n_zs[j] = m.h_zs[h]; n_zb[j] = m.h_zb[h]; n_kh[j] = m.h_kh[h];
+        }
     }
     const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : ygw_raw;
     const double fuSub = f.fuSub;
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
             if (nb[j] >= 0) {
                 const double nsf = n_ysf[j] < 0. ? 0. : n_ysf[j];
                 double ygw_n = n_ygw[j];
-                if (m.has_headbc && (m.flags[nb[j]] & F_HEADBC)) ygw_n = m.ele_yBC[nb[j]];
+                if (m.has_headbc && nb[j] < Ne && (m.flags[nb[j]] & F_HEADBC)) ygw_n = m.ele_yBC[nb[j]];
                 qs = edge_surface(isf, zs, nsf, n_zs[j], depression, dist[j], B[j], arough[j]);
                 qg = edge_sub(ygw, zb, ygw_n, n_zb[j], kh, n_kh[j], dist[j], B[j]);
             } else if (nb[j] <= -2) {
@@ -374,10 +390,13 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                 const unsigned r = (unsigned)(k - i0);
                 if (r < (unsigned)TILE) {  // neighbour inside the tile: shared memory
                     nsf = t_sf[r]; ygw_n = t_gw[r]; zs_n = t_zs[r]; zb_n = t_zb[r]; kh_n = t_kh[r];
-                } else {
+                } else if (k < Ne) {
                     nsf = Y[k]; ygw_n = Y[2 * NE + k]; zs_n = __ldg(m.z_surf + k); zb_n = __ldg(m.z_bottom + k);
                     kh_n = m.effKH[k];
                     if (m.has_headbc && (m.flags[k] & F_HEADBC)) ygw_n = m.ele_yBC[k];
+                } else {  // halo cell of a partition: state from the last halo exchange
+                    const int h = k - Ne;
+                    nsf = m.h_state[2 * h]; ygw_n = m.h_state[2 * h + 1]; zs_n = m.h_zs[h]; zb_n = m.h_zb[h]; kh_n = m.h_kh[h];
                 }
                 nsf = nsf < 0. ? 0. : nsf;
                 qs = edge_surface(isf, zs, nsf, zs_n, depression, dist[j], B[j], arough[j]);
@@ -557,6 +576,15 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
     }
 }
 
+// send side of the halo exchange: (Ysurf, Ygw) of the listed owned cells
+__global__ void k_pack_halo(const double *__restrict__ Y, const int *__restrict__ idx, int n, int Ne, double *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    out[2 * k] = Y[i];
+    out[2 * k + 1] = Y[2 * (size_t)Ne + i];
+}
+
 // carried state from y (Model_Data::updateforcing -> updateElement for every cell, MD_ET.cpp:14-19)
 __global__ void k_prime(DevMesh m, const double *__restrict__ Y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -620,7 +648,7 @@ uint64_t hilbert_d(uint32_t x, uint32_t y) {
 struct shud_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    int Ne = 0, Nr = 0, Ns = 0, Nl = 0;
+    int Ne = 0, Nr = 0, Ns = 0, Nl = 0, Nhalo = 0;
     int64_t NY = 0;
     DevMesh m{};
     DevDiag diag{};
@@ -698,7 +726,12 @@ const double *up_riv(shud_ctx *c, const double *src) {
 extern "C" {
 
 int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
+    return shud_b200_create_partition(M, nullptr, device, out);
+}
+
+int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int device, shud_ctx **out) {
     if (!M || !out || M->Ne <= 0) return SHUD_ERR_ARG;
+    const int Nhalo = (H && H->Nhalo > 0) ? H->Nhalo : 0;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) return SHUD_ERR_NO_DEVICE;
     CK(cudaSetDevice(device));
@@ -807,6 +840,8 @@ int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
                 v = -2;  // slot patched below
             } else if (nb >= 0 && nb < Ne) {
                 v = c->cinv[nb];
+            } else if (nb >= Ne && nb < Ne + Nhalo) {
+                v = nb;  // halo cells keep their place after the owned cells
             }
             nbr[(size_t)j * Ne + i] = v;
         }
@@ -936,6 +971,16 @@ int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
         CK(cudaMemset(m.l_evap_raw, 0, sizeof(double) * std::max(Nl, 1)));
         CK(cudaMemset(m.l_prcp, 0, sizeof(double) * std::max(Nl, 1)));
     }
+    // ---- halo cells of a partition ----
+    m.Nhalo = Nhalo;
+    c->Nhalo = Nhalo;
+    if (Nhalo) {
+        auto uph = [&](const double *src) { return dev_upload(c, std::vector<double>(src, src + Nhalo)); };
+        m.h_zs = uph(H->z_surf); m.h_zb = uph(H->z_bottom); m.h_aqd = uph(H->AquiferDepth); m.h_macD = uph(H->macD);
+        m.h_macKsatH = uph(H->macKsatH); m.h_vAreaF = uph(H->geo_vAreaF); m.h_ksatH = uph(H->KsatH);
+        m.h_kh = dev_alloc<double>(c, Nhalo);
+        CK(cudaMemset(m.h_kh, 0, sizeof(double) * Nhalo));
+    }
     // ---- dynamic arrays ----
     m.netPrep = dev_alloc<double>(c, Ne); m.potEvap = dev_alloc<double>(c, Ne); m.potTran = dev_alloc<double>(c, Ne);
     m.lai = dev_alloc<double>(c, Ne); m.fuSurf = dev_alloc<double>(c, Ne); m.fuSub = dev_alloc<double>(c, Ne);
@@ -1050,6 +1095,20 @@ int shud_b200_from_device_order(shud_ctx *c, const double *dev_dev, double *ref_
     return SHUD_OK;
 }
 
+int shud_b200_set_halo_state_dev(shud_ctx *c, const double *state) {
+    if (!c || (c->Nhalo > 0 && !state)) return SHUD_ERR_ARG;
+    c->m.h_state = state;
+    return SHUD_OK;
+}
+
+int shud_b200_pack_halo_dev(shud_ctx *c, const double *y, const int32_t *idx, int32_t n, double *out) {
+    if (!c || !y || (n > 0 && (!idx || !out))) return SHUD_ERR_ARG;
+    if (n <= 0) return SHUD_OK;
+    k_pack_halo<<<(n + 255) / 256, 256, 0, c->stream>>>(y, idx, n, c->Ne, out);
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+
 int shud_b200_perm(const shud_ctx *c, int32_t *cp, int32_t *rp) {
     if (!c) return SHUD_ERR_ARG;
     if (cp) std::copy(c->cperm.begin(), c->cperm.end(), cp);
@@ -1116,10 +1175,10 @@ template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     const int Ne = c->Ne;
     if (c->split == 2) {
-        k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
         launch_fused<DIAG>(c, y, ydot);
     } else {
-        k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
         launch_cell<DIAG>(c, y, ydot);
     }
     const int nb_riv = (c->Nr + 127) / 128;
@@ -1141,7 +1200,7 @@ int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydo
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
     if (c->split == 2 && stage == 1) launch_fused<false>(c, y, ydot);
-    else if (stage == 0) k_effkh<<<(Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+    else if (stage == 0) k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
     else if (stage == 1) launch_cell<false>(c, y, ydot);
     else if (stage == 2 && nb_riv + c->Nl > 0)
         k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);

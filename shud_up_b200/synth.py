@@ -1,14 +1,20 @@
 """Synthetic SHUD domains of a named size (BASELINE.json configs 4/5):
-a structured-triangulated rectangle (nx x ny quads split alternately, Ne = 2 nx ny), node
-spacing 100 m with +-20 % jitter, 16 soil / 16 geology / 12 land-cover classes drawn from the
-ranges of the ccw tables, dendritic river trees following grid lines down-slope (3 river-element
-segments per reach), optional lake.  Everything random comes from seed 20240611.
+a structured-triangulated rectangle (nx x ny quads split alternately, Ne = 2 nx ny), node spacing 100 m
+with +-20 % jitter, 16 soil / 16 geology / 12 land-cover classes drawn from the ranges of the ccw tables,
+dendritic river trees following grid lines down-slope (3 river-element segments per reach), optional lake.
+Seed 20240611.
 
-Output: dict of numpy arrays with the snapshot naming of oracle/ref_driver.cpp, i.e. exactly
-the static arrays Model_Data::initialize() would hold for such a mesh (geometry per
-_Element::applyGeometry / InitElement / applyNabor, src/classes/Element.cpp:62-270; river
-hand-over per _River::updateFrDownstream, src/classes/River.cpp:74-90), plus one forcing step
-and a state vector with every branch populated.  Host-side set-up only: no RHS arithmetic here.
+Every random field is drawn per grid ROW from its own stream (seed, kind, row), so any horizontal stripe of
+the global mesh can be generated on its own and is identical to that part of the whole mesh: `make(...,
+rows=(r0, r1))` returns the partition owning quad rows [r0, r1) with its halo cells (multi-GPU runs build
+only their own stripe).  The river-tree bands never straddle a stripe boundary that is a multiple of the band
+height, so reaches are never cut.
+
+Output: dict of numpy arrays with the snapshot naming of oracle/ref_driver.cpp, i.e. the static arrays
+Model_Data::initialize() would hold for such a mesh (geometry per _Element::applyGeometry / InitElement /
+applyNabor, src/classes/Element.cpp:62-270; river hand-over per _River::updateFrDownstream,
+src/classes/River.cpp:74-90), plus one forcing step and a state vector with every branch populated.
+Host-side set-up only: no RHS arithmetic here.
 """
 import numpy as np
 
@@ -25,29 +31,46 @@ def named(size):
     raise KeyError(size)
 
 
-def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lake_frac=0.0, dtype=np.float64):
-    rng = np.random.default_rng(seed)
-    # ---------------- nodes ----------------
-    gx, gy = np.meshgrid(np.arange(nx + 1, dtype=np.float64), np.arange(ny + 1, dtype=np.float64), indexing="xy")
-    X = (gx + rng.uniform(-0.2, 0.2, gx.shape)) * 100.0
-    Yc = (gy + rng.uniform(-0.2, 0.2, gy.shape)) * 100.0
-    ph = rng.uniform(0, 2 * np.pi, 6)
+def _rng(seed, kind, row=0):
+    return np.random.default_rng([seed, kind, row])
+
+
+def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lake_frac=0.0, rows=None,
+         stripe_rows=None):
+    """rows=(r0, r1): build only the stripe of quad rows [r0, r1) (+ one halo row on each inner side) and
+    return it as a partition (shud_up_b200.partition.extract) of the global nx x ny mesh; stripe_rows = rows
+    per stripe of the global decomposition (owner rank of a row = row // stripe_rows)."""
+    r0, r1 = (0, ny) if rows is None else rows
+    qa, qb = max(r0 - 1, 0), min(r1 + 1, ny)       # quad rows generated (owned + halo candidates)
+    nq = qb - qa
+    # ---------------- nodes of rows qa .. qb ----------------
+    jx = np.empty((nq + 1, nx + 1)); jy = np.empty((nq + 1, nx + 1))
+    for j in range(nq + 1):
+        u = _rng(seed, 1, qa + j).uniform(-0.2, 0.2, (2, nx + 1))
+        jx[j], jy[j] = u[0], u[1]
+    gx, gy = np.meshgrid(np.arange(nx + 1, dtype=np.float64), np.arange(qa, qb + 1, dtype=np.float64), indexing="xy")
+    X = (gx + jx) * 100.0
+    Yc = (gy + jy) * 100.0
+    ph = _rng(seed, 0).uniform(0, 2 * np.pi, 6)
     noise = (np.sin(X / 3100.0 + ph[0]) * np.cos(Yc / 2300.0 + ph[1]) + 0.5 * np.sin(X / 900.0 + ph[2])
              * np.sin(Yc / 1300.0 + ph[3]) + 0.25 * np.cos(X / 410.0 + ph[4]) * np.cos(Yc / 370.0 + ph[5]))
     Z = 1000.0 + 0.01 * X + 0.005 * Yc + 5.0 * noise
-    nid = lambda ix, iy: iy * (nx + 1) + ix
+    nid = lambda ix, iy: (iy - qa) * (nx + 1) + ix          # local node id of global grid point (ix, iy)
     Xf, Yf, Zf = X.ravel(), Yc.ravel(), Z.ravel()
     # ---------------- triangles: quad (ix,iy) -> cells 2q (touches the bottom edge) and 2q+1 (top edge) -----
-    qx, qy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    qx, qy = np.meshgrid(np.arange(nx), np.arange(qa, qb), indexing="xy")
     qx, qy = qx.ravel(), qy.ravel()
     n00, n10, n01, n11 = nid(qx, qy), nid(qx + 1, qy), nid(qx, qy + 1), nid(qx + 1, qy + 1)
     even = ((qx + qy) % 2) == 0
     # even: diagonal n00-n11 -> (n00,n10,n11) bottom, (n00,n11,n01) top ; odd: diagonal n10-n01
     tb = np.where(even[:, None], np.stack([n00, n10, n11], 1), np.stack([n00, n10, n01], 1))
     tt = np.where(even[:, None], np.stack([n00, n11, n01], 1), np.stack([n10, n11, n01], 1))
-    Ne = 2 * nx * ny
+    Ne = 2 * nx * nq
     node = np.empty((Ne, 3), dtype=np.int64)
     node[0::2], node[1::2] = tb, tt
+    gid = np.empty(Ne, dtype=np.int64)                      # global cell id
+    gid[0::2] = 2 * (qy * nx + qx); gid[1::2] = 2 * (qy * nx + qx) + 1
+    cell_row = np.repeat(qy, 2)
     x1, x2, x3 = Xf[node[:, 0]], Xf[node[:, 1]], Xf[node[:, 2]]
     y1, y2, y3 = Yf[node[:, 0]], Yf[node[:, 1]], Yf[node[:, 2]]
     area = 0.5 * ((x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1))
@@ -72,9 +95,10 @@ def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lak
     nabr[a] = b // 3 + 1
     nabr[b] = a // 3 + 1
     nabr = nabr.reshape(Ne, 3)
-    # ---------------- classes ----------------
+    # ---------------- classes (global tables) and per-cell draws (per quad row) ----------------
     nsoil, ngeol, nlc = 16, 16, 12
-    U = lambda lo_, hi_, n: rng.uniform(lo_, hi_, n)
+    tr = _rng(seed, 3)
+    U = lambda lo_, hi_, n: tr.uniform(lo_, hi_, n)
     soil = dict(infKsatV=U(1.0e-6, 4.8e-6, nsoil), ThetaS=U(0.39, 0.47, nsoil), ThetaR=np.full(nsoil, 0.01) + U(0, 0.03, nsoil),
                 Alpha=U(2.6, 5.9, nsoil), Beta=U(1.13, 1.31, nsoil), hAreaF=U(0.005, 0.02, nsoil),
                 macKsatV=U(0.010, 0.048, nsoil), infD=U(0.08, 0.15, nsoil))
@@ -82,8 +106,17 @@ def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lak
                 geo_vAreaF=U(0.005, 0.02, ngeol), macKsatH=U(7.2e-3, 2.4e-2, ngeol), macD=U(0.5, 2.0, ngeol))
     lc = dict(VegFrac=U(0.0, 0.75, nlc), Rough=U(5.8e-4, 7.5e-4, nlc), RzD=U(0.0, 0.6, nlc), SoilDgrd=U(0.0, 0.1, nlc),
               ImpAF=np.where(np.arange(nlc) % 4 == 0, U(0.0, 0.4, nlc), 0.0), lai=U(0.5, 3.4, nlc))
-    isoil, igeol, ilc = rng.integers(0, nsoil, Ne), rng.integers(0, ngeol, Ne), rng.integers(0, nlc, Ne)
-    aqd = rng.uniform(10.0, 30.0, Ne)
+    NC = 2 * nx
+    R = {k: np.empty(Ne) for k in ("aqd", "pe", "pt", "lai0", "prcp", "netf", "eic0", "eic1", "sf0", "sf1", "gw", "wet0",
+                                   "wet1", "us")}
+    isoil = np.empty(Ne, dtype=np.int64); igeol = np.empty(Ne, dtype=np.int64); ilc = np.empty(Ne, dtype=np.int64)
+    for j in range(nq):
+        g = _rng(seed, 2, qa + j)
+        sl = slice(j * NC, (j + 1) * NC)
+        isoil[sl], igeol[sl], ilc[sl] = g.integers(0, nsoil, NC), g.integers(0, ngeol, NC), g.integers(0, nlc, NC)
+        for k in R:
+            R[k][sl] = g.uniform(0, 1, NC)
+    aqd = 10.0 + 20.0 * R["aqd"]
     m = {}
     m["ele_x"], m["ele_y"] = cx, cy
     m["ele_area"], m["ele_z_surf"], m["ele_z_bottom"] = area, z_surf, z_surf - aqd
@@ -111,11 +144,12 @@ def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lak
     avgr = np.where(has, 0.5 * (m["ele_Rough"][:, None] + m["ele_Rough"][nb0]), m["ele_Rough"][:, None])
     m["ele_iBC"] = np.zeros(Ne, dtype=np.int32)
     m["ele_iSS"] = np.zeros(Ne, dtype=np.int32)
-    # ---------------- lake (optional): a disc of cells around the domain centre ----------------
+    # ---------------- lake (optional, whole-mesh builds only): a disc of cells ----------------
     ilake = np.zeros(Ne, dtype=np.int32)
     lakenabr = np.zeros((Ne, 3), dtype=np.int32)
     Nl = 0
     if lake_frac > 0:
+        assert rows is None, "the lake variant is a single-partition mesh"
         r2 = lake_frac * (nx * 100.0) * (ny * 100.0) / np.pi
         inl = (cx - 0.62 * nx * 100.0) ** 2 + (cy - 0.5 * ny * 100.0) ** 2 < r2
         ilake[inl] = 1
@@ -132,7 +166,7 @@ def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lak
         m["lake_zmin"] = np.zeros(0); m["lake_NumEleLake"] = np.zeros(0, dtype=np.int32)
         m["lake_bathy_ptr"] = np.zeros(1, dtype=np.int32); m["lake_bathy_yi"] = np.zeros(0); m["lake_bathy_ai"] = np.zeros(0)
     m["ele_iLake"] = ilake
-    # ---------------- rivers ----------------
+    # ---------------- rivers: the trees whose band lies inside the owned rows ----------------
     if ntree is None:
         ntree = max(1, ny // 10)
     band = ny // ntree
@@ -143,37 +177,41 @@ def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lak
     trib = (reaches_per_tree - stem) // 4
     assert stem <= nx and trib >= 1
     per = stem + 4 * trib
-    Nr = ntree * per
+    t_all = np.arange(ntree)
+    t_idx = t_all[(t_all * band >= r0) & ((t_all + 1) * band <= r1)]
+    nt = t_idx.size
+    Nr = nt * per
     # river types: depth, bankslope, BottomWidth, rivRough, Cwr, KsatH, BedThick (input/ccw/ccw.sp.riv, 4 rows)
     rtype = np.array([[5.5, 0.0, 52.0, 0.04 / 60, 0.6, 0.1 / 1440, 0.1], [6.0, 0.5, 54.0, 0.04 / 60, 0.6, 0.1 / 1440, 0.1],
                       [6.5, 1.0, 56.0, 0.045 / 60, 0.6, 0.2 / 1440, 0.15], [7.0, 0.0, 58.0, 0.035 / 60, 0.62, 0.1 / 1440, 0.1]])
     r_ix = np.empty(Nr, dtype=np.int64); r_iy = np.empty(Nr, dtype=np.int64)
     r_down = np.empty(Nr, dtype=np.int64); r_type = np.empty(Nr, dtype=np.int64)
-    k = 0
-    t_idx = np.arange(ntree)
     iy0 = t_idx * band + band // 2
     # per tree: stem reaches ix = 0..stem-1 on line iy0 flowing to ix=0 (outlet, down=-3);
     # tributary j on line iy0+off_j covering ix = a_j .. a_j+trib-1, flowing to ix=a_j, joining the stem at ix=a_j
     offs = [1, -1, 1, -1]  # two tributaries per side line, on disjoint ix ranges
     starts = [int(stem * f) for f in (0.15, 0.35, 0.55, 0.75)]
-    base = t_idx * per                              # first reach id (0-based) of each tree
+    base = np.arange(nt) * per                      # first reach id (0-based, local) of each tree
     ixs = np.arange(stem)
-    rid = (base[:, None] + ixs[None, :])            # stem reach ids
-    r_ix[rid] = ixs[None, :]; r_iy[rid] = iy0[:, None]
-    r_down[rid] = np.where(ixs[None, :] == 0, -3, rid - 1 + 1)   # 1-based id of reach ix-1
-    r_type[rid] = np.where(ixs[None, :] < stem // 3, 3, 2)
-    for j in range(4):
-        a = min(starts[j], nx - trib)
-        tix = a + np.arange(trib)
-        tid = base[:, None] + stem + j * trib + np.arange(trib)[None, :]
-        r_ix[tid] = tix[None, :]; r_iy[tid] = (iy0 + offs[j])[:, None]
-        dn = tid - 1 + 1
-        dn[:, 0] = base + min(a, stem - 1) + 1      # joins the stem
-        r_down[tid] = dn
-        r_type[tid] = j % 2
+    if nt:
+        rid = (base[:, None] + ixs[None, :])        # stem reach ids
+        r_ix[rid] = ixs[None, :]; r_iy[rid] = iy0[:, None]
+        r_down[rid] = np.where(ixs[None, :] == 0, -3, rid)      # 1-based id of the reach at ix-1
+        r_type[rid] = np.where(ixs[None, :] < stem // 3, 3, 2)
+        for j in range(4):
+            a = min(starts[j], nx - trib)
+            tix = a + np.arange(trib)
+            tid = base[:, None] + stem + j * trib + np.arange(trib)[None, :]
+            r_ix[tid] = tix[None, :]; r_iy[tid] = (iy0 + offs[j])[:, None]
+            dn = tid.copy()                         # 1-based id of the previous reach of the tributary
+            dn[:, 0] = base + min(a, stem - 1) + 1  # joins the stem
+            r_down[tid] = dn
+            r_type[tid] = j % 2
     # geometry of a reach = the grid edge nodes (ix,iy)-(ix+1,iy)
     na, nb_ = nid(r_ix, r_iy), nid(r_ix + 1, r_iy)
-    sinu = 1.0 + 0.2 * rng.uniform(0, 1, Nr)
+    sinu = np.empty(Nr)
+    for k, t in enumerate(t_idx):
+        sinu[k * per:(k + 1) * per] = 1.0 + 0.2 * _rng(seed, 4, int(t)).uniform(0, 1, per)
     length = np.hypot(Xf[nb_] - Xf[na], Yf[nb_] - Yf[na]) * sinu
     zbed_a, zbed_b = Zf[na], Zf[nb_]
     slope = np.maximum(MINRIVSLOPE, (zbed_b - zbed_a) / length)   # flows towards decreasing x
@@ -190,28 +228,51 @@ def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lak
     m["riv_toLake"] = np.full(Nr, -9999, dtype=np.int32)
     # segments: 3 per reach - cell touching the edge from above (quad row iy, bottom triangle), from below
     # (quad row iy-1, top triangle) and the other triangle of the quad above
-    q_up = r_iy * nx + r_ix
-    q_dn = (r_iy - 1) * nx + r_ix
+    q_up = (r_iy - qa) * nx + r_ix
+    q_dn = (r_iy - 1 - qa) * nx + r_ix
     seg_ele = np.stack([2 * q_up, 2 * q_dn + 1, 2 * q_up + 1], 1).ravel() + 1
     seg_riv = np.repeat(np.arange(Nr) + 1, 3)
     seg_len = (np.stack([np.ones(Nr), np.ones(Nr), 0.3 * np.ones(Nr)], 1) * length[:, None]).ravel()
     if Nl:
         keep = ilake[seg_ele - 1] <= 0  # no river segments on lake cells
         seg_ele, seg_riv, seg_len = seg_ele[keep], seg_riv[keep], seg_len[keep]
-    # order segments the way a .sp.rivseg file is: ascending reach, then as listed
     m["seg_iEle"] = seg_ele.astype(np.int32); m["seg_iRiv"] = seg_riv.astype(np.int32)
     m["seg_length"] = seg_len
     m["seg_Cwr"] = rtype[r_type[seg_riv - 1], 4]
     Ns = seg_ele.size
+    # ---------------- one forcing step (a wet hour) ----------------
+    m["qPotEvap"] = 2.4e-6 * (0.3 + 1.7 * R["pe"])
+    m["qPotTran"] = 1.0e-6 * (0.5 + 3.0 * R["pt"])
+    m["t_lai"] = lc["lai"][ilc] * np.where(R["lai0"] < 0.05, 0.0, 1.0)
+    prcp = 2.0e-6 * (0.8 + 0.4 * R["prcp"])
+    m["qElePrep"] = prcp
+    m["qEleNetPrep"] = prcp * (0.7 + 0.3 * R["netf"])
+    m["fu_Surf"] = np.ones(Ne); m["fu_Sub"] = np.ones(Ne)
+    m["qEleE_IC_in"] = np.where(R["eic0"] < 0.3, 0.0, 1.5 * R["eic1"] * m["qPotTran"])
+    # ---------------- state: every branch populated (SURVEY.md 8(d)) ----------------
+    A = m["ele_AquiferDepth"]
+    ysf = np.where(R["sf0"] < 0.5, 0.0, 0.02 * R["sf1"])
+    ygw = (0.2 + 0.75 * R["gw"]) * A
+    ygw = np.where(R["wet0"] < 0.04, (0.985 + 0.025 * R["wet1"]) * A, ygw)   # water table at / above the surface
+    yus = (0.05 + 0.55 * R["us"]) * np.maximum(A - ygw, 0.02)
+    yriv = np.empty(Nr)
+    for k, t in enumerate(t_idx):
+        yriv[k * per:(k + 1) * per] = _rng(seed, 5, int(t)).uniform(0, 0.5, per)
+    yriv = yriv * m["riv_depth"]
+    ylake = np.full(Nl, 8.0)
+    m["y"] = np.concatenate([ysf, yus, ygw, yriv, ylake])
     # ---------------- random cell numbering (the locality pass has to undo it) ----------------
     if shuffle:
-        p = rng.permutation(Ne)            # new id -> old id
+        p = _rng(seed, 6, r0).permutation(Ne)            # new id -> old id
         inv = np.empty(Ne, dtype=np.int64); inv[p] = np.arange(Ne)
         for kname in list(m.keys()):
-            if kname.startswith("ele_") and m[kname].shape[0] == Ne:
-                m[kname] = m[kname][p]
+            v = m[kname]
+            if v.ndim == 1 and v.shape[0] == Ne and not kname.startswith(("riv_", "seg_", "lake_")) and kname != "y":
+                m[kname] = v[p]
+        m["y"] = np.concatenate([ysf[p], yus[p], ygw[p], yriv, ylake])
         nabr = np.where(nabr[p] > 0, inv[np.maximum(nabr[p] - 1, 0)] + 1, 0)
         edge, d2n, dist2edge, avgr, lakenabr = edge[p], d2n[p], dist2edge[p], avgr[p], lakenabr[p]
+        gid, cell_row = gid[p], cell_row[p]
         m["seg_iEle"] = (inv[m["seg_iEle"] - 1] + 1).astype(np.int32)
     # [3][Ne] edge-major arrays
     m["ele_edge"] = np.ascontiguousarray(edge.T).ravel(); m["ele_Dist2Nabor"] = np.ascontiguousarray(d2n.T).ravel()
@@ -220,25 +281,12 @@ def make(nx, ny, ntree=None, reaches_per_tree=None, seed=SEED, shuffle=True, lak
     m["ele_lakenabr"] = np.ascontiguousarray(lakenabr.T).ravel().astype(np.int32)
     for kname, v in (("Ne", Ne), ("Nr", Nr), ("Ns", Ns), ("Nl", Nl), ("close_boundary", 1), ("lakeon", 1 if Nl else 0)):
         m[kname] = np.array([v], dtype=np.int32)
-    # ---------------- one forcing step (a wet hour) ----------------
-    ilc_s = ilc[p] if shuffle else ilc
-    pe = 2.4e-6 * rng.uniform(0.3, 2.0, Ne)
-    m["qPotEvap"] = pe
-    m["qPotTran"] = 1.0e-6 * rng.uniform(0.5, 3.5, Ne)
-    m["t_lai"] = lc["lai"][ilc_s] * np.where(rng.uniform(0, 1, Ne) < 0.05, 0.0, 1.0)
-    prcp = 2.0e-6 * rng.uniform(0.8, 1.2, Ne)
-    m["qElePrep"] = prcp
-    m["qEleNetPrep"] = prcp * rng.uniform(0.7, 1.0, Ne)
-    m["fu_Surf"] = np.ones(Ne); m["fu_Sub"] = np.ones(Ne)
-    m["qEleE_IC_in"] = np.where(rng.uniform(0, 1, Ne) < 0.3, 0.0, 1.5 * rng.uniform(0, 1, Ne) * m["qPotTran"])
-    # ---------------- state: every branch populated (SURVEY.md 8(d)) ----------------
-    A = m["ele_AquiferDepth"]
-    ysf = np.where(rng.uniform(0, 1, Ne) < 0.5, 0.0, rng.uniform(0, 0.02, Ne))
-    ygw = rng.uniform(0.2, 0.95, Ne) * A
-    wet = rng.uniform(0, 1, Ne) < 0.04          # water table at / above the surface: Eg, Tg, exfiltration branches
-    ygw = np.where(wet, rng.uniform(0.985, 1.01, Ne) * A, ygw)
-    yus = rng.uniform(0.05, 0.6, Ne) * np.maximum(A - ygw, 0.02)
-    yriv = rng.uniform(0, 0.5, Nr) * m["riv_depth"]
-    ylake = np.full(Nl, 8.0)
-    m["y"] = np.concatenate([ysf, yus, ygw, yriv, ylake])
-    return m
+    m["ele_gid"] = gid
+    if rows is None:
+        return m
+    # ---------------- cut the owned rows out, keep the neighbours across the cut as halo ----------------
+    from . import partition
+    owned = (cell_row >= r0) & (cell_row < r1)
+    part = cell_row // (stripe_rows or (r1 - r0))
+    loc = partition.extract(m, owned, gid=gid, part_of_cell=part)
+    return loc

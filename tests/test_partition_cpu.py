@@ -1,0 +1,137 @@
+"""Multi-GPU host logic on the CPU: stripes of the synthetic mesh generated on their own equal the same part
+of the whole mesh; the partition + halo exchange reproduces the single-domain RHS bit for bit (checked with
+the CPU oracle on 'owned + halo' meshes); the exchange itself runs over torch.distributed gloo, world_size 2."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from shud_up_b200 import partition, synth
+
+NX, NY, NT, RPT = 40, 40, 4, 40
+
+
+@pytest.fixture(scope="module")
+def whole():
+    return synth.make(NX, NY, ntree=NT, reaches_per_tree=RPT)
+
+
+def _stripes():
+    return [synth.make(NX, NY, ntree=NT, reaches_per_tree=RPT, rows=(r0, r0 + 20), stripe_rows=20) for r0 in (0, 20)]
+
+
+def test_stripe_generated_alone_equals_that_part_of_the_whole_mesh(whole):
+    gid_w = whole["ele_gid"]
+    pos = np.empty(gid_w.max() + 1, dtype=np.int64); pos[gid_w] = np.arange(gid_w.size)
+    tot = 0
+    for loc in _stripes():
+        sel = pos[loc["own_gid"]]
+        tot += sel.size
+        for k in ("ele_area", "ele_z_surf", "ele_AquiferDepth", "ele_KsatH", "ele_Beta", "qPotEvap", "t_lai", "qEleE_IC_in"):
+            assert np.array_equal(np.sort(loc[k]), np.sort(whole[k][sel])), k
+        ne = int(loc["Ne"][0])
+        # state of owned cells, matched through the global id
+        o = np.argsort(loc["own_gid"]); w = np.argsort(gid_w[sel])
+        Ne_w = int(whole["Ne"][0])
+        for b in range(3):
+            assert np.array_equal(loc["y"][b * ne:(b + 1) * ne][o], whole["y"][b * Ne_w + sel][w])
+        assert loc["halo_gid"].size == NX and int(loc["Nr"][0]) == 2 * RPT
+    assert tot == gid_w.size
+
+
+def _extended(mesh, loc):
+    """'owned + halo' as one ordinary mesh the CPU oracle can run: halo cells become real cells whose own
+    far-side neighbours are cut off (their ydot is garbage and ignored)."""
+    Ne = int(mesh["Ne"][0])
+    own, halo = loc["_own_ref"], loc["_halo_ref"]
+    cells = np.concatenate([own, halo])
+    new = np.zeros(Ne, dtype=np.int64); new[cells] = np.arange(1, cells.size + 1)
+    ext = {k: v for k, v in loc.items() if not k.startswith(("halo_", "_", "own_"))}
+    for k, v in mesh.items():
+        v = np.asarray(v)
+        if k in partition.EDGE_KEYS:
+            ext[k] = np.ascontiguousarray(v.reshape(3, Ne)[:, cells]).ravel()
+        elif (k.startswith("ele_") or k in partition.CELL_DYN) and v.ndim == 1 and v.shape[0] == Ne:
+            ext[k] = v[cells]
+    nab = np.asarray(mesh["ele_nabr"]).reshape(3, Ne)[:, cells]
+    ext["ele_nabr"] = np.where(nab > 0, new[np.maximum(nab - 1, 0)], 0).astype(np.int32).ravel()
+    ext["ele_lakenabr"] = np.zeros(3 * cells.size, dtype=np.int32)
+    ext["Ne"] = np.array([cells.size], dtype=np.int32)
+    return ext, own.size, cells.size
+
+
+def test_partitioned_rhs_equals_single_domain_bitwise(whole):
+    Ne, Nr = int(whole["Ne"][0]), int(whole["Nr"][0])
+    whole = dict(whole)
+    whole["ele_u_satn"] = oracle_lib.oracle_prime(whole, whole["y"])
+    ref = oracle_lib.oracle_rhs(whole, want_diag=False)["ydot"]
+    row = whole["ele_gid"] // (2 * NX)
+    part = row // 20
+    locs = [partition.extract(whole, part == p, gid=whole["ele_gid"], part_of_cell=part, keep_full_halo=True) for p in (0, 1)]
+    # in-process emulation of the exchange: what rank p receives is what the owners hold
+    send_ids = [partition.exchange_plan(l["own_gid"], l["halo_gid"], [x["halo_gid"] for x in locs]) for l in locs]
+    for p, loc in enumerate(locs):
+        ne = int(loc["Ne"][0])
+        q = 1 - p
+        ids_q, gids_q = send_ids[q][0][p], send_ids[q][1][p]          # what q sends to p, ordered by gid
+        yq, neq = locs[q]["y"], int(locs[q]["Ne"][0])
+        msg = np.stack([yq[ids_q], yq[2 * neq + ids_q]], 1).ravel()
+        pos = partition.recv_positions(loc["halo_gid"], gids_q)
+        assert np.array_equal(pos, np.arange(pos.size))               # (owner, gid) order: lands in place
+        assert np.array_equal(msg, loc["halo_state_expected"])
+        # the RHS of 'owned + halo' with the exchanged halo state == the single-domain RHS on the owned cells
+        ext, nown, ntot = _extended(whole, loc)
+        nh = ntot - nown
+        y = np.concatenate([np.r_[loc["y"][0:ne], msg[0::2]], np.r_[loc["y"][ne:2 * ne], np.zeros(nh)],
+                            np.r_[loc["y"][2 * ne:3 * ne], msg[1::2]], loc["y"][3 * ne:]])
+        ext["y"] = y
+        ext["ele_u_satn"] = np.r_[loc["ele_u_satn"], np.zeros(nh)]
+        out = oracle_lib.oracle_rhs(ext, want_diag=False)["ydot"]
+        own = loc["_own_ref"]
+        for b in range(3):
+            assert np.array_equal(out[b * ntot:b * ntot + nown], ref[b * Ne + own]), (p, b)
+        nr = int(loc["Nr"][0])
+        assert np.array_equal(out[3 * ntot:3 * ntot + nr], ref[3 * Ne + loc["_riv_ref"]])
+
+
+def test_cut_river_is_refused(whole):
+    row = whole["ele_gid"] // (2 * NX)
+    with pytest.raises(NotImplementedError):
+        partition.extract(whole, row < 5)      # row 5 is the main stem of the first tree
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    loc = synth.make(NX, NY, ntree=NT, reaches_per_tree=RPT, rows=(20 * rank, 20 * rank + 20), stripe_rows=20)
+    hx = partition.HaloExchange(loc, dist, torch.device("cpu"))
+    y = torch.from_numpy(loc["y"].copy())
+    got = hx.exchange(y)[:2 * hx.nr].numpy().copy()
+    ok = bool(np.array_equal(got, loc["halo_state_expected"])) and hx.in_place and hx.nr == NX
+    # the distributed WRMS norm: local sum of squares + allreduce + global length
+    w = torch.full_like(y, 0.5)
+    s = torch.tensor([float(((y * w) ** 2).sum())], dtype=torch.float64)
+    n = torch.tensor([float(y.numel())], dtype=torch.float64)
+    dist.all_reduce(s); dist.all_reduce(n)
+    q.put((rank, ok, float(torch.sqrt(s / n))))
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_over_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == res[1][2] > 0

@@ -1,0 +1,76 @@
+"""Partitioned RHS on the GPU: two partition contexts (both on cuda:0, the exchange done in-process through
+the same pack kernel and buffers the NCCL path uses) reproduce the single-domain CUDA RHS bit for bit on the
+owned cells - ydot needs no cross-partition sum (owner-computes)."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import parity
+from shud_up_b200 import partition, synth
+
+pytestmark = pytest.mark.gpu
+NX, NY, NT, RPT = 60, 40, 4, 60
+
+
+def _run(mesh, halo_state=None, hx=None):
+    import torch
+    from shud_up_b200.api import ShudRHS
+    rhs = ShudRHS(mesh)
+    rhs.set_forcing(mesh, qEleE_IC=mesh["qEleE_IC_in"])
+    rhs.prime(mesh["y"])
+    st = rhs.torch_stream()
+    with torch.cuda.stream(st):
+        y_ref = torch.from_numpy(np.ascontiguousarray(mesh["y"])).cuda()
+        y, yd, yd_ref = torch.empty_like(y_ref), torch.empty_like(y_ref), torch.empty_like(y_ref)
+        rhs.to_device_order(y_ref, y)
+    return rhs, st, y, yd, yd_ref
+
+
+def test_two_partitions_equal_single_domain_bitwise():
+    import torch
+    whole = synth.make(NX, NY, ntree=NT, reaches_per_tree=RPT)
+    Ne = int(whole["Ne"][0])
+    rhs, st, y, yd, yd_ref = _run(whole)
+    with torch.cuda.stream(st):
+        rhs.f_dev(0.0, y, yd)
+        rhs.from_device_order(yd, yd_ref)
+    st.synchronize()
+    assert rhs.check()[0] == 0
+    ref = yd_ref.cpu().numpy()
+    # and the single-domain CUDA result agrees with the oracle
+    w2 = dict(whole); w2["ele_u_satn"] = oracle_lib.oracle_prime(whole, whole["y"])
+    o = oracle_lib.oracle_rhs(w2)
+    assert parity.mismatches(ref, o["ydot"], parity.ydot_scale(w2, o)).size == 0
+    gid_w = whole["ele_gid"]
+    pos = np.empty(gid_w.max() + 1, dtype=np.int64); pos[gid_w] = np.arange(Ne)
+    locs = [synth.make(NX, NY, ntree=NT, reaches_per_tree=RPT, rows=(r0, r0 + 20), stripe_rows=20) for r0 in (0, 20)]
+    ctxs = [_run(l) for l in locs]
+    all_halo = [l["halo_gid"] for l in locs]
+    # exchange plan exactly as HaloExchange builds it, the all_to_all replaced by a device copy
+    plans = [partition.exchange_plan(l["own_gid"], l["halo_gid"], all_halo) for l in locs]
+    for p, (loc, (r, s, yy, ydd, ydr)) in enumerate(zip(locs, ctxs)):
+        q = 1 - p
+        rq, sq, yq = ctxs[q][0], ctxs[q][1], ctxs[q][2]
+        ids_q = plans[q][0][p]                                   # reference-local ids rank q sends to p
+        inv = np.empty(rq.Ne, dtype=np.int64); inv[rq.perm()[0]] = np.arange(rq.Ne)
+        idx = torch.from_numpy(inv[ids_q].astype(np.int32)).cuda()
+        buf = torch.zeros(2 * idx.numel(), dtype=torch.float64, device="cuda")
+        with torch.cuda.stream(sq):
+            rq.pack_halo(yq, idx, buf)
+        sq.synchronize()
+        assert np.array_equal(buf.cpu().numpy(), loc["halo_state_expected"])
+        r.set_halo_state(buf)
+        with torch.cuda.stream(s):
+            r.f_dev(0.0, yy, ydd)
+            r.from_device_order(ydd, ydr)
+        s.synchronize()
+        assert r.check()[0] == 0
+        got = ydr.cpu().numpy()
+        ne = r.Ne
+        sel = pos[loc["own_gid"]]
+        for b in range(3):
+            assert np.array_equal(got[b * ne:(b + 1) * ne], ref[b * Ne + sel]), (p, b)
+    # reaches: both partitions own whole trees; their ydot equals the single-domain one (same tree order)
+    nr0 = ctxs[0][0].Nr
+    assert np.array_equal(np.r_[ctxs[0][4].cpu().numpy()[3 * ctxs[0][0].Ne:], ctxs[1][4].cpu().numpy()[3 * ctxs[1][0].Ne:]],
+                          ref[3 * Ne:])
