@@ -154,6 +154,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     mesh = stripe_mesh(world, rank)
     Ne, Nr, Ns, Nl = (int(mesh[k][0]) for k in ("Ne", "Nr", "Ns", "Nl"))
@@ -200,12 +201,11 @@ def main():
         ev1.record(st)
         barrier()
         ms_dev = ev0.elapsed_time(ev1)
-        if ms_dev < 1500:  # keep the region long enough for a few clock samples
-            reps = int(1500 / max(ms_dev, 1e-3)) + 1
-            for _ in range(reps):
-                for _ in range(steps):
-                    step()
-            torch.cuda.synchronize()
+        # keep the GPU under the same load long enough for a few 100-ms clock samples; the count depends on
+        # `steps` only, so every rank issues the same number of collectives
+        for _ in range(max(0, 6000 - steps)):
+            step()
+        torch.cuda.synchronize()
     code, where = rhs.check()
     assert code == 0, (code, where)
     clocks = clk.summary()
@@ -268,7 +268,7 @@ def main():
         value = total_cells * steps / (ms_dev_max * 1e-3)
         b_rhs = B_CELL * Ne + B_RIV * Nr + B_SEG * Ns
         dom = int(np.argmax(kt))
-        names = ["k_effkh", "k_cell", "k_river_lake"]
+        names = ["k_effkh", "k_fused", "k_river_lake"]
         # bytes of the dominant (cell) kernel: everything per cell and per segment except what the effKH
         # pre-pass alone touches (its 4 parameters + its effKH store: 40 B/cell), DESIGN.md section 4
         b_dom = {0: 60 * Ne, 1: (B_CELL - 40) * Ne + B_SEG * Ns, 2: B_RIV * Nr + 16 * Ns}[dom]
@@ -295,9 +295,18 @@ def main():
             out["cpu_baseline"] = {"value": Ne / per, "unit": UNIT, "cores": ncpu, "kind": "port",
                                    "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP on {ncpu} threads",
                                    "ms_per_step": per * 1e3}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    # orderly teardown while the CUDA context is still alive, then leave without running interpreter-exit
+    # destructors (torch's event/stream destructors otherwise race the context teardown under torchrun)
+    torch.cuda.synchronize()
+    del hx
+    rhs.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
