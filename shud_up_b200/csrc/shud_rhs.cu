@@ -33,6 +33,7 @@ constexpr int NSEG_SHIFT = 8;
 
 struct DevMesh {
     int Ne, Nr, Ns, Nl, close_boundary, has_headbc, nbank;
+    int ld;  // Ne rounded up to a multiple of 128: every per-cell array this library allocates is padded to it
     // static per cell
     const double *area, *z_surf, *z_bottom, *depression, *aqd, *sy, *infD, *infKsatV, *macKsatV, *hAreaF, *thetaS,
         *thetaR, *thetaFC, *beta, *ksatH, *ksatV, *macKsatH, *macD, *vAreaF, *vegFrac, *impAF, *wetland, *rootReach,
@@ -45,6 +46,7 @@ struct DevMesh {
     // everything static the cell side of a segment needs, copied next to each other so that the only
     // dependent gather left is the reach stage
     const int *cs_seg, *cs_riv, *cs_bc;  // segment id (device order), reach id (device order), reach BC code
+    const int *cs_cell;                  // owning cell (device order) of the slot
     const double *cs_len, *cs_cwr, *cs_depth, *cs_zbank, *cs_ksatH, *cs_bed;
     // forcing step
     double *netPrep, *potEvap, *potTran, *lai, *fuSurf, *fuSub, *eic, *satn, *ele_yBC, *ele_QBC;
@@ -117,12 +119,13 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int Ne = m.Ne;
     const size_t NE = (size_t)Ne;
+    const size_t LD = (size_t)m.ld;  // padded leading dimension of the static [3][.] arrays
     if (i >= Ne) return;
     // ---- phase 0: every load this cell owns is issued before anything is consumed, so one warp keeps
     //      ~45 coalesced 256-byte requests in flight (the kernel is latency-bound otherwise) ----
     const unsigned fl = __ldg(m.flags + i);
     const int seg0 = __ldg(m.cell_seg_first + i);
-    const int nb0 = __ldg(m.nbr + i), nb1 = __ldg(m.nbr + NE + i), nb2 = __ldg(m.nbr + 2 * NE + i);
+    const int nb0 = __ldg(m.nbr + i), nb1 = __ldg(m.nbr + LD + i), nb2 = __ldg(m.nbr + 2 * LD + i);
     const double ysf = Y[i], yus = Y[NE + i], ygw_raw = Y[2 * NE + i];
     const double kh = m.effKH[i];
     const double satn_prev = m.satn[i], eic_in = m.eic[i];
@@ -140,9 +143,9 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
     double B[3], dist[3], arough[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        B[j] = __ldg(m.edge + j * NE + i);
-        dist[j] = __ldg(m.dist + j * NE + i);
-        arough[j] = __ldg(m.avgRough + j * NE + i);
+        B[j] = __ldg(m.edge + j * LD + i);
+        dist[j] = __ldg(m.dist + j * LD + i);
+        arough[j] = __ldg(m.avgRough + j * LD + i);
     }
     // ---- phase 1: neighbour gathers, unconditional (index clamped to the cell itself where there is no
     //      neighbour cell) so that all 15 go out together as soon as the indices land ----
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
                 qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], dist[j], B[j]);
             } else if (!m.close_boundary) {
                 // open boundary (MD_ElementFlux.cpp:81-92,139-151)
-                const double d2e = m.dist2edge[j * NE + i];
+                const double d2e = m.dist2edge[j * LD + i];
                 if (isf > depression) {
                     const double s = isf / d2e * 0.5;
                     if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B[j] / m.rough[i];
@@ -291,23 +294,25 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
 // the one-thread-per-cell form, with no extra HBM traffic.  No atomics; every sum in a fixed order.
 // ---------------------------------------------------------------------------------------------
 constexpr int TILE = 128;
+constexpr int SEGCAP = 256;  // segment slots per tile kept in shared memory (more: read back from global)
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <bool DIAG, int MINB>
 __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, const double *__restrict__ Y,
                                                           double *__restrict__ DY) {
-    __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE];
+    __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE];
     __shared__ double x_P1[TILE], x_Es[TILE], x_G1[TILE], x_Eg[TILE], x_Tg[TILE], x_isf2[TILE];
+    __shared__ double sq_s[SEGCAP], sq_g[SEGCAP];  // river-segment fluxes of the tile, slot order
     const int Ne = m.Ne;
     const size_t NE = (size_t)Ne;
+    const size_t LD = (size_t)m.ld;  // padded leading dimension of the static [3][.] arrays
     const int lane_cell = threadIdx.x & (TILE - 1);
     const int i0 = blockIdx.x * TILE;
     const int i = i0 + lane_cell;
     const bool valid = i < Ne;
     const int ic = valid ? i : Ne - 1;  // clamped index: tail threads load something harmless
     const unsigned fl = __ldg(m.flags + ic);
-
     if (threadIdx.x >= TILE) {
         // =============================== vertical role ===============================
         const double ysf = Y[ic], yus = Y[NE + ic], ygw_raw = Y[2 * NE + ic];
@@ -336,6 +341,28 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         x_Eg[lane_cell] = v.Eg;
         x_Tg[lane_cell] = v.Tg;
         x_isf2[lane_cell] = dmax(0., isf2);
+        // ---- river segments of the whole tile, one thread per segment slot (dense lanes instead of a per-cell
+        //      loop at ~15 % lane use): fun_Seg_surface / fun_Seg_sub, MD_RiverFlux.cpp:100-126.  Needs the
+        //      lateral role's staged tile (barrier 3) and every x_isf2 of this role (same barrier). ----
+        bar_sync(3, 2 * TILE);
+        {
+            const int q0 = __ldg(m.cell_seg_first + i0);
+            const int q1 = __ldg(m.cell_seg_first + (i0 + TILE < Ne ? i0 + TILE : Ne));
+            for (int tq = lane_cell; tq < q1 - q0; tq += TILE) {
+                const int q = q0 + tq;
+                const int lc = __ldg(m.cs_cell + q) - i0, sgm = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
+                const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
+                const double zs_c = t_zs[lc];
+                const double zr = zs_c - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
+                const double qs = weir_jtoi(zs_c, x_isf2[lc], zr, yr, zs_c + __ldg(m.cs_zbank + q), __ldg(m.cs_cwr + q),
+                                            len, t_dep[lc]);
+                const double qg = flux_r2e_gw(yr, zr, t_gw[lc], t_zb[lc], t_kh[lc], __ldg(m.cs_ksatH + q), len,
+                                              __ldg(m.cs_bed + q)) * t_fus[lc];
+                m.QsegSurf[sgm] = qs;
+                m.QsegSub[sgm] = qg;
+                if (tq < SEGCAP) { sq_s[tq] = qs; sq_g[tq] = qg; }
+            }
+        }
         bar_arrive(2, 2 * TILE);  // hand-over: the lateral warps wait on barrier 2
         if (valid) {
             m.eic[i] = v.eic;
@@ -361,22 +388,24 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     }
     // =============================== lateral role ===============================
     const int seg0 = __ldg(m.cell_seg_first + ic);
-    const int nb[3] = {__ldg(m.nbr + ic), __ldg(m.nbr + NE + ic), __ldg(m.nbr + 2 * NE + ic)};
+    const int nb[3] = {__ldg(m.nbr + ic), __ldg(m.nbr + LD + ic), __ldg(m.nbr + 2 * LD + ic)};
     const double ysf = Y[ic], ygw_raw = Y[2 * NE + ic];
     const double kh = m.effKH[ic];
     const double zs = __ldg(m.z_surf + ic), zb = __ldg(m.z_bottom + ic);
     const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
-    t_sf[lane_cell] = ysf; t_gw[lane_cell] = ygw; t_zs[lane_cell] = zs; t_zb[lane_cell] = zb; t_kh[lane_cell] = kh;
     const double fuSub = __ldg(m.fuSub + ic), depression = __ldg(m.depression + ic);
+    t_sf[lane_cell] = ysf; t_gw[lane_cell] = ygw; t_zs[lane_cell] = zs; t_zb[lane_cell] = zb; t_kh[lane_cell] = kh;
+    t_dep[lane_cell] = depression; t_fus[lane_cell] = fuSub;
     const double area = __ldg(m.area + ic), sy = __ldg(m.sy + ic);
     double B[3], dist[3], arough[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        B[j] = __ldg(m.edge + j * NE + ic);
-        dist[j] = __ldg(m.dist + j * NE + ic);
-        arough[j] = __ldg(m.avgRough + j * NE + ic);
+        B[j] = __ldg(m.edge + j * LD + ic);
+        dist[j] = __ldg(m.dist + j * LD + ic);
+        arough[j] = __ldg(m.avgRough + j * LD + ic);
     }
-    bar_sync(1, TILE);  // the tile's own values are in shared memory (lateral warps only)
+    bar_sync(1, TILE);           // the tile's own values are in shared memory (lateral warps)
+    bar_arrive(3, 2 * TILE);     // ... and the vertical warps may use them for the segment pass
     int err = 0;
     double Qs[3] = {0., 0., 0.}, Qg[3] = {0., 0., 0.};
     if (!(fl & F_LAKE)) {
@@ -408,7 +437,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                 qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, B[j], 0.01);
                 qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], dist[j], B[j]);
             } else if (!m.close_boundary) {
-                const double d2e = m.dist2edge[j * NE + ic];
+                const double d2e = m.dist2edge[j * LD + ic];
                 if (isf > depression) {
                     const double s = isf / d2e * 0.5;
                     if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B[j] / m.rough[ic];
@@ -426,19 +455,16 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     const double P1 = x_P1[lane_cell], Es = x_Es[lane_cell], G1 = x_G1[lane_cell], Eg = x_Eg[lane_cell],
                  Tg = x_Tg[lane_cell];
     if (!valid) return;
+    // element side of PassValue (MD_f.cpp:228-235): sum of this cell's segment fluxes, ascending segment id
     double e2rS = 0., e2rG = 0.;
     const int nseg = (int)(fl >> NSEG_SHIFT);
     if (nseg) {
-        const double isf2 = x_isf2[lane_cell];
+        const int tq0 = seg0 - __ldg(m.cell_seg_first + i0);
         for (int k = 0; k < nseg; k++) {
-            const int q = seg0 + k;
-            const int s = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
-            const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
-            const double zr = zs - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
-            const double qs = weir_jtoi(zs, isf2, zr, yr, zs + __ldg(m.cs_zbank + q), __ldg(m.cs_cwr + q), len, depression);
-            const double qg = flux_r2e_gw(yr, zr, ygw, zb, kh, __ldg(m.cs_ksatH + q), len, __ldg(m.cs_bed + q)) * fuSub;
-            m.QsegSurf[s] = qs;
-            m.QsegSub[s] = qg;
+            const int tq = tq0 + k;
+            double qs, qg;
+            if (tq < SEGCAP) { qs = sq_s[tq]; qg = sq_g[tq]; }
+            else { const int sgm = __ldg(m.cs_seg + seg0 + k); qs = m.QsegSurf[sgm]; qg = m.QsegSub[sgm]; }
             e2rS += -qs;
             e2rG += -qg;
         }
@@ -465,6 +491,330 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
 #pragma unroll
         for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
         d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, TMA-pipelined form of the warp-specialised cell kernel (the default when Ne is even).
+// One block per resident slot (2 per SM) walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// A producer warp streams every per-cell input slice of the NEXT tile (40 x 1 KB doubles + 5 x 512 B ints)
+// into a 2-stage shared-memory ring with cp.async.bulk (TMA) and mbarrier transaction counts, while the
+// 4 lateral + 4 vertical warps compute the CURRENT tile out of shared memory: HBM latency is off the
+// critical path, no input is parked in registers (no spills), and the staged slices double as the
+// in-tile neighbour table.  Arithmetic and evaluation order are those of k_fused.
+// ---------------------------------------------------------------------------------------------
+enum {
+    A_YSF = 0, A_YUS, A_YGW, A_SATN, A_EIC, A_NETP, A_PE, A_PT, A_LAI, A_FUS, A_FUB, A_AQD, A_SY, A_INFD, A_INFK,
+    A_MACKV, A_HAF, A_THS, A_THR, A_THFC, A_BETA, A_KSV, A_VEG, A_IMP, A_WET, A_ROOT,
+    A_KH, A_ZS, A_ZB, A_DEP, A_AREA, A_E0, A_E1, A_E2, A_D0, A_D1, A_D2, A_R0, A_R1, A_R2,
+    A_ND
+};
+enum { I_NB0 = 0, I_NB1, I_NB2, I_FL, I_SEG0, I_NI };
+constexpr int STAGE_DBL = A_ND * TILE;                                   // doubles per stage
+constexpr int STAGE_BYTES = STAGE_DBL * 8 + I_NI * TILE * 4;             // 43520
+constexpr int PIPE_XCH_DBL = 6 * TILE + 2 * SEGCAP;                      // hand-over + segment slots
+constexpr int pipe_smem(int stages) { return stages * STAGE_BYTES + PIPE_XCH_DBL * 8 + 64; }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned a = smem_u32(b);
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    }
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool DIAG, int PIPE_STAGES, int MINB>
+__global__ void __launch_bounds__(2 * TILE + 32, MINB) k_pipe(DevMesh m, DevDiag d, const double *__restrict__ Y,
+                                                              double *__restrict__ DY, int ntiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *xch = reinterpret_cast<double *>(smem_raw + PIPE_STAGES * STAGE_BYTES);
+    double *x_P1 = xch, *x_Es = xch + TILE, *x_G1 = xch + 2 * TILE, *x_Eg = xch + 3 * TILE, *x_Tg = xch + 4 * TILE,
+           *x_isf2 = xch + 5 * TILE, *sq_s = xch + 6 * TILE, *sq_g = xch + 6 * TILE + SEGCAP;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(xch + PIPE_XCH_DBL);
+    uint64_t *full = bars, *empty = bars + PIPE_STAGES;
+    const int Ne = m.Ne;
+    const size_t NE = (size_t)Ne, LD = (size_t)m.ld;
+    const bool y_staged = (Ne & 1) == 0;  // Y blocks are 16-byte aligned only then
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= 2 * TILE) {
+        // =============================== producer warp ===============================
+        // all 32 lanes issue copies (one or two each); lane 0 arms the transaction count
+        const int lane = threadIdx.x - 2 * TILE;
+        int k = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+            const int s = k % PIPE_STAGES;
+            if (k >= PIPE_STAGES) mbar_wait(&empty[s], ((k / PIPE_STAGES) - 1) & 1);
+            const size_t i0 = (size_t)tile * TILE;
+            double *sd = reinterpret_cast<double *>(smem_raw + (size_t)s * STAGE_BYTES);
+            int *si = reinterpret_cast<int *>(sd + STAGE_DBL);
+            const bool ytile = y_staged && (i0 + TILE <= NE);
+            if (lane == 0) mbar_expect_tx(&full[s], (unsigned)(STAGE_BYTES - (ytile ? 0 : 3 * TILE * 8)));
+            // copy table: slot a of the stage <- source pointer
+            for (int a = lane; a < A_ND + I_NI; a += 32) {
+                const void *src = nullptr;
+                void *dst;
+                unsigned bytes = TILE * 8;
+                if (a < A_ND) dst = sd + a * TILE; else { dst = si + (a - A_ND) * TILE; bytes = TILE * 4; }
+                switch (a) {
+                    case A_YSF: src = ytile ? Y + i0 : nullptr; break;
+                    case A_YUS: src = ytile ? Y + NE + i0 : nullptr; break;
+                    case A_YGW: src = ytile ? Y + 2 * NE + i0 : nullptr; break;
+                    case A_SATN: src = m.satn + i0; break;
+                    case A_EIC: src = m.eic + i0; break;
+                    case A_NETP: src = m.netPrep + i0; break;
+                    case A_PE: src = m.potEvap + i0; break;
+                    case A_PT: src = m.potTran + i0; break;
+                    case A_LAI: src = m.lai + i0; break;
+                    case A_FUS: src = m.fuSurf + i0; break;
+                    case A_FUB: src = m.fuSub + i0; break;
+                    case A_AQD: src = m.aqd + i0; break;
+                    case A_SY: src = m.sy + i0; break;
+                    case A_INFD: src = m.infD + i0; break;
+                    case A_INFK: src = m.infKsatV + i0; break;
+                    case A_MACKV: src = m.macKsatV + i0; break;
+                    case A_HAF: src = m.hAreaF + i0; break;
+                    case A_THS: src = m.thetaS + i0; break;
+                    case A_THR: src = m.thetaR + i0; break;
+                    case A_THFC: src = m.thetaFC + i0; break;
+                    case A_BETA: src = m.beta + i0; break;
+                    case A_KSV: src = m.ksatV + i0; break;
+                    case A_VEG: src = m.vegFrac + i0; break;
+                    case A_IMP: src = m.impAF + i0; break;
+                    case A_WET: src = m.wetland + i0; break;
+                    case A_ROOT: src = m.rootReach + i0; break;
+                    case A_KH: src = m.effKH + i0; break;
+                    case A_ZS: src = m.z_surf + i0; break;
+                    case A_ZB: src = m.z_bottom + i0; break;
+                    case A_DEP: src = m.depression + i0; break;
+                    case A_AREA: src = m.area + i0; break;
+                    case A_E0: case A_E1: case A_E2: src = m.edge + (a - A_E0) * LD + i0; break;
+                    case A_D0: case A_D1: case A_D2: src = m.dist + (a - A_D0) * LD + i0; break;
+                    case A_R0: case A_R1: case A_R2: src = m.avgRough + (a - A_R0) * LD + i0; break;
+                    case A_ND + I_NB0: case A_ND + I_NB1: case A_ND + I_NB2: src = m.nbr + (a - A_ND - I_NB0) * LD + i0; break;
+                    case A_ND + I_FL: src = m.flags + i0; break;
+                    case A_ND + I_SEG0: src = m.cell_seg_first + i0; break;
+                }
+                if (src) tma_load(dst, src, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    const int lane_cell = threadIdx.x & (TILE - 1);
+    const bool vertical = threadIdx.x >= TILE;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+        const int s = k % PIPE_STAGES;
+        const double *sd = reinterpret_cast<const double *>(smem_raw + (size_t)s * STAGE_BYTES);
+        double *sdw = reinterpret_cast<double *>(smem_raw + (size_t)s * STAGE_BYTES);
+        const int *si = reinterpret_cast<const int *>(sd + STAGE_DBL);
+        const int i0 = tile * TILE;
+        const int i = i0 + lane_cell;
+        const bool valid = i < Ne;
+        const int ic = valid ? i : Ne - 1;
+        const bool ytile = y_staged && (i0 + TILE <= Ne);
+        mbar_wait(&full[s], (k / PIPE_STAGES) & 1);
+        const unsigned fl = valid ? (unsigned)si[I_FL * TILE + lane_cell] : 0u;
+#define SD(a) sd[(a) * TILE + lane_cell]
+        if (vertical) {
+            // =============================== vertical role ===============================
+            const double ysf = ytile ? SD(A_YSF) : Y[ic], yus = ytile ? SD(A_YUS) : Y[NE + ic];
+            const double ygw_raw = ytile ? SD(A_YGW) : Y[2 * NE + ic];
+            CellForc f;
+            f.netPrep = SD(A_NETP); f.potEvap = SD(A_PE); f.potTran = SD(A_PT); f.lai = SD(A_LAI);
+            f.fuSurf = SD(A_FUS); f.fuSub = SD(A_FUB);
+            CellParams p;
+            p.aqd = SD(A_AQD); p.sy = SD(A_SY); p.infD = SD(A_INFD); p.infKsatV = SD(A_INFK); p.macKsatV = SD(A_MACKV);
+            p.hAreaF = SD(A_HAF); p.thetaS = SD(A_THS); p.thetaR = SD(A_THR); p.thetaFC = SD(A_THFC); p.beta = SD(A_BETA);
+            p.ksatV = SD(A_KSV); p.vegFrac = SD(A_VEG); p.impAF = SD(A_IMP); p.wetland = SD(A_WET); p.rootReach = SD(A_ROOT);
+            const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
+            CellVert v;
+            if (fl & F_LAKE) {
+                v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
+                v.satn = 1.; v.infil = v.exfil = v.rech = 0.; v.err = 0;
+            } else {
+                v = cell_vertical(p, f, ysf, yus, ygw, SD(A_SATN), SD(A_EIC));
+            }
+            double isf2 = ysf - v.infil + v.exfil;
+            x_P1[lane_cell] = f.netPrep - v.infil + v.exfil;
+            x_Es[lane_cell] = v.Es;
+            x_G1[lane_cell] = v.rech - v.exfil;
+            x_Eg[lane_cell] = v.Eg;
+            x_Tg[lane_cell] = v.Tg;
+            x_isf2[lane_cell] = dmax(0., isf2);
+            bar_sync(3, 2 * TILE);  // lateral role has fixed up the staged tile; every x_isf2 is written
+            {
+                const int q0 = si[I_SEG0 * TILE];
+                const int q1 = __ldg(m.cell_seg_first + (i0 + TILE < Ne ? i0 + TILE : Ne));
+                for (int tq = lane_cell; tq < q1 - q0; tq += TILE) {
+                    const int q = q0 + tq;
+                    const int lc = __ldg(m.cs_cell + q) - i0, sgm = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
+                    const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
+                    const double zs_c = sd[A_ZS * TILE + lc];
+                    const double zr = zs_c - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
+                    const double qs = weir_jtoi(zs_c, x_isf2[lc], zr, yr, zs_c + __ldg(m.cs_zbank + q),
+                                                __ldg(m.cs_cwr + q), len, sd[A_DEP * TILE + lc]);
+                    const double ygw_c = ytile ? sd[A_YGW * TILE + lc] : sdw[A_YGW * TILE + lc];
+                    const double qg = flux_r2e_gw(yr, zr, ygw_c, sd[A_ZB * TILE + lc], sd[A_KH * TILE + lc],
+                                                  __ldg(m.cs_ksatH + q), len, __ldg(m.cs_bed + q)) * sd[A_FUB * TILE + lc];
+                    m.QsegSurf[sgm] = qs;
+                    m.QsegSub[sgm] = qg;
+                    if (tq < SEGCAP) { sq_s[tq] = qs; sq_g[tq] = qg; }
+                }
+            }
+            bar_arrive(2, 2 * TILE);
+            if (valid) {
+                m.eic[i] = v.eic;
+                m.satn[i] = v.satn;
+                double dus = v.infil - v.rech - v.Eu - v.Tu;
+                dus = SHUD_DIVS(dus, p.sy);
+                if (fl & F_LAKE) dus = 0.;
+                DY[NE + i] = dus;
+                if (v.err) raise_err(m.err, v.err, i + 1);
+                if (DIAG) {
+                    if (fl & F_LAKE) {
+                        d.qEleTrans[i] = 0.; d.qEleEvapo[i] = f.potEvap; d.qEleETA[i] = 0. + f.potEvap + 0.;
+                    } else {
+                        const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
+                        d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
+                        d.iBeta[i] = v.iBeta;
+                    }
+                    d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech;
+                    d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
+                }
+            }
+        } else {
+            // =============================== lateral role ===============================
+            const int seg0 = si[I_SEG0 * TILE + lane_cell];
+            const int nb[3] = {si[I_NB0 * TILE + lane_cell], si[I_NB1 * TILE + lane_cell], si[I_NB2 * TILE + lane_cell]};
+            const double ysf = ytile ? SD(A_YSF) : Y[ic];
+            const double ygw_raw = ytile ? SD(A_YGW) : Y[2 * NE + ic];
+            const double kh = SD(A_KH), zs = SD(A_ZS), zb = SD(A_ZB);
+            const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
+            // the staged slices are the in-tile neighbour table: make them hold what a neighbour must see
+            // (clamped tail cells, head-BC groundwater, Y of a tile whose Y was not TMA-staged)
+            if (!ytile) { sdw[A_YSF * TILE + lane_cell] = ysf; }
+            if (!ytile || (fl & F_HEADBC)) sdw[A_YGW * TILE + lane_cell] = ygw;
+            const double fuSub = SD(A_FUB), depression = SD(A_DEP);
+            const double area = SD(A_AREA), sy = SD(A_SY);
+            bar_sync(1, TILE);
+            bar_arrive(3, 2 * TILE);
+            int err = 0;
+            double Qs[3] = {0., 0., 0.}, Qg[3] = {0., 0., 0.};
+            if (valid && !(fl & F_LAKE)) {
+                const double isf = ysf < 0. ? 0. : ysf;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double qs = 0., qg = 0.;
+                    const int kk = nb[j];
+                    const double Bj = SD(A_E0 + j), distj = SD(A_D0 + j), roughj = SD(A_R0 + j);
+                    if (kk >= 0) {
+                        double nsf, ygw_n, zs_n, zb_n, kh_n;
+                        const unsigned r = (unsigned)(kk - i0);
+                        if (r < (unsigned)TILE) {
+                            nsf = sd[A_YSF * TILE + r]; ygw_n = sd[A_YGW * TILE + r]; zs_n = sd[A_ZS * TILE + r];
+                            zb_n = sd[A_ZB * TILE + r]; kh_n = sd[A_KH * TILE + r];
+                        } else if (kk < Ne) {
+                            nsf = Y[kk]; ygw_n = Y[2 * NE + kk]; zs_n = __ldg(m.z_surf + kk); zb_n = __ldg(m.z_bottom + kk);
+                            kh_n = m.effKH[kk];
+                            if (m.has_headbc && (m.flags[kk] & F_HEADBC)) ygw_n = m.ele_yBC[kk];
+                        } else {
+                            const int h = kk - Ne;
+                            nsf = m.h_state[2 * h]; ygw_n = m.h_state[2 * h + 1]; zs_n = m.h_zs[h]; zb_n = m.h_zb[h];
+                            kh_n = m.h_kh[h];
+                        }
+                        nsf = nsf < 0. ? 0. : nsf;
+                        qs = edge_surface(isf, zs, nsf, zs_n, depression, distj, Bj, roughj);
+                        qg = edge_sub(ygw, zb, ygw_n, zb_n, kh, kh_n, distj, Bj);
+                    } else if (kk <= -2) {
+                        const int slot = -2 - kk, l = m.bank_lake[slot];
+                        const double yl = Y[3 * NE + m.Nr + l];
+                        const double nsf = yl < 0. ? 0. : yl;
+                        qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, Bj, 0.01);
+                        qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], distj, Bj);
+                    } else if (!m.close_boundary) {
+                        const double d2e = m.dist2edge[j * LD + ic];
+                        if (isf > depression) {
+                            const double sl = isf / d2e * 0.5;
+                            if (sl > 0.) qs = sqrt(sl) * cbrt(isf * isf * isf * isf * isf) * Bj / m.rough[ic];
+                        }
+                        if (ygw > depression * 10.) {
+                            const double grad = ygw / d2e * 0.5;
+                            if (grad > 0.) qg = kh * grad;
+                        }
+                    }
+                    Qs[j] = qs;
+                    Qg[j] = qg * fuSub;
+                }
+            }
+            bar_sync(2, 2 * TILE);  // vertical role has handed over (and finished the segment pass)
+            if (valid) {
+                const double P1 = x_P1[lane_cell], Es = x_Es[lane_cell], G1 = x_G1[lane_cell], Eg = x_Eg[lane_cell],
+                             Tg = x_Tg[lane_cell];
+                double e2rS = 0., e2rG = 0.;
+                const int nseg = (int)(fl >> NSEG_SHIFT);
+                if (nseg) {
+                    const int tq0 = seg0 - si[I_SEG0 * TILE];
+                    for (int kq = 0; kq < nseg; kq++) {
+                        const int tq = tq0 + kq;
+                        double qs, qg;
+                        if (tq < SEGCAP) { qs = sq_s[tq]; qg = sq_g[tq]; }
+                        else { const int sgm = __ldg(m.cs_seg + seg0 + kq); qs = m.QsegSurf[sgm]; qg = m.QsegSub[sgm]; }
+                        e2rS += -qs;
+                        e2rG += -qg;
+                    }
+                }
+                double surfTot = e2rS, subTot = e2rG;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    surfTot += Qs[j];
+                    subTot += Qg[j];
+                    if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
+                }
+                double dsf = P1 - SHUD_DIVS(surfTot, area) - Es;
+                double dgw = G1 - SHUD_DIVS(subTot, area) - Eg - Tg;
+                if (fl & F_HEADBC) dgw = 0;
+                else if (fl & F_FLUXBC) dgw += SHUD_DIVS(m.ele_QBC[i], area);
+                if (fl & F_SS_SURF) dsf += SHUD_DIVS(m.qss[i], area);
+                else if (fl & F_SS_GW) dgw += SHUD_DIVS(m.qss[i], area);
+                dgw = SHUD_DIVS(dgw, sy);
+                if (fl & F_LAKE) { dsf = 0.; dgw = 0.; }
+                DY[i] = dsf;
+                DY[2 * NE + i] = dgw;
+                if (err) raise_err(m.err, err, i + 1);
+                if (DIAG) {
+#pragma unroll
+                    for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
+                    d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
+                }
+            }
+        }
+#undef SD
+        // every reader of stage s and of the hand-over arrays is done: release the stage to the producer
+        bar_sync(4, 2 * TILE);
+        if (threadIdx.x == 0) mbar_arrive(&empty[s]);
     }
 }
 
@@ -510,6 +860,7 @@ template <bool DIAG>
 __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const double *__restrict__ Y,
                                                     double *__restrict__ DY, int nb_riv) {
     const size_t NE = (size_t)m.Ne;
+    const size_t LD = (size_t)m.ld;
     const double *Yr = Y + 3 * NE;
     if ((int)blockIdx.x < nb_riv) {
         const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -550,10 +901,10 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
         double ysf = Y[i];
         const double isf = ysf < 0. ? 0. : ysf, zs = m.z_surf[i];
         const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : Y[2 * NE + i];
-        const double B = m.edge[j * NE + i];
+        const double B = m.edge[j * LD + i];
         qs += weir_jtoi(m.l_zmin[l], yl < 0. ? 0. : yl, zs, isf, zs, 0.6, B, 0.01);
         // QLakeSub takes Q before the fu_Sub factor (MD_ElementFlux.cpp:121 precedes :153)
-        qg += edge_sub(ygw, m.z_bottom[i], yl, m.l_yi0[l], m.effKH[i], m.bank_kh[k], m.dist[j * NE + i], B);
+        qg += edge_sub(ygw, m.z_bottom[i], yl, m.l_yi0[l], m.effKH[i], m.bank_kh[k], m.dist[j * LD + i], B);
     }
     int err = 0;
     for (int k = m.l_rin_ptr[l] + threadIdx.x; k < m.l_rin_ptr[l + 1]; k += blockDim.x)
@@ -649,6 +1000,7 @@ struct shud_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int Ne = 0, Nr = 0, Ns = 0, Nl = 0, Nhalo = 0;
+    int ld = 0;  // Ne rounded up to a multiple of 128
     int64_t NY = 0;
     DevMesh m{};
     DevDiag diag{};
@@ -665,6 +1017,12 @@ struct shud_ctx {
     size_t h_pinned_n = 0;
     bool has_ebc_arrays = false;
     int fused_minb = 4;
+    int pipe_grid = 296;  // persistent blocks of k_pipe: 2 per SM (2 stages) or 4 per SM (1 stage)
+    int pipe_stages = 2;
+    // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
+    int use_graph = 1;
+    struct GraphEntry { const double *y; double *yd; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;
     int split = 2;      // 2: warp-specialised fused cell kernel (default); 0: one-thread-per-cell k_cell (SHUD_SPLIT, A/B only)
     int cell_minb = 4;  // resident blocks per SM the cell kernel is compiled for (tuning knob)
 };
@@ -701,17 +1059,19 @@ inline double divisor(double x) { return 1.0 / x; }
 #else
 inline double divisor(double x) { return x; }
 #endif
+// per-cell arrays are padded to c->ld (multiple of 128) so that a 128-cell tile is always one whole,
+// 16-byte aligned 1 KB slice (TMA bulk copies); the pad holds 1.0 (harmless in every formula)
 const double *up_cell(shud_ctx *c, const double *src, bool as_divisor = false) {
-    std::vector<double> h(c->Ne);
+    std::vector<double> h(c->ld, 1.0);
     for (int i = 0; i < c->Ne; i++) h[i] = as_divisor ? divisor(src[c->cperm[i]]) : src[c->cperm[i]];
     return dev_upload(c, h);
 }
 const double *up_edge(shud_ctx *c, const double *src, bool as_divisor = false) {
-    std::vector<double> h(3 * (size_t)c->Ne);
+    std::vector<double> h(3 * (size_t)c->ld, 1.0);
     for (int j = 0; j < 3; j++)
         for (int i = 0; i < c->Ne; i++) {
             const double x = src[(size_t)j * c->Ne + c->cperm[i]];
-            h[(size_t)j * c->Ne + i] = as_divisor ? divisor(x) : x;
+            h[(size_t)j * c->ld + i] = as_divisor ? divisor(x) : x;
         }
     return dev_upload(c, h);
 }
@@ -724,6 +1084,8 @@ const double *up_riv(shud_ctx *c, const double *src) {
 }  // namespace
 
 extern "C" {
+
+static void drop_graphs(shud_ctx *c);
 
 int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
     return shud_b200_create_partition(M, nullptr, device, out);
@@ -739,6 +1101,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     c->device = device;
     const int Ne = c->Ne = M->Ne, Nr = c->Nr = M->Nr, Ns = c->Ns = M->Ns, Nl = c->Nl = M->Nl;
     c->NY = 3 * (int64_t)Ne + Nr + Nl;
+    c->ld = ((Ne + 127) / 128) * 128;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
     // ---- cell order: Hilbert curve over centroids (if given) ----
@@ -787,11 +1150,15 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
 
     DevMesh &m = c->m;
     m.Ne = Ne; m.Nr = Nr; m.Ns = Ns; m.Nl = Nl;
+    m.ld = c->ld;
+    const int LDh = c->ld;
     m.close_boundary = M->close_boundary;
     {
         const char *e1 = getenv("SHUD_CELL_MINB");
         if (e1) c->cell_minb = atoi(e1);
         if (getenv("SHUD_SPLIT")) c->split = atoi(getenv("SHUD_SPLIT"));
+        if (getenv("SHUD_PIPE_GRID")) c->pipe_grid = atoi(getenv("SHUD_PIPE_GRID"));
+        if (getenv("SHUD_GRAPH")) c->use_graph = atoi(getenv("SHUD_GRAPH"));
         if (getenv("SHUD_FUSED_MINB")) c->fused_minb = atoi(getenv("SHUD_FUSED_MINB"));
     }
 
@@ -810,8 +1177,8 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
 
     // ---- topology, flags, bank edges ----
     const bool lakeon = M->lakeon != 0 && Nl > 0;
-    std::vector<unsigned> flags(Ne, 0u);
-    std::vector<int> nbr(3 * (size_t)Ne, -1);
+    std::vector<unsigned> flags(LDh, 0u);
+    std::vector<int> nbr(3 * (size_t)LDh, -1);
     std::vector<int> bank_cell, bank_j, bank_lake;
     std::vector<double> bank_kh;
     // bank edges in ascending reference (cell, edge) order, grouped by lake afterwards
@@ -843,7 +1210,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             } else if (nb >= Ne && nb < Ne + Nhalo) {
                 v = nb;  // halo cells keep their place after the owned cells
             }
-            nbr[(size_t)j * Ne + i] = v;
+            nbr[(size_t)j * LDh + i] = v;
         }
     }
     if (M->iLake && !lakeon)
@@ -855,7 +1222,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     for (size_t k = 0; k < banks.size(); k++) {
         const Bank &b = banks[k];
         const int i = c->cinv[b.ref_cell];
-        nbr[(size_t)b.j * Ne + i] = -2 - (int)k;
+        nbr[(size_t)b.j * LDh + i] = -2 - (int)k;
         bank_cell.push_back(i); bank_j.push_back(b.j); bank_lake.push_back(b.lake); bank_kh.push_back(b.kh);
         l_bank_ptr[b.lake + 1]++;
     }
@@ -864,11 +1231,16 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     m.has_headbc = has_headbc;
 
     // ---- cell -> segments (ascending reference segment id) ----
-    std::vector<int> nseg(Ne, 0), cell_seg_first(Ne, 0), cell_seg_idx(Ns);
+    std::vector<int> nseg(Ne, 0), cell_seg_first(LDh + 1, 0), cell_seg_idx(Ns), cs_cell_h(Ns);
     for (int s = 0; s < Ns; s++) nseg[c->cinv[M->seg_iEle[s] - 1]]++;
     {
         int acc = 0;
-        for (int i = 0; i < Ne; i++) { cell_seg_first[i] = acc; acc += nseg[i]; }
+        for (int i = 0; i < Ne; i++) {
+            cell_seg_first[i] = acc;
+            for (int k = 0; k < nseg[i]; k++) cs_cell_h[acc + k] = i;
+            acc += nseg[i];
+        }
+        for (int i = Ne; i <= LDh; i++) cell_seg_first[i] = acc;
         std::vector<int> fill(Ne, 0);
         for (int s = 0; s < Ns; s++) {  // ascending reference id
             const int i = c->cinv[M->seg_iEle[s] - 1];
@@ -893,6 +1265,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             cs_zbank[q] = M->riv_zbank[ro]; cs_ksatH[q] = M->riv_KsatH[ro]; cs_bed[q] = M->riv_BedThick[ro];
         }
         m.cs_seg = dev_upload(c, cs_seg); m.cs_riv = dev_upload(c, cs_riv); m.cs_bc = dev_upload(c, cs_bc);
+        m.cs_cell = dev_upload(c, cs_cell_h);
         m.cs_len = dev_upload(c, cs_len); m.cs_cwr = dev_upload(c, cs_cwr); m.cs_depth = dev_upload(c, cs_depth);
         m.cs_zbank = dev_upload(c, cs_zbank); m.cs_ksatH = dev_upload(c, cs_ksatH); m.cs_bed = dev_upload(c, cs_bed);
     }
@@ -982,16 +1355,16 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         CK(cudaMemset(m.h_kh, 0, sizeof(double) * Nhalo));
     }
     // ---- dynamic arrays ----
-    m.netPrep = dev_alloc<double>(c, Ne); m.potEvap = dev_alloc<double>(c, Ne); m.potTran = dev_alloc<double>(c, Ne);
-    m.lai = dev_alloc<double>(c, Ne); m.fuSurf = dev_alloc<double>(c, Ne); m.fuSub = dev_alloc<double>(c, Ne);
-    m.eic = dev_alloc<double>(c, Ne); m.satn = dev_alloc<double>(c, Ne);
-    m.ele_yBC = dev_alloc<double>(c, Ne); m.ele_QBC = dev_alloc<double>(c, Ne);
+    m.netPrep = dev_alloc<double>(c, LDh); m.potEvap = dev_alloc<double>(c, LDh); m.potTran = dev_alloc<double>(c, LDh);
+    m.lai = dev_alloc<double>(c, LDh); m.fuSurf = dev_alloc<double>(c, LDh); m.fuSub = dev_alloc<double>(c, LDh);
+    m.eic = dev_alloc<double>(c, LDh); m.satn = dev_alloc<double>(c, LDh);
+    m.ele_yBC = dev_alloc<double>(c, LDh); m.ele_QBC = dev_alloc<double>(c, LDh);
     m.r_yBC = dev_alloc<double>(c, Nr); m.r_qBC = dev_alloc<double>(c, Nr);
-    m.effKH = dev_alloc<double>(c, Ne); m.QsegSurf = dev_alloc<double>(c, Ns); m.QsegSub = dev_alloc<double>(c, Ns);
+    m.effKH = dev_alloc<double>(c, LDh); m.QsegSurf = dev_alloc<double>(c, Ns); m.QsegSub = dev_alloc<double>(c, Ns);
     m.err = dev_alloc<int>(c, 2);
     for (double *p : {m.netPrep, m.potEvap, m.potTran, m.lai, m.fuSurf, m.fuSub, m.eic, m.satn, m.ele_yBC, m.ele_QBC,
                       m.effKH})
-        CK(cudaMemset(p, 0, sizeof(double) * Ne));
+        CK(cudaMemset(p, 0, sizeof(double) * LDh));
     CK(cudaMemset(m.r_yBC, 0, sizeof(double) * std::max(Nr, 1)));
     CK(cudaMemset(m.r_qBC, 0, sizeof(double) * std::max(Nr, 1)));
     CK(cudaMemset(m.err, 0, sizeof(int) * 2));
@@ -1000,6 +1373,16 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     c->ydot_dev = dev_alloc<double>(c, c->NY);
     c->h_pinned_n = (size_t)std::max(Ne, Nr);
     CK(cudaMallocHost(&c->h_pinned, sizeof(double) * c->h_pinned_n));
+    {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        if (getenv("SHUD_PIPE_STAGES")) c->pipe_stages = atoi(getenv("SHUD_PIPE_STAGES"));
+        if (!getenv("SHUD_PIPE_GRID")) c->pipe_grid = (c->pipe_stages == 1 ? 4 : 2) * nsm;
+        CK(cudaFuncSetAttribute(k_pipe<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(2)));
+        CK(cudaFuncSetAttribute(k_pipe<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(2)));
+        CK(cudaFuncSetAttribute(k_pipe<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(1)));
+        CK(cudaFuncSetAttribute(k_pipe<true, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(1)));
+    }
     CK(cudaDeviceSynchronize());
     *out = c;
     return SHUD_OK;
@@ -1009,6 +1392,7 @@ void shud_b200_destroy(shud_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->stream);
@@ -1098,6 +1482,7 @@ int shud_b200_from_device_order(shud_ctx *c, const double *dev_dev, double *ref_
 int shud_b200_set_halo_state_dev(shud_ctx *c, const double *state) {
     if (!c || (c->Nhalo > 0 && !state)) return SHUD_ERR_ARG;
     c->m.h_state = state;
+    drop_graphs(c);  // kernel parameters changed
     return SHUD_OK;
 }
 
@@ -1163,6 +1548,15 @@ static void launch_cell(shud_ctx *c, const double *y, double *ydot) {
     }
 }
 template <bool DIAG>
+static void launch_pipe(shud_ctx *c, const double *y, double *ydot) {
+    const int ntiles = (c->Ne + TILE - 1) / TILE;
+    const int grid = std::min(ntiles, c->pipe_grid);
+    if (c->pipe_stages == 1)
+        k_pipe<DIAG, 1, 4><<<grid, 2 * TILE + 32, pipe_smem(1), c->stream>>>(c->m, c->diag, y, ydot, ntiles);
+    else
+        k_pipe<DIAG, 2, 2><<<grid, 2 * TILE + 32, pipe_smem(2), c->stream>>>(c->m, c->diag, y, ydot, ntiles);
+}
+template <bool DIAG>
 static void launch_fused(shud_ctx *c, const double *y, double *ydot) {
     const int nb = (c->Ne + TILE - 1) / TILE;
     switch (c->fused_minb) {
@@ -1174,7 +1568,10 @@ static void launch_fused(shud_ctx *c, const double *y, double *ydot) {
 template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     const int Ne = c->Ne;
-    if (c->split == 2) {
+    if (c->split == 3) {
+        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        launch_pipe<DIAG>(c, y, ydot);
+    } else if (c->split == 2) {
         k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
         launch_fused<DIAG>(c, y, ydot);
     } else {
@@ -1189,17 +1586,50 @@ static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
 }
 extern "C" {
 
+static void drop_graphs(shud_ctx *c) {
+    for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+
 int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     (void)t;  // f() depends on t only through values uploaded by shud_b200_set_forcing
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
-    return launch_rhs<false>(c, y, ydot);
+    if (!c->use_graph) return launch_rhs<false>(c, y, ydot);
+    // the launch sequence is fixed; only the two vector pointers vary between calls (CVODE alternates
+    // between a handful of work vectors) -> one instantiated graph per pointer pair, launched as one unit
+    for (auto &g : c->graphs)
+        if (g.y == y && g.yd == ydot) {
+            CK(cudaGraphLaunch(g.exec, c->stream));
+            return SHUD_OK;
+        }
+    if (c->graphs.size() >= 32) drop_graphs(c);
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_rhs<false>(c, y, ydot);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != SHUD_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        c->use_graph = 0;  // capture unavailable: plain launches
+        return launch_rhs<false>(c, y, ydot);
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        c->use_graph = 0;
+        return launch_rhs<false>(c, y, ydot);
+    }
+    c->graphs.push_back({y, ydot, exec});
+    CK(cudaGraphLaunch(exec, c->stream));
+    return SHUD_OK;
 }
 
 // one launch of the sequence on its own (profiling / per-kernel CUDA-event timing in bench.py)
 int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydot) {
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
-    if (c->split == 2 && stage == 1) launch_fused<false>(c, y, ydot);
+    if (c->split == 3 && stage == 1) launch_pipe<false>(c, y, ydot);
+    else if (c->split == 2 && stage == 1) launch_fused<false>(c, y, ydot);
     else if (stage == 0) k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
     else if (stage == 1) launch_cell<false>(c, y, ydot);
     else if (stage == 2 && nb_riv + c->Nl > 0)

@@ -137,3 +137,16 @@ def test_device_error_word_mirrors_reference_exit_codes():
     rhs.set_carried(snap["ele_u_satn"])
     with pytest.raises(ShudError, match="code 10"):
         rhs.f(0.0, y, np.empty_like(y))
+
+
+@pytest.mark.parametrize("basin,case", [("qhh", "mut5"), ("ccw", "mut2")])
+def test_tma_pipelined_kernel_variant(basin, case, monkeypatch):
+    """the opt-in persistent TMA-pipelined form of the cell kernel (SHUD_SPLIT=3) computes
+    the same ydot as the default kernel, bit for bit"""
+    snap = oracle_lib.load_case(basin, case)
+    rhs, a = _run_gpu(snap, diag=False)
+    monkeypatch.setenv("SHUD_SPLIT", "3")
+    rhs2, b = _run_gpu(snap, diag=False)
+    assert a["code"] == 0 and b["code"] == 0
+    assert np.array_equal(a["ydot"], b["ydot"])
+    assert np.array_equal(a["u_satn_out"], b["u_satn_out"]) and np.array_equal(a["qEleE_IC_out"], b["qEleE_IC_out"])
