@@ -17,7 +17,11 @@
  * the outputs are those of the second call.
  *
  * usage: shud_ref <prj> <out.bin> [--t MIN] [--state ic|rand:<seed>]
- *                 [--mutate a,b,..] [--time REPS]
+ *                 [--mutate a,b,..] [--time REPS] [--forcing-seq NSTEPS]
+ *   --forcing-seq N: additionally replay the reference's land-surface step for N consecutive ET steps of
+ *   60 min (updateAllTimeSeries + updateforcing + ET, src/Model/shud.cpp:106-109) and dump what each hands to
+ *   the RHS (fseq_<array>, [N][Ne]); these depend on the forcing files and the snow / interception buckets
+ *   only, not on the solver state, so they can drive a full run without the reference at hand.
  *   run from a cwd that contains input/<prj>/ .
  */
 #include <cstdio>
@@ -148,12 +152,13 @@ int main(int argc, char **argv) {
     }
     std::string prj = argv[1], outfn = argv[2], state = "ic", mutate = "";
     double t_arg = NAN;
-    int reps = 0;
+    int reps = 0, fseq = 0;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--t") && a + 1 < argc) t_arg = atof(argv[++a]);
         else if (!strcmp(argv[a], "--state") && a + 1 < argc) state = argv[++a];
         else if (!strcmp(argv[a], "--mutate") && a + 1 < argc) mutate = argv[++a];
         else if (!strcmp(argv[a], "--time") && a + 1 < argc) reps = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--forcing-seq") && a + 1 < argc) fseq = atoi(argv[++a]);
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
 
@@ -391,6 +396,26 @@ int main(int argc, char **argv) {
         putd("QLakeSub", MD->QLakeSub, Nl); putd("QLakeRivIn", MD->QLakeRivIn, Nl);
         putd("QLakeRivOut", MD->QLakeRivOut, Nl); putd("qLakeEvap", MD->qLakeEvap, Nl);
         putd("qLakePrcp", MD->qLakePrcp, Nl);
+    }
+    if (fseq > 0) {
+        const char *names[] = {"qEleNetPrep", "qPotEvap", "qPotTran", "t_lai", "qEleE_IC", "qElePrep", "fu_Surf", "fu_Sub"};
+        std::vector<std::vector<double>> seq(8);
+        std::vector<double> tt;
+        double tf = MD->CS.StartTime;
+        /* a fresh model: the buckets must start from the initial condition */
+        Model_Data *M2 = new Model_Data(fin, fout);
+        M2->loadinput(); M2->initialize(); M2->CheckInputData(); M2->LoadIC();
+        for (int k = 0; k < fseq; k++, tf += 60.) {
+            M2->updateAllTimeSeries(tf);
+            M2->updateforcing(tf);
+            M2->ET(tf, tf + 60.);
+            const double *src[] = {M2->qEleNetPrep, M2->qPotEvap, M2->qPotTran, M2->t_lai, M2->qEleE_IC, M2->qElePrep,
+                                   M2->fu_Surf, M2->fu_Sub};
+            for (int a = 0; a < 8; a++) seq[a].insert(seq[a].end(), src[a], src[a] + Ne);
+            tt.push_back(tf);
+        }
+        for (int a = 0; a < 8; a++) putd((std::string("fseq_") + names[a]).c_str(), seq[a]);
+        putd("fseq_t", tt);
     }
     fclose(g_out);
 

@@ -287,7 +287,7 @@ int shud_nv_ws_create(int device, void *stream, shud_nvws **out) {
 void shud_nv_ws_destroy(shud_nvws *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    cudaStreamSynchronize(ws->stream);
+    cudaDeviceSynchronize();  // not the stream: its owner may have destroyed it already
     cudaFree(ws->partial); cudaFree(ws->counter); cudaFree(ws->d_out); cudaFreeHost(ws->h_out);
     delete ws;
 }

@@ -79,7 +79,9 @@ def _coef(c):
 class NVectorOps:
     """The ops table, bound to one device and one CUDA stream (a cudaStream_t handle or 0)."""
 
-    def __init__(self, device=0, stream_ptr=None, n_global=None):
+    def __init__(self, device=0, stream_ptr=None, n_global=None, owner=None):
+        """owner: the object that owns the stream (kept alive for as long as this table exists)"""
+        self._owner = owner
         L = _lib()
         h = C.c_void_p()
         api._chk(L.shud_nv_ws_create(int(device), C.c_void_p(stream_ptr or 0), C.byref(h)), "shud_nv_ws_create")

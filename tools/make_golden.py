@@ -93,6 +93,16 @@ def main():
             dyn[k] = v
         dyn["_cmd"] = np.array(" ".join(cmd[1:]))
         np.savez_compressed(os.path.join(OUT, f"{basin}.{case}.npz"), **dyn)
+    # forcing sequence for a short full run (tests/test_integrator_*.py): 48 hourly land-surface steps of ccw
+    binf = os.path.join(WORK, "ccw.fseq.bin")
+    cmd = [EXE, "ccw", binf, "--forcing-seq", "48"]
+    r = subprocess.run(cmd, cwd=WORK, capture_output=True, text=True, errors="replace")
+    if r.returncode != 0:
+        sys.exit(f"reference run failed: {cmd}\n{r.stdout[-2000:]}")
+    snap = snapshot.read_bin(binf)
+    keep = {k: v for k, v in snap.items() if k.startswith("fseq_") and k not in ("fseq_fu_Surf", "fseq_fu_Sub")}
+    keep["_cmd"] = np.array(" ".join(cmd[1:]))
+    np.savez_compressed(os.path.join(OUT, "ccw.fseq.npz"), **keep)
     sz = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {len(os.listdir(OUT))} files, {sz/1e6:.2f} MB")
 
