@@ -254,6 +254,40 @@ def main():
             y_ref.copy_(yh); rhs.to_device_order(y_ref, y)
         st.synchronize()
 
+    # ---------------- RHS + SPGMR together (configs[3]): BDF/Newton steps with the device N_Vector ----------------
+    nk = None
+    if world == 1:
+        from shud_up_b200.integrator import BDFKrylov
+        from shud_up_b200.nvector import DeviceSPGMR, NVectorOps
+        ops = NVectorOps(local_rank, rhs.stream_ptr, owner=rhs)
+        ls = DeviceSPGMR(ops, rhs, maxl=5)
+
+        def newv():
+            with torch.cuda.stream(st):
+                return torch.zeros(rhs.NY, dtype=torch.float64, device=dev)
+        integ = BDFKrylov(ops, newv, lambda t_, a_, b_: rhs.f_dev(t_, a_, b_), rhs.NY, rtol=1e-4, atol=1e-4,
+                          max_step=10.0, init_step=1e-3, linear_solver=ls)
+        integ.init(0.0, y)
+        for _ in range(3):
+            integ.step(1e9)
+        st.synchronize()
+        s0 = dict(integ.stats)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            integ.step(1e9)
+        st.synchronize()
+        w_nk = time.perf_counter() - t0
+        dlt = {k_: integ.stats[k_] - s0[k_] for k_ in s0}
+        nk = {"bdf_steps": 20, "rhs_calls": dlt["nfe"], "newton_iters": dlt["nni"], "krylov_iters": dlt["nli"],
+              "wall_ms": w_nk * 1e3, "cell_updates_per_s": dlt["nfe"] * Ne / w_nk,
+              "ms_per_rhs_call_incl_vector_ops": w_nk * 1e3 / max(dlt["nfe"], 1),
+              "what": "variable-step BDF + modified Newton + device-resident SPGMR(5) with difference-quotient Jv "
+                      "(shud_up_b200/integrator.py, shud_spgmr_solve); every vector op on the device N_Vector"}
+        ls.close(); ops.close()
+        with torch.cuda.stream(st):
+            rhs.to_device_order(y_ref, y)
+        st.synchronize()
+
     # ---------------- reduce over ranks: max time ----------------
     tt = torch.tensor([ms_dev, s_e2e * 1e3], dtype=torch.float64, device=dev)
     cells = torch.tensor([float(Ne)], dtype=torch.float64, device=dev)
@@ -290,6 +324,8 @@ def main():
                             "rhs_frac": b_rhs / (ms_step * 1e-3) / 1e9 / peak},
                "e2e": {"value": total_cells / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * rhs.NY * world,
                        "d2h_bytes_per_step": 8 * rhs.NY * world, "ms_per_step": ms_e2e_max}}
+        if nk is not None:
+            out["newton_krylov"] = nk
         if world == 1:
             per, n = cpu_oracle_time(mesh, ncpu, budget_s=a.cpu_budget)
             out["cpu_baseline"] = {"value": Ne / per, "unit": UNIT, "cores": ncpu, "kind": "port",

@@ -66,6 +66,36 @@ int shud_nv_scalevectorarray(shud_nvws *ws, int64_t n, int nvec, const double *c
 int shud_nv_constvectorarray(shud_nvws *ws, int64_t n, int nvec, double c, double *const *Z);
 int shud_nv_wrmsnormvectorarray(shud_nvws *ws, int64_t n, int nvec, const double *const *X, const double *const *W, int64_t n_global, double *out);
 
+/* ---- integrator-level fusions: the vector work CVLS + SPGMR wrap around each
+ * difference-quotient Jacobian-vector product, one launch each instead of two / three ops-table calls ----
+ * shud_nv_dq_perturb:  ytemp = y + sigma * (vs ./ ewt)          (unscale the Krylov vector, perturb the state)
+ * shud_nv_dq_combine:  out = ewt .* ( (vs ./ ewt) - gamma * (fpert - fy) / sigma )
+ *                      = scaled (I - gamma J) applied to the unscaled Krylov vector, J v by difference quotient */
+int shud_nv_dq_perturb(shud_nvws *ws, int64_t n, double sigma, const double *vs, const double *ewt, const double *y, double *ytemp);
+int shud_nv_dq_combine(shud_nvws *ws, int64_t n, double sigma, double gamma, const double *vs, const double *ewt,
+                       const double *fpert, const double *fy, double *out);
+
+/* shud_nv_ewt:           ewt = 1 ./ (rtol |y| + atol)                 (CVODE's cvEwtSetSS: Abs, Scale, AddConst, Inv)
+ * shud_nv_newton_resid:  r = gamma f + psi - y                        (right-hand side of the Newton system)
+ * shud_nv_newton_update: y += x; acor += x; *del = ||x||_WRMS(ewt)    (Newton correction + its convergence norm) */
+int shud_nv_ewt(shud_nvws *ws, int64_t n, double rtol, double atol, const double *y, double *ewt);
+int shud_nv_newton_resid(shud_nvws *ws, int64_t n, double gamma, const double *f, const double *psi, const double *y, double *r);
+int shud_nv_newton_update(shud_nvws *ws, int64_t n, const double *x, const double *ewt, int64_t n_global, double *y,
+                          double *acor, double *del);
+
+/* ---- SPGMR on the device (replaces SUNLinSol_SPGMR + CVLS' difference-quotient Jv for this model;
+ * reference settings src/Equations/cvode_config.cpp:172-179: PREC_NONE, maxl 5, modified Gram-Schmidt, no
+ * restarts).  Solves (I - gamma J(t,y)) x = b scaled on both sides by ewt; J v = (f(y + sigma v) - fy)/sigma
+ * through shud_b200_rhs_dev of `gpu`.  `tol` is on the 2-norm of the scaled residual (CVLS: eplifac * tq4 *
+ * sqrt(N)).  One host synchronisation per Krylov iteration.  All vectors: device pointers, length ny(gpu).
+ * returns 0 converged, 1 residual reduced but tol not met (SUNLS_RES_REDUCED), 2 not reduced, <0 error. ---- */
+struct shud_ctx;
+typedef struct shud_spgmr shud_spgmr;
+int shud_spgmr_create(struct shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_global, shud_spgmr **out);
+void shud_spgmr_destroy(shud_spgmr *s);
+int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, const double *fy, const double *ewt,
+                     const double *b, double tol, double *x, int *nli, double *resnorm);
+
 #ifdef __cplusplus
 }
 #endif

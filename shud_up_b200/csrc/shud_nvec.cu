@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <vector>
 
 #include "shud_b200.h"
 #include "shud_nvector.h"
@@ -87,6 +88,26 @@ struct FLinSumVA {
 struct FScaleVA {
     int nv; Coef c; Ptrs X; MPtrs Z;
     __device__ void operator()(int64_t i) const { for (int k = 0; k < nv; k++) Z.p[k][i] = c.c[k] * X.p[k][i]; }
+};
+struct FDqPerturb {
+    double sigma; const double *vs, *ewt, *y; double *yt;
+    __device__ void operator()(int64_t i) const { yt[i] = sigma * (vs[i] / ewt[i]) + y[i]; }
+};
+struct FDqCombine {
+    double sigma, gamma; const double *vs, *ewt, *fp, *fy; double *out;
+    __device__ void operator()(int64_t i) const {
+        const double w = ewt[i], v = vs[i] / w;
+        const double jv = (1.0 / sigma) * fp[i] + (-1.0 / sigma) * fy[i];
+        out[i] = w * (v + (-gamma) * jv);
+    }
+};
+struct FEwt {
+    double rtol, atol; const double *y; double *w;
+    __device__ void operator()(int64_t i) const { w[i] = 1.0 / (rtol * fabs(y[i]) + atol); }
+};
+struct FNewtonResid {
+    double gamma; const double *f, *psi, *y; double *r;
+    __device__ void operator()(int64_t i) const { r[i] = (gamma * f[i] + psi[i]) - y[i]; }
 };
 struct FConstVA {
     int nv; double c; MPtrs Z;
@@ -181,6 +202,16 @@ struct TMinQuot {
     const double *num, *den;
     __device__ double term(int, int64_t i) const { return den[i] != 0.0 ? num[i] / den[i] : DBL_MAX; }
 };
+struct TNewtonUpdate {  // y += x, acor += x as a side effect; term = (x w)^2
+    const double *x, *w; double *y, *acor;
+    __device__ double term(int, int64_t i) const {
+        const double xi = x[i];
+        y[i] = y[i] + xi;
+        acor[i] = acor[i] + xi;
+        const double t = xi * w[i];
+        return t * t;
+    }
+};
 struct TDotMulti { const double *x; Ptrs Y; __device__ double term(int k, int64_t i) const { return x[i] * Y.p[k][i]; } };
 struct TWSqrMulti {
     Ptrs X, W;
@@ -251,6 +282,16 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
     CKN(cudaGetLastError());
     CKN(cudaStreamSynchronize(ws->stream));
     for (int k = 0; k < nv; k++) out[k] = ws->h_out[k];
+    return SHUD_OK;
+}
+// same reduction, result left in device memory (d_result), no synchronisation: for device-resident
+// solver loops (shud_spgmr_solve) that consume the scalar in a following kernel
+template <int KIND, class F>
+int run_reduce_dev(shud_nvws *ws, int64_t n, F f, double *d_result) {
+    if (!ws || !d_result || n <= 0) return SHUD_ERR_ARG;
+    k_reduce<KIND, 1, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, 1, ws->partial, ws->counter, d_result,
+                                                             ws->h_out_dev + (SHUD_NV_MAXVEC - 1), 0, 1.0);
+    CKN(cudaGetLastError());
     return SHUD_OK;
 }
 bool fill(Ptrs &P, const double *const *X, int nv) {
@@ -386,11 +427,178 @@ int shud_nv_constvectorarray(shud_nvws *ws, int64_t n, int nv, double c, double 
     if (!fill(f.Z, Z, nv)) return SHUD_ERR_ARG;
     return run_map(ws, n, f);
 }
+int shud_nv_ewt(shud_nvws *ws, int64_t n, double rtol, double atol, const double *y, double *ewt) {
+    return run_map(ws, n, FEwt{rtol, atol, y, ewt});
+}
+int shud_nv_newton_resid(shud_nvws *ws, int64_t n, double gamma, const double *f, const double *psi, const double *y,
+                         double *r) {
+    return run_map(ws, n, FNewtonResid{gamma, f, psi, y, r});
+}
+int shud_nv_newton_update(shud_nvws *ws, int64_t n, const double *x, const double *ewt, int64_t ng, double *y, double *acor,
+                          double *del) {
+    return run_reduce<R_SUM, 1>(ws, n, TNewtonUpdate{x, ewt, y, acor}, 1, 1, (double)(ng > 0 ? ng : n), del);
+}
+int shud_nv_dq_perturb(shud_nvws *ws, int64_t n, double sigma, const double *vs, const double *ewt, const double *y,
+                       double *yt) {
+    return run_map(ws, n, FDqPerturb{sigma, vs, ewt, y, yt});
+}
+int shud_nv_dq_combine(shud_nvws *ws, int64_t n, double sigma, double gamma, const double *vs, const double *ewt,
+                       const double *fp, const double *fy, double *out) {
+    return run_map(ws, n, FDqCombine{sigma, gamma, vs, ewt, fp, fy, out});
+}
 int shud_nv_wrmsnormvectorarray(shud_nvws *ws, int64_t n, int nv, const double *const *X, const double *const *W,
                                 int64_t ng, double *out) {
     TWSqrMulti f;
     if (!fill(f.X, X, nv) || !fill(f.W, W, nv)) return SHUD_ERR_ARG;
     return run_reduce<R_SUM, SHUD_NV_MAXVEC>(ws, n, f, nv, 1, (double)(ng > 0 ? ng : n), out);
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// SPGMR on the device: the linear solver CVLS hands every Newton iteration to
+// (reference: SUNLinSol_SPGMR(udata, PREC_NONE, 0) + CVodeSetLinearSolver(mem, LS, NULL),
+// src/Equations/cvode_config.cpp:172-179: maxl = 5, modified Gram-Schmidt, no restarts, matrix-free with
+// difference-quotient J v).  The whole Arnoldi loop stays on the device: Gram-Schmidt coefficients are
+// device scalars consumed by the next kernel, and the host synchronises ONCE per Krylov iteration to
+// apply the Givens rotations and test convergence (k+2 scalars), instead of once per dot product.
+// =============================================================================================
+namespace {
+struct FProdTo { const double *a, *b; double *z; __device__ void operator()(int64_t i) const { z[i] = a[i] * b[i]; } };
+struct FAxpyDevNeg {  // w -= h[0] * v
+    const double *h, *v; double *w;
+    __device__ void operator()(int64_t i) const { w[i] = w[i] + (-h[0]) * v[i]; }
+};
+struct FNormalizeDev {  // w /= sqrt(n2[0])  (left untouched when the norm is 0)
+    const double *n2; double *w;
+    __device__ void operator()(int64_t i) const {
+        const double s = sqrt(n2[0]);
+        if (s != 0.0) w[i] = (1.0 / s) * w[i];
+    }
+};
+struct FScaleTo { double c; const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = c * x[i]; } };
+struct FLinCombDiv {  // x = (sum c_k V_k) ./ ewt
+    int nv; Coef c; Ptrs V; const double *ewt; double *x;
+    __device__ void operator()(int64_t i) const {
+        double s = c.c[0] * V.p[0][i];
+        for (int k = 1; k < nv; k++) s += c.c[k] * V.p[k][i];
+        x[i] = s / ewt[i];
+    }
+};
+}  // namespace
+
+struct shud_spgmr {
+    shud_ctx *gpu;
+    shud_nvws *ws;
+    int maxl;
+    int64_t n;
+    double sqrtN;
+    std::vector<double *> V;   // maxl+1 Krylov vectors
+    double *ytemp, *ftemp;
+    double *dH;                // device scalars: Gram-Schmidt coefficients of the current column + squared norm
+    double *hH;                // pinned host copy
+};
+
+extern "C" {
+
+int shud_spgmr_create(shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_global, shud_spgmr **out) {
+    if (!gpu || !ws || !out || maxl < 1 || maxl >= SHUD_NV_MAXVEC) return SHUD_ERR_ARG;
+    if ((void *)ws->stream != shud_b200_stream(gpu)) return SHUD_ERR_ARG;  // RHS and vector work share one stream
+    shud_spgmr *s = new shud_spgmr();
+    s->gpu = gpu; s->ws = ws; s->maxl = maxl; s->n = shud_b200_ny(gpu);
+    s->sqrtN = sqrt((double)(n_global > 0 ? n_global : s->n));
+    CKN(cudaSetDevice(ws->device));
+    for (int k = 0; k <= maxl; k++) {
+        double *p = nullptr;
+        CKN(cudaMalloc(&p, sizeof(double) * s->n));
+        s->V.push_back(p);
+    }
+    CKN(cudaMalloc(&s->ytemp, sizeof(double) * s->n));
+    CKN(cudaMalloc(&s->ftemp, sizeof(double) * s->n));
+    CKN(cudaMalloc(&s->dH, sizeof(double) * (maxl + 2)));
+    CKN(cudaMallocHost(&s->hH, sizeof(double) * (maxl + 2)));
+    *out = s;
+    return SHUD_OK;
+}
+
+void shud_spgmr_destroy(shud_spgmr *s) {
+    if (!s) return;
+    cudaSetDevice(s->ws->device);
+    cudaDeviceSynchronize();
+    for (double *p : s->V) cudaFree(p);
+    cudaFree(s->ytemp); cudaFree(s->ftemp); cudaFree(s->dH); cudaFreeHost(s->hH);
+    delete s;
+}
+
+int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, const double *fy, const double *ewt,
+                     const double *b, double tol, double *x, int *nli_out, double *res_out) {
+    if (!s || !y || !fy || !ewt || !b || !x) return SHUD_ERR_ARG;
+    shud_nvws *ws = s->ws;
+    const int64_t n = s->n;
+    const int maxl = s->maxl;
+    int rc;
+    // r0 = S b, beta = ||r0||_2
+    if ((rc = run_map(ws, n, FProdTo{ewt, b, s->V[0]}))) return rc;
+    if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[0], s->V[0]}, s->dH))) return rc;
+    CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    CKN(cudaStreamSynchronize(ws->stream));
+    const double beta = sqrt(s->hH[0]);
+    if (nli_out) *nli_out = 0;
+    if (res_out) *res_out = beta;
+    if (beta <= tol) {
+        if ((rc = run_map(ws, n, FConst{0.0, x}))) return rc;
+        return 0;
+    }
+    if ((rc = run_map(ws, n, FScaleTo{1.0 / beta, s->V[0], s->V[0]}))) return rc;
+    double H[SHUD_NV_MAXVEC + 1][SHUD_NV_MAXVEC] = {{0}};
+    double g[SHUD_NV_MAXVEC + 1] = {0}, cs[SHUD_NV_MAXVEC] = {0}, sn[SHUD_NV_MAXVEC] = {0};
+    g[0] = beta;
+    int k_used = 0;
+    bool conv = false;
+    const double sig = s->sqrtN;  // 1/||S^-1 v_k||_WRMS: v_k has unit 2-norm (CVLS' sigma without a reduction)
+    for (int k = 0; k < maxl; k++) {
+        // w = S (I - gamma J) S^-1 v_k, J by difference quotient: 1 RHS call
+        if ((rc = shud_nv_dq_perturb(ws, n, sig, s->V[k], ewt, y, s->ytemp))) return rc;
+        if ((rc = shud_b200_rhs_dev(s->gpu, t, s->ytemp, s->ftemp))) return rc;
+        if ((rc = shud_nv_dq_combine(ws, n, sig, gamma, s->V[k], ewt, s->ftemp, fy, s->V[k + 1]))) return rc;
+        // modified Gram-Schmidt, coefficients stay on the device
+        for (int i = 0; i <= k; i++) {
+            if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[k + 1], s->V[i]}, s->dH + i))) return rc;
+            if ((rc = run_map(ws, n, FAxpyDevNeg{s->dH + i, s->V[i], s->V[k + 1]}))) return rc;
+        }
+        if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[k + 1], s->V[k + 1]}, s->dH + k + 1))) return rc;
+        if ((rc = run_map(ws, n, FNormalizeDev{s->dH + k + 1, s->V[k + 1]}))) return rc;
+        CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, ws->stream));
+        CKN(cudaStreamSynchronize(ws->stream));  // the one host synchronisation of this Krylov iteration
+        for (int i = 0; i <= k; i++) H[i][k] = s->hH[i];
+        H[k + 1][k] = sqrt(s->hH[k + 1]);
+        for (int i = 0; i < k; i++) {
+            const double tmp = cs[i] * H[i][k] + sn[i] * H[i + 1][k];
+            H[i + 1][k] = -sn[i] * H[i][k] + cs[i] * H[i + 1][k];
+            H[i][k] = tmp;
+        }
+        const double den = hypot(H[k][k], H[k + 1][k]);
+        if (den != 0.0) { cs[k] = H[k][k] / den; sn[k] = H[k + 1][k] / den; } else { cs[k] = 1.0; sn[k] = 0.0; }
+        H[k][k] = cs[k] * H[k][k] + sn[k] * H[k + 1][k];
+        H[k + 1][k] = 0.0;
+        g[k + 1] = -sn[k] * g[k];
+        g[k] = cs[k] * g[k];
+        k_used = k + 1;
+        if (fabs(g[k + 1]) <= tol) { conv = true; break; }
+    }
+    FLinCombDiv f;
+    f.nv = k_used; f.ewt = ewt; f.x = x;
+    double yk[SHUD_NV_MAXVEC] = {0};
+    for (int i = k_used - 1; i >= 0; i--) {
+        double acc = g[i];
+        for (int j = i + 1; j < k_used; j++) acc -= H[i][j] * yk[j];
+        yk[i] = acc / H[i][i];
+    }
+    for (int i = 0; i < k_used; i++) { f.c.c[i] = yk[i]; f.V.p[i] = s->V[i]; }
+    if ((rc = run_map(ws, n, f))) return rc;
+    if (nli_out) *nli_out = k_used;
+    if (res_out) *res_out = fabs(g[k_used]);
+    return conv ? 0 : (fabs(g[k_used]) < beta ? 1 : 2);
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ def run(model, fseq, y0, n_steps, solver_step=10.0, et_step=60.0, rtol=1e-4, ato
     fseq: dict of [n][Ne] forcing arrays; returns dict(t, y_end, q_out[n_steps][n_outlets], stats, wall_s)."""
     y = model.load_state(y0)
     integ = BDFKrylov(model.ops, model.new_vector, model.rhs, int(y0.size), rtol=rtol, atol=atol, max_step=max_step,
-                      init_step=init_step, max_order=max_order)
+                      init_step=init_step, max_order=max_order, linear_solver=getattr(model, "linear_solver", None))
     t = float(fseq["fseq_t"][0])
     integ.init(t, y)
     q_out, times = [], []
@@ -46,6 +46,8 @@ class GpuModel:
         self.shud = ShudRHS(mesh, device=device)
         self.stream = self.shud.torch_stream()
         self.ops = NVectorOps(device, self.shud.stream_ptr, owner=self.shud)
+        from .nvector import DeviceSPGMR
+        self.linear_solver = DeviceSPGMR(self.ops, self.shud, maxl=5)
         self.dev = torch.device(f"cuda:{device}")
         self.Ne, self.Nr = self.shud.Ne, self.shud.Nr
         self.outlets = np.nonzero(np.asarray(mesh["riv_down"]) < 0)[0]
@@ -53,6 +55,7 @@ class GpuModel:
 
     def close(self):
         self.torch.cuda.synchronize()
+        self.linear_solver.close()
         self.ops.close()
         self.shud.close()
 

@@ -22,8 +22,11 @@ import numpy as np
 
 class BDFKrylov:
     def __init__(self, ops, new_vector, rhs, n, rtol=1e-4, atol=1e-4, max_step=10.0, init_step=1.0, min_step=1e-6,
-                 max_order=2, maxl=5, n_global=None):
-        """ops: N_V* table; new_vector(): allocate a device vector; rhs(t, y, ydot): CVRhsFn on device vectors."""
+                 max_order=2, maxl=5, n_global=None, linear_solver=None):
+        """ops: N_V* table; new_vector(): allocate a device vector; rhs(t, y, ydot): CVRhsFn on device vectors.
+        linear_solver: optional object with solve(t, gamma, y, fy, ewt, b, tol, x) -> (flag, nli, res), e.g. the
+        device-resident DeviceSPGMR; default: the SPGMR below, written on the ops table."""
+        self.linear_solver = linear_solver
         self.ops, self.new, self.rhs, self.n = ops, new_vector, rhs, n
         self.rtol, self.atol = rtol, atol
         self.hmax, self.h0, self.hmin = max_step, init_step, min_step
@@ -45,6 +48,9 @@ class BDFKrylov:
 
     def _set_ewt(self, y):
         o = self.ops
+        if hasattr(o, "EwtSet"):
+            o.EwtSet(self.rtol, self.atol, y, self.ewt)
+            return
         o.N_VAbs(y, self.ewt)
         o.N_VScale(self.rtol, self.ewt, self.ewt)
         o.N_VAddConst(self.ewt, self.atol, self.ewt)
@@ -115,11 +121,20 @@ class BDFKrylov:
         g = np.zeros(maxl + 1); g[0] = beta
         cs, sn = np.zeros(maxl), np.zeros(maxl)
         k_used, conv = 0, False
+        fused = hasattr(o, "DQPerturb")
         for k in range(maxl):
             self.stats["nli"] += 1
-            o.N_VDiv(V[k], self.ewt, self.delta)                          # unscale: v = S^-1 v_k
-            self._atimes(self.delta, gamma, t, y, fy, V[k + 1])
-            o.N_VProd(self.ewt, V[k + 1], V[k + 1])                       # w = S A S^-1 v_k
+            if fused:
+                # ||S^-1 v_k||_WRMS = ||v_k||_2 / sqrt(N) = 1/sqrt(N) exactly (v_k is normalised): CVLS' sigma
+                # without a reduction; unscale+perturb and the whole scaled (I - gamma J) v in one launch each
+                sig = self.sqrtN
+                o.DQPerturb(sig, V[k], self.ewt, y, self.tmp)
+                self._f(t, self.tmp, self.tmp2)
+                o.DQCombine(sig, gamma, V[k], self.ewt, self.tmp2, fy, V[k + 1])
+            else:
+                o.N_VDiv(V[k], self.ewt, self.delta)                      # unscale: v = S^-1 v_k
+                self._atimes(self.delta, gamma, t, y, fy, V[k + 1])
+                o.N_VProd(self.ewt, V[k + 1], V[k + 1])                   # w = S A S^-1 v_k
             for i in range(k + 1):                                        # modified Gram-Schmidt
                 H[i, k] = o.N_VDotProd(V[k + 1], V[i])
                 o.N_VLinearSum(1.0, V[k + 1], -H[i, k], V[i], V[k + 1])
@@ -178,15 +193,27 @@ class BDFKrylov:
                 self.stats["nni"] += 1
                 self._f(tn1, self.ycur, self.ftemp)
                 # residual of the Newton system: r = gamma f + psi - y
-                o.N_VLinearSum(gamma, self.ftemp, 1.0, self.b, self.tmp)
-                o.N_VLinearSum(1.0, self.tmp, -1.0, self.ycur, self.tmp)
                 rhsvec = self.V[self.maxl]                                # borrowed: free until _spgmr normalises V[0]
-                o.N_VScale(1.0, self.tmp, rhsvec)
+                if hasattr(o, "NewtonResid"):
+                    o.NewtonResid(gamma, self.ftemp, self.b, self.ycur, rhsvec)
+                else:
+                    o.N_VLinearSum(gamma, self.ftemp, 1.0, self.b, self.tmp)
+                    o.N_VLinearSum(1.0, self.tmp, -1.0, self.ycur, rhsvec)
                 x = self.hist[-1]                                         # scratch: the slot about to be overwritten
-                ok, _ = self._spgmr(rhsvec, x, gamma, tn1, self.ycur, self.ftemp, 0.05 * 0.1 * self.sqrtN)
-                dele = o.N_VWrmsNorm(x, self.ewt)
-                o.N_VLinearSum(1.0, self.ycur, 1.0, x, self.ycur)
-                o.N_VLinearSum(1.0, self.acor, 1.0, x, self.acor)
+                if self.linear_solver is not None:
+                    flag, nli, _ = self.linear_solver.solve(tn1, gamma, self.ycur, self.ftemp, self.ewt, rhsvec,
+                                                            0.05 * 0.1 * self.sqrtN, x)
+                    ok = flag <= 1
+                    self.stats["nli"] += nli
+                    self.stats["nfe"] += nli
+                else:
+                    ok, _ = self._spgmr(rhsvec, x, gamma, tn1, self.ycur, self.ftemp, 0.05 * 0.1 * self.sqrtN)
+                if hasattr(o, "NewtonUpdate"):
+                    dele = o.NewtonUpdate(x, self.ewt, self.ycur, self.acor)
+                else:
+                    dele = o.N_VWrmsNorm(x, self.ewt)
+                    o.N_VLinearSum(1.0, self.ycur, 1.0, x, self.ycur)
+                    o.N_VLinearSum(1.0, self.acor, 1.0, x, self.acor)
                 if mnewt > 0:
                     crate = max(0.3 * crate, dele / delp) if delp > 0 else crate
                 dcon = dele * min(1.0, crate) / 0.1

@@ -51,6 +51,13 @@ def _lib():
             "shud_nv_scalevectorarray": [vp, i64, ci, _PD, PP, PP],
             "shud_nv_constvectorarray": [vp, i64, ci, dbl, PP],
             "shud_nv_wrmsnormvectorarray": [vp, i64, ci, PP, PP, i64, _PD],
+            "shud_spgmr_create": [vp, vp, ci, i64, C.POINTER(vp)],
+            "shud_spgmr_solve": [vp, dbl, dbl, vp, vp, vp, vp, dbl, vp, C.POINTER(ci), _PD],
+            "shud_nv_ewt": [vp, i64, dbl, dbl, vp, vp],
+            "shud_nv_newton_resid": [vp, i64, dbl, vp, vp, vp, vp],
+            "shud_nv_newton_update": [vp, i64, vp, vp, i64, vp, vp, _PD],
+            "shud_nv_dq_perturb": [vp, i64, dbl, vp, vp, vp, vp],
+            "shud_nv_dq_combine": [vp, i64, dbl, dbl, vp, vp, vp, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -58,6 +65,8 @@ def _lib():
             fn.argtypes = args
         L.shud_nv_ws_destroy.restype = None
         L.shud_nv_ws_destroy.argtypes = [vp]
+        L.shud_spgmr_destroy.restype = None
+        L.shud_spgmr_destroy.argtypes = [vp]
         _sigs_done = True
     return L
 
@@ -208,3 +217,52 @@ class NVectorOps:
                                                     int(self.n_global or X[0].numel()), out.ctypes.data_as(_PD)),
                 "N_VWrmsNormVectorArray")
         return out
+
+    # ---- integrator-level fusions ----
+    def EwtSet(self, rtol, atol, y, ewt):
+        self._c(self._L.shud_nv_ewt(self._h, y.numel(), rtol, atol, _p(y), _p(ewt)), "EwtSet")
+
+    def NewtonResid(self, gamma, f, psi, y, r):
+        self._c(self._L.shud_nv_newton_resid(self._h, y.numel(), gamma, _p(f), _p(psi), _p(y), _p(r)), "NewtonResid")
+
+    def NewtonUpdate(self, x, ewt, y, acor):
+        out = C.c_double(0.0)
+        self._c(self._L.shud_nv_newton_update(self._h, x.numel(), _p(x), _p(ewt), int(self.n_global or x.numel()), _p(y),
+                                              _p(acor), C.byref(out)), "NewtonUpdate")
+        return out.value
+
+    def DQPerturb(self, sigma, vs, ewt, y, ytemp):
+        self._c(self._L.shud_nv_dq_perturb(self._h, y.numel(), sigma, _p(vs), _p(ewt), _p(y), _p(ytemp)), "DQPerturb")
+
+    def DQCombine(self, sigma, gamma, vs, ewt, fpert, fy, out):
+        self._c(self._L.shud_nv_dq_combine(self._h, fy.numel(), sigma, gamma, _p(vs), _p(ewt), _p(fpert), _p(fy), _p(out)),
+                "DQCombine")
+
+
+class DeviceSPGMR:
+    """SUNLinSol_SPGMR + CVLS difference-quotient Jv, resident on the device (shud_spgmr_* of the C ABI)."""
+
+    def __init__(self, ops, shud_rhs, maxl=5, n_global=0):
+        self._ops, self._rhs, self._L = ops, shud_rhs, _lib()
+        h = C.c_void_p()
+        api._chk(self._L.shud_spgmr_create(shud_rhs._h, ops._h, int(maxl), int(n_global), C.byref(h)), "shud_spgmr_create")
+        self._h = h
+
+    def solve(self, t, gamma, y, fy, ewt, b, tol, x):
+        nli, res = C.c_int(0), C.c_double(0.0)
+        rc = self._L.shud_spgmr_solve(self._h, float(t), float(gamma), _p(y), _p(fy), _p(ewt), _p(b), float(tol), _p(x),
+                                      C.byref(nli), C.byref(res))
+        if rc < 0:
+            api._chk(rc, "shud_spgmr_solve")
+        return rc, nli.value, res.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.shud_spgmr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -127,3 +127,17 @@ def test_fused_ops(ops, n, nv):
     for k in range(nv):
         r = np.sqrt(np.sum((X[k] * Y[k]) ** 2) / n)
         assert abs(nrm[k] - r) <= 1e-13 * r
+
+
+def test_dq_fusions(ops):
+    import torch
+    n = 100_003
+    (vs, ewt, y, fp, fy), (dvs, dewt, dy, dfp, dfy) = _mk(n, 9, 5)
+    ewt = np.abs(ewt) + 0.5; dewt = torch.from_numpy(ewt).cuda()
+    dout = torch.empty_like(dy); torch.cuda.synchronize()
+    sig, gam = 37.5, 0.125
+    ops.DQPerturb(sig, dvs, dewt, dy, dout); ops._st.synchronize()
+    assert np.array_equal(dout.cpu().numpy(), sig * (vs / ewt) + y)
+    ops.DQCombine(sig, gam, dvs, dewt, dfp, dfy, dout); ops._st.synchronize()
+    jv = (1.0 / sig) * fp + (-1.0 / sig) * fy
+    assert np.array_equal(dout.cpu().numpy(), ewt * (vs / ewt + (-gam) * jv))
