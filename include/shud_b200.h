@@ -152,6 +152,13 @@ int shud_b200_rhs_stage_dev(shud_ctx *ctx, int stage, const double *y_dev, doubl
 int shud_b200_rhs_diag_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
 /* Download the flux arrays left by the last shud_b200_rhs_diag_dev (host pointers). */
 int shud_b200_get_diag(shud_ctx *ctx, const shud_diag *out);
+/* Device-side output accumulation.  Replaces the host loop of
+ * Print_Ctrl::PrintData (src/classes/Model_Control.cpp:930-962): every SolverStep `buffer[i] += *PrintVar[i]`,
+ * and at the end of the output interval `buffer[i] *= tau / NumUpdate`, write, reset.  _accumulate adds the flux
+ * arrays left by the last shud_b200_rhs_diag_dev into device-resident buffers (NumUpdate++), no PCIe traffic;
+ * _flush downloads buffer * (tau / NumUpdate) into the host arrays of `out` (reference order) and resets. */
+int shud_b200_output_accumulate(shud_ctx *ctx);
+int shud_b200_output_flush(shud_ctx *ctx, double tau, const shud_diag *out, int32_t *num_update);
 /* Synchronise and read the device error word: code in the return value, offending
  * 1-based cell/reach id in *where (may be NULL).  Mirrors myexit(code)
  * (src/Equations/functions.cpp:10-36) without killing the process. */

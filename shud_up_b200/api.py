@@ -61,6 +61,8 @@ def lib():
         "shud_b200_rhs_stage_dev": (C.c_int, [vp, C.c_int, vp, vp]),
         "shud_b200_rhs_diag_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_get_diag": (C.c_int, [vp, C.POINTER(abi.ShudDiag)]),
+        "shud_b200_output_accumulate": (C.c_int, [vp]),
+        "shud_b200_output_flush": (C.c_int, [vp, C.c_double, C.POINTER(abi.ShudDiag), _PI]),
         "shud_b200_check": (C.c_int, [vp, _PI]),
         "shud_b200_launches_per_rhs": (C.c_int, [vp]),
     }
@@ -195,6 +197,17 @@ class ShudRHS:
         where = C.c_int32(0)
         code = lib().shud_b200_check(self._h, C.byref(where))
         return code, where.value
+
+    def output_accumulate(self):
+        """Print_Ctrl::PrintData's `buffer += value` for every flux array, on the device (after a diag RHS)"""
+        _chk(lib().shud_b200_output_accumulate(self._h), "shud_b200_output_accumulate")
+
+    def output_flush(self, tau):
+        """interval means * tau of every flux array (host, reference order); resets the device buffers"""
+        d, arrs = abi.make_diag(self.Ne, self.Nr, self.Ns, self.Nl)
+        n = C.c_int32(0)
+        _chk(lib().shud_b200_output_flush(self._h, float(tau), C.byref(d), C.byref(n)), "shud_b200_output_flush")
+        return arrs, n.value
 
     def get_diag(self):
         d, arrs = abi.make_diag(self.Ne, self.Nr, self.Ns, self.Nl)

@@ -936,6 +936,18 @@ __global__ void k_pack_halo(const double *__restrict__ Y, const int *__restrict_
     out[2 * k + 1] = Y[2 * (size_t)Ne + i];
 }
 
+// Print_Ctrl::PrintData on the device: acc += value (Model_Control.cpp:933-935)
+__global__ void k_accumulate(double *__restrict__ acc, const double *__restrict__ v, size_t n) {
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        acc[k] += v[k];
+}
+__global__ void k_scale_copy(double *__restrict__ dst, double *__restrict__ acc, double s, size_t n) {
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        dst[k] = acc[k] * s;  // buffer *= tau / NumUpdate (Model_Control.cpp:944-946)
+        acc[k] = 0.;          // reset (Model_Control.cpp:958-960)
+    }
+}
+
 // carried state from y (Model_Data::updateforcing -> updateElement for every cell, MD_ET.cpp:14-19)
 __global__ void k_prime(DevMesh m, const double *__restrict__ Y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1005,6 +1017,11 @@ struct shud_ctx {
     DevMesh m{};
     DevDiag diag{};
     bool diag_alloc = false;
+    DevDiag acc{};          // output accumulators (same shapes as diag) + effKH/satn/Qseg copies
+    double *acc_effKH = nullptr, *acc_satn = nullptr, *acc_QsegSurf = nullptr, *acc_QsegSub = nullptr;
+    double *acc_tmp = nullptr;
+    bool acc_alloc = false;
+    int num_update = 0;
     std::vector<void *> allocs;
     std::vector<int> cperm, rperm, sperm;  // device id -> reference id (0-based)
     std::vector<int> cinv, rinv;           // reference id -> device id
@@ -1680,8 +1697,87 @@ int shud_b200_rhs(shud_ctx *c, double t, const double *y_host, double *ydot_host
     return shud_b200_check(c, nullptr);
 }
 
+static int download_diag(shud_ctx *c, const DevDiag &d, const double *effKH, const double *satn, const double *qsegS,
+                         const double *qsegG, const shud_diag *o);
+
+// the (array, accumulator, length) triples of the output accumulation
+static void acc_list(shud_ctx *c, std::vector<const double *> &src, std::vector<double *> &dst, std::vector<size_t> &len) {
+    const size_t Ne = c->Ne, Nr = c->Nr, Ns = c->Ns, Nl = c->Nl;
+    const DevDiag &d = c->diag;
+    DevDiag &a = c->acc;
+    auto add = [&](const double *s_, double *d_, size_t n_) { src.push_back(s_); dst.push_back(d_); len.push_back(n_); };
+    add(d.qEleInfil, a.qEleInfil, Ne); add(d.qEleExfil, a.qEleExfil, Ne); add(d.qEleRecharge, a.qEleRecharge, Ne);
+    add(d.qEs, a.qEs, Ne); add(d.qEu, a.qEu, Ne); add(d.qEg, a.qEg, Ne); add(d.qTu, a.qTu, Ne); add(d.qTg, a.qTg, Ne);
+    add(d.qEleTrans, a.qEleTrans, Ne); add(d.qEleEvapo, a.qEleEvapo, Ne); add(d.qEleETA, a.qEleETA, Ne);
+    add(d.iBeta, a.iBeta, Ne); add(d.QeleSurf, a.QeleSurf, 3 * Ne); add(d.QeleSub, a.QeleSub, 3 * Ne);
+    add(d.QeleSurfTot, a.QeleSurfTot, Ne); add(d.QeleSubTot, a.QeleSubTot, Ne); add(d.Qe2r_Surf, a.Qe2r_Surf, Ne);
+    add(d.Qe2r_Sub, a.Qe2r_Sub, Ne); add(d.QrivSurf, a.QrivSurf, Nr); add(d.QrivSub, a.QrivSub, Nr);
+    add(d.QrivUp, a.QrivUp, Nr); add(d.QrivDown, a.QrivDown, Nr); add(d.y2LakeArea, a.y2LakeArea, Nl);
+    add(d.QLakeSurf, a.QLakeSurf, Nl); add(d.QLakeSub, a.QLakeSub, Nl); add(d.QLakeRivIn, a.QLakeRivIn, Nl);
+    add(d.QLakeRivOut, a.QLakeRivOut, Nl); add(d.qLakeEvap, a.qLakeEvap, Nl); add(d.qLakePrcp, a.qLakePrcp, Nl);
+    add(c->m.effKH, c->acc_effKH, Ne); add(c->m.satn, c->acc_satn, Ne);
+    add(c->m.QsegSurf, c->acc_QsegSurf, Ns); add(c->m.QsegSub, c->acc_QsegSub, Ns);
+}
+
+int shud_b200_output_accumulate(shud_ctx *c) {
+    if (!c || !c->diag_alloc) return SHUD_ERR_ARG;  // needs a shud_b200_rhs_diag_dev before
+    CK(cudaSetDevice(c->device));
+    if (!c->acc_alloc) {
+        const size_t Ne = c->Ne, Nr = c->Nr, Ns = c->Ns, Nl = c->Nl;
+        DevDiag &a = c->acc;
+        auto z = [&](size_t n_) { double *p_ = dev_alloc<double>(c, n_); if (p_) cudaMemset(p_, 0, sizeof(double) * std::max<size_t>(n_, 1)); return p_; };
+        a.qEleInfil = z(Ne); a.qEleExfil = z(Ne); a.qEleRecharge = z(Ne); a.qEs = z(Ne); a.qEu = z(Ne); a.qEg = z(Ne);
+        a.qTu = z(Ne); a.qTg = z(Ne); a.qEleTrans = z(Ne); a.qEleEvapo = z(Ne); a.qEleETA = z(Ne); a.iBeta = z(Ne);
+        a.QeleSurf = z(3 * Ne); a.QeleSub = z(3 * Ne); a.QeleSurfTot = z(Ne); a.QeleSubTot = z(Ne); a.Qe2r_Surf = z(Ne);
+        a.Qe2r_Sub = z(Ne); a.QrivSurf = z(Nr); a.QrivSub = z(Nr); a.QrivUp = z(Nr); a.QrivDown = z(Nr);
+        a.y2LakeArea = z(Nl); a.QLakeSurf = z(Nl); a.QLakeSub = z(Nl); a.QLakeRivIn = z(Nl); a.QLakeRivOut = z(Nl);
+        a.qLakeEvap = z(Nl); a.qLakePrcp = z(Nl);
+        c->acc_effKH = z(Ne); c->acc_satn = z(Ne); c->acc_QsegSurf = z(Ns); c->acc_QsegSub = z(Ns);
+        c->acc_alloc = true;
+    }
+    std::vector<const double *> src; std::vector<double *> dst; std::vector<size_t> len;
+    acc_list(c, src, dst, len);
+    for (size_t k = 0; k < src.size(); k++)
+        if (len[k]) k_accumulate<<<(unsigned)std::min<size_t>((len[k] + 255) / 256, 1184), 256, 0, c->stream>>>(dst[k], src[k], len[k]);
+    CK(cudaGetLastError());
+    c->num_update++;
+    return SHUD_OK;
+}
+
+int shud_b200_output_flush(shud_ctx *c, double tau, const shud_diag *o, int32_t *num_update) {
+    if (!c || !o || !c->acc_alloc || c->num_update <= 0) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    const double s = tau / c->num_update;
+    // scale in place into a scratch copy laid out like the diag arrays, reset the accumulators, download
+    std::vector<const double *> src; std::vector<double *> dst; std::vector<size_t> len;
+    acc_list(c, src, dst, len);
+    std::vector<double *> tmp(dst.size(), nullptr);
+    for (size_t k = 0; k < dst.size(); k++) {
+        if (!len[k]) continue;
+        CK(cudaMalloc(&tmp[k], sizeof(double) * len[k]));
+        k_scale_copy<<<(unsigned)std::min<size_t>((len[k] + 255) / 256, 1184), 256, 0, c->stream>>>(tmp[k], dst[k], s, len[k]);
+    }
+    CK(cudaGetLastError());
+    DevDiag t{};
+    double **slots[] = {&t.qEleInfil, &t.qEleExfil, &t.qEleRecharge, &t.qEs, &t.qEu, &t.qEg, &t.qTu, &t.qTg, &t.qEleTrans,
+                        &t.qEleEvapo, &t.qEleETA, &t.iBeta, &t.QeleSurf, &t.QeleSub, &t.QeleSurfTot, &t.QeleSubTot,
+                        &t.Qe2r_Surf, &t.Qe2r_Sub, &t.QrivSurf, &t.QrivSub, &t.QrivUp, &t.QrivDown, &t.y2LakeArea,
+                        &t.QLakeSurf, &t.QLakeSub, &t.QLakeRivIn, &t.QLakeRivOut, &t.qLakeEvap, &t.qLakePrcp};
+    for (size_t k = 0; k < 29; k++) *slots[k] = tmp[k];
+    int rc = download_diag(c, t, tmp[29], tmp[30], tmp[31], tmp[32], o);
+    for (double *p_ : tmp) if (p_) cudaFree(p_);
+    if (num_update) *num_update = c->num_update;
+    c->num_update = 0;
+    return rc;
+}
+
 int shud_b200_get_diag(shud_ctx *c, const shud_diag *o) {
     if (!c || !o || !c->diag_alloc) return SHUD_ERR_ARG;
+    return download_diag(c, c->diag, c->m.effKH, c->m.satn, c->m.QsegSurf, c->m.QsegSub, o);
+}
+
+static int download_diag(shud_ctx *c, const DevDiag &d, const double *effKH, const double *satn, const double *qsegS,
+                         const double *qsegG, const shud_diag *o) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     const int Ne = c->Ne, Nr = c->Nr, Ns = c->Ns, Nl = c->Nl;
@@ -1712,18 +1808,17 @@ int shud_b200_get_diag(shud_ctx *c, const shud_diag *o) {
         if (!dst || Nl == 0) return 0;
         return cudaMemcpy(dst, dsrc, sizeof(double) * Nl, cudaMemcpyDeviceToHost) != cudaSuccess;
     };
-    const DevDiag &d = c->diag;
     int bad = 0;
     bad |= cell(d.qEleInfil, o->qEleInfil, 1); bad |= cell(d.qEleExfil, o->qEleExfil, 1);
     bad |= cell(d.qEleRecharge, o->qEleRecharge, 1); bad |= cell(d.qEs, o->qEs, 1); bad |= cell(d.qEu, o->qEu, 1);
     bad |= cell(d.qEg, o->qEg, 1); bad |= cell(d.qTu, o->qTu, 1); bad |= cell(d.qTg, o->qTg, 1);
     bad |= cell(d.qEleTrans, o->qEleTrans, 1); bad |= cell(d.qEleEvapo, o->qEleEvapo, 1);
     bad |= cell(d.qEleETA, o->qEleETA, 1); bad |= cell(d.iBeta, o->iBeta, 1);
-    bad |= cell(c->m.effKH, o->u_effKH, 1); bad |= cell(c->m.satn, o->u_satn, 1);
+    bad |= cell(effKH, o->u_effKH, 1); bad |= cell(satn, o->u_satn, 1);
     bad |= cell(d.QeleSurf, o->QeleSurf, 3); bad |= cell(d.QeleSub, o->QeleSub, 3);
     bad |= cell(d.QeleSurfTot, o->QeleSurfTot, 1); bad |= cell(d.QeleSubTot, o->QeleSubTot, 1);
     bad |= cell(d.Qe2r_Surf, o->Qe2r_Surf, 1); bad |= cell(d.Qe2r_Sub, o->Qe2r_Sub, 1);
-    bad |= seg(c->m.QsegSurf, o->QsegSurf); bad |= seg(c->m.QsegSub, o->QsegSub);
+    bad |= seg(qsegS, o->QsegSurf); bad |= seg(qsegG, o->QsegSub);
     bad |= riv(d.QrivSurf, o->QrivSurf); bad |= riv(d.QrivSub, o->QrivSub); bad |= riv(d.QrivUp, o->QrivUp);
     bad |= riv(d.QrivDown, o->QrivDown);
     bad |= lake(d.y2LakeArea, o->y2LakeArea); bad |= lake(d.QLakeSurf, o->QLakeSurf);

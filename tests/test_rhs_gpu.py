@@ -150,3 +150,36 @@ def test_tma_pipelined_kernel_variant(basin, case, monkeypatch):
     assert a["code"] == 0 and b["code"] == 0
     assert np.array_equal(a["ydot"], b["ydot"])
     assert np.array_equal(a["u_satn_out"], b["u_satn_out"]) and np.array_equal(a["qEleE_IC_out"], b["qEleE_IC_out"])
+
+
+def test_device_side_output_accumulation():
+    """Print_Ctrl::PrintData semantics (src/classes/Model_Control.cpp:930-962): buffer += value per SolverStep,
+    buffer *= tau/NumUpdate at the interval end, reset - done on the device, one download per interval."""
+    import torch
+    snap = oracle_lib.load_case("qhh", "rand4")
+    rhs, first = _run_gpu(snap)               # one diag RHS
+    d1 = {k: first[k].copy() for k in abi.DIAG_ALL}
+    rhs.output_accumulate()
+    st = rhs.torch_stream()
+    with torch.cuda.stream(st):
+        y_ref = torch.from_numpy(np.ascontiguousarray(snap["y"] * 1.01)).cuda()
+        y = torch.empty_like(y_ref); yd = torch.empty_like(y_ref)
+        rhs.to_device_order(y_ref, y)
+        rhs.f_dev(0.0, y, yd, diag=True)
+    d2 = rhs.get_diag()
+    rhs.output_accumulate()
+    mean, n = rhs.output_flush(tau=1440.0)
+    assert n == 2
+    lake = snap["ele_iLake"] > 0
+    for k in abi.DIAG_ALL:
+        if d1[k].size == 0:
+            continue
+        want = (d1[k] + d2[k]) * (1440.0 / 2)
+        got = mean[k]
+        if k == "iBeta":
+            want, got = want[~lake], got[~lake]
+        assert np.array_equal(got, want), k
+    # buffers were reset
+    rhs.output_accumulate()
+    again, n = rhs.output_flush(tau=2.0)
+    assert n == 1 and np.array_equal(again["QrivDown"], d2["QrivDown"] * 2.0)
