@@ -29,6 +29,14 @@ UNIT = "cell-updates/s"
 B_CELL, B_RIV, B_SEG = 392, 124, 72  # algorithmic bytes per unit and f() call
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -38,23 +46,33 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every 50 ms; nvidia-smi, the
+    recipe's command, once as a cross-check - spawning it takes ~1 s on these hosts, too slow to sample with)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
         self.th = threading.Thread(target=self.run, daemon=True)
+        self.smi = None
 
     def run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop:
+                self.rows.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx, int(get_reasons(h))))
+                time.sleep(0.05)
+        except Exception:
+            pass
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            self.smi = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader"],
+                                      capture_output=True, text=True, timeout=10).stdout.strip()
+        except Exception:
+            pass
 
     def __enter__(self):
         self.th.start()
@@ -62,15 +80,15 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.stop = True
-        self.th.join(timeout=6)
+        self.th.join(timeout=15)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        # NVML reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal_slowdown, 0x40 hw_thermal_slowdown
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for bit, n in names.items() if r[2] & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "reasons": reasons, "samples": len(sm), "nvidia_smi_after": self.smi}
 
 
 def stripe_mesh(world, rank):
@@ -317,7 +335,7 @@ def main():
                "gpu_launches": nst * steps,
                "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": ach / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": b_dom, "kernel_ms": kt[dom],
                             "all_kernels_ms": dict(zip(names, kt)),
                             "rhs_bytes": b_rhs, "rhs_achieved_gbs": b_rhs / (ms_step * 1e-3) / 1e9,

@@ -87,6 +87,9 @@ __device__ __forceinline__ void raise_err(int *err, int code, int where) {
 // K0: horizontal effective conductivity of every cell (neighbours need it before any edge flux)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restrict__ Y) {
+    // programmatic dependent launch: the cell kernel may start now; it waits (griddepcontrol.wait) only where it
+    // first needs effKH, so its vertical role overlaps this pre-pass
+    asm volatile("griddepcontrol.launch_dependents;");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.Ne) {
         const int h = i - m.Ne;  // halo cell: same formula on the exchanged groundwater head
@@ -390,6 +393,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     const int seg0 = __ldg(m.cell_seg_first + ic);
     const int nb[3] = {__ldg(m.nbr + ic), __ldg(m.nbr + LD + ic), __ldg(m.nbr + 2 * LD + ic)};
     const double ysf = Y[ic], ygw_raw = Y[2 * NE + ic];
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // effKH of this call is complete (k_effkh, PDL)
     const double kh = m.effKH[ic];
     const double zs = __ldg(m.z_surf + ic), zb = __ldg(m.z_bottom + ic);
     const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
@@ -1038,6 +1042,7 @@ struct shud_ctx {
     int pipe_stages = 2;
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
     int use_graph = 1;
+    int use_pdl = 1;   // programmatic dependent launch of the cell kernel behind k_effkh (SHUD_PDL)
     struct GraphEntry { const double *y; double *yd; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;
     int split = 2;      // 2: warp-specialised fused cell kernel (default); 0: one-thread-per-cell k_cell (SHUD_SPLIT, A/B only)
@@ -1175,6 +1180,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         if (e1) c->cell_minb = atoi(e1);
         if (getenv("SHUD_SPLIT")) c->split = atoi(getenv("SHUD_SPLIT"));
         if (getenv("SHUD_PIPE_GRID")) c->pipe_grid = atoi(getenv("SHUD_PIPE_GRID"));
+        if (getenv("SHUD_PDL")) c->use_pdl = atoi(getenv("SHUD_PDL"));
         if (getenv("SHUD_GRAPH")) c->use_graph = atoi(getenv("SHUD_GRAPH"));
         if (getenv("SHUD_FUSED_MINB")) c->fused_minb = atoi(getenv("SHUD_FUSED_MINB"));
     }
@@ -1574,8 +1580,20 @@ static void launch_pipe(shud_ctx *c, const double *y, double *ydot) {
         k_pipe<DIAG, 2, 2><<<grid, 2 * TILE + 32, pipe_smem(2), c->stream>>>(c->m, c->diag, y, ydot, ntiles);
 }
 template <bool DIAG>
-static void launch_fused(shud_ctx *c, const double *y, double *ydot) {
+static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = false) {
     const int nb = (c->Ne + TILE - 1) / TILE;
+    if (pdl && c->use_pdl && c->fused_minb == 4) {
+        // launched while k_effkh is still running (programmatic stream serialisation)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nb); cfg.blockDim = dim3(2 * TILE); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4>, c->m, c->diag, y, ydot) == cudaSuccess) return;
+        cudaGetLastError();
+        c->use_pdl = 0;
+    }
     switch (c->fused_minb) {
         case 2: k_fused<DIAG, 2><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
         case 3: k_fused<DIAG, 3><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
@@ -1590,7 +1608,7 @@ static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
         launch_pipe<DIAG>(c, y, ydot);
     } else if (c->split == 2) {
         k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
-        launch_fused<DIAG>(c, y, ydot);
+        launch_fused<DIAG>(c, y, ydot, true);
     } else {
         k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
         launch_cell<DIAG>(c, y, ydot);
