@@ -183,3 +183,22 @@ def test_device_side_output_accumulation():
     rhs.output_accumulate()
     again, n = rhs.output_flush(tau=2.0)
     assert n == 1 and np.array_equal(again["QrivDown"], d2["QrivDown"] * 2.0)
+
+
+@pytest.mark.parametrize("nx,ny,lake", [(40, 30, 0.03), (37, 23, 0.0), (64, 64, 0.05)])
+def test_synthetic_meshes_match_oracle(nx, ny, lake):
+    """synthetic domains (bench generator): odd sizes / tail tiles, a lake with hundreds of bank edges and lake
+    cells (tree reduction of the lake sums), dense river trees - ydot against the oracle at 1e-12"""
+    from shud_up_b200 import synth
+    mesh = synth.make(nx, ny, ntree=max(1, ny // 10), reaches_per_tree=min(nx, 40), lake_frac=lake)
+    mesh["ele_u_satn"] = oracle_lib.oracle_prime(mesh, mesh["y"])
+    ref = oracle_lib.oracle_rhs(mesh)
+    assert ref["err"] == 0
+    rhs, got = _run_gpu(mesh)
+    assert got["code"] == 0
+    bad = parity.mismatches(got["ydot"], ref["ydot"], parity.ydot_scale(mesh, ref))
+    assert bad.size == 0, (bad[:5], got["ydot"][bad[:5]], ref["ydot"][bad[:5]])
+    for name in ("QsegSurf", "QsegSub", "QrivDown", "qEleInfil", "qEleRecharge", "u_effKH"):
+        assert parity.mismatches(got[name], ref[name]).size == 0, name
+    if lake:
+        assert int(mesh["Nl"][0]) == 1 and (mesh["ele_lakenabr"] > 0).sum() > 20
