@@ -28,6 +28,26 @@ __device__ __forceinline__ bool bad_nonneg(double x) {
     return x < 0.0 || not_finite(x) || fabs(x - kNA_VALUE) < kZERO;
 }
 
+// Square root.  Default: the IEEE library sqrt (a 49-instruction CALL).  -DSHUD_LEAN_SQRT swaps in an inline
+// MUFU.RSQ64H-seeded Newton sequence (<= 1 ulp); measured on B200 it does not change the kernel time
+// (137.4 vs 137.2 us: the kernel is latency-, not instruction-bound there), so it stays off.
+__device__ __forceinline__ double fsqrt(double x) {
+#ifdef SHUD_LEAN_SQRT
+    if (!(x > 2.3e-308 && x < 1.7e308)) return sqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);
+    y = fma(y * 0.5, e, y);
+    e = fma(-(x * y), y, 1.0);
+    y = fma(y * 0.5, e, y);
+    double r = x * y;
+    const double d = fma(-r, r, x);
+    return fma(d, 0.5 * y, r);
+#else
+    return sqrt(x);
+#endif
+}
+
 // Division by a STATIC quantity.  Default: the IEEE division the reference performs.  With SHUD_RCP the
 // host stores the reciprocal of that static array instead and the kernel multiplies (<= 1.5 ulp away
 // from the quotient; inside the 1e-12 parity tolerance, not bit-identical).
@@ -41,15 +61,15 @@ __device__ __forceinline__ bool bad_nonneg(double x) {
 __device__ __forceinline__ double manning(double area, double rough, double R, double S) {
     const double c = cbrt(R);
     const double p23 = c * c;
-    if (S > 0) return sqrt(S) * area * p23 / rough;
-    return -1.0 * sqrt(-S) * area * p23 / rough;
+    if (S > 0) return fsqrt(S) * area * p23 / rough;
+    return -1.0 * fsqrt(-S) * area * p23 / rough;
 }
 // same, for a cell edge: `rough` is the static avgRough[j] (or its reciprocal under SHUD_RCP)
 __device__ __forceinline__ double manning_edge(double area, double rough, double R, double S) {
     const double c = cbrt(R);
     const double p23 = c * c;
-    if (S > 0) return SHUD_DIVS(sqrt(S) * area * p23, rough);
-    return SHUD_DIVS(-1.0 * sqrt(-S) * area * p23, rough);
+    if (S > 0) return SHUD_DIVS(fsqrt(S) * area * p23, rough);
+    return SHUD_DIVS(-1.0 * fsqrt(-S) * area * p23, rough);
 }
 
 // effKH, src/Equations/Equations.cpp:116-134.  Range violation -> *err = 13 (myexit(ERRDATAIN)).
@@ -80,7 +100,7 @@ __device__ __forceinline__ double pow01(double x, double a) {
 }
 __device__ __forceinline__ double sat_kr(double s, double n) {
     const double t = -1. + pow01(1. - pow01(s, n / (n - 1.)), (n - 1.) / n);
-    return sqrt(s) * t * t;
+    return fsqrt(s) * t * t;
 }
 
 // SoilMoistureStress, src/Equations/is_sm_et.cpp:131-142
@@ -99,12 +119,12 @@ __device__ __forceinline__ double weir_jtoi(double zi, double yi, double zj, dou
     if (dh > 0.) {
         if (y > 0. && yj > thr) {
             if (hi > zbank) y = dh;
-            Q = cwr * sqrt(2. * kGRAV * y) * width * y * 60.;
+            Q = cwr * fsqrt(2. * kGRAV * y) * width * y * 60.;
         }
     } else {
         if (y > 0. && yi > thr) {
             if (hj > zbank) y = -dh;
-            Q = -1. * cwr * sqrt(2. * kGRAV * y) * width * y * 60.;
+            Q = -1. * cwr * fsqrt(2. * kGRAV * y) * width * y * 60.;
         }
     }
     return Q;
@@ -318,14 +338,19 @@ __device__ __forceinline__ double cell_satn(double aqd, double thetaS, double th
 // (avgY_sf: src/Equations/Equations.cpp:8-51).  isf / nsf already clamped at 0.
 __device__ __forceinline__ double edge_surface(double isf, double zs, double nsf, double zs_n, double depression,
                                                double dist, double B, double rough) {
+    // written without branches (selects only) so that the three edges of a cell, which are independent, are
+    // interleaved by the scheduler instead of being three serial sqrt / cbrt / multiply chains
     const double h1 = zs + isf, h2 = zs_n + nsf;
     const double dh = (isf + zs) - (nsf + zs_n);
     double ym = (h1 > h2) ? ((isf > depression) ? isf : 0.) : ((nsf > depression) ? nsf : 0.);
     ym = dmin(ym, kMAXYSURF);
-    if (ym <= 0.) return 0.;
     const double s = SHUD_DIVS(dh, dist);
-    if ((s > 0 && isf <= 0) || (s < 0 && nsf <= 0)) return 0.;
-    return manning_edge(ym * B, rough, ym, s);
+    const bool off = (ym <= 0.) || (s > 0 && isf <= 0) || (s < 0 && nsf <= 0);
+    const double yms = off ? 1.0 : ym;                    // keep the dead lanes on harmless arguments
+    const double as = (s > 0) ? s : -s;
+    const double c = cbrt(yms);
+    const double q = SHUD_DIVS(fsqrt(off ? 1.0 : as) * (yms * B) * (c * c), rough);   // ManningEquation, |S| form
+    return off ? 0. : ((s > 0) ? q : -1.0 * q);
 }
 
 // groundwater flux through one edge, fun_Ele_sub, src/ModelData/MD_ElementFlux.cpp:107-138 (before fu_Sub).
@@ -333,11 +358,12 @@ __device__ __forceinline__ double edge_surface(double isf, double zs, double nsf
 __device__ __forceinline__ double edge_sub(double ygw, double zb, double y_n, double z_n, double kh, double kh_n,
                                            double dist, double B) {
     const double dh = (ygw + zb) - (y_n + z_n);
-    if ((dh > 0. && ygw <= 0.02) || (dh < 0. && y_n <= 0.02)) return 0.;
+    const bool off = (dh > 0. && ygw <= 0.02) || (dh < 0. && y_n <= 0.02);
     const double ym = (dmax(ygw, 0.) + dmax(y_n, 0.)) * .5;  // avgY_gw, Equations.cpp:52-56
     const double grad = SHUD_DIVS(dh, dist);
     const double km = 0.5 * (kh + kh_n);
-    return km * grad * ym * B;
+    const double q = km * grad * ym * B;
+    return off ? 0. : q;
 }
 
 }  // namespace shud
