@@ -227,14 +227,13 @@ struct CellVert {  // results
     int err;
 };
 
-// f_etFlux (src/ModelData/MD_ET.cpp:343-404) -> _Element::updateElement (src/classes/Element.cpp:347-384,
-// minus the dead u_phius / u_effkInfi stores) -> Flux_Infiltration (Element.cpp:271-303) ->
-// Flux_Recharge (Element.cpp:304-335), with the fu_Surf / fu_Sub factors of MD_ElementFlux.cpp:24-34.
-__device__ __forceinline__ CellVert cell_vertical(const CellParams &p, const CellForc &f, double ysf, double yus,
-                                                  double ygw, double satn_prev, double eic_in) {
-    CellVert r;
-    r.err = 0;
-    // ---- ET partition ----
+// The cell's vertical processes in two independent halves (so that two warp roles can share them):
+//   cell_et   : f_etFlux, src/ModelData/MD_ET.cpp:343-404 (uses the saturation of the PREVIOUS call)
+//   cell_soil : _Element::updateElement (src/classes/Element.cpp:347-384, minus the dead u_phius / u_effkInfi
+//               stores) -> Flux_Infiltration (Element.cpp:271-303) -> Flux_Recharge (Element.cpp:304-335), with the
+//               fu_Surf / fu_Sub factors of MD_ElementFlux.cpp:24-34
+__device__ __forceinline__ void cell_et(const CellParams &p, const CellForc &f, double ysf, double yus, double ygw,
+                                        double satn_prev, double eic_in, CellVert &r) {
     {
         const double va = p.vegFrac, vb = 1. - p.vegFrac, pj = 1. - p.impAF;
         const double ib = soil_moisture_stress(p.thetaS, p.thetaR, satn_prev);
@@ -261,7 +260,10 @@ __device__ __forceinline__ CellVert cell_vertical(const CellParams &p, const Cel
             r.err = 10;
         r.Es = Es; r.Eu = Eu; r.Eg = Eg; r.Tu = Tu; r.Tg = Tg; r.eic = eic; r.iBeta = ib;
     }
-    // ---- updateElement ----
+}
+
+__device__ __forceinline__ void cell_soil(const CellParams &p, const CellForc &f, double ysf, double yus, double ygw,
+                                          CellVert &r) {
     double deficit = p.aqd - ygw, satn, theta, satKr;
     const double kmax = p.infKsatV * (1. - p.hAreaF) + p.macKsatV * p.hAreaF;
     if (deficit <= 0.) {
@@ -320,6 +322,14 @@ __device__ __forceinline__ CellVert cell_vertical(const CellParams &p, const Cel
         }
         r.rech = qr * f.fuSub;
     }
+}
+
+__device__ __forceinline__ CellVert cell_vertical(const CellParams &p, const CellForc &f, double ysf, double yus,
+                                                  double ygw, double satn_prev, double eic_in) {
+    CellVert r;
+    r.err = 0;
+    cell_et(p, f, ysf, yus, ygw, satn_prev, eic_in, r);
+    cell_soil(p, f, ysf, yus, ygw, r);
     return r;
 }
 

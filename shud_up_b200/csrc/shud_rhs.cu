@@ -297,7 +297,13 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
 // the one-thread-per-cell form, with no extra HBM traffic.  No atomics; every sum in a fixed order.
 // ---------------------------------------------------------------------------------------------
 constexpr int TILE = 128;
+constexpr int V_NIN = 26;     // per-cell inputs of the vertical role
 constexpr int SEGCAP = 256;  // segment slots per tile kept in shared memory (more: read back from global)
+// 8-byte asynchronous copy global -> shared (SASS: LDGSTS)
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -307,6 +313,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE];
     __shared__ double x_P1[TILE], x_Es[TILE], x_G1[TILE], x_Eg[TILE], x_Tg[TILE], x_isf2[TILE];
     __shared__ double sq_s[SEGCAP], sq_g[SEGCAP];  // river-segment fluxes of the tile, slot order
+    __shared__ double v_in[V_NIN][TILE];           // inputs of the vertical role, landed by cp.async
     const int Ne = m.Ne;
     const size_t NE = (size_t)Ne;
     const size_t LD = (size_t)m.ld;  // padded leading dimension of the static [3][.] arrays
@@ -318,17 +325,30 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     const unsigned fl = __ldg(m.flags + ic);
     if (threadIdx.x >= TILE) {
         // =============================== vertical role ===============================
-        const double ysf = Y[ic], yus = Y[NE + ic], ygw_raw = Y[2 * NE + ic];
-        const double satn_prev = m.satn[ic], eic_in = m.eic[ic];
+        // The 26 inputs of this role go global -> shared memory with per-thread 8-byte cp.async (LDGSTS): all
+        // of them are in flight at once and none is parked in a register.  (With plain loads and a 64-register
+        // budget the compiler spills freshly loaded values, and every spill store waits for its load, which
+        // serialises the load phase into several DRAM round trips.)
+        {
+            const double *const src[V_NIN] = {Y + ic, Y + NE + ic, Y + 2 * NE + ic, m.satn + ic, m.eic + ic, m.netPrep + ic,
+                                              m.potEvap + ic, m.potTran + ic, m.lai + ic, m.fuSurf + ic, m.fuSub + ic,
+                                              m.aqd + ic, m.sy + ic, m.infD + ic, m.infKsatV + ic, m.macKsatV + ic,
+                                              m.hAreaF + ic, m.thetaS + ic, m.thetaR + ic, m.thetaFC + ic, m.beta + ic,
+                                              m.ksatV + ic, m.vegFrac + ic, m.impAF + ic, m.wetland + ic, m.rootReach + ic};
+#pragma unroll
+            for (int a = 0; a < V_NIN; a++) cp_async8(&v_in[a][lane_cell], src[a]);
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        }
+#define VIN(a) v_in[a][lane_cell]
+        const double ysf = VIN(0), yus = VIN(1), ygw_raw = VIN(2);
+        const double satn_prev = VIN(3), eic_in = VIN(4);
         CellForc f;
-        f.netPrep = __ldg(m.netPrep + ic); f.potEvap = __ldg(m.potEvap + ic); f.potTran = __ldg(m.potTran + ic);
-        f.lai = __ldg(m.lai + ic); f.fuSurf = __ldg(m.fuSurf + ic); f.fuSub = __ldg(m.fuSub + ic);
+        f.netPrep = VIN(5); f.potEvap = VIN(6); f.potTran = VIN(7); f.lai = VIN(8); f.fuSurf = VIN(9); f.fuSub = VIN(10);
         CellParams p;
-        p.aqd = __ldg(m.aqd + ic); p.sy = __ldg(m.sy + ic); p.infD = __ldg(m.infD + ic);
-        p.infKsatV = __ldg(m.infKsatV + ic); p.macKsatV = __ldg(m.macKsatV + ic); p.hAreaF = __ldg(m.hAreaF + ic);
-        p.thetaS = __ldg(m.thetaS + ic); p.thetaR = __ldg(m.thetaR + ic); p.thetaFC = __ldg(m.thetaFC + ic);
-        p.beta = __ldg(m.beta + ic); p.ksatV = __ldg(m.ksatV + ic); p.vegFrac = __ldg(m.vegFrac + ic);
-        p.impAF = __ldg(m.impAF + ic); p.wetland = __ldg(m.wetland + ic); p.rootReach = __ldg(m.rootReach + ic);
+        p.aqd = VIN(11); p.sy = VIN(12); p.infD = VIN(13); p.infKsatV = VIN(14); p.macKsatV = VIN(15); p.hAreaF = VIN(16);
+        p.thetaS = VIN(17); p.thetaR = VIN(18); p.thetaFC = VIN(19); p.beta = VIN(20); p.ksatV = VIN(21);
+        p.vegFrac = VIN(22); p.impAF = VIN(23); p.wetland = VIN(24); p.rootReach = VIN(25);
+#undef VIN
         const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
         CellVert v;
         if (fl & F_LAKE) {
