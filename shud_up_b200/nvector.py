@@ -266,3 +266,48 @@ class DeviceSPGMR:
             self.close()
         except Exception:
             pass
+
+
+class DistributedOps:
+    """N_Vector ops of a vector distributed over the ranks of a torch.distributed group (one partition per GPU):
+    streaming ops are local; every reduction is the local kernel followed by an allreduce of the scalar(s)
+    (SUNDIALS' nvdotprodlocal / nvwsqrsumlocal / nvmaxnormlocal / nvminlocal + nvgetcommunicator pattern).
+    `local` is an NVectorOps (or any table with the same N_V* methods); n_global = sum of the local lengths."""
+
+    def __init__(self, local, dist, device, n_global):
+        import torch
+        self._l, self._dist, self._torch, self._dev, self.n_global = local, dist, torch, device, int(n_global)
+
+    def __getattr__(self, name):          # streaming and fused streaming ops: purely local
+        return getattr(self._l, name)
+
+    def _allreduce(self, vals, op):
+        t = self._torch.tensor(vals, dtype=self._torch.float64, device=self._dev)
+        self._dist.all_reduce(t, op=op)
+        return t.tolist()
+
+    def N_VDotProd(self, x, y):
+        return self._allreduce([self._l.N_VDotProd(x, y)], self._dist.ReduceOp.SUM)[0]
+
+    def N_VDotProdMulti(self, x, Y):
+        import numpy as np
+        return np.array(self._allreduce(list(self._l.N_VDotProdMulti(x, Y)), self._dist.ReduceOp.SUM))
+
+    def N_VMaxNorm(self, x):
+        return self._allreduce([self._l.N_VMaxNorm(x)], self._dist.ReduceOp.MAX)[0]
+
+    def N_VMin(self, x):
+        return self._allreduce([self._l.N_VMin(x)], self._dist.ReduceOp.MIN)[0]
+
+    def N_VL1Norm(self, x):
+        return self._allreduce([self._l.N_VL1Norm(x)], self._dist.ReduceOp.SUM)[0]
+
+    def N_VWSqrSumLocal(self, x, w):
+        return self._l.N_VWSqrSumLocal(x, w)
+
+    def N_VWrmsNorm(self, x, w):
+        s = self._allreduce([self._l.N_VWSqrSumLocal(x, w)], self._dist.ReduceOp.SUM)[0]
+        return (s / self.n_global) ** 0.5
+
+    def N_VWL2Norm(self, x, w):
+        return self._allreduce([self._l.N_VWSqrSumLocal(x, w)], self._dist.ReduceOp.SUM)[0] ** 0.5

@@ -17,6 +17,10 @@ class HostOps:
     def N_VDotProd(self, x, y): return float(np.dot(x, y))
     def N_VWrmsNorm(self, x, w): return float(np.sqrt(np.sum((x * w) ** 2) / x.size))
     def N_VMaxNorm(self, x): return float(np.abs(x).max())
+    def N_VMin(self, x): return float(x.min())
+    def N_VL1Norm(self, x): return float(np.abs(x).sum())
+    def N_VWSqrSumLocal(self, x, w): return float(np.sum((x * w) ** 2))
+    def N_VDotProdMulti(self, x, Y): return np.array([float(np.dot(x, y)) for y in Y])
 
     def N_VLinearCombination(self, c, X, z):
         s = c[0] * X[0]

@@ -121,6 +121,44 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_nvec_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from host_model import HostOps
+    from shud_up_b200.nvector import DistributedOps
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    xg, yg, wg = rng.standard_normal(1001), rng.standard_normal(1001), rng.uniform(0.5, 2, 1001)
+    sl = slice(0, 400) if rank == 0 else slice(400, 1001)      # uneven partition of one global vector
+    ops = DistributedOps(HostOps(), dist, torch.device("cpu"), n_global=1001)
+    x, y, w = xg[sl].copy(), yg[sl].copy(), wg[sl].copy()
+    res = dict(dot=ops.N_VDotProd(x, y), wrms=ops.N_VWrmsNorm(x, w), mx=ops.N_VMaxNorm(x), mn=ops.N_VMin(x),
+               l1=ops.N_VL1Norm(x), multi=ops.N_VDotProdMulti(x, [y, w]).tolist())
+    ref = dict(dot=float(xg @ yg), wrms=float(np.sqrt(np.sum((xg * wg) ** 2) / 1001)), mx=float(np.abs(xg).max()),
+               mn=float(xg.min()), l1=float(np.abs(xg).sum()), multi=[float(xg @ yg), float(xg @ wg)])
+    ok = all(np.allclose(res[k], ref[k], rtol=1e-13) for k in ref)
+    q.put((rank, ok, res["dot"]))
+    dist.destroy_process_group()
+
+
+def test_distributed_nvector_reductions_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_gloo_nvec_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == res[1][2]          # every rank holds the same global value
+
+
 def test_halo_exchange_over_gloo_world_size_2():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
