@@ -145,6 +145,15 @@ int shud_b200_perm(const shud_ctx *ctx, int32_t *cell_perm /*[Ne]*/, int32_t *re
  * returns the device error word (0, or SHUD_ERRNAN / SHUD_ERRDATAIN / SHUD_ERRRIVBC). */
 int shud_b200_rhs_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
 int shud_b200_rhs(shud_ctx *ctx, double t, const double *y_host, double *ydot_host);
+/* The RHS of a partition in two parts, so that the halo exchange overlaps the bulk of the work: _interior needs no
+ * exchanged data (effKH of the owned cells + every tile of cells that sees no halo cell); _boundary (after the
+ * exchange has landed in the halo state buffer) does the halo effKH, the remaining tiles and the river/lake kernel.
+ * interior followed by boundary == shud_b200_rhs_dev.  `halo_stream` (cudaStream_t) is the stream on which the
+ * exchange completes: the halo-dependent tiles are enqueued there (behind an event for the owned cells' effKH) and
+ * run beside the interior tiles; the context stream then waits for them before the river/lake kernel.  NULL = the
+ * context stream (the exchange was ordered on it; everything serial). */
+int shud_b200_rhs_interior_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+int shud_b200_rhs_boundary_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev, void *halo_stream);
 /* One launch of the RHS sequence alone (stage 0 effKH pre-pass, 1 cell kernel, 2 river+lake kernel):
  * for per-kernel CUDA-event timing and ncu; shud_b200_rhs_dev == stages 0,1,2 in order. */
 int shud_b200_rhs_stage_dev(shud_ctx *ctx, int stage, const double *y_dev, double *ydot_dev);

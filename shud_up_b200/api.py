@@ -59,6 +59,8 @@ def lib():
         "shud_b200_rhs_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_stage_dev": (C.c_int, [vp, C.c_int, vp, vp]),
+        "shud_b200_rhs_interior_dev": (C.c_int, [vp, C.c_double, vp, vp]),
+        "shud_b200_rhs_boundary_dev": (C.c_int, [vp, C.c_double, vp, vp, vp]),
         "shud_b200_rhs_diag_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_get_diag": (C.c_int, [vp, C.POINTER(abi.ShudDiag)]),
         "shud_b200_output_accumulate": (C.c_int, [vp]),
@@ -189,6 +191,16 @@ class ShudRHS:
         """asynchronous RHS on device vectors in device order (torch cuda float64 tensors)."""
         fn = lib().shud_b200_rhs_diag_dev if diag else lib().shud_b200_rhs_dev
         _chk(fn(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "shud_b200_rhs_dev")
+
+    def f_interior_dev(self, t, y_dev, ydot_dev):
+        """part of the RHS of a partition that needs no exchanged halo data (overlaps the halo exchange)"""
+        _chk(lib().shud_b200_rhs_interior_dev(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "rhs_interior_dev")
+
+    def f_boundary_dev(self, t, y_dev, ydot_dev, halo_stream=None):
+        """the rest of the RHS, after the halo exchange has landed; `halo_stream` = the torch stream the exchange
+        completes on (its halo-dependent tiles run there, beside the interior tiles), None = the context stream"""
+        hs = C.c_void_p(halo_stream.cuda_stream) if halo_stream is not None else None
+        _chk(lib().shud_b200_rhs_boundary_dev(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev), hs), "rhs_boundary_dev")
 
     def f_stage_dev(self, stage, y_dev, ydot_dev):
         _chk(lib().shud_b200_rhs_stage_dev(self._h, int(stage), _ptr(y_dev), _ptr(ydot_dev)), "rhs_stage_dev")

@@ -86,11 +86,11 @@ __device__ __forceinline__ void raise_err(int *err, int code, int where) {
 // ---------------------------------------------------------------------------------------------
 // K0: horizontal effective conductivity of every cell (neighbours need it before any edge flux)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restrict__ Y) {
+__global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restrict__ Y, int first) {
     // programmatic dependent launch: the cell kernel may start now; it waits (griddepcontrol.wait) only where it
     // first needs effKH, so its vertical role overlaps this pre-pass
     asm volatile("griddepcontrol.launch_dependents;");
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;  // first = 0, or Ne for the halo cells alone
     if (i >= m.Ne) {
         const int h = i - m.Ne;  // halo cell: same formula on the exchanged groundwater head
         if (h < m.Nhalo) {
@@ -309,7 +309,7 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 
 template <bool DIAG, int MINB>
 __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, const double *__restrict__ Y,
-                                                          double *__restrict__ DY) {
+                                                          double *__restrict__ DY, const int *__restrict__ tiles) {
     __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE];
     __shared__ double x_P1[TILE], x_Es[TILE], x_G1[TILE], x_Eg[TILE], x_Tg[TILE], x_isf2[TILE];
     __shared__ double sq_s[SEGCAP], sq_g[SEGCAP];  // river-segment fluxes of the tile, slot order
@@ -1058,6 +1058,10 @@ struct shud_ctx {
     size_t h_pinned_n = 0;
     bool has_ebc_arrays = false;
     int fused_minb = 4;
+    // partition: tiles whose cells see no halo cell (interior) / the others (boundary) - overlap of the exchange
+    int *d_int_tiles = nullptr, *d_bnd_tiles = nullptr;
+    int n_int_tiles = 0, n_bnd_tiles = 0;
+    cudaEvent_t ev_kh = nullptr, ev_bnd = nullptr;  // effKH of the owned cells done / boundary tiles done (rhs_boundary_dev)
     int pipe_grid = 296;  // persistent blocks of k_pipe: 2 per SM (2 stages) or 4 per SM (1 stage)
     int pipe_stages = 2;
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
@@ -1387,6 +1391,18 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         CK(cudaMemset(m.l_evap_raw, 0, sizeof(double) * std::max(Nl, 1)));
         CK(cudaMemset(m.l_prcp, 0, sizeof(double) * std::max(Nl, 1)));
     }
+    // ---- interior / boundary tiles of a partition ----
+    {
+        const int ntile = (Ne + TILE - 1) / TILE;
+        std::vector<char> isb(ntile, 0);
+        for (int j = 0; j < 3; j++)
+            for (int i = 0; i < Ne; i++)
+                if (nbr[(size_t)j * LDh + i] >= Ne) isb[i / TILE] = 1;
+        std::vector<int> it, bt;
+        for (int t = 0; t < ntile; t++) (isb[t] ? bt : it).push_back(t);
+        c->n_int_tiles = (int)it.size(); c->n_bnd_tiles = (int)bt.size();
+        c->d_int_tiles = dev_upload(c, it); c->d_bnd_tiles = dev_upload(c, bt);
+    }
     // ---- halo cells of a partition ----
     m.Nhalo = Nhalo;
     c->Nhalo = Nhalo;
@@ -1435,6 +1451,8 @@ void shud_b200_destroy(shud_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->ev_kh) cudaEventDestroy(c->ev_kh);
+    if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1610,27 +1628,27 @@ static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4>, c->m, c->diag, y, ydot) == cudaSuccess) return;
+        if (cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4>, c->m, c->diag, y, ydot, (const int *)nullptr) == cudaSuccess) return;
         cudaGetLastError();
         c->use_pdl = 0;
     }
     switch (c->fused_minb) {
-        case 2: k_fused<DIAG, 2><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
-        case 3: k_fused<DIAG, 3><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
-        default: k_fused<DIAG, 4><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
+        case 2: k_fused<DIAG, 2><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, nullptr); break;
+        case 3: k_fused<DIAG, 3><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, nullptr); break;
+        default: k_fused<DIAG, 4><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, nullptr); break;
     }
 }
 template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     const int Ne = c->Ne;
     if (c->split == 3) {
-        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
         launch_pipe<DIAG>(c, y, ydot);
     } else if (c->split == 2) {
-        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
         launch_fused<DIAG>(c, y, ydot, true);
     } else {
-        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
         launch_cell<DIAG>(c, y, ydot);
     }
     const int nb_riv = (c->Nr + 127) / 128;
@@ -1679,13 +1697,51 @@ int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     return SHUD_OK;
 }
 
+// The RHS of a partition in two parts so that the halo exchange overlaps the bulk of the work:
+//   interior: effKH of the owned cells + the cell kernel on every tile that sees no halo cell (needs no exchanged data)
+//   boundary: effKH of the halo cells + the cell kernel on the remaining tiles + the river/lake kernel
+int shud_b200_rhs_interior_dev(shud_ctx *c, double t, const double *y, double *ydot) {
+    (void)t;
+    if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    k_effkh<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
+    if (!c->ev_kh) {
+        CK(cudaEventCreateWithFlags(&c->ev_kh, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->ev_kh, c->stream));
+    if (c->n_int_tiles > 0)
+        k_fused<false, 4><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, c->d_int_tiles);
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *ydot, void *halo_stream) {
+    (void)t;
+    if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    // the halo-dependent tiles go on the stream the exchange completes on: they run beside the interior tiles of
+    // the context stream (a few hundred blocks in the gaps of ~8000) instead of as a short serial pass behind them
+    cudaStream_t hs = halo_stream ? (cudaStream_t)halo_stream : c->stream;
+    const bool side = hs != c->stream && c->ev_kh;
+    if (side) CK(cudaStreamWaitEvent(hs, c->ev_kh, 0));
+    if (c->Nhalo > 0) k_effkh<<<(c->Nhalo + 255) / 256, 256, 0, hs>>>(c->m, y, c->Ne);
+    if (c->n_bnd_tiles > 0)
+        k_fused<false, 4><<<c->n_bnd_tiles, 2 * TILE, 0, hs>>>(c->m, c->diag, y, ydot, c->d_bnd_tiles);
+    if (side) {
+        CK(cudaEventRecord(c->ev_bnd, hs));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
+    }
+    const int nb_riv = (c->Nr + 127) / 128;
+    if (nb_riv + c->Nl > 0) k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+
 // one launch of the sequence on its own (profiling / per-kernel CUDA-event timing in bench.py)
 int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydot) {
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
     if (c->split == 3 && stage == 1) launch_pipe<false>(c, y, ydot);
     else if (c->split == 2 && stage == 1) launch_fused<false>(c, y, ydot);
-    else if (stage == 0) k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y);
+    else if (stage == 0) k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
     else if (stage == 1) launch_cell<false>(c, y, ydot);
     else if (stage == 2 && nb_riv + c->Nl > 0)
         k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);

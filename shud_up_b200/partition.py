@@ -189,10 +189,54 @@ class HaloExchange:
         self.sbuf = torch.zeros(2 * max(ns, 1), dtype=torch.float64, device=device)
         self.rbuf = torch.zeros(2 * max(nr, 1), dtype=torch.float64, device=device)
         self.in_place = bool(nr == 0 or np.array_equal(pos, np.arange(nr)))
+        self.side, self._work = None, None
         self.halo_state = self.rbuf if self.in_place else torch.zeros(2 * max(nr, 1), dtype=torch.float64, device=device)
         self.ns, self.nr = ns, nr
         self.pack_fn = pack_fn
         self.bytes_per_exchange = 16 * ns
+
+    def start(self, y):
+        """pack on the current stream and post the exchange on the side stream `self.side`: the caller overlaps it
+        with the interior part of the RHS (ShudRHS.f_interior_dev), then calls finish() and hands the side stream to
+        ShudRHS.f_boundary_dev, which runs the halo-dependent tiles there"""
+        import torch
+        ns, nr = self.ns, self.nr
+        if self.pack_fn is not None:
+            if ns:
+                self.pack_fn(y, self.send_idx, self.sbuf)
+        elif ns:
+            idx = self.send_idx.long()
+            self.sbuf[0:2 * ns:2] = y[idx]
+            self.sbuf[1:2 * ns:2] = y[2 * self.Ne + idx]
+        self._work = None
+        if self.side is None and y.is_cuda:
+            self.side = torch.cuda.Stream(device=y.device, priority=-1)
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream(y.device))
+        if self.world > 1:
+            if self.side is not None:
+                with torch.cuda.stream(self.side):
+                    self._work = self._post()
+            else:
+                self._work = self._post()
+
+    def _post(self):
+        return self.dist.all_to_all_single(self.rbuf[:2 * self.nr], self.sbuf[:2 * self.ns], [2 * c for c in self.recv_counts],
+                                           [2 * c for c in self.send_counts], async_op=True)
+
+    def finish(self):
+        """order the side stream (CPU tensors: the caller) behind the posted exchange; returns the side stream, on
+        which the halo state buffer is then valid (None on CPU)"""
+        import contextlib
+        import torch
+        ctx = torch.cuda.stream(self.side) if self.side is not None else contextlib.nullcontext()
+        with ctx:
+            if self._work is not None:
+                self._work.wait()
+                self._work = None
+            if self.nr and not self.in_place:
+                self.halo_state.view(-1, 2)[:self.nr].index_copy_(0, self.recv_pos, self.rbuf[:2 * self.nr].view(-1, 2))
+        return self.side
 
     def exchange(self, y):
         """y: my state vector [3 Ne + Nr + Nl] (device order of the context when pack_fn is the CUDA pack).

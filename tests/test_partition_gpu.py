@@ -70,6 +70,27 @@ def test_two_partitions_equal_single_domain_bitwise():
         sel = pos[loc["own_gid"]]
         for b in range(3):
             assert np.array_equal(got[b * ne:(b + 1) * ne], ref[b * Ne + sel]), (p, b)
+        # the interior / boundary split (what overlaps the NCCL exchange) gives the same bits
+        r.prime(loc["y"]); r.set_forcing(loc, qEleE_IC=loc["qEleE_IC_in"])
+        yd2 = torch.full_like(ydd, float("nan"))
+        with torch.cuda.stream(s):
+            r.f_interior_dev(0.0, yy, yd2)
+            r.f_boundary_dev(0.0, yy, yd2)
+            r.from_device_order(yd2, ydr)
+        s.synchronize()
+        assert r.check()[0] == 0
+        assert np.array_equal(ydr.cpu().numpy(), got)
+        # ... and with the halo-dependent tiles on a second stream (where the exchange completes)
+        side = torch.cuda.Stream(priority=-1)
+        r.prime(loc["y"]); r.set_forcing(loc, qEleE_IC=loc["qEleE_IC_in"])
+        yd3 = torch.full_like(ydd, float("nan"))
+        with torch.cuda.stream(s):
+            r.f_interior_dev(0.0, yy, yd3)
+            r.f_boundary_dev(0.0, yy, yd3, halo_stream=side)
+            r.from_device_order(yd3, ydr)
+        s.synchronize()
+        assert r.check()[0] == 0
+        assert np.array_equal(ydr.cpu().numpy(), got)
     # reaches: both partitions own whole trees; their ydot equals the single-domain one (same tree order)
     nr0 = ctxs[0][0].Nr
     assert np.array_equal(np.r_[ctxs[0][4].cpu().numpy()[3 * ctxs[0][0].Ne:], ctxs[1][4].cpu().numpy()[3 * ctxs[1][0].Ne:]],
