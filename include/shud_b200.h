@@ -153,6 +153,8 @@ int shud_b200_rhs(shud_ctx *ctx, double t, const double *y_host, double *ydot_ho
  * run beside the interior tiles; the context stream then waits for them before the river/lake kernel.  NULL = the
  * context stream (the exchange was ordered on it; everything serial). */
 int shud_b200_rhs_interior_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+/* number of 128-cell tiles in each part (interior + boundary = ceil(Ne/128)) */
+int shud_b200_tile_counts(const shud_ctx *ctx, int *n_interior, int *n_boundary);
 int shud_b200_rhs_boundary_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev, void *halo_stream);
 /* One launch of the RHS sequence alone (stage 0 effKH pre-pass, 1 cell kernel, 2 river+lake kernel):
  * for per-kernel CUDA-event timing and ncu; shud_b200_rhs_dev == stages 0,1,2 in order. */

@@ -117,8 +117,8 @@ def make_mesh(snap):
             a, p = conv(snap[_key(snap, n)])
             keep.append(a)
             setattr(m, n, p)
-    for n in ("x", "y"):  # optional centroids
-        src = snap.get(n, snap.get("ele_" + n))
+    for n in ("x", "y"):  # optional centroids ("y" alone is the state vector of a snapshot, never a centroid)
+        src = snap.get("ele_" + n)
         if src is not None:
             a, p = _d(src)
             keep.append(a)

@@ -61,6 +61,7 @@ def lib():
         "shud_b200_rhs_stage_dev": (C.c_int, [vp, C.c_int, vp, vp]),
         "shud_b200_rhs_interior_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_boundary_dev": (C.c_int, [vp, C.c_double, vp, vp, vp]),
+        "shud_b200_tile_counts": (C.c_int, [vp, _PI, _PI]),
         "shud_b200_rhs_diag_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_get_diag": (C.c_int, [vp, C.POINTER(abi.ShudDiag)]),
         "shud_b200_output_accumulate": (C.c_int, [vp]),
@@ -201,6 +202,12 @@ class ShudRHS:
         completes on (its halo-dependent tiles run there, beside the interior tiles), None = the context stream"""
         hs = C.c_void_p(halo_stream.cuda_stream) if halo_stream is not None else None
         _chk(lib().shud_b200_rhs_boundary_dev(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev), hs), "rhs_boundary_dev")
+
+    def tile_counts(self):
+        """(interior, boundary) 128-cell tiles of this partition"""
+        a, b = C.c_int(0), C.c_int(0)
+        _chk(lib().shud_b200_tile_counts(self._h, C.byref(a), C.byref(b)), "tile_counts")
+        return a.value, b.value
 
     def f_stage_dev(self, stage, y_dev, ydot_dev):
         _chk(lib().shud_b200_rhs_stage_dev(self._h, int(stage), _ptr(y_dev), _ptr(ydot_dev)), "rhs_stage_dev")

@@ -262,25 +262,38 @@ __device__ __forceinline__ void cell_et(const CellParams &p, const CellForc &f, 
     }
 }
 
-__device__ __forceinline__ void cell_soil(const CellParams &p, const CellForc &f, double ysf, double yus, double ygw,
-                                          CellVert &r) {
-    double deficit = p.aqd - ygw, satn, theta, satKr;
-    const double kmax = p.infKsatV * (1. - p.hAreaF) + p.macKsatV * p.hAreaF;
+// cell_soil in two steps, so that a caller short of registers can fetch the second step's inputs after the pow()s:
+//   cell_soil_state : updateElement -> deficit, theta, satn, satKr     (inputs aqd, thetaS, thetaR, beta)
+//   cell_soil_flux  : Flux_Infiltration + Flux_Recharge                 (everything else)
+struct SoilState {
+    double deficit, theta, satn, satKr;
+};
+__device__ __forceinline__ SoilState cell_soil_state(double aqd, double thetaS, double thetaR, double beta, double yus,
+                                                     double ygw) {
+    SoilState s;
+    double deficit = aqd - ygw, satn, theta, satKr;
     if (deficit <= 0.) {
         deficit = 0.;
         satn = 1.;
-        theta = p.thetaS;
+        theta = thetaS;
     } else {
-        theta = yus / deficit * p.thetaS;
-        satn = (theta - p.thetaR) / (p.thetaS - p.thetaR);
+        theta = yus / deficit * thetaS;
+        satn = (theta - thetaR) / (thetaS - thetaR);
     }
     if (satn > 0.99) {
-        satn = 1.0; satKr = 1.0; theta = p.thetaS;
+        satn = 1.0; satKr = 1.0; theta = thetaS;
     } else if (satn <= kZERO) {
-        satn = 0.; satKr = 0.; theta = p.thetaR;
+        satn = 0.; satKr = 0.; theta = thetaR;
     } else {
-        satKr = sat_kr(satn, p.beta);
+        satKr = sat_kr(satn, beta);
     }
+    s.deficit = deficit; s.theta = theta; s.satn = satn; s.satKr = satKr;
+    return s;
+}
+__device__ __forceinline__ void cell_soil_flux(const CellParams &p, const CellForc &f, double ysf, double yus, double ygw,
+                                               const SoilState &st, CellVert &r) {
+    const double deficit = st.deficit, theta = st.theta, satn = st.satn, satKr = st.satKr;
+    const double kmax = p.infKsatV * (1. - p.hAreaF) + p.macKsatV * p.hAreaF;
     r.satn = satn;
     // ---- infiltration / exfiltration ----
     {
@@ -322,6 +335,11 @@ __device__ __forceinline__ void cell_soil(const CellParams &p, const CellForc &f
         }
         r.rech = qr * f.fuSub;
     }
+}
+__device__ __forceinline__ void cell_soil(const CellParams &p, const CellForc &f, double ysf, double yus, double ygw,
+                                          CellVert &r) {
+    const SoilState st = cell_soil_state(p.aqd, p.thetaS, p.thetaR, p.beta, yus, ygw);
+    cell_soil_flux(p, f, ysf, yus, ygw, st, r);
 }
 
 __device__ __forceinline__ CellVert cell_vertical(const CellParams &p, const CellForc &f, double ysf, double yus,

@@ -309,7 +309,7 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 
 template <bool DIAG, int MINB>
 __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, const double *__restrict__ Y,
-                                                          double *__restrict__ DY, const int *__restrict__ tiles) {
+                                                          double *__restrict__ DY, int tile0) {
     __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE];
     __shared__ double x_P1[TILE], x_Es[TILE], x_G1[TILE], x_Eg[TILE], x_Tg[TILE], x_isf2[TILE];
     __shared__ double sq_s[SEGCAP], sq_g[SEGCAP];  // river-segment fluxes of the tile, slot order
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     const size_t NE = (size_t)Ne;
     const size_t LD = (size_t)m.ld;  // padded leading dimension of the static [3][.] arrays
     const int lane_cell = threadIdx.x & (TILE - 1);
-    const int i0 = blockIdx.x * TILE;
+    const int i0 = ((int)blockIdx.x + tile0) * TILE;  // tile0: first tile of this launch (interior / boundary parts)
     const int i = i0 + lane_cell;
     const bool valid = i < Ne;
     const int ic = valid ? i : Ne - 1;  // clamped index: tail threads load something harmless
@@ -340,30 +340,76 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         }
 #define VIN(a) v_in[a][lane_cell]
-        const double ysf = VIN(0), yus = VIN(1), ygw_raw = VIN(2);
-        const double satn_prev = VIN(3), eic_in = VIN(4);
-        CellForc f;
-        f.netPrep = VIN(5); f.potEvap = VIN(6); f.potTran = VIN(7); f.lai = VIN(8); f.fuSurf = VIN(9); f.fuSub = VIN(10);
-        CellParams p;
-        p.aqd = VIN(11); p.sy = VIN(12); p.infD = VIN(13); p.infKsatV = VIN(14); p.macKsatV = VIN(15); p.hAreaF = VIN(16);
-        p.thetaS = VIN(17); p.thetaR = VIN(18); p.thetaFC = VIN(19); p.beta = VIN(20); p.ksatV = VIN(21);
-        p.vegFrac = VIN(22); p.impAF = VIN(23); p.wetland = VIN(24); p.rootReach = VIN(25);
-#undef VIN
-        const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
-        CellVert v;
-        if (fl & F_LAKE) {
-            v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
-            v.satn = 1.; v.infil = v.exfil = v.rech = 0.; v.err = 0;
-        } else {
-            v = cell_vertical(p, f, ysf, yus, ygw, satn_prev, eic_in);
+#define VFENCE() asm volatile("" ::: "memory")
+        // The role runs in three steps, each fetching only its own inputs from the staged slots and parking what a
+        // later step needs back in shared memory: nothing is held in a register across the pow() calls of the
+        // middle step (the 64-register budget would spill it to local memory, i.e. to L2).
+        int verr = 0;
+        if (fl & F_HEADBC) VIN(2) = m.ele_yBC[ic];
+        // ---- step 1: ET partition (f_etFlux) -> x_Es, x_Eg, x_Tg; Eu, Tu parked in slots 6, 7; carried E_IC ----
+        {
+            CellVert v;
+            v.err = 0;
+            const double potEvap = VIN(6);
+            if (fl & F_LAKE) {
+                v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
+            } else {
+                CellParams p;
+                CellForc f;
+                p.thetaS = VIN(17); p.thetaR = VIN(18); p.vegFrac = VIN(22); p.impAF = VIN(23); p.wetland = VIN(24);
+                p.rootReach = VIN(25);
+                f.potEvap = potEvap; f.potTran = VIN(7); f.lai = VIN(8);
+                cell_et(p, f, VIN(0), VIN(1), VIN(2), VIN(3), VIN(4), v);
+            }
+            x_Es[lane_cell] = v.Es; x_Eg[lane_cell] = v.Eg; x_Tg[lane_cell] = v.Tg;
+            VIN(6) = v.Eu; VIN(7) = v.Tu;
+            verr = v.err;
+            if (valid) {
+                m.eic[i] = v.eic;
+                if (DIAG) {
+                    if (fl & F_LAKE) {
+                        d.qEleTrans[i] = 0.; d.qEleEvapo[i] = potEvap; d.qEleETA[i] = 0. + potEvap + 0.;
+                    } else {
+                        const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
+                        d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
+                        d.iBeta[i] = v.iBeta;
+                    }
+                    d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
+                }
+            }
         }
-        double isf2 = ysf - v.infil + v.exfil;
-        x_P1[lane_cell] = f.netPrep - v.infil + v.exfil;
-        x_Es[lane_cell] = v.Es;
-        x_G1[lane_cell] = v.rech - v.exfil;
-        x_Eg[lane_cell] = v.Eg;
-        x_Tg[lane_cell] = v.Tg;
-        x_isf2[lane_cell] = dmax(0., isf2);
+        VFENCE();
+        // ---- step 2: updateElement (2 pow) ----
+        SoilState st;
+        if (fl & F_LAKE) { st.deficit = 0.; st.theta = 0.; st.satn = 1.; st.satKr = 0.; }
+        else st = cell_soil_state(VIN(11), VIN(17), VIN(18), VIN(20), VIN(1), VIN(2));
+        VFENCE();
+        // ---- step 3: infiltration / exfiltration / recharge, ydot[unsat], hand-over values ----
+        {
+            CellVert v;
+            v.satn = 1.; v.infil = v.exfil = v.rech = 0.;
+            const double ysf = VIN(0), netPrep = VIN(5);
+            if (!(fl & F_LAKE)) {
+                CellParams p;
+                CellForc f;
+                p.aqd = VIN(11); p.infD = VIN(13); p.infKsatV = VIN(14); p.macKsatV = VIN(15); p.hAreaF = VIN(16);
+                p.thetaR = VIN(18); p.thetaFC = VIN(19); p.ksatV = VIN(21);
+                f.netPrep = netPrep; f.fuSurf = VIN(9); f.fuSub = VIN(10);
+                cell_soil_flux(p, f, ysf, VIN(1), VIN(2), st, v);
+            }
+            const double isf2 = ysf - v.infil + v.exfil;
+            x_P1[lane_cell] = netPrep - v.infil + v.exfil;
+            x_G1[lane_cell] = v.rech - v.exfil;
+            x_isf2[lane_cell] = dmax(0., isf2);
+            if (valid) {
+                m.satn[i] = v.satn;
+                double dus = v.infil - v.rech - VIN(6) - VIN(7);
+                dus = SHUD_DIVS(dus, VIN(12));
+                if (fl & F_LAKE) dus = 0.;
+                DY[NE + i] = dus;
+                if (DIAG) { d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech; }
+            }
+        }
         // ---- river segments of the whole tile, one thread per segment slot (dense lanes instead of a per-cell
         //      loop at ~15 % lane use): fun_Seg_surface / fun_Seg_sub, MD_RiverFlux.cpp:100-126.  Needs the
         //      lateral role's staged tile (barrier 3) and every x_isf2 of this role (same barrier). ----
@@ -387,26 +433,9 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             }
         }
         bar_arrive(2, 2 * TILE);  // hand-over: the lateral warps wait on barrier 2
-        if (valid) {
-            m.eic[i] = v.eic;
-            m.satn[i] = v.satn;
-            double dus = v.infil - v.rech - v.Eu - v.Tu;
-            dus = SHUD_DIVS(dus, p.sy);
-            if (fl & F_LAKE) dus = 0.;
-            DY[NE + i] = dus;
-            if (v.err) raise_err(m.err, v.err, i + 1);
-            if (DIAG) {
-                if (fl & F_LAKE) {
-                    d.qEleTrans[i] = 0.; d.qEleEvapo[i] = f.potEvap; d.qEleETA[i] = 0. + f.potEvap + 0.;
-                } else {
-                    const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
-                    d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
-                    d.iBeta[i] = v.iBeta;
-                }
-                d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech;
-                d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
-            }
-        }
+        if (valid && verr) raise_err(m.err, verr, i + 1);
+#undef VIN
+#undef VFENCE
         return;
     }
     // =============================== lateral role ===============================
@@ -441,9 +470,12 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             if (k >= 0) {
                 double nsf, ygw_n, zs_n, zb_n, kh_n;
                 const unsigned r = (unsigned)(k - i0);
+#ifndef SHUD_NBR_GLOBAL
                 if (r < (unsigned)TILE) {  // neighbour inside the tile: shared memory
                     nsf = t_sf[r]; ygw_n = t_gw[r]; zs_n = t_zs[r]; zb_n = t_zb[r]; kh_n = t_kh[r];
-                } else if (k < Ne) {
+                } else
+#endif
+                if (k < Ne) {
                     nsf = Y[k]; ygw_n = Y[2 * NE + k]; zs_n = __ldg(m.z_surf + k); zb_n = __ldg(m.z_bottom + k);
                     kh_n = m.effKH[k];
                     if (m.has_headbc && (m.flags[k] & F_HEADBC)) ygw_n = m.ele_yBC[k];
@@ -1059,7 +1091,6 @@ struct shud_ctx {
     bool has_ebc_arrays = false;
     int fused_minb = 4;
     // partition: tiles whose cells see no halo cell (interior) / the others (boundary) - overlap of the exchange
-    int *d_int_tiles = nullptr, *d_bnd_tiles = nullptr;
     int n_int_tiles = 0, n_bnd_tiles = 0;
     cudaEvent_t ev_kh = nullptr, ev_bnd = nullptr;  // effKH of the owned cells done / boundary tiles done (rhs_boundary_dev)
     int pipe_grid = 296;  // persistent blocks of k_pipe: 2 per SM (2 stages) or 4 per SM (1 stage)
@@ -1167,6 +1198,33 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             key[i] = hilbert_d(hx, hy);
         }
         std::stable_sort(c->cperm.begin(), c->cperm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    }
+    // ---- a partition keeps the tiles that see a halo cell behind the others: the device order is
+    //      [interior tiles | boundary tiles (+ the ragged last tile)], so each part of the RHS is one contiguous
+    //      tile range (shud_b200_rhs_interior_dev / _boundary_dev) ----
+    {
+        const int ntile = (Ne + TILE - 1) / TILE, nfull = Ne / TILE;
+        c->n_int_tiles = ntile; c->n_bnd_tiles = 0;
+        if (Nhalo > 0) {
+            std::vector<char> isb(ntile, 0);
+            for (int i = 0; i < Ne; i++) {
+                const int o = c->cperm[i];
+                for (int j = 0; j < 3; j++)
+                    if (M->nabr[(size_t)j * Ne + o] - 1 >= Ne) isb[i / TILE] = 1;
+            }
+            std::vector<int> order;
+            order.reserve(Ne);
+            int n_int = 0;
+            for (int pass = 0; pass < 2; pass++)
+                for (int t = 0; t < nfull; t++)
+                    if ((int)isb[t] == pass) {
+                        if (!pass) n_int++;
+                        for (int k = 0; k < TILE; k++) order.push_back(c->cperm[(size_t)t * TILE + k]);
+                    }
+            for (int i = nfull * TILE; i < Ne; i++) order.push_back(c->cperm[i]);
+            c->cperm.swap(order);
+            c->n_int_tiles = n_int; c->n_bnd_tiles = ntile - n_int;
+        }
     }
     c->cinv.resize(Ne);
     for (int i = 0; i < Ne; i++) c->cinv[c->cperm[i]] = i;
@@ -1390,18 +1448,6 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         m.l_evap_raw = dev_alloc<double>(c, Nl); m.l_prcp = dev_alloc<double>(c, Nl);
         CK(cudaMemset(m.l_evap_raw, 0, sizeof(double) * std::max(Nl, 1)));
         CK(cudaMemset(m.l_prcp, 0, sizeof(double) * std::max(Nl, 1)));
-    }
-    // ---- interior / boundary tiles of a partition ----
-    {
-        const int ntile = (Ne + TILE - 1) / TILE;
-        std::vector<char> isb(ntile, 0);
-        for (int j = 0; j < 3; j++)
-            for (int i = 0; i < Ne; i++)
-                if (nbr[(size_t)j * LDh + i] >= Ne) isb[i / TILE] = 1;
-        std::vector<int> it, bt;
-        for (int t = 0; t < ntile; t++) (isb[t] ? bt : it).push_back(t);
-        c->n_int_tiles = (int)it.size(); c->n_bnd_tiles = (int)bt.size();
-        c->d_int_tiles = dev_upload(c, it); c->d_bnd_tiles = dev_upload(c, bt);
     }
     // ---- halo cells of a partition ----
     m.Nhalo = Nhalo;
@@ -1628,14 +1674,14 @@ static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4>, c->m, c->diag, y, ydot, (const int *)nullptr) == cudaSuccess) return;
+        if (cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4>, c->m, c->diag, y, ydot, 0) == cudaSuccess) return;
         cudaGetLastError();
         c->use_pdl = 0;
     }
     switch (c->fused_minb) {
-        case 2: k_fused<DIAG, 2><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, nullptr); break;
-        case 3: k_fused<DIAG, 3><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, nullptr); break;
-        default: k_fused<DIAG, 4><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, nullptr); break;
+        case 2: k_fused<DIAG, 2><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0); break;
+        case 3: k_fused<DIAG, 3><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0); break;
+        default: k_fused<DIAG, 4><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0); break;
     }
 }
 template <bool DIAG>
@@ -1710,7 +1756,7 @@ int shud_b200_rhs_interior_dev(shud_ctx *c, double t, const double *y, double *y
     }
     CK(cudaEventRecord(c->ev_kh, c->stream));
     if (c->n_int_tiles > 0)
-        k_fused<false, 4><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, c->d_int_tiles);
+        k_fused<false, 4><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
     CK(cudaGetLastError());
     return SHUD_OK;
 }
@@ -1724,7 +1770,7 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
     if (side) CK(cudaStreamWaitEvent(hs, c->ev_kh, 0));
     if (c->Nhalo > 0) k_effkh<<<(c->Nhalo + 255) / 256, 256, 0, hs>>>(c->m, y, c->Ne);
     if (c->n_bnd_tiles > 0)
-        k_fused<false, 4><<<c->n_bnd_tiles, 2 * TILE, 0, hs>>>(c->m, c->diag, y, ydot, c->d_bnd_tiles);
+        k_fused<false, 4><<<c->n_bnd_tiles, 2 * TILE, 0, hs>>>(c->m, c->diag, y, ydot, c->n_int_tiles);
     if (side) {
         CK(cudaEventRecord(c->ev_bnd, hs));
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
@@ -1732,6 +1778,13 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
     const int nb_riv = (c->Nr + 127) / 128;
     if (nb_riv + c->Nl > 0) k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
     CK(cudaGetLastError());
+    return SHUD_OK;
+}
+
+int shud_b200_tile_counts(const shud_ctx *c, int *n_interior, int *n_boundary) {
+    if (!c) return SHUD_ERR_ARG;
+    if (n_interior) *n_interior = c->n_int_tiles;
+    if (n_boundary) *n_boundary = c->n_bnd_tiles;
     return SHUD_OK;
 }
 

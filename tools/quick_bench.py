@@ -11,6 +11,10 @@ from shud_up_b200.api import ShudRHS
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 size = sys.argv[2] if len(sys.argv) > 2 else "1M"
 mesh = synth.make(**synth.named(size))
+order = os.environ.get("QB_ORDER", "hilbert")  # experiment: what the locality ordering is worth
+if order == "xsort": mesh["ele_y"] = np.zeros_like(mesh["ele_y"])
+elif order == "ysort": mesh["ele_x"] = np.zeros_like(mesh["ele_x"])
+elif order == "none": mesh.pop("ele_x"); mesh.pop("ele_y")
 rhs = ShudRHS(mesh)
 rhs.set_forcing(mesh, qEleE_IC=mesh["qEleE_IC_in"])
 rhs.prime(mesh["y"])
@@ -34,5 +38,11 @@ Ne, Nr, Ns = rhs.Ne, rhs.Nr, rhs.Ns
 b = 392 * Ne + 124 * Nr + 72 * Ns
 res["rhs_GBs"] = b / res["rhs_us"] / 1e3
 res["Gcells_s"] = Ne / res["rhs_us"] / 1e3
+with torch.cuda.stream(st):
+    rhs.prime(mesh["y"]); rhs.set_forcing(mesh, qEleE_IC=mesh["qEleE_IC_in"])
+    rhs.f_dev(0.0, y, ydot); rhs.from_device_order(ydot, y_ref)
+st.synchronize()
+yd = y_ref.cpu().numpy()
+res["sum"] = float(np.cumsum(yd)[-1]); res["asum"] = float(np.cumsum(np.abs(yd))[-1])
 res["code"] = rhs.check()[0]
 print(json.dumps(res))
