@@ -48,6 +48,8 @@ struct DevMesh {
     const int *cs_seg, *cs_riv, *cs_bc;  // segment id (device order), reach id (device order), reach BC code
     const int *cs_cell;                  // owning cell (device order) of the slot
     const double *cs_len, *cs_cwr, *cs_depth, *cs_zbank, *cs_ksatH, *cs_bed;
+    const double *cs_zr, *cs_zbk;        // z_surf[cell] - depth (river bed), z_surf[cell] + zbank (bank top): static
+    double *cs_yr;                       // stage of the slot's reach for this call (BC applied), written by k_effkh
     // forcing step
     double *netPrep, *potEvap, *potTran, *lai, *fuSurf, *fuSub, *eic, *satn, *ele_yBC, *ele_QBC;
     // work
@@ -90,6 +92,14 @@ __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restri
     // programmatic dependent launch: the cell kernel may start now; it waits (griddepcontrol.wait) only where it
     // first needs effKH, so its vertical role overlaps this pre-pass
     asm volatile("griddepcontrol.launch_dependents;");
+    if (first == 0) {
+        // stage of every segment slot's reach, so that the cell kernel reads it without a dependent gather
+        const size_t NE3 = 3 * (size_t)m.Ne;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < m.Ns; q += gridDim.x * blockDim.x) {
+            const int r = __ldg(m.cs_riv + q);
+            m.cs_yr[q] = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[NE3 + r];
+        }
+    }
     const int i = first + blockIdx.x * blockDim.x + threadIdx.x;  // first = 0, or Ne for the halo cells alone
     if (i >= m.Ne) {
         const int h = i - m.Ne;  // halo cell: same formula on the exchanged groundwater head
@@ -310,10 +320,14 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 template <bool DIAG, int MINB>
 __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, const double *__restrict__ Y,
                                                           double *__restrict__ DY, int tile0) {
-    __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE];
-    __shared__ double x_P1[TILE], x_Es[TILE], x_G1[TILE], x_Eg[TILE], x_Tg[TILE], x_isf2[TILE];
+    __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE], t_area[TILE];
+    __shared__ double e_B[3][TILE], e_dist[3][TILE], e_rough[3][TILE];  // per-edge statics of the lateral role
+    __shared__ int t_seg0[TILE];
     __shared__ double sq_s[SEGCAP], sq_g[SEGCAP];  // river-segment fluxes of the tile, slot order
     __shared__ double v_in[V_NIN][TILE];           // inputs of the vertical role, landed by cp.async
+    // hand-over values vertical -> lateral live in input slots the vertical role has finished with
+    double *const x_P1 = v_in[5], *const x_G1 = v_in[13], *const x_isf2 = v_in[14];  // netPrep, infD, infKsatV
+    double *const x_Es = v_in[22], *const x_Eg = v_in[23], *const x_Tg = v_in[24];   // vegFrac, impAF, wetland
     const int Ne = m.Ne;
     const size_t NE = (size_t)Ne;
     const size_t LD = (size_t)m.ld;  // padded leading dimension of the static [3][.] arrays
@@ -410,28 +424,6 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                 if (DIAG) { d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech; }
             }
         }
-        // ---- river segments of the whole tile, one thread per segment slot (dense lanes instead of a per-cell
-        //      loop at ~15 % lane use): fun_Seg_surface / fun_Seg_sub, MD_RiverFlux.cpp:100-126.  Needs the
-        //      lateral role's staged tile (barrier 3) and every x_isf2 of this role (same barrier). ----
-        bar_sync(3, 2 * TILE);
-        {
-            const int q0 = __ldg(m.cell_seg_first + i0);
-            const int q1 = __ldg(m.cell_seg_first + (i0 + TILE < Ne ? i0 + TILE : Ne));
-            for (int tq = lane_cell; tq < q1 - q0; tq += TILE) {
-                const int q = q0 + tq;
-                const int lc = __ldg(m.cs_cell + q) - i0, sgm = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
-                const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
-                const double zs_c = t_zs[lc];
-                const double zr = zs_c - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
-                const double qs = weir_jtoi(zs_c, x_isf2[lc], zr, yr, zs_c + __ldg(m.cs_zbank + q), __ldg(m.cs_cwr + q),
-                                            len, t_dep[lc]);
-                const double qg = flux_r2e_gw(yr, zr, t_gw[lc], t_zb[lc], t_kh[lc], __ldg(m.cs_ksatH + q), len,
-                                              __ldg(m.cs_bed + q)) * t_fus[lc];
-                m.QsegSurf[sgm] = qs;
-                m.QsegSub[sgm] = qg;
-                if (tq < SEGCAP) { sq_s[tq] = qs; sq_g[tq] = qg; }
-            }
-        }
         bar_arrive(2, 2 * TILE);  // hand-over: the lateral warps wait on barrier 2
         if (valid && verr) raise_err(m.err, verr, i + 1);
 #undef VIN
@@ -439,26 +431,34 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         return;
     }
     // =============================== lateral role ===============================
-    const int seg0 = __ldg(m.cell_seg_first + ic);
+    // Only the neighbour ids are loaded into registers (the gathers need them as addresses); every other value of
+    // the cell goes global -> shared memory with cp.async, all in flight at once, and is read where it is used:
+    // the role holds no parameter in a register across the three edges (no local-memory spills).
     const int nb[3] = {__ldg(m.nbr + ic), __ldg(m.nbr + LD + ic), __ldg(m.nbr + 2 * LD + ic)};
-    const double ysf = Y[ic], ygw_raw = Y[2 * NE + ic];
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // effKH of this call is complete (k_effkh, PDL)
-    const double kh = m.effKH[ic];
-    const double zs = __ldg(m.z_surf + ic), zb = __ldg(m.z_bottom + ic);
-    const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
-    const double fuSub = __ldg(m.fuSub + ic), depression = __ldg(m.depression + ic);
-    t_sf[lane_cell] = ysf; t_gw[lane_cell] = ygw; t_zs[lane_cell] = zs; t_zb[lane_cell] = zb; t_kh[lane_cell] = kh;
-    t_dep[lane_cell] = depression; t_fus[lane_cell] = fuSub;
-    const double area = __ldg(m.area + ic), sy = __ldg(m.sy + ic);
-    double B[3], dist[3], arough[3];
+    const int q1 = __ldg(m.cell_seg_first + (i0 + TILE < Ne ? i0 + TILE : Ne));  // end of the tile's segment slots
+    cp_async8(&t_sf[lane_cell], Y + ic);
+    cp_async8(&t_gw[lane_cell], Y + 2 * NE + ic);
+    cp_async8(&t_zs[lane_cell], m.z_surf + ic);
+    cp_async8(&t_zb[lane_cell], m.z_bottom + ic);
+    cp_async8(&t_dep[lane_cell], m.depression + ic);
+    cp_async8(&t_fus[lane_cell], m.fuSub + ic);
+    cp_async8(&t_area[lane_cell], m.area + ic);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        B[j] = __ldg(m.edge + j * LD + ic);
-        dist[j] = __ldg(m.dist + j * LD + ic);
-        arough[j] = __ldg(m.avgRough + j * LD + ic);
+        cp_async8(&e_B[j][lane_cell], m.edge + j * LD + ic);
+        cp_async8(&e_dist[j][lane_cell], m.dist + j * LD + ic);
+        cp_async8(&e_rough[j][lane_cell], m.avgRough + j * LD + ic);
     }
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&t_seg0[lane_cell])),
+                 "l"(m.cell_seg_first + ic)
+                 : "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // effKH of this call is complete (k_effkh, PDL)
+    cp_async8(&t_kh[lane_cell], m.effKH + ic);
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    if (fl & F_HEADBC) t_gw[lane_cell] = m.ele_yBC[ic];
     bar_sync(1, TILE);           // the tile's own values are in shared memory (lateral warps)
-    bar_arrive(3, 2 * TILE);     // ... and the vertical warps may use them for the segment pass
+    const double ysf = t_sf[lane_cell], ygw = t_gw[lane_cell], zs = t_zs[lane_cell], zb = t_zb[lane_cell];
+    const double kh = t_kh[lane_cell], depression = t_dep[lane_cell], fuSub = t_fus[lane_cell];
     int err = 0;
     double Qs[3] = {0., 0., 0.}, Qg[3] = {0., 0., 0.};
     if (!(fl & F_LAKE)) {
@@ -484,19 +484,21 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                     nsf = m.h_state[2 * h]; ygw_n = m.h_state[2 * h + 1]; zs_n = m.h_zs[h]; zb_n = m.h_zb[h]; kh_n = m.h_kh[h];
                 }
                 nsf = nsf < 0. ? 0. : nsf;
-                qs = edge_surface(isf, zs, nsf, zs_n, depression, dist[j], B[j], arough[j]);
-                qg = edge_sub(ygw, zb, ygw_n, zb_n, kh, kh_n, dist[j], B[j]);
+                const double Bj = e_B[j][lane_cell], dj = e_dist[j][lane_cell];
+                qs = edge_surface(isf, zs, nsf, zs_n, depression, dj, Bj, e_rough[j][lane_cell]);
+                qg = edge_sub(ygw, zb, ygw_n, zb_n, kh, kh_n, dj, Bj);
             } else if (k <= -2) {
                 const int slot = -2 - k, l = m.bank_lake[slot];
                 const double yl = Y[3 * NE + m.Nr + l];
                 const double nsf = yl < 0. ? 0. : yl;
-                qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, B[j], 0.01);
-                qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], dist[j], B[j]);
+                const double Bj = e_B[j][lane_cell];
+                qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, Bj, 0.01);
+                qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], e_dist[j][lane_cell], Bj);
             } else if (!m.close_boundary) {
                 const double d2e = m.dist2edge[j * LD + ic];
                 if (isf > depression) {
                     const double s = isf / d2e * 0.5;
-                    if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B[j] / m.rough[ic];
+                    if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * e_B[j][lane_cell] / m.rough[ic];
                 }
                 if (ygw > depression * 10.) {
                     const double grad = ygw / d2e * 0.5;
@@ -507,7 +509,44 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             Qg[j] = qg * fuSub;
         }
     }
+    // ---- river segments of the whole tile, one lane per segment slot (dense lanes instead of a per-cell loop at
+    //      ~15 % lane use): fun_Seg_sub / fun_Seg_surface, MD_RiverFlux.cpp:100-126.  The groundwater exchange needs
+    //      nothing of the vertical role: it and every load of the pass run here, in the time this role would wait
+    //      for the hand-over; only the weir (needs the ponding left after infiltration) comes after it. ----
+    const int q0 = t_seg0[0], nsq = q1 - q0;
+    const bool has_seg = lane_cell < nsq;
+    int s_lc = 0, s_sgm = 0;
+    double s_yr = 0., s_zr = 0., s_zbk = 0., s_cwr = 0., s_len = 0.;
+    if (has_seg) {
+        const int q = q0 + lane_cell;
+        s_lc = __ldg(m.cs_cell + q) - i0; s_sgm = __ldg(m.cs_seg + q);
+        s_yr = m.cs_yr[q]; s_zr = __ldg(m.cs_zr + q); s_zbk = __ldg(m.cs_zbk + q); s_cwr = __ldg(m.cs_cwr + q);
+        s_len = __ldg(m.cs_len + q);
+        const double qg = flux_r2e_gw(s_yr, s_zr, t_gw[s_lc], t_zb[s_lc], t_kh[s_lc], __ldg(m.cs_ksatH + q), s_len,
+                                      __ldg(m.cs_bed + q)) * t_fus[s_lc];
+        m.QsegSub[s_sgm] = qg;
+        sq_g[lane_cell] = qg;
+    }
     bar_sync(2, 2 * TILE);  // vertical role has handed over
+    if (has_seg) {
+        const double qs = weir_jtoi(t_zs[s_lc], x_isf2[s_lc], s_zr, s_yr, s_zbk, s_cwr, s_len, t_dep[s_lc]);
+        m.QsegSurf[s_sgm] = qs;
+        sq_s[lane_cell] = qs;
+    }
+    for (int tq = TILE + lane_cell; tq < nsq; tq += TILE) {  // tiles with more than 128 segments (rare)
+        const int q = q0 + tq;
+        const int lc = __ldg(m.cs_cell + q) - i0, sgm = __ldg(m.cs_seg + q);
+        const double yr = m.cs_yr[q], zr = __ldg(m.cs_zr + q), len = __ldg(m.cs_len + q);
+        const double qs = weir_jtoi(t_zs[lc], x_isf2[lc], zr, yr, __ldg(m.cs_zbk + q), __ldg(m.cs_cwr + q), len, t_dep[lc]);
+        const double qg = flux_r2e_gw(yr, zr, t_gw[lc], t_zb[lc], t_kh[lc], __ldg(m.cs_ksatH + q), len,
+                                      __ldg(m.cs_bed + q)) * t_fus[lc];
+        m.QsegSurf[sgm] = qs;
+        m.QsegSub[sgm] = qg;
+        if (tq < SEGCAP) { sq_s[tq] = qs; sq_g[tq] = qg; }
+    }
+    bar_sync(1, TILE);  // segment fluxes of the tile are in shared memory
+    const double area = t_area[lane_cell], sy = v_in[12][lane_cell];
+    const int seg0 = t_seg0[lane_cell];
     const double P1 = x_P1[lane_cell], Es = x_Es[lane_cell], G1 = x_G1[lane_cell], Eg = x_Eg[lane_cell],
                  Tg = x_Tg[lane_cell];
     if (!valid) return;
@@ -515,7 +554,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     double e2rS = 0., e2rG = 0.;
     const int nseg = (int)(fl >> NSEG_SHIFT);
     if (nseg) {
-        const int tq0 = seg0 - __ldg(m.cell_seg_first + i0);
+        const int tq0 = seg0 - q0;
         for (int k = 0; k < nseg; k++) {
             const int tq = tq0 + k;
             double qs, qg;
@@ -1361,6 +1400,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     {
         std::vector<int> cs_seg(Ns), cs_riv(Ns), cs_bc(Ns);
         std::vector<double> cs_len(Ns), cs_cwr(Ns), cs_depth(Ns), cs_zbank(Ns), cs_ksatH(Ns), cs_bed(Ns);
+        std::vector<double> cs_zr(Ns), cs_zbk(Ns);
         for (int q = 0; q < Ns; q++) {
             const int sd = cell_seg_idx[q];   // segment, device order
             const int so = c->sperm[sd];      // segment, reference id
@@ -1368,11 +1408,17 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             cs_seg[q] = sd; cs_riv[q] = c->rinv[ro]; cs_bc[q] = M->riv_BC[ro];
             cs_len[q] = M->seg_length[so]; cs_cwr[q] = M->seg_Cwr[so]; cs_depth[q] = M->riv_depth[ro];
             cs_zbank[q] = M->riv_zbank[ro]; cs_ksatH[q] = M->riv_KsatH[ro]; cs_bed[q] = M->riv_BedThick[ro];
+            // the two sums fun_Seg_surface forms from statics (MD_RiverFlux.cpp:104-109), same IEEE operations
+            const double zs_cell = M->z_surf[c->cperm[cs_cell_h[q]]];
+            cs_zr[q] = zs_cell - cs_depth[q];
+            cs_zbk[q] = zs_cell + cs_zbank[q];
         }
         m.cs_seg = dev_upload(c, cs_seg); m.cs_riv = dev_upload(c, cs_riv); m.cs_bc = dev_upload(c, cs_bc);
         m.cs_cell = dev_upload(c, cs_cell_h);
         m.cs_len = dev_upload(c, cs_len); m.cs_cwr = dev_upload(c, cs_cwr); m.cs_depth = dev_upload(c, cs_depth);
         m.cs_zbank = dev_upload(c, cs_zbank); m.cs_ksatH = dev_upload(c, cs_ksatH); m.cs_bed = dev_upload(c, cs_bed);
+        m.cs_zr = dev_upload(c, cs_zr); m.cs_zbk = dev_upload(c, cs_zbk);
+        m.cs_yr = dev_alloc<double>(c, Ns);
     }
     m.bank_cell = dev_upload(c, bank_cell); m.bank_j = dev_upload(c, bank_j); m.bank_lake = dev_upload(c, bank_lake);
     m.bank_kh = dev_upload(c, bank_kh);
