@@ -325,9 +325,8 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     __shared__ int t_seg0[TILE];
     __shared__ double sq_s[SEGCAP], sq_g[SEGCAP];  // river-segment fluxes of the tile, slot order
     __shared__ double v_in[V_NIN][TILE];           // inputs of the vertical role, landed by cp.async
-    // hand-over values vertical -> lateral live in input slots the vertical role has finished with
+    // values handed between the roles live in input slots the vertical role has finished with
     double *const x_P1 = v_in[5], *const x_G1 = v_in[13], *const x_isf2 = v_in[14];  // netPrep, infD, infKsatV
-    double *const x_Es = v_in[22], *const x_Eg = v_in[23], *const x_Tg = v_in[24];   // vegFrac, impAF, wetland
     const int Ne = m.Ne;
     const size_t NE = (size_t)Ne;
     const size_t LD = (size_t)m.ld;  // padded leading dimension of the static [3][.] arrays
@@ -336,7 +335,9 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     const int i = i0 + lane_cell;
     const bool valid = i < Ne;
     const int ic = valid ? i : Ne - 1;  // clamped index: tail threads load something harmless
-    const unsigned fl = __ldg(m.flags + ic);
+    // the river/lake kernel may be scheduled once every block of this grid is running (it fills the last wave and
+    // does its state-only part; griddepcontrol.wait there holds the rest until this grid has completed)
+    asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x >= TILE) {
         // =============================== vertical role ===============================
         // The 26 inputs of this role go global -> shared memory with per-thread 8-byte cp.async (LDGSTS): all
@@ -351,54 +352,24 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                                               m.ksatV + ic, m.vegFrac + ic, m.impAF + ic, m.wetland + ic, m.rootReach + ic};
 #pragma unroll
             for (int a = 0; a < V_NIN; a++) cp_async8(&v_in[a][lane_cell], src[a]);
-            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
+        const unsigned fl = __ldg(m.flags + ic);  // issued behind the copies, not ahead of them
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #define VIN(a) v_in[a][lane_cell]
 #define VFENCE() asm volatile("" ::: "memory")
-        // The role runs in three steps, each fetching only its own inputs from the staged slots and parking what a
-        // later step needs back in shared memory: nothing is held in a register across the pow() calls of the
-        // middle step (the 64-register budget would spill it to local memory, i.e. to L2).
-        int verr = 0;
+        // The role runs in steps, each fetching only its own inputs from the staged slots and parking what a later
+        // step needs back in shared memory: nothing is held in a register across the pow() calls (the 64-register
+        // budget would spill it to local memory, i.e. to L2).  Order: soil first - the lateral role needs only its
+        // results (P1, G1, ponding) - then the ET partition while the lateral role does the weir and the lateral
+        // sums, then the three balance equations of the cell.
         if (fl & F_HEADBC) VIN(2) = m.ele_yBC[ic];
-        // ---- step 1: ET partition (f_etFlux) -> x_Es, x_Eg, x_Tg; Eu, Tu parked in slots 6, 7; carried E_IC ----
-        {
-            CellVert v;
-            v.err = 0;
-            const double potEvap = VIN(6);
-            if (fl & F_LAKE) {
-                v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
-            } else {
-                CellParams p;
-                CellForc f;
-                p.thetaS = VIN(17); p.thetaR = VIN(18); p.vegFrac = VIN(22); p.impAF = VIN(23); p.wetland = VIN(24);
-                p.rootReach = VIN(25);
-                f.potEvap = potEvap; f.potTran = VIN(7); f.lai = VIN(8);
-                cell_et(p, f, VIN(0), VIN(1), VIN(2), VIN(3), VIN(4), v);
-            }
-            x_Es[lane_cell] = v.Es; x_Eg[lane_cell] = v.Eg; x_Tg[lane_cell] = v.Tg;
-            VIN(6) = v.Eu; VIN(7) = v.Tu;
-            verr = v.err;
-            if (valid) {
-                m.eic[i] = v.eic;
-                if (DIAG) {
-                    if (fl & F_LAKE) {
-                        d.qEleTrans[i] = 0.; d.qEleEvapo[i] = potEvap; d.qEleETA[i] = 0. + potEvap + 0.;
-                    } else {
-                        const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
-                        d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
-                        d.iBeta[i] = v.iBeta;
-                    }
-                    d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
-                }
-            }
-        }
-        VFENCE();
-        // ---- step 2: updateElement (2 pow) ----
+        // ---- step 1: updateElement (2 pow) ----
         SoilState st;
         if (fl & F_LAKE) { st.deficit = 0.; st.theta = 0.; st.satn = 1.; st.satKr = 0.; }
         else st = cell_soil_state(VIN(11), VIN(17), VIN(18), VIN(20), VIN(1), VIN(2));
         VFENCE();
-        // ---- step 3: infiltration / exfiltration / recharge, ydot[unsat], hand-over values ----
+        // ---- step 2: infiltration / exfiltration / recharge; hand-over ----
         {
             CellVert v;
             v.satn = 1.; v.infil = v.exfil = v.rech = 0.;
@@ -415,17 +386,64 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             x_P1[lane_cell] = netPrep - v.infil + v.exfil;
             x_G1[lane_cell] = v.rech - v.exfil;
             x_isf2[lane_cell] = dmax(0., isf2);
+            bar_arrive(2, 2 * TILE);  // hand-over: the lateral warps wait on barrier 2
+            VIN(15) = v.infil - v.rech;  // first difference of ydot[unsat], finished after the ET step
             if (valid) {
                 m.satn[i] = v.satn;
-                double dus = v.infil - v.rech - VIN(6) - VIN(7);
-                dus = SHUD_DIVS(dus, VIN(12));
-                if (fl & F_LAKE) dus = 0.;
-                DY[NE + i] = dus;
                 if (DIAG) { d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech; }
             }
         }
-        bar_arrive(2, 2 * TILE);  // hand-over: the lateral warps wait on barrier 2
-        if (valid && verr) raise_err(m.err, verr, i + 1);
+        VFENCE();
+        // ---- step 3: ET partition (f_etFlux), with the saturation carried from the previous call ----
+        CellVert v;
+        v.err = 0;
+        {
+            const double potEvap = VIN(6);
+            if (fl & F_LAKE) {
+                v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
+            } else {
+                CellParams p;
+                CellForc f;
+                p.thetaS = VIN(17); p.thetaR = VIN(18); p.vegFrac = VIN(22); p.impAF = VIN(23); p.wetland = VIN(24);
+                p.rootReach = VIN(25);
+                f.potEvap = potEvap; f.potTran = VIN(7); f.lai = VIN(8);
+                cell_et(p, f, VIN(0), VIN(1), VIN(2), VIN(3), VIN(4), v);
+            }
+            if (valid) {
+                m.eic[i] = v.eic;
+                if (DIAG) {
+                    if (fl & F_LAKE) {
+                        d.qEleTrans[i] = 0.; d.qEleEvapo[i] = potEvap; d.qEleETA[i] = 0. + potEvap + 0.;
+                    } else {
+                        const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
+                        d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
+                        d.iBeta[i] = v.iBeta;
+                    }
+                    d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
+                }
+            }
+        }
+        // ---- step 4: the balance equations (f_applyDY, MD_f.cpp:52-215).  The lateral role has left
+        //      P1 - SurfTot/area and G1 - SubTot/area in the P1 / G1 slots (barrier 3). ----
+        bar_sync(3, 2 * TILE);
+        if (!valid) return;
+        {
+            const double area = t_area[lane_cell], sy = VIN(12);
+            double dsf = x_P1[lane_cell] - v.Es;
+            double dgw = x_G1[lane_cell] - v.Eg - v.Tg;
+            if (fl & F_HEADBC) dgw = 0;
+            else if (fl & F_FLUXBC) dgw += SHUD_DIVS(m.ele_QBC[i], area);
+            if (fl & F_SS_SURF) dsf += SHUD_DIVS(m.qss[i], area);
+            else if (fl & F_SS_GW) dgw += SHUD_DIVS(m.qss[i], area);
+            dgw = SHUD_DIVS(dgw, sy);
+            double dus = VIN(15) - v.Eu - v.Tu;
+            dus = SHUD_DIVS(dus, sy);
+            if (fl & F_LAKE) { dsf = 0.; dus = 0.; dgw = 0.; }
+            DY[i] = dsf;
+            DY[NE + i] = dus;
+            DY[2 * NE + i] = dgw;
+            if (v.err) raise_err(m.err, v.err, i + 1);
+        }
 #undef VIN
 #undef VFENCE
         return;
@@ -454,7 +472,9 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                  : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // effKH of this call is complete (k_effkh, PDL)
     cp_async8(&t_kh[lane_cell], m.effKH + ic);
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const unsigned fl = __ldg(m.flags + ic);  // issued behind the copies, not ahead of them
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (fl & F_HEADBC) t_gw[lane_cell] = m.ele_yBC[ic];
     bar_sync(1, TILE);           // the tile's own values are in shared memory (lateral warps)
     const double ysf = t_sf[lane_cell], ygw = t_gw[lane_cell], zs = t_zs[lane_cell], zb = t_zb[lane_cell];
@@ -545,47 +565,40 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         if (tq < SEGCAP) { sq_s[tq] = qs; sq_g[tq] = qg; }
     }
     bar_sync(1, TILE);  // segment fluxes of the tile are in shared memory
-    const double area = t_area[lane_cell], sy = v_in[12][lane_cell];
-    const int seg0 = t_seg0[lane_cell];
-    const double P1 = x_P1[lane_cell], Es = x_Es[lane_cell], G1 = x_G1[lane_cell], Eg = x_Eg[lane_cell],
-                 Tg = x_Tg[lane_cell];
-    if (!valid) return;
-    // element side of PassValue (MD_f.cpp:228-235): sum of this cell's segment fluxes, ascending segment id
-    double e2rS = 0., e2rG = 0.;
-    const int nseg = (int)(fl >> NSEG_SHIFT);
-    if (nseg) {
-        const int tq0 = seg0 - q0;
-        for (int k = 0; k < nseg; k++) {
-            const int tq = tq0 + k;
-            double qs, qg;
-            if (tq < SEGCAP) { qs = sq_s[tq]; qg = sq_g[tq]; }
-            else { const int sgm = __ldg(m.cs_seg + seg0 + k); qs = m.QsegSurf[sgm]; qg = m.QsegSub[sgm]; }
-            e2rS += -qs;
-            e2rG += -qg;
+    {
+        // element side of PassValue (MD_f.cpp:228-235): sum of this cell's segment fluxes, ascending segment id
+        double e2rS = 0., e2rG = 0.;
+        const int nseg = (int)(fl >> NSEG_SHIFT);
+        if (nseg) {
+            const int seg0 = t_seg0[lane_cell], tq0 = seg0 - q0;
+            for (int k = 0; k < nseg; k++) {
+                const int tq = tq0 + k;
+                double qs, qg;
+                if (tq < SEGCAP) { qs = sq_s[tq]; qg = sq_g[tq]; }
+                else { const int sgm = __ldg(m.cs_seg + seg0 + k); qs = m.QsegSurf[sgm]; qg = m.QsegSub[sgm]; }
+                e2rS += -qs;
+                e2rG += -qg;
+            }
         }
-    }
-    double surfTot = e2rS, subTot = e2rG;
+        double surfTot = e2rS, subTot = e2rG;
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        surfTot += Qs[j];
-        subTot += Qg[j];
-        if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
-    }
-    double dsf = P1 - SHUD_DIVS(surfTot, area) - Es;
-    double dgw = G1 - SHUD_DIVS(subTot, area) - Eg - Tg;
-    if (fl & F_HEADBC) dgw = 0;
-    else if (fl & F_FLUXBC) dgw += SHUD_DIVS(m.ele_QBC[i], area);
-    if (fl & F_SS_SURF) dsf += SHUD_DIVS(m.qss[i], area);
-    else if (fl & F_SS_GW) dgw += SHUD_DIVS(m.qss[i], area);
-    dgw = SHUD_DIVS(dgw, sy);
-    if (fl & F_LAKE) { dsf = 0.; dgw = 0.; }
-    DY[i] = dsf;
-    DY[2 * NE + i] = dgw;
-    if (err) raise_err(m.err, err, i + 1);
-    if (DIAG) {
+        for (int j = 0; j < 3; j++) {
+            surfTot += Qs[j];
+            subTot += Qg[j];
+            if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
+        }
+        // first two terms of dYsf and dYgw; the vertical role subtracts its ET terms and finishes (barrier 3)
+        const double area = t_area[lane_cell];
+        x_P1[lane_cell] = x_P1[lane_cell] - SHUD_DIVS(surfTot, area);
+        x_G1[lane_cell] = x_G1[lane_cell] - SHUD_DIVS(subTot, area);
+        bar_arrive(3, 2 * TILE);
+        if (!valid) return;
+        if (err) raise_err(m.err, err, i + 1);
+        if (DIAG) {
 #pragma unroll
-        for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
-        d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
+            for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
+            d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
+        }
     }
 }
 
@@ -964,8 +977,12 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
         const double qdown = reach_down_flux(m, Yr, r, &err);
         double up = 0.;
         for (int k = m.r_up_ptr[r]; k < m.r_up_ptr[r + 1]; k++) up += -reach_down_flux(m, Yr, m.r_up_idx[k], &err);
+        const int s0 = m.r_seg_ptr[r], s1 = m.r_seg_ptr[r + 1];
+        // everything above needs the state only; the segment fluxes come from the cell kernel (programmatic
+        // dependent launch: this grid starts in the cell kernel's last wave and waits here)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         double surf = 0., sub = 0.;
-        for (int s = m.r_seg_ptr[r]; s < m.r_seg_ptr[r + 1]; s++) {
+        for (int s = s0; s < s1; s++) {
             surf += m.QsegSurf[s];
             sub += m.QsegSub[s];
         }
@@ -988,6 +1005,7 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
     // ---- lake l ----
     __shared__ double sm[8];
     const int l = blockIdx.x - nb_riv;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const double yl = Y[3 * NE + m.Nr + l];
     double qs = 0., qg = 0., qin = 0.;
     for (int k = m.l_bank_ptr[l] + threadIdx.x; k < m.l_bank_ptr[l + 1]; k += blockDim.x) {
@@ -1744,8 +1762,20 @@ static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
         launch_cell<DIAG>(c, y, ydot);
     }
     const int nb_riv = (c->Nr + 127) / 128;
-    if (nb_riv + c->Nl > 0)
-        k_river_lake<DIAG><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    if (nb_riv + c->Nl > 0) {
+        bool done = false;
+        if (c->use_pdl && c->split == 2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nb_riv + c->Nl); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            done = cudaLaunchKernelEx(&cfg, k_river_lake<DIAG>, c->m, c->diag, y, ydot, nb_riv) == cudaSuccess;
+            if (!done) { cudaGetLastError(); c->use_pdl = 0; }
+        }
+        if (!done) k_river_lake<DIAG><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    }
     CK(cudaGetLastError());
     return SHUD_OK;
 }
