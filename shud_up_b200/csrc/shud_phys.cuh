@@ -99,7 +99,16 @@ __device__ __forceinline__ double pow01(double x, double a) {
 #endif
 }
 __device__ __forceinline__ double sat_kr(double s, double n) {
-    const double t = -1. + pow01(1. - pow01(s, n / (n - 1.)), (n - 1.) / n);
+    // -1 + (1 - s^(n/(n-1)))^((n-1)/n): the two pow() as two trips of one loop, so that the kernel holds one copy
+    // of pow()'s ~150 instructions instead of two (instruction-cache footprint of the cell kernel)
+    double x = s, e = n / (n - 1.), r = 0.;
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        r = pow01(x, e);
+        x = 1. - r;
+        e = (n - 1.) / n;
+    }
+    const double t = -1. + r;
     return fsqrt(s) * t * t;
 }
 
