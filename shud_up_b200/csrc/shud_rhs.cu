@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE], t_area[TILE];
     __shared__ double e_B[3][TILE], e_dist[3][TILE], e_rough[3][TILE];  // per-edge statics of the lateral role
     __shared__ int t_seg0[TILE];
+    __shared__ unsigned t_flv[TILE];  // the vertical role's copy of the cell flags (not worth a register for 3 steps)
     __shared__ double sq_s[SEGCAP], sq_g[SEGCAP];  // river-segment fluxes of the tile, slot order
     __shared__ double v_in[V_NIN][TILE];           // inputs of the vertical role, landed by cp.async
     // values handed between the roles live in input slots the vertical role has finished with
@@ -354,8 +355,9 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             for (int a = 0; a < V_NIN; a++) cp_async8(&v_in[a][lane_cell], src[a]);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        const unsigned fl = __ldg(m.flags + ic);  // issued behind the copies, not ahead of them
+        t_flv[lane_cell] = __ldg(m.flags + ic);  // issued behind the copies, not ahead of them
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+#define VFL() t_flv[lane_cell]
 #define VIN(a) v_in[a][lane_cell]
 #define VFENCE() asm volatile("" ::: "memory")
         // The role runs in steps, each fetching only its own inputs from the staged slots and parking what a later
@@ -363,10 +365,10 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         // budget would spill it to local memory, i.e. to L2).  Order: soil first - the lateral role needs only its
         // results (P1, G1, ponding) - then the ET partition while the lateral role does the weir and the lateral
         // sums, then the three balance equations of the cell.
-        if (fl & F_HEADBC) VIN(2) = m.ele_yBC[ic];
+        if (VFL() & F_HEADBC) VIN(2) = m.ele_yBC[ic];
         // ---- step 1: updateElement (2 pow) ----
         SoilState st;
-        if (fl & F_LAKE) { st.deficit = 0.; st.theta = 0.; st.satn = 1.; st.satKr = 0.; }
+        if (VFL() & F_LAKE) { st.deficit = 0.; st.theta = 0.; st.satn = 1.; st.satKr = 0.; }
         else st = cell_soil_state(VIN(11), VIN(17), VIN(18), VIN(20), VIN(1), VIN(2));
         VFENCE();
         // ---- step 2: infiltration / exfiltration / recharge; hand-over ----
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             CellVert v;
             v.satn = 1.; v.infil = v.exfil = v.rech = 0.;
             const double ysf = VIN(0), netPrep = VIN(5);
-            if (!(fl & F_LAKE)) {
+            if (!(VFL() & F_LAKE)) {
                 CellParams p;
                 CellForc f;
                 p.aqd = VIN(11); p.infD = VIN(13); p.infKsatV = VIN(14); p.macKsatV = VIN(15); p.hAreaF = VIN(16);
@@ -399,6 +401,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         v.err = 0;
         {
             const double potEvap = VIN(6);
+            const unsigned fl = VFL();
             if (fl & F_LAKE) {
                 v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
             } else {
@@ -428,6 +431,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         bar_sync(3, 2 * TILE);
         if (!valid) return;
         {
+            const unsigned fl = VFL();
             const double area = t_area[lane_cell], sy = VIN(12);
             double dsf = x_P1[lane_cell] - v.Es;
             double dgw = x_G1[lane_cell] - v.Eg - v.Tg;
@@ -446,6 +450,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         }
 #undef VIN
 #undef VFENCE
+#undef VFL
         return;
     }
     // =============================== lateral role ===============================
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     {
         // element side of PassValue (MD_f.cpp:228-235): sum of this cell's segment fluxes, ascending segment id
         double e2rS = 0., e2rG = 0.;
-        const int nseg = (int)(fl >> NSEG_SHIFT);
+        const int nseg = (int)(t_flv[lane_cell] >> NSEG_SHIFT);  // flags as the vertical role staged them (barrier 2)
         if (nseg) {
             const int seg0 = t_seg0[lane_cell], tq0 = seg0 - q0;
             for (int k = 0; k < nseg; k++) {
@@ -980,32 +985,34 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
     if ((int)blockIdx.x < nb_riv) {
         const int r = blockIdx.x * blockDim.x + threadIdx.x;
         if (r >= m.Nr) return;
+        const int s0 = m.r_seg_ptr[r], s1 = m.r_seg_ptr[r + 1], u0 = m.r_up_ptr[r], u1 = m.r_up_ptr[r + 1];
+        const int bc = m.r_bc[r];
+        const double yraw = Yr[r], w0 = m.r_w0[r], bank = m.r_bank[r], len = m.r_len[r];
+        const double qbc = (bc < 0) ? m.r_qBC[r] : 0.;
+        const RivGeom g = riv_geom(yraw, w0, bank);
+        // Flux_RiverDown of this reach and of its upstream reaches (re-evaluated rather than exchanged: state only)
         int err = 0;
         const double qdown = reach_down_flux(m, Yr, r, &err);
         double up = 0.;
-        for (int k = m.r_up_ptr[r]; k < m.r_up_ptr[r + 1]; k++) up += -reach_down_flux(m, Yr, m.r_up_idx[k], &err);
-        const int s0 = m.r_seg_ptr[r], s1 = m.r_seg_ptr[r + 1];
-        // everything above needs the state only; the segment fluxes come from the cell kernel (programmatic
-        // dependent launch: this grid starts in the cell kernel's last wave and waits here)
+        for (int k = u0; k < u1; k++) up += -reach_down_flux(m, Yr, m.r_up_idx[k], &err);
+        if (err) raise_err(m.err, err, r + 1);
+        // everything above needs statics and the state only; the segment fluxes come from the cell kernel
+        // (programmatic dependent launch: this grid starts in the cell kernel's last wave and waits here)
         asm volatile("griddepcontrol.wait;" ::: "memory");
         double surf = 0., sub = 0.;
         for (int s = s0; s < s1; s++) {
             surf += m.QsegSurf[s];
             sub += m.QsegSub[s];
         }
-        const int bc = m.r_bc[r];
         double dy;
         if (bc > 0) {
             dy = 0.;
         } else {
-            const double qbc = (bc < 0) ? m.r_qBC[r] : 0.;
-            const RivGeom g = riv_geom(Yr[r], m.r_w0[r], m.r_bank[r]);
-            dy = (-up - surf - sub - qdown + qbc) / m.r_len[r];
+            dy = (-up - surf - sub - qdown + qbc) / len;
             if (dy < -1. * g.csArea) dy = -1. * g.csArea;
-            dy = dA_to_dY(dy, g.topWidth, m.r_bank[r]);
+            dy = dA_to_dY(dy, g.topWidth, bank);
         }
         DY[3 * NE + r] = dy;
-        if (err) raise_err(m.err, err, r + 1);
         if (DIAG) { d.QrivSurf[r] = surf; d.QrivSub[r] = sub; d.QrivUp[r] = up; d.QrivDown[r] = qdown; }
         return;
     }
@@ -1026,9 +1033,8 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
         // QLakeSub takes Q before the fu_Sub factor (MD_ElementFlux.cpp:121 precedes :153)
         qg += edge_sub(ygw, m.z_bottom[i], yl, m.l_yi0[l], m.effKH[i], m.bank_kh[k], m.dist[j * LD + i], B);
     }
-    int err = 0;
     for (int k = m.l_rin_ptr[l] + threadIdx.x; k < m.l_rin_ptr[l + 1]; k += blockDim.x)
-        qin += reach_down_flux(m, Yr, m.l_rin_idx[k], &err);
+    { int e2 = 0; qin += reach_down_flux(m, Yr, m.l_rin_idx[k], &e2); }
     qs = block_sum<128>(qs, sm);
     qg = block_sum<128>(qg, sm);
     qin = block_sum<128>(qin, sm);
