@@ -218,10 +218,29 @@ def main():
         with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
             eager_step()
         barrier_()
-        def step():
+        def graph_step():
             with torch.cuda.stream(st):
                 g.replay()
-        step_mode = "cuda-graph"
+        # keep whichever launch mode is faster on this box (max over ranks, so every rank decides alike): with 8
+        # ranks the replayed NCCL node has been measured slower than the eager collective, with 2-4 ranks faster
+        def probe(fn, n=40):
+            for _ in range(5):
+                fn()
+            barrier_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(n):
+                fn()
+            e1.record(st)
+            barrier_()
+            t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        t_eager, t_graph = probe(eager_step), probe(graph_step)
+        if t_graph <= t_eager:
+            step, step_mode = graph_step, f"cuda-graph (probe: graph {t_graph * 1e3:.0f} us, eager {t_eager * 1e3:.0f} us)"
+        else:
+            step, step_mode = eager_step, f"eager (probe: graph {t_graph * 1e3:.0f} us, eager {t_eager * 1e3:.0f} us)"
 
     def barrier():
         if world > 1:
@@ -336,6 +355,12 @@ def main():
         dist.all_reduce(cells, op=dist.ReduceOp.SUM)
     ms_dev_max, ms_e2e_max = float(tt[0]), float(tt[1])
     total_cells = float(cells[0])
+    per_rank = [ms_dev / steps]
+    if world > 1:  # the per-rank device times (the reported one is their max) and tile split, for the record
+        allt = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        n_int, n_bnd = rhs.tile_counts()
+        dist.all_gather(allt, torch.tensor([ms_dev / steps, n_int, n_bnd], dtype=torch.float64, device=dev))
+        per_rank = [[round(float(a[0]), 5), int(a[1]), int(a[2])] for a in allt]
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         ms_step = ms_dev_max / steps
@@ -354,7 +379,7 @@ def main():
                           "seed": 20240611, "l2": "inputs 400 MB per rank > 126 MB L2, no flush needed",
                           "multi_gpu": (f"{world} stripes of 1M cells of the {world}M-cell mesh, NCCL all_to_all halo exchange of "
                                         f"{hx.bytes_per_exchange} B per rank and f(), overlapped with the interior tiles; "
-                                        f"step launched as: {step_mode}") if world > 1 else "single GPU"},
+                                        f"step launched as: {step_mode}; per rank [ms/step, interior tiles, boundary tiles]: {per_rank}") if world > 1 else "single GPU"},
                "gpu_launches": (nst + (3 if world > 1 else 0)) * steps,
                "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
