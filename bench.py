@@ -46,7 +46,7 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML every 50 ms; nvidia-smi, the
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every 100 ms; nvidia-smi, the
     recipe's command, once as a cross-check - spawning it takes ~1 s on these hosts, too slow to sample with)."""
 
     def __init__(self, index):
@@ -64,7 +64,7 @@ class ClockSampler:
                 pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop:
                 self.rows.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx, int(get_reasons(h))))
-                time.sleep(0.05)
+                time.sleep(0.1)
         except Exception:
             pass
         try:
@@ -206,7 +206,7 @@ def main():
         else:
             rhs.f_dev(0.0, y, ydot)
 
-    eager_step, step_mode, g = step, "eager", None
+    eager_step, step_mode, g, native = step, "eager", None, False
     if hx is not None and os.environ.get("SHUD_BENCH_GRAPH", "1") != "0":
         # N>1: the step is 7 short launches + one NCCL call from Python; capture it (collective included) into one
         # CUDA graph so that the host does one launch per f(), as the single-GPU path does inside the library
@@ -223,24 +223,46 @@ def main():
                 g.replay()
         # keep whichever launch mode is faster on this box (max over ranks, so every rank decides alike): with 8
         # ranks the replayed NCCL node has been measured slower than the eager collective, with 2-4 ranks faster
-        def probe(fn, n=40):
+        def probe(fn, n=max(steps, 40)):
+            # same conditions as the timed region below: as many back-to-back steps, clock sampler running (with 8
+            # ranks a short burst of graph replays has been measured 3x faster than a long one)
             for _ in range(5):
                 fn()
             barrier_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st)
-            for _ in range(n):
-                fn()
-            e1.record(st)
-            barrier_()
+            with ClockSampler(local_rank):
+                e0.record(st)
+                for _ in range(n):
+                    fn()
+                e1.record(st)
+                barrier_()
             t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t[0])
         t_eager, t_graph = probe(eager_step), probe(graph_step)
-        if t_graph <= t_eager:
-            step, step_mode = graph_step, f"cuda-graph (probe: graph {t_graph * 1e3:.0f} us, eager {t_eager * 1e3:.0f} us)"
+        # third candidate, the product path: the C library drives the exchange itself (own NCCL communicator,
+        # grouped ncclSend/ncclRecv per neighbour, one C call per f(): shud_b200_rhs_exchange_dev)
+        t_native = float("inf")
+        if os.environ.get("SHUD_BENCH_NATIVE", "1") != "0":
+            rhs.comm_init(dist, dev)
+            rhs.exchange_plan(*hx.native_plan())
+            def native_step():
+                rhs.f_exchange_dev(0.0, y, ydot)
+            t_native = probe(native_step)
+            # the two exchange implementations must give the same bits (the state is stationary after warm-up)
+            native_step(); torch.cuda.synchronize(); yd_native = ydot.clone()
+            rhs.set_halo_state(hx.halo_state); eager_step(); torch.cuda.synchronize()
+            assert torch.equal(yd_native, ydot), "library-driven exchange differs from the torch.distributed one"
+            rhs.exchange_plan(*hx.native_plan())
+        probes = f"probe: library-NCCL {t_native * 1e3:.0f} us, torch graph {t_graph * 1e3:.0f} us, torch eager {t_eager * 1e3:.0f} us"
+        if t_native <= min(t_graph, t_eager):
+            step, step_mode, native = native_step, "one C call per f(), NCCL sends/receives issued by the library (" + probes + ")", True
         else:
-            step, step_mode = eager_step, f"eager (probe: graph {t_graph * 1e3:.0f} us, eager {t_eager * 1e3:.0f} us)"
+            rhs.set_halo_state(hx.halo_state)  # back to the buffer the torch collective fills
+            if t_graph <= t_eager:
+                step, step_mode = graph_step, "cuda-graph incl. the torch NCCL collective (" + probes + ")"
+            else:
+                step, step_mode = eager_step, "eager torch collective (" + probes + ")"
 
     def barrier():
         if world > 1:
@@ -292,9 +314,12 @@ def main():
             with torch.cuda.stream(st):
                 y_ref.copy_(yh, non_blocking=True)
                 rhs.to_device_order(y_ref, y)
-                hx.start(y)
-                rhs.f_interior_dev(0.0, y, ydot)
-                rhs.f_boundary_dev(0.0, y, ydot, halo_stream=hx.finish())
+                if native:
+                    rhs.f_exchange_dev(0.0, y, ydot)
+                else:
+                    hx.start(y)
+                    rhs.f_interior_dev(0.0, y, ydot)
+                    rhs.f_boundary_dev(0.0, y, ydot, halo_stream=hx.finish())
                 rhs.from_device_order(ydot, y_ref)
                 ydh.copy_(y_ref, non_blocking=True)
             st.synchronize()

@@ -153,6 +153,23 @@ int shud_b200_rhs(shud_ctx *ctx, double t, const double *y_host, double *ydot_ho
  * run beside the interior tiles; the context stream then waits for them before the river/lake kernel.  NULL = the
  * context stream (the exchange was ordered on it; everything serial). */
 int shud_b200_rhs_interior_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+/* The halo exchange driven by the library itself (replaces the MPI/NCCL calls a host code would place around the
+ * RHS, SURVEY.md section 8(e) "grouped ncclSend/ncclRecv per neighbour pair"): NCCL is opened at run time from
+ * `nccl_lib` (path of libnccl.so.2; NULL = the loader's default) - the library does not link it.
+ *   shud_b200_comm_unique_id  rank 0 obtains the 128-byte ncclUniqueId; the host distributes it (MPI_Bcast, ...)
+ *   shud_b200_comm_init       every rank, same id; creates the communicator and the exchange stream
+ *   shud_b200_exchange_plan   neighbours of this partition: rank, number of owned cells sent, number of halo cells
+ *                             received (halo cells are numbered by (owner rank, global id), so the receives land
+ *                             contiguously in halo order; sum recv_count == Nhalo); `send_cells`: 0-based local
+ *                             reference ids of the cells sent, concatenated by peer, each peer's in the order the
+ *                             peer numbers them as its halo cells.  Allocates the send / halo buffers.
+ *   shud_b200_rhs_exchange_dev  one f(): pack -> sends/receives on the exchange stream -> interior part beside
+ *                             them -> boundary part.  Asynchronous on the context stream like shud_b200_rhs_dev. */
+int shud_b200_comm_unique_id(const char *nccl_lib, void *id128);
+int shud_b200_comm_init(shud_ctx *ctx, const char *nccl_lib, const void *id128, int rank, int world);
+int shud_b200_exchange_plan(shud_ctx *ctx, int npeers, const int32_t *peer_rank, const int32_t *send_count,
+                            const int32_t *recv_count, const int32_t *send_cells);
+int shud_b200_rhs_exchange_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
 /* number of 128-cell tiles in each part (interior + boundary = ceil(Ne/128)) */
 int shud_b200_tile_counts(const shud_ctx *ctx, int *n_interior, int *n_boundary);
 int shud_b200_rhs_boundary_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev, void *halo_stream);

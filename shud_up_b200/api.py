@@ -62,6 +62,10 @@ def lib():
         "shud_b200_rhs_interior_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_boundary_dev": (C.c_int, [vp, C.c_double, vp, vp, vp]),
         "shud_b200_tile_counts": (C.c_int, [vp, _PI, _PI]),
+        "shud_b200_comm_unique_id": (C.c_int, [C.c_char_p, vp]),
+        "shud_b200_comm_init": (C.c_int, [vp, C.c_char_p, vp, C.c_int, C.c_int]),
+        "shud_b200_exchange_plan": (C.c_int, [vp, C.c_int, _PI, _PI, _PI, _PI]),
+        "shud_b200_rhs_exchange_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_diag_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_get_diag": (C.c_int, [vp, C.POINTER(abi.ShudDiag)]),
         "shud_b200_output_accumulate": (C.c_int, [vp]),
@@ -202,6 +206,42 @@ class ShudRHS:
         completes on (its halo-dependent tiles run there, beside the interior tiles), None = the context stream"""
         hs = C.c_void_p(halo_stream.cuda_stream) if halo_stream is not None else None
         _chk(lib().shud_b200_rhs_boundary_dev(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev), hs), "rhs_boundary_dev")
+
+    # ---- halo exchange driven by the library over its own NCCL communicator ----
+    @staticmethod
+    def nccl_library():
+        """libnccl.so.2 of the running process (the copy torch has loaded, so no second NCCL enters the process)"""
+        try:
+            import nvidia.nccl
+            for d in nvidia.nccl.__path__:
+                p = os.path.join(d, "lib", "libnccl.so.2")
+                if os.path.exists(p):
+                    return p
+        except ImportError:
+            pass
+        return "libnccl.so.2"
+
+    def comm_init(self, dist, device, nccl_lib=None):
+        """collective over the ranks of `dist` (torch.distributed: used once, to hand rank 0's id to the others)"""
+        import torch
+        path = (nccl_lib or self.nccl_library()).encode()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _chk(lib().shud_b200_comm_unique_id(path, buf), "comm_unique_id")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+        dist.broadcast(t, 0)
+        raw = (C.c_ubyte * 128)(*[int(v) for v in t.cpu().tolist()])
+        _chk(lib().shud_b200_comm_init(self._h, path, raw, rank, world), "comm_init")
+
+    def exchange_plan(self, peers, send_counts, recv_counts, send_cells):
+        a = [np.ascontiguousarray(v, dtype=np.int32) for v in (peers, send_counts, recv_counts, send_cells)]
+        ptr = [v.ctypes.data_as(_PI) for v in a]
+        _chk(lib().shud_b200_exchange_plan(self._h, int(a[0].size), *ptr), "exchange_plan")
+
+    def f_exchange_dev(self, t, y_dev, ydot_dev):
+        """one f() of a partition: pack, NCCL sends/receives, interior part beside them, boundary part"""
+        _chk(lib().shud_b200_rhs_exchange_dev(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "rhs_exchange_dev")
 
     def tile_counts(self):
         """(interior, boundary) 128-cell tiles of this partition"""

@@ -14,7 +14,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               # static divisors (area, Sy, Dist2Nabor, avgRough) are stored as reciprocals: x*(1/d) instead of
               # x/d, <= 1.5 ulp apart, inside the 1e-12 parity tolerance (shud_phys.cuh)
               "-DSHUD_RCP",
-              "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
 
 def needs_build():

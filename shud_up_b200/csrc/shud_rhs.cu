@@ -12,6 +12,7 @@
 // Device vectors are in DEVICE ORDER (permuted); shud_b200_rhs() (host pointers, reference
 // order) permutes on the way in and out.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -1163,6 +1164,18 @@ struct shud_ctx {
     // partition: tiles whose cells see no halo cell (interior) / the others (boundary) - overlap of the exchange
     int n_int_tiles = 0, n_bnd_tiles = 0;
     cudaEvent_t ev_kh = nullptr, ev_bnd = nullptr;  // effKH of the owned cells done / boundary tiles done (rhs_boundary_dev)
+    // halo exchange over NCCL driven from here (shud_b200_comm_init / shud_b200_exchange_plan / shud_b200_rhs_exchange_dev)
+    void *nccl_dl = nullptr, *nccl_comm = nullptr;
+    int (*nccl_send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*nccl_recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*nccl_group_start)() = nullptr, (*nccl_group_end)() = nullptr;
+    int (*nccl_comm_destroy)(void *) = nullptr;
+    cudaStream_t xstream = nullptr;   // the exchange (and the boundary tiles) run here, beside the interior tiles
+    cudaEvent_t ev_pack = nullptr;
+    std::vector<int> x_peer, x_scount, x_rcount;  // per neighbour partition: rank, cells sent, halo cells received
+    int *x_sidx = nullptr;            // device-order ids of the cells sent, concatenated by peer
+    double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
+    int x_nsend = 0;
     int pipe_grid = 296;  // persistent blocks of k_pipe: 2 per SM (2 stages) or 4 per SM (1 stage)
     int pipe_stages = 2;
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
@@ -1574,6 +1587,10 @@ void shud_b200_destroy(shud_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->xstream) cudaStreamSynchronize(c->xstream);
+    if (c->nccl_comm && c->nccl_comm_destroy) c->nccl_comm_destroy(c->nccl_comm);
+    if (c->xstream) cudaStreamDestroy(c->xstream);
+    if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ev_kh) cudaEventDestroy(c->ev_kh);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
@@ -1676,6 +1693,95 @@ int shud_b200_pack_halo_dev(shud_ctx *c, const double *y, const int32_t *idx, in
     k_pack_halo<<<(n + 255) / 256, 256, 0, c->stream>>>(y, idx, n, c->Ne, out);
     CK(cudaGetLastError());
     return SHUD_OK;
+}
+
+// ---- halo exchange over NCCL, driven by the library (one call per f(), no host framework in the step) ----
+namespace {
+struct nccl_uid { char internal[128]; };  // ncclUniqueId
+void *nccl_open(const char *path) {
+    void *h = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    return h;
+}
+}  // namespace
+
+int shud_b200_comm_unique_id(const char *nccl_lib, void *id128) {
+    if (!id128) return SHUD_ERR_ARG;
+    void *h = nccl_open(nccl_lib);
+    if (!h) return SHUD_ERR_CUDA;
+    auto get = (int (*)(nccl_uid *))dlsym(h, "ncclGetUniqueId");
+    if (!get || get((nccl_uid *)id128) != 0) return SHUD_ERR_CUDA;
+    return SHUD_OK;
+}
+
+int shud_b200_comm_init(shud_ctx *c, const char *nccl_lib, const void *id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->nccl_dl = nccl_open(nccl_lib);
+    if (!c->nccl_dl) return SHUD_ERR_CUDA;
+    auto init = (int (*)(void **, int, nccl_uid, int))dlsym(c->nccl_dl, "ncclCommInitRank");
+    c->nccl_send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(c->nccl_dl, "ncclSend");
+    c->nccl_recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(c->nccl_dl, "ncclRecv");
+    c->nccl_group_start = (int (*)())dlsym(c->nccl_dl, "ncclGroupStart");
+    c->nccl_group_end = (int (*)())dlsym(c->nccl_dl, "ncclGroupEnd");
+    c->nccl_comm_destroy = (int (*)(void *))dlsym(c->nccl_dl, "ncclCommDestroy");
+    if (!init || !c->nccl_send || !c->nccl_recv || !c->nccl_group_start || !c->nccl_group_end) return SHUD_ERR_CUDA;
+    nccl_uid id;
+    memcpy(&id, id128, sizeof(id));
+    if (init(&c->nccl_comm, world, id, rank) != 0) return SHUD_ERR_CUDA;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+    return SHUD_OK;
+}
+
+int shud_b200_exchange_plan(shud_ctx *c, int npeers, const int32_t *peer_rank, const int32_t *send_count,
+                            const int32_t *recv_count, const int32_t *send_cells) {
+    if (!c || npeers < 0 || (npeers > 0 && (!peer_rank || !send_count || !recv_count))) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->x_peer.assign(peer_rank, peer_rank + npeers);
+    c->x_scount.assign(send_count, send_count + npeers);
+    c->x_rcount.assign(recv_count, recv_count + npeers);
+    int ns = 0, nr = 0;
+    for (int p = 0; p < npeers; p++) { ns += send_count[p]; nr += recv_count[p]; }
+    if (nr != c->Nhalo || (ns > 0 && !send_cells)) return SHUD_ERR_ARG;
+    std::vector<int> idx(ns);
+    for (int k = 0; k < ns; k++) {  // reference-local ids (0-based) -> device order
+        if (send_cells[k] < 0 || send_cells[k] >= c->Ne) return SHUD_ERR_ARG;
+        idx[k] = c->cinv[send_cells[k]];
+    }
+    c->x_nsend = ns;
+    c->x_sidx = dev_upload(c, idx);
+    c->x_sbuf = dev_alloc<double>(c, 2 * (size_t)std::max(ns, 1));
+    c->x_hstate = dev_alloc<double>(c, 2 * (size_t)std::max(nr, 1));
+    CK(cudaMemset(c->x_hstate, 0, sizeof(double) * 2 * (size_t)std::max(nr, 1)));
+    return shud_b200_set_halo_state_dev(c, c->x_hstate);
+}
+
+int shud_b200_rhs_exchange_dev(shud_ctx *c, double t, const double *y, double *ydot) {
+    if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    if (!c->nccl_comm || !c->xstream) return SHUD_ERR_ARG;  // shud_b200_comm_init + shud_b200_exchange_plan first
+    // pack my boundary cells -> post the sends / receives on the exchange stream -> interior part of f() beside
+    // them on the context stream -> boundary part (its tiles on the exchange stream, behind the receives)
+    if (c->x_nsend > 0)
+        k_pack_halo<<<(c->x_nsend + 255) / 256, 256, 0, c->stream>>>(y, c->x_sidx, c->x_nsend, c->Ne, c->x_sbuf);
+    CK(cudaEventRecord(c->ev_pack, c->stream));
+    CK(cudaStreamWaitEvent(c->xstream, c->ev_pack, 0));
+    if (!c->x_peer.empty()) {
+        const int f64 = 8;  // ncclFloat64
+        if (c->nccl_group_start() != 0) return SHUD_ERR_CUDA;
+        size_t so = 0, ro = 0;
+        for (size_t p = 0; p < c->x_peer.size(); p++) {
+            const size_t ns = 2 * (size_t)c->x_scount[p], nr = 2 * (size_t)c->x_rcount[p];
+            if (ns && c->nccl_send(c->x_sbuf + so, ns, f64, c->x_peer[p], c->nccl_comm, c->xstream) != 0) return SHUD_ERR_CUDA;
+            if (nr && c->nccl_recv(c->x_hstate + ro, nr, f64, c->x_peer[p], c->nccl_comm, c->xstream) != 0) return SHUD_ERR_CUDA;
+            so += ns; ro += nr;
+        }
+        if (c->nccl_group_end() != 0) return SHUD_ERR_CUDA;
+    }
+    int rc = shud_b200_rhs_interior_dev(c, t, y, ydot);
+    if (rc) return rc;
+    return shud_b200_rhs_boundary_dev(c, t, y, ydot, c->xstream);
 }
 
 int shud_b200_perm(const shud_ctx *c, int32_t *cp, int32_t *rp) {

@@ -178,6 +178,7 @@ class HaloExchange:
         self.recv_counts = [int(g.size) for g in recv_gid]
         assert sum(self.recv_counts) == self.Nhalo, (sum(self.recv_counts), self.Nhalo)
         ids = np.concatenate(send_ids) if send_ids else np.zeros(0, dtype=np.int64)
+        self.send_cells_ref = ids.astype(np.int32)  # reference-local ids, concatenated by peer rank
         if cell_perm is not None:  # reference-local id -> device-order id of the context
             inv = np.empty(self.Ne, dtype=np.int64); inv[np.asarray(cell_perm)] = np.arange(self.Ne)
             ids = inv[ids]
@@ -194,6 +195,16 @@ class HaloExchange:
         self.ns, self.nr = ns, nr
         self.pack_fn = pack_fn
         self.bytes_per_exchange = 16 * ns
+
+    def native_plan(self):
+        """(peer ranks, send counts, recv counts, send cells) for shud_b200_exchange_plan: the same exchange driven by
+        the C library over its own NCCL communicator.  Needs the receives to land in halo order (they do when halo
+        cells are numbered by (owner rank, global id), which partition.extract and synth stripes guarantee)."""
+        if not self.in_place:
+            raise NotImplementedError("halo cells are not ordered by (owner, global id)")
+        peers = [q for q in range(self.world) if self.send_counts[q] or self.recv_counts[q]]
+        return (np.asarray(peers, dtype=np.int32), np.asarray([self.send_counts[q] for q in peers], dtype=np.int32),
+                np.asarray([self.recv_counts[q] for q in peers], dtype=np.int32), self.send_cells_ref)
 
     def start(self, y):
         """pack on the current stream and post the exchange on the side stream `self.side`: the caller overlaps it
