@@ -1176,13 +1176,14 @@ struct shud_ctx {
     int *x_sidx = nullptr;            // device-order ids of the cells sent, concatenated by peer
     double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
     int x_nsend = 0;
+    int use_xgraph = 1;               // SHUD_XGRAPH: rhs_exchange_dev replayed as one CUDA graph per (y, ydot)
     int pipe_grid = 296;  // persistent blocks of k_pipe: 2 per SM (2 stages) or 4 per SM (1 stage)
     int pipe_stages = 2;
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
     int use_graph = 1;
     int use_pdl = 1;   // programmatic dependent launch of the cell kernel behind k_effkh (SHUD_PDL)
     struct GraphEntry { const double *y; double *yd; cudaGraphExec_t exec; };
-    std::vector<GraphEntry> graphs;
+    std::vector<GraphEntry> graphs, xgraphs;
     int split = 2;      // 2: warp-specialised fused cell kernel (default); 0: one-thread-per-cell k_cell (SHUD_SPLIT, A/B only)
     int cell_minb = 4;  // resident blocks per SM the cell kernel is compiled for (tuning knob)
 };
@@ -1347,6 +1348,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         if (getenv("SHUD_PIPE_GRID")) c->pipe_grid = atoi(getenv("SHUD_PIPE_GRID"));
         if (getenv("SHUD_PDL")) c->use_pdl = atoi(getenv("SHUD_PDL"));
         if (getenv("SHUD_GRAPH")) c->use_graph = atoi(getenv("SHUD_GRAPH"));
+        if (getenv("SHUD_XGRAPH")) c->use_xgraph = atoi(getenv("SHUD_XGRAPH"));
         if (getenv("SHUD_FUSED_MINB")) c->fused_minb = atoi(getenv("SHUD_FUSED_MINB"));
     }
 
@@ -1758,9 +1760,7 @@ int shud_b200_exchange_plan(shud_ctx *c, int npeers, const int32_t *peer_rank, c
     return shud_b200_set_halo_state_dev(c, c->x_hstate);
 }
 
-int shud_b200_rhs_exchange_dev(shud_ctx *c, double t, const double *y, double *ydot) {
-    if (!c || !y || !ydot) return SHUD_ERR_ARG;
-    if (!c->nccl_comm || !c->xstream) return SHUD_ERR_ARG;  // shud_b200_comm_init + shud_b200_exchange_plan first
+static int exchange_launch(shud_ctx *c, double t, const double *y, double *ydot) {
     // pack my boundary cells -> post the sends / receives on the exchange stream -> interior part of f() beside
     // them on the context stream -> boundary part (its tiles on the exchange stream, behind the receives)
     if (c->x_nsend > 0)
@@ -1782,6 +1782,41 @@ int shud_b200_rhs_exchange_dev(shud_ctx *c, double t, const double *y, double *y
     int rc = shud_b200_rhs_interior_dev(c, t, y, ydot);
     if (rc) return rc;
     return shud_b200_rhs_boundary_dev(c, t, y, ydot, c->xstream);
+}
+
+int shud_b200_rhs_exchange_dev(shud_ctx *c, double t, const double *y, double *ydot) {
+    if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    if (!c->nccl_comm || !c->xstream) return SHUD_ERR_ARG;  // shud_b200_comm_init + shud_b200_exchange_plan first
+    if (!c->use_xgraph) return exchange_launch(c, t, y, ydot);
+    // as shud_b200_rhs_dev: the sequence (collective included) is fixed, one instantiated graph per pointer pair
+    for (auto &g : c->xgraphs)
+        if (g.y == y && g.yd == ydot) {
+            CK(cudaGraphLaunch(g.exec, c->stream));
+            return SHUD_OK;
+        }
+    if (c->xgraphs.size() >= 32) {
+        for (auto &g : c->xgraphs) cudaGraphExecDestroy(g.exec);
+        c->xgraphs.clear();
+    }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        c->use_xgraph = 0;
+        return exchange_launch(c, t, y, ydot);
+    }
+    int rc = exchange_launch(c, t, y, ydot);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == SHUD_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != SHUD_OK || e != cudaSuccess || !exec) {
+        cudaGetLastError();
+        c->use_xgraph = 0;  // capture of the collective unavailable: plain launches
+        return exchange_launch(c, t, y, ydot);
+    }
+    c->xgraphs.push_back({y, ydot, exec});
+    CK(cudaGraphLaunch(exec, c->stream));
+    return SHUD_OK;
 }
 
 int shud_b200_perm(const shud_ctx *c, int32_t *cp, int32_t *rp) {
@@ -1903,6 +1938,8 @@ extern "C" {
 static void drop_graphs(shud_ctx *c) {
     for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
     c->graphs.clear();
+    for (auto &g : c->xgraphs) cudaGraphExecDestroy(g.exec);
+    c->xgraphs.clear();
 }
 
 int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
