@@ -170,6 +170,46 @@ int shud_b200_comm_init(shud_ctx *ctx, const char *nccl_lib, const void *id128, 
 int shud_b200_exchange_plan(shud_ctx *ctx, int npeers, const int32_t *peer_rank, const int32_t *send_count,
                             const int32_t *recv_count, const int32_t *send_cells);
 int shud_b200_rhs_exchange_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+/* ---- land-surface step on the device ----
+ * Replaces the per-cell loops of Model_Data::updateforcing / tReadForcing (src/ModelData/MD_ET.cpp:14-281:
+ * lapse-rate temperature, terrain-radiation factor, Penman-Monteith potential evaporation / transpiration) and
+ * Model_Data::ET (MD_ET.cpp:282-342: snow and interception buckets, net precipitation), which the reference runs
+ * on the host once per ET step (src/Model/shud.cpp:106-109).  The results are written straight into the device
+ * arrays the RHS reads (what shud_b200_set_forcing would upload: qEleNetPrep, qPotEvap, qPotTran, t_lai, fu_Surf,
+ * fu_Sub, qEleE_IC, and the lake means of qPotEvap / qElePrep), so the 9*Ne doubles no longer cross PCIe.
+ * What stays on the host is O(stations + classes) per step: the time-series lookups and solarPosition(). */
+typedef struct shud_land {
+    int32_t nforc, nlc, nmf;                         /* forcing stations, land-cover classes, melt-factor classes */
+    const int32_t *iForc, *iLC, *iMF;                /* [Ne] 1-based ids, Element.hpp:49-52 */
+    const double *Albedo, *FixPressure, *windH;      /* [Ne] */
+    const double *nx, *ny, *nz;                      /* [Ne] unit surface normal (terrain radiation), Element.hpp:38 */
+    const double *forc_z;                            /* [nforc] station elevation; -9999 = none (no lapse-rate shift) */
+    double cPrep, cTemp, cLAItsd, cMF, cETP, cISmax; /* calibration multipliers, ModelConfigure.hpp (globalCal) */
+    int32_t radiation_is_net;                        /* RADIATION_INPUT_MODE == SWNET (MD_ET.cpp:208-214) */
+    int32_t terrain_radiation;                       /* TERRAIN_RADIATION */
+    int32_t cryosphere;                              /* CRYOSPHERE: 1 is not supported yet (SHUD_ERR_ARG) */
+    double rad_factor_cap, rad_cosz_min;
+} shud_land;
+
+typedef struct shud_land_step {
+    const double *forc;      /* [nforc][5] prcp, temp, rh, wind, rn of each station's current interval (i_prcp..i_rn) */
+    const double *lai, *mf;  /* [nlc], [nmf] tsd_LAI / tsd_MF value of each class at t */
+    int32_t tsr_n;           /* solar samples of the forcing interval (host: solarPosition(), MD_ET.cpp:74-138);
+                                < 0: the interval start is not finite (factor 0, MD_ET.cpp:66-67) */
+    const double *tsr_sx, *tsr_sy, *tsr_sz, *tsr_wdt;  /* [tsr_n] */
+    double tsr_den;
+    double dt_min;           /* tnext - t of ET(t, tnext) */
+} shud_land_step;
+
+typedef struct shud_land_out { /* host arrays [Ne] in reference order, any may be NULL */
+    double *qElePrep, *qPotEvap, *qPotTran, *qEleETP, *t_lai, *t_temp, *t_mf, *qEleNetPrep, *qEleE_IC, *fu_Surf,
+        *fu_Sub, *rn_factor, *yEleSnow, *yEleIS;
+} shud_land_out;
+
+int shud_b200_land_create(shud_ctx *ctx, const shud_land *L);
+int shud_b200_land_set_state(shud_ctx *ctx, const double *yEleSnow, const double *yEleIS); /* host [Ne] */
+int shud_b200_land_step(shud_ctx *ctx, const shud_land_step *S); /* asynchronous on the context stream */
+int shud_b200_land_get(shud_ctx *ctx, const shud_land_out *out);  /* synchronises */
 /* number of 128-cell tiles in each part (interior + boundary = ceil(Ne/128)) */
 int shud_b200_tile_counts(const shud_ctx *ctx, int *n_interior, int *n_boundary);
 int shud_b200_rhs_boundary_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev, void *halo_stream);

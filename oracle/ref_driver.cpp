@@ -18,6 +18,10 @@
  *
  * usage: shud_ref <prj> <out.bin> [--t MIN] [--state ic|rand:<seed>]
  *                 [--mutate a,b,..] [--time REPS] [--forcing-seq NSTEPS]
+ *   --land-seq N [--land-t0 MIN]: replay N consecutive land-surface steps (updateAllTimeSeries + updateforcing + ET) on a fresh
+ *   model and dump, per step, everything the per-cell part consumes (station rows, LAI / melt-factor class
+ *   values, the terrain-radiation solar samples of the forcing interval) and produces: the pin of the
+ *   land-surface step.
  *   --forcing-seq N: additionally replay the reference's land-surface step for N consecutive ET steps of
  *   60 min (updateAllTimeSeries + updateforcing + ET, src/Model/shud.cpp:106-109) and dump what each hands to
  *   the RHS (fseq_<array>, [N][Ne]); these depend on the forcing files and the snow / interception buckets
@@ -151,14 +155,16 @@ int main(int argc, char **argv) {
         return 2;
     }
     std::string prj = argv[1], outfn = argv[2], state = "ic", mutate = "";
-    double t_arg = NAN;
-    int reps = 0, fseq = 0;
+    double t_arg = NAN, land_t0 = NAN;
+    int reps = 0, fseq = 0, lseq = 0;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--t") && a + 1 < argc) t_arg = atof(argv[++a]);
         else if (!strcmp(argv[a], "--state") && a + 1 < argc) state = argv[++a];
         else if (!strcmp(argv[a], "--mutate") && a + 1 < argc) mutate = argv[++a];
         else if (!strcmp(argv[a], "--time") && a + 1 < argc) reps = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--forcing-seq") && a + 1 < argc) fseq = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--land-seq") && a + 1 < argc) lseq = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--land-t0") && a + 1 < argc) land_t0 = atof(argv[++a]);
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
 
@@ -416,6 +422,66 @@ int main(int argc, char **argv) {
         }
         for (int a = 0; a < 8; a++) putd((std::string("fseq_") + names[a]).c_str(), seq[a]);
         putd("fseq_t", tt);
+    }
+    if (lseq > 0) {
+        Model_Data *M3 = new Model_Data(fin, fout);
+        M3->loadinput(); M3->initialize(); M3->CheckInputData(); M3->LoadIC();
+        const int nf = M3->NumForc;
+        int nlc = 0, nmf = 0;
+        {
+            std::vector<int> iForc(Ne), iLC(Ne), iMF(Ne);
+            std::vector<double> alb(Ne), fp(Ne), wh(Ne), nx(Ne), ny(Ne), nz(Ne);
+            for (int i = 0; i < Ne; i++) {
+                iForc[i] = M3->Ele[i].iForc; iLC[i] = M3->Ele[i].iLC; iMF[i] = M3->Ele[i].iMF;
+                alb[i] = M3->Ele[i].Albedo; fp[i] = M3->Ele[i].FixPressure; wh[i] = M3->Ele[i].windH;
+                nx[i] = M3->Ele[i].nx; ny[i] = M3->Ele[i].ny; nz[i] = M3->Ele[i].nz;
+                nlc = std::max(nlc, iLC[i]); nmf = std::max(nmf, iMF[i]);
+            }
+            puti("land_iForc", iForc); puti("land_iLC", iLC); puti("land_iMF", iMF);
+            putd("land_Albedo", alb); putd("land_FixPressure", fp); putd("land_windH", wh);
+            putd("land_nx", nx); putd("land_ny", ny); putd("land_nz", nz);
+            std::vector<double> fz(nf);
+            for (int k = 0; k < nf; k++) fz[k] = M3->forcing ? M3->forcing->z(k) : M3->tsd_weather[k].xyz[2];
+            putd("land_forc_z", fz);
+            const double gcv[] = {M3->gc.cPrep, M3->gc.cTemp, M3->gc.cLAItsd, M3->gc.cMF, M3->gc.cETP, M3->gc.cISmax};
+            putd("land_gc", gcv, 6);
+            const double csv[] = {(double)M3->CS.radiation_input_mode, (double)M3->CS.terrain_radiation, (double)M3->CS.cryosphere,
+                                  M3->CS.rad_factor_cap, M3->CS.rad_cosz_min, (double)SWNET};
+            putd("land_cs", csv, 6);
+            putd("land_yEleSnow0", M3->yEleSnow, Ne); putd("land_yEleIS0", M3->yEleIS, Ne);
+        }
+        const char *onames[] = {"qElePrep", "qPotEvap", "qPotTran", "qEleETP", "t_lai", "t_temp", "t_mf", "qEleNetPrep",
+                                "qEleE_IC", "yEleSnow", "yEleIS", "fu_Surf", "fu_Sub", "rn_factor"};
+        std::vector<std::vector<double>> out(14);
+        std::vector<double> tt, frows, lai, mf, sx, sy, sz, wdt, den;
+        std::vector<int> sn;
+        double tf = std::isnan(land_t0) ? M3->CS.StartTime : land_t0;
+        for (int k = 0; k < lseq; k++, tf += 60.) {
+            M3->updateAllTimeSeries(tf);
+            M3->updateforcing(tf);
+            M3->ET(tf, tf + 60.);
+            for (int st = 0; st < nf; st++)
+                for (int col = 1; col <= 5; col++)
+                    frows.push_back(M3->forcing ? M3->forcing->get(st, col) : M3->tsd_weather[st].getX(tf, col));
+            for (int c = 1; c <= nlc; c++) lai.push_back(M3->tsd_LAI.getX(tf, c));
+            for (int c = 1; c <= nmf; c++) mf.push_back(M3->tsd_MF.getX(tf, c));
+            sn.push_back(M3->tsr_forcing_n);
+            den.push_back(M3->tsr_forcing_den);
+            sx.insert(sx.end(), M3->tsr_forcing_sx.begin(), M3->tsr_forcing_sx.end());
+            sy.insert(sy.end(), M3->tsr_forcing_sy.begin(), M3->tsr_forcing_sy.end());
+            sz.insert(sz.end(), M3->tsr_forcing_sz.begin(), M3->tsr_forcing_sz.end());
+            wdt.insert(wdt.end(), M3->tsr_forcing_wdt.begin(), M3->tsr_forcing_wdt.end());
+            const double *src[] = {M3->qElePrep, M3->qPotEvap, M3->qPotTran, M3->qEleETP, M3->t_lai, M3->t_temp, M3->t_mf,
+                                   M3->qEleNetPrep, M3->qEleE_IC, M3->yEleSnow, M3->yEleIS, M3->fu_Surf, M3->fu_Sub,
+                                   M3->ele_rn_factor};
+            for (int a = 0; a < 14; a++) out[a].insert(out[a].end(), src[a], src[a] + Ne);
+            tt.push_back(tf);
+        }
+        put1i("land_nforc", nf); put1i("land_nlc", nlc); put1i("land_nmf", nmf);
+        putd("lseq_t", tt); putd("lseq_forc", frows); putd("lseq_lai", lai); putd("lseq_mf", mf);
+        puti("lseq_tsr_n", sn); putd("lseq_tsr_den", den);
+        putd("lseq_tsr_sx", sx); putd("lseq_tsr_sy", sy); putd("lseq_tsr_sz", sz); putd("lseq_tsr_wdt", wdt);
+        for (int a = 0; a < 14; a++) putd((std::string("lseq_") + onames[a]).c_str(), out[a]);
     }
     fclose(g_out);
 

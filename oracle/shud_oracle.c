@@ -769,3 +769,187 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *F, double *u_satn_io
     }
     return err;
 }
+
+
+/* =====================================================================================================
+ * Land-surface step: restatement of Model_Data::tReadForcing
+ * (src/ModelData/MD_ET.cpp:21-281) and Model_Data::ET (MD_ET.cpp:282-342) with the helpers of
+ * src/Equations/is_sm_et.hpp / is_sm_et.cpp, Equations.hpp:66-72 and functions.hpp:191-201.
+ * Pinned by tests/golden/ccw.land.npz: 30 consecutive steps of the reference itself (oracle/ref_driver.cpp
+ * --land-seq), rain, snow accumulation and melt, interception, day and night, terrain radiation on.
+ * ===================================================================================================== */
+#define L_SecADay 86400          /* Macros.hpp:43 */
+#define L_dTdZ 0.0065            /* Macros.hpp:50 */
+#define L_Tsnow (-3.0)           /* Macros.hpp:59 */
+#define L_Train 1.0              /* Macros.hpp:60 */
+#define L_To 0.0                 /* Macros.hpp:61 */
+#define L_ROUGHNESS_WATER 0.00137 /* Macros.hpp:62 */
+#define L_CONST_RH 0.01          /* Macros.hpp:63 */
+#define L_IC_MAX 0.0002          /* Macros.hpp:65 */
+#define L_VON_KARMAN 0.4         /* Macros.hpp:70 */
+#define L_Cp 1.013e-3            /* Macros.hpp:72 */
+#define L_NA (-9999)             /* Macros.hpp:83 */
+static double lmin(double a, double b) { return a > b ? b : a; } /* functions.hpp:117-123 */
+static double lmax(double a, double b) { return a < b ? b : a; }
+static double frozen_fraction(double T, double high, double low) { /* functions.hpp:191-201 */
+    if (T > high) return 0;
+    if (T < low) return 1;
+    return lmin(1.0, lmax((high - T) / (high - low), 0.0));
+}
+
+int shud_oracle_land_step(const shud_mesh *m, const shud_land *L, const shud_land_step *S, double *yEleSnow,
+                          double *yEleIS, const shud_land_out *out) {
+    const int Ne = m->Ne;
+    int rc = 0;
+    const double DT_min = S->dt_min;
+    for (int i = 0; i < Ne; i++) {
+        /* ---------------- tReadForcing, MD_ET.cpp:21-281 ---------------- */
+        const int idx = L->iForc[i] - 1;
+        const double *row = S->forc + 5 * idx;
+        double t_prcp = row[0] * L->cPrep;
+        const double t0 = row[1];
+        const double Zt = L->forc_z[idx], Zi = m->z_surf[i];
+        double t_temp; /* TemperatureOnElevation, Equations.hpp:66-72 */
+        if (fabs(Zi - L_NA) < ZERO || fabs(Zt - L_NA) < ZERO) t_temp = t0;
+        else t_temp = t0 + (Zt - Zi) * L_dTdZ;
+        t_temp = t_temp + L->cTemp;
+        const double lai = S->lai[L->iLC[i] - 1] * L->cLAItsd;
+        const double t_mf = S->mf[L->iMF[i] - 1] * L->cMF / 1440.;
+        const double dswrf_h = row[4];
+        double dswrf_t = dswrf_h, factor = 1.0;
+        if (L->terrain_radiation) {
+            if (S->tsr_n < 0) {
+                factor = 0.0;
+            } else {
+                double num = 0.0;
+                const double cap = L->rad_factor_cap, cosz_min = L->rad_cosz_min;
+                if (S->tsr_den > 0.0 && S->tsr_n > 0) {
+                    const double nx = L->nx[i], ny = L->ny[i], nz = L->nz[i];
+                    for (int k = 0; k < S->tsr_n; k++) {
+                        const double wdt = S->tsr_wdt[k];
+                        if (!(wdt > 0.0)) continue;
+                        const double sx = S->tsr_sx[k], sy = S->tsr_sy[k], sz = S->tsr_sz[k];
+                        const double cosi = nx * sx + ny * sy + nz * sz;
+                        if (!(cosi > 0.0) || !isfinite(cosi)) continue;
+                        double denom = sz;
+                        if (denom < cosz_min) denom = cosz_min;
+                        if (!(denom > 0.0) || !isfinite(denom)) continue;
+                        double fk = cosi / denom;
+                        if (!isfinite(fk) || !(fk > 0.0)) continue;
+                        if (fk > cap) fk = cap;
+                        num += wdt * fk;
+                    }
+                }
+                double feff = 0.0;
+                if (S->tsr_den > 0.0) {
+                    feff = num / S->tsr_den;
+                    if (!isfinite(feff) || !(feff > 0.0)) feff = 0.0;
+                    if (feff > L->rad_factor_cap) feff = L->rad_factor_cap;
+                }
+                factor = feff;
+            }
+            dswrf_t = dswrf_h * factor;
+        }
+        double t_rn = L->radiation_is_net ? dswrf_t : dswrf_t * (1 - L->Albedo[i]);
+        const double Uz = fabs(row[3]) + 0.001;
+        double t_rh = row[2];
+        t_prcp = t_prcp * 0.001 / 1440.;
+        t_rn = t_rn * 1.0e-6;
+        t_rh = lmin(lmax(t_rh, L_CONST_RH), 1.0);
+        const double lambda = 2.501 - 0.002361 * t_temp;                       /* LatentHeat */
+        const double Gamma = 0.0016286 * L->FixPressure[i] / lambda;           /* PsychrometricConstant */
+        const double es = 0.6108 * exp(17.27 * t_temp / (t_temp + 237.3));     /* VaporPressure_Sat */
+        const double ea = es * t_rh;
+        const double ed = es - ea;
+        const double tt = t_temp + 237.3;
+        const double Delta = 4098. * es / (tt * tt);                           /* SlopeSatVaporPressure */
+        const double rho = 3.486 * L->FixPressure[i] / (275. + t_temp);        /* AirDensity */
+        const int lake = m->iLake[i] > 0;
+        double GroundHeatFlux;
+        if (lake) GroundHeatFlux = 0.;
+        else if (lai > 0) GroundHeatFlux = 0.4 * exp(-0.5 * lai) * t_rn;
+        else GroundHeatFlux = 0.1 * t_rn;
+        const double RG = t_rn - GroundHeatFlux;
+        /* WindProfile(2.0, Uz, windH, 0., ROUGHNESS_WATER) */
+        const double U2 = Uz * log((2.0 - 0.) / L_ROUGHNESS_WATER) / log((L->windH[i] - 0.) / L_ROUGHNESS_WATER);
+        double pm_ow; /* PET_PM_openwater, is_sm_et.cpp:57-64 */
+        {
+            double ETp = (Delta * RG * L_SecADay + Gamma * 6.43 * (1.0 + 0.536 * U2) * ed) / (Delta + Gamma);
+            ETp = ETp / lambda;
+            ETp = ETp * 0.001 / L_SecADay;
+            pm_ow = ETp;
+        }
+        const double qPotEvap = L->cETP * pm_ow * 60.;
+        double qPotTran, etp;
+        if (lake) {
+            qPotTran = L->cETP * 0.;
+            etp = qPotEvap;
+        } else if (lai <= 0.) {
+            qPotTran = L->cETP * 0.;
+            etp = qPotEvap;
+        } else {
+            const double hc = lai * 0.5;
+            const double Zmeasure = hc * 1.3333;
+            double ra; /* AerodynamicResistance(Uz, hc, Zmeasure, Zmeasure), is_sm_et.hpp */
+            {
+                const double d = 0.67 * hc, Z_om = 0.123 * hc, Z_ov = 0.0123 * hc;
+                ra = log(fabs(Zmeasure - d) / Z_om) * log(fabs(Zmeasure - d) / (Z_ov)) / (L_VON_KARMAN * L_VON_KARMAN * Uz);
+            }
+            if (ra <= 0.0 || isnan(ra) || isinf(ra) || fabs(ra - L_NA) < ZERO) rc = 10; /* CheckNonZero */
+            const double rs = 200. / lai; /* BulkSurfaceResistance(lai) */
+            double pm; /* PET_Penman_Monteith, is_sm_et.cpp:32-56 */
+            {
+                const double E_rad = Delta * RG;
+                const double E_air = rho * L_Cp * ed / ra;
+                const double r_sa = rs / ra;
+                double ETp = (E_rad + E_air) / (Delta + Gamma * (1 + r_sa));
+                ETp = ETp / lambda;
+                ETp = ETp * 0.001;
+                pm = ETp;
+            }
+            qPotTran = L->cETP * pm * 60.;
+            etp = qPotTran * m->VegFrac[i] + qPotEvap * (1. - m->VegFrac[i]);
+            if (isnan(qPotTran)) rc = 10;
+        }
+        /* ---------------- ET, MD_ET.cpp:282-342 ---------------- */
+        const double T = t_temp, prcp = t_prcp, MF = t_mf;
+        double snStg = yEleSnow[i];
+        const double snFrac = frozen_fraction(T, L_Train, L_Tsnow);
+        const double fu_Sub = 1., fu_Surf = 1.; /* cryosphere = 0 (CS.cryosphere = 1 needs the AccT accumulators) */
+        const double snAcc = snFrac * prcp;
+        double snMelt = (T > L_To ? (T - L_To) * MF : 0.);
+        snMelt = lmin(lmax(0., snStg / DT_min), lmax(0., snMelt));
+        snStg += (snAcc - snMelt) * DT_min;
+        const double vgFrac = m->VegFrac[i];
+        double icStg = (vgFrac > ZERO) ? (yEleIS[i] / vgFrac) : 0.0;
+        double icAcc, icEvap;
+        if (lai > ZERO) {
+            const double icMax = L->cISmax * L_IC_MAX * lai;
+            icAcc = lmin(prcp - snAcc, lmax(0., (icMax - icStg) / DT_min));
+            icEvap = lmin(lmax(0., icStg / DT_min), qPotEvap);
+        } else {
+            icAcc = 0.;
+            icEvap = 0.;
+        }
+        icStg += (icAcc - icEvap) * DT_min;
+        yEleIS[i] = icStg * vgFrac;
+        yEleSnow[i] = snStg;
+        if (out) {
+            if (out->qElePrep) out->qElePrep[i] = t_prcp;
+            if (out->qPotEvap) out->qPotEvap[i] = qPotEvap;
+            if (out->qPotTran) out->qPotTran[i] = qPotTran;
+            if (out->qEleETP) out->qEleETP[i] = etp;
+            if (out->t_lai) out->t_lai[i] = lai;
+            if (out->t_temp) out->t_temp[i] = t_temp;
+            if (out->t_mf) out->t_mf[i] = t_mf;
+            if (out->qEleNetPrep) out->qEleNetPrep[i] = (1. - snFrac) * prcp + snMelt - icAcc * vgFrac;
+            if (out->qEleE_IC) out->qEleE_IC[i] = icEvap * vgFrac;
+            if (out->fu_Surf) out->fu_Surf[i] = fu_Surf;
+            if (out->fu_Sub) out->fu_Sub[i] = fu_Sub;
+            if (out->rn_factor) out->rn_factor[i] = factor;
+            if (out->yEleSnow) out->yEleSnow[i] = snStg;
+            if (out->yEleIS) out->yEleIS[i] = icStg * vgFrac;
+        }
+    }
+    return rc;
+}

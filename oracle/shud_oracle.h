@@ -18,6 +18,12 @@ int shud_oracle_rhs(const shud_mesh *m, const shud_forcing *f, double *u_satn, d
 /* Ele[i].u_satn as Model_Data::updateforcing -> _Element::updateElement leaves it
  * (src/ModelData/MD_ET.cpp:14-19, src/classes/Element.cpp:347-373). */
 void shud_oracle_prime(const shud_mesh *m, const double *y, double *u_satn);
+/* One land-surface step: Model_Data::updateforcing -> tReadForcing (src/ModelData/MD_ET.cpp:14-281) followed by
+ * Model_Data::ET (MD_ET.cpp:282-342), per cell, on the SoA inputs of shud_land / shud_land_step.
+ *   z_surf, VegFrac, iLake : the shud_mesh members;  yEleSnow, yEleIS [Ne] in/out;  out: any pointer may be NULL
+ * returns 0, or 10 where the reference exits (CheckNonZero of the aerodynamic resistance, NaN qPotTran). */
+int shud_oracle_land_step(const shud_mesh *m, const shud_land *L, const shud_land_step *S, double *yEleSnow,
+                          double *yEleIS, const shud_land_out *out);
 /* how many scratch doubles per call the oracle allocates (informational) */
 const char *shud_oracle_version(void);
 #ifdef __cplusplus

@@ -84,6 +84,29 @@ class ShudDiag(C.Structure):
     _fields_ = [(n, _PD) for n in DIAG_ALL]
 
 
+LAND_OUT = ["qElePrep", "qPotEvap", "qPotTran", "qEleETP", "t_lai", "t_temp", "t_mf", "qEleNetPrep", "qEleE_IC", "fu_Surf",
+            "fu_Sub", "rn_factor", "yEleSnow", "yEleIS"]
+
+
+class ShudLand(C.Structure):  # include/shud_b200.h: shud_land
+    _fields_ = ([("nforc", C.c_int32), ("nlc", C.c_int32), ("nmf", C.c_int32)]
+                + [(n, _PI) for n in ("iForc", "iLC", "iMF")]
+                + [(n, _PD) for n in ("Albedo", "FixPressure", "windH", "nx", "ny", "nz", "forc_z")]
+                + [(n, C.c_double) for n in ("cPrep", "cTemp", "cLAItsd", "cMF", "cETP", "cISmax")]
+                + [(n, C.c_int32) for n in ("radiation_is_net", "terrain_radiation", "cryosphere")]
+                + [("rad_factor_cap", C.c_double), ("rad_cosz_min", C.c_double)])
+
+
+class ShudLandStep(C.Structure):  # shud_land_step
+    _fields_ = ([("forc", _PD), ("lai", _PD), ("mf", _PD), ("tsr_n", C.c_int32)]
+                + [(n, _PD) for n in ("tsr_sx", "tsr_sy", "tsr_sz", "tsr_wdt")]
+                + [("tsr_den", C.c_double), ("dt_min", C.c_double)])
+
+
+class ShudLandOut(C.Structure):  # shud_land_out
+    _fields_ = [(n, _PD) for n in LAND_OUT]
+
+
 def _d(a):
     a = np.ascontiguousarray(a, dtype=np.float64)
     return a, a.ctypes.data_as(_PD)
@@ -169,3 +192,41 @@ def make_diag(Ne, Nr, Ns, Nl):
         arrs[n] = a
         setattr(d, n, a.ctypes.data_as(_PD) if k > 0 else None)
     return d, arrs
+
+
+def make_land(snap):
+    """land_* arrays of a --land-seq snapshot (oracle/ref_driver.cpp) -> (ShudLand, keepalive)"""
+    L, keep = ShudLand(), []
+    L.nforc, L.nlc, L.nmf = int(snap["land_nforc"][0]), int(snap["land_nlc"][0]), int(snap["land_nmf"][0])
+    for n in ("iForc", "iLC", "iMF"):
+        a, p = _i(snap["land_" + n]); keep.append(a); setattr(L, n, p)
+    for n in ("Albedo", "FixPressure", "windH", "nx", "ny", "nz", "forc_z"):
+        a, p = _d(snap["land_" + n]); keep.append(a); setattr(L, n, p)
+    gc, cs = snap["land_gc"], snap["land_cs"]
+    L.cPrep, L.cTemp, L.cLAItsd, L.cMF, L.cETP, L.cISmax = [float(v) for v in gc]
+    L.radiation_is_net = int(cs[0] == cs[5])
+    L.terrain_radiation, L.cryosphere = int(cs[1]), int(cs[2])
+    L.rad_factor_cap, L.rad_cosz_min = float(cs[3]), float(cs[4])
+    return L, keep
+
+
+def land_steps(snap):
+    """iterate the per-step inputs of a --land-seq snapshot: yields (k, ShudLandStep, keepalive)"""
+    nf, nlc, nmf = int(snap["land_nforc"][0]), int(snap["land_nlc"][0]), int(snap["land_nmf"][0])
+    n = np.asarray(snap["lseq_tsr_n"]); off = np.concatenate([[0], np.cumsum(n)])
+    for k in range(n.size):
+        S, keep = ShudLandStep(), []
+        for name, src in (("forc", snap["lseq_forc"][5 * nf * k:5 * nf * (k + 1)]), ("lai", snap["lseq_lai"][nlc * k:nlc * (k + 1)]),
+                          ("mf", snap["lseq_mf"][nmf * k:nmf * (k + 1)])):
+            a, p = _d(src); keep.append(a); setattr(S, name, p)
+        for name in ("sx", "sy", "sz", "wdt"):
+            a, p = _d(np.asarray(snap["lseq_tsr_" + name][off[k]:off[k + 1]])); keep.append(a); setattr(S, "tsr_" + name, p)
+        S.tsr_n, S.tsr_den, S.dt_min = int(n[k]), float(snap["lseq_tsr_den"][k]), 60.0
+        yield k, S, keep
+
+
+def make_land_out(Ne):
+    o, arrs = ShudLandOut(), {}
+    for n in LAND_OUT:
+        a = np.full(Ne, np.nan); arrs[n] = a; setattr(o, n, a.ctypes.data_as(_PD))
+    return o, arrs

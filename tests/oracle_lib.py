@@ -71,3 +71,23 @@ def oracle_prime(snap, y):
     satn = np.empty(mesh.Ne, dtype=np.float64)
     lib().shud_oracle_prime(C.byref(mesh), _pd(y), _pd(satn))
     return satn
+
+
+def oracle_land_seq(mesh_snap, land_snap):
+    """replay every step of a --land-seq snapshot through the oracle; returns dict name -> [nstep, Ne]"""
+    mesh, keep = abi.make_mesh(mesh_snap)
+    L, keep2 = abi.make_land(land_snap)
+    Ne = mesh.Ne
+    snow = np.array(land_snap["land_yEleSnow0"], dtype=np.float64, copy=True)
+    ics = np.array(land_snap["land_yEleIS0"], dtype=np.float64, copy=True)
+    fn = lib().shud_oracle_land_step
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 3 + [C.POINTER(C.c_double)] * 2 + [C.c_void_p]
+    res = {n: [] for n in abi.LAND_OUT}
+    for k, S, keep3 in abi.land_steps(land_snap):
+        o, arrs = abi.make_land_out(Ne)
+        rc = fn(C.byref(mesh), C.byref(L), C.byref(S), _pd(snow), _pd(ics), C.byref(o))
+        assert rc == 0, rc
+        for n in abi.LAND_OUT:
+            res[n].append(arrs[n].copy())
+    return {n: np.stack(v) for n, v in res.items()}

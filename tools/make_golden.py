@@ -103,6 +103,19 @@ def main():
     keep = {k: v for k, v in snap.items() if k.startswith("fseq_") and k not in ("fseq_fu_Surf", "fseq_fu_Sub")}
     keep["_cmd"] = np.array(" ".join(cmd[1:]))
     np.savez_compressed(os.path.join(OUT, "ccw.fseq.npz"), **keep)
+    # land-surface step (updateforcing + ET) sequences: per-step inputs and outputs of the reference itself
+    # (ccw: 30 hourly steps through a rain / snow / melt event with terrain radiation; qhh: 8 steps, lake cells,
+    # 3-hourly forcing so that three steps share one forcing interval)
+    for basin, n, t0 in (("ccw", 30, 4254000), ("qhh", 8, 225120)):
+        binf = os.path.join(WORK, f"{basin}.land.bin")
+        cmd = [EXE, basin, binf, "--land-seq", str(n), "--land-t0", str(t0)]
+        r = subprocess.run(cmd, cwd=WORK, capture_output=True, text=True, errors="replace")
+        if r.returncode != 0:
+            sys.exit(f"reference run failed: {cmd}\n{r.stdout[-2000:]}")
+        snap = snapshot.read_bin(binf)
+        keep = {k: v for k, v in snap.items() if k.startswith("land_") or k.startswith("lseq_")}
+        keep["_cmd"] = np.array(" ".join(cmd[1:]))
+        np.savez_compressed(os.path.join(OUT, f"{basin}.land.npz"), **keep)
     sz = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {len(os.listdir(OUT))} files, {sz/1e6:.2f} MB")
 
