@@ -62,6 +62,10 @@ def lib():
         "shud_b200_rhs_interior_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_boundary_dev": (C.c_int, [vp, C.c_double, vp, vp, vp]),
         "shud_b200_tile_counts": (C.c_int, [vp, _PI, _PI]),
+        "shud_b200_land_create": (C.c_int, [vp, C.POINTER(abi.ShudLand)]),
+        "shud_b200_land_set_state": (C.c_int, [vp, _PD, _PD]),
+        "shud_b200_land_step": (C.c_int, [vp, C.POINTER(abi.ShudLandStep)]),
+        "shud_b200_land_get": (C.c_int, [vp, C.POINTER(abi.ShudLandOut)]),
         "shud_b200_comm_unique_id": (C.c_int, [C.c_char_p, vp]),
         "shud_b200_comm_init": (C.c_int, [vp, C.c_char_p, vp, C.c_int, C.c_int]),
         "shud_b200_exchange_plan": (C.c_int, [vp, C.c_int, _PI, _PI, _PI, _PI]),
@@ -206,6 +210,24 @@ class ShudRHS:
         completes on (its halo-dependent tiles run there, beside the interior tiles), None = the context stream"""
         hs = C.c_void_p(halo_stream.cuda_stream) if halo_stream is not None else None
         _chk(lib().shud_b200_rhs_boundary_dev(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev), hs), "rhs_boundary_dev")
+
+    # ---- land-surface step on the device (updateforcing + ET of the reference) ----
+    def land_create(self, land):
+        """land: abi.ShudLand (abi.make_land builds it from a snapshot)"""
+        _chk(lib().shud_b200_land_create(self._h, C.byref(land)), "land_create")
+
+    def land_set_state(self, yEleSnow, yEleIS):
+        a = np.ascontiguousarray(yEleSnow, dtype=np.float64); b = np.ascontiguousarray(yEleIS, dtype=np.float64)
+        _chk(lib().shud_b200_land_set_state(self._h, a.ctypes.data_as(_PD), b.ctypes.data_as(_PD)), "land_set_state")
+
+    def land_step(self, step):
+        """step: abi.ShudLandStep; writes the RHS's forcing arrays on the device (no set_forcing needed)"""
+        _chk(lib().shud_b200_land_step(self._h, C.byref(step)), "land_step")
+
+    def land_get(self):
+        o, arrs = abi.make_land_out(self.Ne)
+        _chk(lib().shud_b200_land_get(self._h, C.byref(o)), "land_get")
+        return arrs
 
     # ---- halo exchange driven by the library over its own NCCL communicator ----
     @staticmethod

@@ -82,6 +82,22 @@ struct DevDiag {
         *QrivDown, *y2LakeArea, *QLakeSurf, *QLakeSub, *QLakeRivIn, *QLakeRivOut, *qLakeEvap, *qLakePrcp;
 };
 
+// land-surface step (shud_land.cuh): statics, bucket states, per-step tables, outputs kept for the host
+struct DevLand {
+    int nforc, nlc, nmf;
+    const int *iForc, *iLC, *iMF;
+    const double *albedo, *fixP, *windH, *nx, *ny, *nz, *forc_z;
+    double cPrep, cTemp, cLAItsd, cMF, cETP, cISmax;
+    int net, tsr;
+    double cap, cosz_min;
+    double *snow, *ics;                         // yEleSnow, yEleIS (device order)
+    double *tab;                                // per-step tables: forc[5 nforc] | lai[nlc] | mf[nmf] | sx|sy|sz|wdt [tsr_cap each]
+    int tsr_cap;
+    double *prep, *etp, *temp, *tmf, *factor;   // qElePrep, qEleETP, t_temp, t_mf, terrain factor
+    const int *lk_ptr, *lk_cell;                // lake -> its cells (device ids), ascending reference id
+    const double *lk_rnele;                     // lake -> (double)NumEleLake
+};
+
 __device__ __forceinline__ void raise_err(int *err, int code, int where) {
     if (atomicMax(&err[0], code) < code) err[1] = where;
 }
@@ -1143,6 +1159,9 @@ struct shud_ctx {
     int64_t NY = 0;
     DevMesh m{};
     DevDiag diag{};
+    DevLand land{};
+    bool has_land = false;
+    double *land_stage = nullptr;  // pinned staging of the per-step tables
     bool diag_alloc = false;
     DevDiag acc{};          // output accumulators (same shapes as diag) + effKH/satn/Qseg copies
     double *acc_effKH = nullptr, *acc_satn = nullptr, *acc_QsegSurf = nullptr, *acc_QsegSub = nullptr;
@@ -1589,6 +1608,7 @@ void shud_b200_destroy(shud_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->land_stage) cudaFreeHost(c->land_stage);
     if (c->xstream) cudaStreamSynchronize(c->xstream);
     if (c->nccl_comm && c->nccl_comm_destroy) c->nccl_comm_destroy(c->nccl_comm);
     if (c->xstream) cudaStreamDestroy(c->xstream);
@@ -2208,3 +2228,5 @@ static int download_diag(shud_ctx *c, const DevDiag &d, const double *effKH, con
 }
 
 }  // extern "C"
+
+#include "shud_land.cuh"
