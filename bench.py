@@ -338,6 +338,48 @@ def main():
             y_ref.copy_(yh); rhs.to_device_order(y_ref, y)
         st.synchronize()
 
+    # ---------------- land-surface step on the device (updateforcing + ET), against the upload it replaces --------
+    land_rec = None
+    if world == 1:
+        from shud_up_b200 import abi as _abi
+        rng = np.random.default_rng(20240611 + 7)
+        tilt = rng.normal(0, 0.15, (2, Ne)); nz_ = 1 / np.sqrt(1 + (tilt ** 2).sum(0))
+        lsnap = {"land_nforc": [1], "land_nlc": [12], "land_nmf": [1], "land_iForc": np.ones(Ne, np.int32),
+                 "land_iLC": rng.integers(1, 13, Ne).astype(np.int32), "land_iMF": np.ones(Ne, np.int32),
+                 "land_Albedo": rng.uniform(0.1, 0.3, Ne), "land_FixPressure": rng.uniform(85, 95, Ne),
+                 "land_windH": np.full(Ne, 10.0), "land_nx": tilt[0] * nz_, "land_ny": tilt[1] * nz_, "land_nz": nz_,
+                 "land_forc_z": [-9999.0], "land_gc": [1, 0, 1, 1, 1, 1], "land_cs": [0, 1, 0, 5.0, 0.05, 1]}
+        Lnd, _k1 = _abi.make_land(lsnap)
+        rhs.land_create(Lnd)
+        rhs.land_set_state(np.zeros(Ne), np.zeros(Ne))
+        S = _abi.ShudLandStep()
+        _arr = {"forc": np.array([12.0, 1.5, 0.85, 2.0, 150.0]), "lai": rng.uniform(0.3, 5.0, 12), "mf": np.array([0.0013]),
+                "tsr_sx": np.array([-0.6, -0.5]), "tsr_sy": np.array([-0.5, -0.4]), "tsr_sz": np.array([0.62, 0.77]),
+                "tsr_wdt": np.array([18.6, 23.1])}
+        for k_, v_ in _arr.items():
+            setattr(S, k_, v_.ctypes.data_as(_abi._PD))
+        S.tsr_n, S.tsr_den, S.dt_min = 2, 41.7, 60.0
+        for _ in range(3):
+            rhs.land_step(S)
+        st.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            rhs.land_step(S)
+        st.synchronize()
+        ms_land = (time.perf_counter() - t0) / 20 * 1e3
+        assert rhs.check()[0] == 0
+        t0 = time.perf_counter()
+        for _ in range(5):
+            rhs.set_forcing(mesh, qEleE_IC=mesh["qEleE_IC_in"])
+        st.synchronize()
+        ms_up = (time.perf_counter() - t0) / 5 * 1e3
+        rhs.prime(mesh["y"])
+        land_rec = {"ms_per_step": ms_land, "bytes_per_cell": 208, "achieved_gbs": 208 * Ne / (ms_land * 1e-3) / 1e9,
+                    "replaces_upload_ms": ms_up,
+                    "what": "shud_b200_land_step: tReadForcing + ET per cell on the device (terrain radiation on), host call "
+                            "to completion incl. the table upload; replaces_upload_ms = shud_b200_set_forcing of the 7 per-cell "
+                            "arrays the reference's host loop would hand over each ET step"}
+
     # ---------------- RHS + SPGMR together (configs[3]): BDF/Newton steps with the device N_Vector ----------------
     nk = None
     if world == 1:
@@ -417,6 +459,8 @@ def main():
                        "d2h_bytes_per_step": 8 * rhs.NY * world, "ms_per_step": ms_e2e_max}}
         if nk is not None:
             out["newton_krylov"] = nk
+        if land_rec is not None:
+            out["land_surface_step"] = land_rec
         if world == 1:
             per, n = cpu_oracle_time(mesh, ncpu, budget_s=a.cpu_budget)
             out["cpu_baseline"] = {"value": Ne / per, "unit": UNIT, "cores": ncpu, "kind": "port",
