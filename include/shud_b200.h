@@ -187,8 +187,11 @@ typedef struct shud_land {
     double cPrep, cTemp, cLAItsd, cMF, cETP, cISmax; /* calibration multipliers, ModelConfigure.hpp (globalCal) */
     int32_t radiation_is_net;                        /* RADIATION_INPUT_MODE == SWNET (MD_ET.cpp:208-214) */
     int32_t terrain_radiation;                       /* TERRAIN_RADIATION */
-    int32_t cryosphere;                              /* CRYOSPHERE: 1 is not supported yet (SHUD_ERR_ARG) */
+    int32_t cryosphere;                              /* CRYOSPHERE: frozen-soil factors fu_Surf / fu_Sub (MD_ET.cpp:301-311) */
     double rad_factor_cap, rad_cosz_min;
+    /* CRYOSPHERE = 1: window lengths [days] and thresholds of the two running means of the daily mean air
+     * temperature (calib_frozen, ModelConfigure.hpp:43-52; _AccTemp, AccTemperature.hpp) */
+    double FT_surf_day, FT_surf_max, FT_surf_min, FT_sub_day, FT_sub_max, FT_sub_min;
 } shud_land;
 
 typedef struct shud_land_step {
@@ -199,6 +202,7 @@ typedef struct shud_land_step {
     const double *tsr_sx, *tsr_sy, *tsr_sz, *tsr_wdt;  /* [tsr_n] */
     double tsr_den;
     double dt_min;           /* tnext - t of ET(t, tnext) */
+    double t;                /* t of ET(t, tnext) [min]: clock of the frozen-soil accumulators (CRYOSPHERE = 1) */
 } shud_land_step;
 
 typedef struct shud_land_out { /* host arrays [Ne] in reference order, any may be NULL */

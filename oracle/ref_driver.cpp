@@ -18,7 +18,7 @@
  *
  * usage: shud_ref <prj> <out.bin> [--t MIN] [--state ic|rand:<seed>]
  *                 [--mutate a,b,..] [--time REPS] [--forcing-seq NSTEPS]
- *   --land-seq N [--land-t0 MIN]: replay N consecutive land-surface steps (updateAllTimeSeries + updateforcing + ET) on a fresh
+ *   --land-seq N [--land-t0 MIN] [--land-stride K] [--mutate cryo]: replay N consecutive land-surface steps (updateAllTimeSeries + updateforcing + ET) on a fresh
  *   model and dump, per step, everything the per-cell part consumes (station rows, LAI / melt-factor class
  *   values, the terrain-radiation solar samples of the forcing interval) and produces: the pin of the
  *   land-surface step.
@@ -156,7 +156,7 @@ int main(int argc, char **argv) {
     }
     std::string prj = argv[1], outfn = argv[2], state = "ic", mutate = "";
     double t_arg = NAN, land_t0 = NAN;
-    int reps = 0, fseq = 0, lseq = 0;
+    int reps = 0, fseq = 0, lseq = 0, lstride = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--t") && a + 1 < argc) t_arg = atof(argv[++a]);
         else if (!strcmp(argv[a], "--state") && a + 1 < argc) state = argv[++a];
@@ -165,6 +165,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[a], "--forcing-seq") && a + 1 < argc) fseq = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--land-seq") && a + 1 < argc) lseq = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--land-t0") && a + 1 < argc) land_t0 = atof(argv[++a]);
+        else if (!strcmp(argv[a], "--land-stride") && a + 1 < argc) lstride = atoi(argv[++a]);
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
 
@@ -426,6 +427,13 @@ int main(int argc, char **argv) {
     if (lseq > 0) {
         Model_Data *M3 = new Model_Data(fin, fout);
         M3->loadinput(); M3->initialize(); M3->CheckInputData(); M3->LoadIC();
+        /* frozen-soil factors (CS.cryosphere, MD_ET.cpp:301-311): no shipped basin switches them on.  The
+         * accumulators' ACC member has no initialiser (AccTemperature.hpp:24): start it at 0 explicitly. */
+        if (has(mutate, "cryo")) {
+            M3->CS.cryosphere = 1;
+            M3->gc.cTemp = -6.0; /* calibration offset: ccw's winter is too mild to freeze anything otherwise */
+            for (int i = 0; i < Ne; i++) { M3->AccT_surf[i].ACC = 0.; M3->AccT_sub[i].ACC = 0.; }
+        }
         const int nf = M3->NumForc;
         int nlc = 0, nmf = 0;
         {
@@ -449,12 +457,15 @@ int main(int argc, char **argv) {
                                   M3->CS.rad_factor_cap, M3->CS.rad_cosz_min, (double)SWNET};
             putd("land_cs", csv, 6);
             putd("land_yEleSnow0", M3->yEleSnow, Ne); putd("land_yEleIS0", M3->yEleIS, Ne);
+            const double frz[] = {(double)M3->AccT_surf[0].MaxLen, M3->AccT_surf_max, M3->AccT_surf_min,
+                                 (double)M3->AccT_sub[0].MaxLen, M3->AccT_sub_max, M3->AccT_sub_min};
+            putd("land_frozen", frz, 6);
         }
         const char *onames[] = {"qElePrep", "qPotEvap", "qPotTran", "qEleETP", "t_lai", "t_temp", "t_mf", "qEleNetPrep",
                                 "qEleE_IC", "yEleSnow", "yEleIS", "fu_Surf", "fu_Sub", "rn_factor"};
         std::vector<std::vector<double>> out(14);
         std::vector<double> tt, frows, lai, mf, sx, sy, sz, wdt, den;
-        std::vector<int> sn;
+        std::vector<int> sn, kept;
         double tf = std::isnan(land_t0) ? M3->CS.StartTime : land_t0;
         for (int k = 0; k < lseq; k++, tf += 60.) {
             M3->updateAllTimeSeries(tf);
@@ -474,12 +485,15 @@ int main(int argc, char **argv) {
             const double *src[] = {M3->qElePrep, M3->qPotEvap, M3->qPotTran, M3->qEleETP, M3->t_lai, M3->t_temp, M3->t_mf,
                                    M3->qEleNetPrep, M3->qEleE_IC, M3->yEleSnow, M3->yEleIS, M3->fu_Surf, M3->fu_Sub,
                                    M3->ele_rn_factor};
-            for (int a = 0; a < 14; a++) out[a].insert(out[a].end(), src[a], src[a] + Ne);
+            if (k % lstride == lstride - 1 || k == lseq - 1) {  /* outputs kept every lstride-th step; inputs always */
+                for (int a = 0; a < 14; a++) out[a].insert(out[a].end(), src[a], src[a] + Ne);
+                kept.push_back(k);
+            }
             tt.push_back(tf);
         }
         put1i("land_nforc", nf); put1i("land_nlc", nlc); put1i("land_nmf", nmf);
         putd("lseq_t", tt); putd("lseq_forc", frows); putd("lseq_lai", lai); putd("lseq_mf", mf);
-        puti("lseq_tsr_n", sn); putd("lseq_tsr_den", den);
+        puti("lseq_tsr_n", sn); putd("lseq_tsr_den", den); puti("lseq_kept", kept);
         putd("lseq_tsr_sx", sx); putd("lseq_tsr_sy", sy); putd("lseq_tsr_sz", sz); putd("lseq_tsr_wdt", wdt);
         for (int a = 0; a < 14; a++) putd((std::string("lseq_") + onames[a]).c_str(), out[a]);
     }

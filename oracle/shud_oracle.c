@@ -797,11 +797,41 @@ static double frozen_fraction(double T, double high, double low) { /* functions.
     return lmin(1.0, lmax((high - T) / (high - low), 0.0));
 }
 
+long shud_oracle_cryo_size(const shud_mesh *m, const shud_land *L) {
+    return 8 + (long)m->Ne * (3 + (long)L->FT_surf_day + (long)L->FT_sub_day);
+}
+
 int shud_oracle_land_step(const shud_mesh *m, const shud_land *L, const shud_land_step *S, double *yEleSnow,
-                          double *yEleIS, const shud_land_out *out) {
+                          double *yEleIS, const shud_land_out *out, double *cryo) {
     const int Ne = m->Ne;
     int rc = 0;
     const double DT_min = S->dt_min;
+    /* _AccTemp::push(x, tnow), AccTemperature.hpp:47-57: both accumulators see the same pushes, so the day sum,
+     * its count and the day clock are shared; a daily mean is queued when >= 1440 min have passed */
+    const int Ls = (int)L->FT_surf_day, Lb = (int)L->FT_sub_day;
+    double *Tacc = NULL, *ACCs = NULL, *ACCb = NULL, *ringS = NULL, *ringB = NULL;
+    int do_push = 0, popS = 0, popB = 0, slotS = 0, slotB = 0;
+    double nday = 0., sizeS = 1., sizeB = 1.;
+    if (L->cryosphere) {
+        if (!cryo) return -2;
+        Tacc = cryo + 8; ACCs = Tacc + Ne; ACCb = ACCs + Ne; ringS = ACCb + Ne; ringB = ringS + (size_t)Ls * Ne;
+        cryo[1] += 1.;                     /* N_of_day++ */
+        nday = cryo[1];
+        do_push = (S->t - cryo[0]) >= 1440.;
+        if (do_push) {
+            /* que.push; if (size > MaxLen) pop the oldest: ring of MaxLen slots, the new value takes the slot
+             * of the value it displaces */
+            int size = (int)cryo[2], head = (int)cryo[3];
+            if (size == Ls) { popS = 1; slotS = head; cryo[3] = (head + 1) % Ls; }
+            else { slotS = (head + size) % Ls; cryo[2] = size + 1; }
+            size = (int)cryo[4]; head = (int)cryo[5];
+            if (size == Lb) { popB = 1; slotB = head; cryo[5] = (head + 1) % Lb; }
+            else { slotB = (head + size) % Lb; cryo[4] = size + 1; }
+            cryo[0] = S->t;
+            cryo[1] = 0.;
+        }
+        sizeS = cryo[2]; sizeB = cryo[4];
+    }
     for (int i = 0; i < Ne; i++) {
         /* ---------------- tReadForcing, MD_ET.cpp:21-281 ---------------- */
         const int idx = L->iForc[i] - 1;
@@ -915,7 +945,23 @@ int shud_oracle_land_step(const shud_mesh *m, const shud_land *L, const shud_lan
         const double T = t_temp, prcp = t_prcp, MF = t_mf;
         double snStg = yEleSnow[i];
         const double snFrac = frozen_fraction(T, L_Train, L_Tsnow);
-        const double fu_Sub = 1., fu_Surf = 1.; /* cryosphere = 0 (CS.cryosphere = 1 needs the AccT accumulators) */
+        double fu_Sub = 1., fu_Surf = 1.;
+        if (L->cryosphere) { /* MD_ET.cpp:301-307 */
+            Tacc[i] += T;
+            if (do_push) {
+                const double x = Tacc[i] / nday;
+                ACCs[i] += x;
+                if (popS) ACCs[i] -= ringS[(size_t)slotS * Ne + i];
+                ringS[(size_t)slotS * Ne + i] = x;
+                ACCb[i] += x;
+                if (popB) ACCb[i] -= ringB[(size_t)slotB * Ne + i];
+                ringB[(size_t)slotB * Ne + i] = x;
+                Tacc[i] = 0.;
+            }
+            const double ta_surf = ACCs[i] / sizeS, ta_sub = ACCb[i] / sizeB;
+            fu_Sub = 1. - frozen_fraction(ta_sub, L->FT_sub_max, L->FT_sub_min);
+            fu_Surf = 1. - frozen_fraction(ta_surf, L->FT_surf_max, L->FT_surf_min);
+        }
         const double snAcc = snFrac * prcp;
         double snMelt = (T > L_To ? (T - L_To) * MF : 0.);
         snMelt = lmin(lmax(0., snStg / DT_min), lmax(0., snMelt));

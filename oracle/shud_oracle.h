@@ -23,7 +23,12 @@ void shud_oracle_prime(const shud_mesh *m, const double *y, double *u_satn);
  *   z_surf, VegFrac, iLake : the shud_mesh members;  yEleSnow, yEleIS [Ne] in/out;  out: any pointer may be NULL
  * returns 0, or 10 where the reference exits (CheckNonZero of the aerodynamic resistance, NaN qPotTran). */
 int shud_oracle_land_step(const shud_mesh *m, const shud_land *L, const shud_land_step *S, double *yEleSnow,
-                          double *yEleIS, const shud_land_out *out);
+                          double *yEleIS, const shud_land_out *out, double *cryo);
+/* `cryo` (CRYOSPHERE = 1, else NULL): the two _AccTemp accumulators of every cell (AccTemperature.hpp), carried
+ * between calls.  8 scalars [Time_start, N_of_day, size_surf, head_surf, size_sub, head_sub, -, -] then per-cell
+ * arrays T_AccDay[Ne], ACC_surf[Ne], ACC_sub[Ne], ring_surf[FT_surf_day][Ne], ring_sub[FT_sub_day][Ne].
+ * Initial state: all zeros except Time_start = -9999 (shud_oracle_cryo_size doubles). */
+long shud_oracle_cryo_size(const shud_mesh *m, const shud_land *L);
 /* how many scratch doubles per call the oracle allocates (informational) */
 const char *shud_oracle_version(void);
 #ifdef __cplusplus

@@ -94,13 +94,15 @@ class ShudLand(C.Structure):  # include/shud_b200.h: shud_land
                 + [(n, _PD) for n in ("Albedo", "FixPressure", "windH", "nx", "ny", "nz", "forc_z")]
                 + [(n, C.c_double) for n in ("cPrep", "cTemp", "cLAItsd", "cMF", "cETP", "cISmax")]
                 + [(n, C.c_int32) for n in ("radiation_is_net", "terrain_radiation", "cryosphere")]
-                + [("rad_factor_cap", C.c_double), ("rad_cosz_min", C.c_double)])
+                + [("rad_factor_cap", C.c_double), ("rad_cosz_min", C.c_double)]
+                + [(n, C.c_double) for n in ("FT_surf_day", "FT_surf_max", "FT_surf_min", "FT_sub_day", "FT_sub_max",
+                                             "FT_sub_min")])
 
 
 class ShudLandStep(C.Structure):  # shud_land_step
     _fields_ = ([("forc", _PD), ("lai", _PD), ("mf", _PD), ("tsr_n", C.c_int32)]
                 + [(n, _PD) for n in ("tsr_sx", "tsr_sy", "tsr_sz", "tsr_wdt")]
-                + [("tsr_den", C.c_double), ("dt_min", C.c_double)])
+                + [("tsr_den", C.c_double), ("dt_min", C.c_double), ("t", C.c_double)])
 
 
 class ShudLandOut(C.Structure):  # shud_land_out
@@ -207,6 +209,8 @@ def make_land(snap):
     L.radiation_is_net = int(cs[0] == cs[5])
     L.terrain_radiation, L.cryosphere = int(cs[1]), int(cs[2])
     L.rad_factor_cap, L.rad_cosz_min = float(cs[3]), float(cs[4])
+    fz = snap["land_frozen"] if "land_frozen" in snap else [7., -1., -5., 28., -3., -10.]  # calib_frozen defaults
+    L.FT_surf_day, L.FT_surf_max, L.FT_surf_min, L.FT_sub_day, L.FT_sub_max, L.FT_sub_min = [float(v) for v in fz]
     return L, keep
 
 
@@ -221,7 +225,7 @@ def land_steps(snap):
             a, p = _d(src); keep.append(a); setattr(S, name, p)
         for name in ("sx", "sy", "sz", "wdt"):
             a, p = _d(np.asarray(snap["lseq_tsr_" + name][off[k]:off[k + 1]])); keep.append(a); setattr(S, "tsr_" + name, p)
-        S.tsr_n, S.tsr_den, S.dt_min = int(n[k]), float(snap["lseq_tsr_den"][k]), 60.0
+        S.tsr_n, S.tsr_den, S.dt_min, S.t = int(n[k]), float(snap["lseq_tsr_den"][k]), 60.0, float(snap["lseq_t"][k])
         yield k, S, keep
 
 

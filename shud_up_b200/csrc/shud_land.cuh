@@ -25,7 +25,7 @@ __device__ __forceinline__ double frozen_fraction(double T, double high, double 
     return l_min(1.0, l_max((high - T) / (high - low), 0.0));
 }
 
-__global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, double tsr_den, double DT_min) {
+__global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, double tsr_den, double DT_min, CryoStep cs) {
     __shared__ double s_sx[kTsrSmem], s_sy[kTsrSmem], s_sz[kTsrSmem], s_wdt[kTsrSmem];
     const double *t_forc = L.tab, *t_lai = t_forc + 5 * L.nforc, *t_mf = t_lai + L.nlc;
     const double *g_sx = t_mf + L.nmf, *g_sy = g_sx + L.tsr_cap, *g_sz = g_sy + L.tsr_cap, *g_wdt = g_sz + L.tsr_cap;
@@ -133,8 +133,28 @@ __global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, d
         etp = qPotTran * vgFrac + qPotEvap * (1. - vgFrac);
         if (isnan(qPotTran)) err = 10;
     }
-    // ---------------- ET, MD_ET.cpp:282-342 (CS.cryosphere = 0: fu_Surf = fu_Sub = 1) ----------------
+    // ---------------- ET, MD_ET.cpp:282-342 ----------------
     const double T = t_temp, prcp = t_prcp;
+    double fu_Surf = 1., fu_Sub = 1.;
+    if (L.cryo) {  // MD_ET.cpp:301-307; _AccTemp::push / getACC, AccTemperature.hpp:28-60
+        const size_t ld = (size_t)m.ld;
+        double tacc = L.tacc[i] + T, as = L.acc_s[i], ab = L.acc_b[i];
+        if (cs.do_push) {
+            const double x = tacc / cs.nday;  // mean of the day that just ended
+            as += x;
+            if (cs.pop_s) as -= L.ring_s[cs.slot_s * ld + i];
+            L.ring_s[cs.slot_s * ld + i] = x;
+            ab += x;
+            if (cs.pop_b) ab -= L.ring_b[cs.slot_b * ld + i];
+            L.ring_b[cs.slot_b * ld + i] = x;
+            tacc = 0.;
+            L.acc_s[i] = as;
+            L.acc_b[i] = ab;
+        }
+        L.tacc[i] = tacc;
+        fu_Sub = 1. - frozen_fraction(ab / cs.size_b, L.sub_max, L.sub_min);
+        fu_Surf = 1. - frozen_fraction(as / cs.size_s, L.surf_max, L.surf_min);
+    }
     double snStg = L.snow[i];
     const double snFrac = frozen_fraction(T, kL_Train, kL_Tsnow);
     const double snAcc = snFrac * prcp;
@@ -159,8 +179,8 @@ __global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, d
     m.potEvap[i] = qPotEvap;
     m.potTran[i] = qPotTran;
     m.lai[i] = lai;
-    m.fuSurf[i] = 1.;
-    m.fuSub[i] = 1.;
+    m.fuSurf[i] = fu_Surf;
+    m.fuSub[i] = fu_Sub;
     m.eic[i] = icEvap * vgFrac;
     // kept for the host (Print_Ctrl arrays, water-balance diagnostics) and the lake means
     L.prep[i] = t_prcp;
@@ -200,7 +220,8 @@ int shud_b200_land_create(shud_ctx *c, const shud_land *L) {
     if (!c || !L || L->nforc <= 0 || L->nlc <= 0 || L->nmf <= 0) return SHUD_ERR_ARG;
     if (!L->iForc || !L->iLC || !L->iMF || !L->Albedo || !L->FixPressure || !L->windH || !L->forc_z) return SHUD_ERR_ARG;
     if (L->terrain_radiation && (!L->nx || !L->ny || !L->nz)) return SHUD_ERR_ARG;
-    if (L->cryosphere) return SHUD_ERR_ARG;  // the AccT accumulators (AccTemperature.hpp) are not on the device yet
+    if (L->cryosphere && (L->FT_surf_day < 1. || L->FT_sub_day < 1. || L->FT_surf_day > 366. || L->FT_sub_day > 366.))
+        return SHUD_ERR_ARG;
     CK(cudaSetDevice(c->device));
     for (int i = 0; i < c->Ne; i++)
         if (L->iForc[i] < 1 || L->iForc[i] > L->nforc || L->iLC[i] < 1 || L->iLC[i] > L->nlc || L->iMF[i] < 1 ||
@@ -221,6 +242,19 @@ int shud_b200_land_create(shud_ctx *c, const shud_land *L) {
     for (double *p : {d.snow, d.ics, d.prep, d.etp, d.temp, d.tmf, d.factor}) {
         if (!p) return SHUD_ERR_CUDA;
         CK(cudaMemset(p, 0, sizeof(double) * ld));
+    }
+    d.cryo = L->cryosphere ? 1 : 0;
+    if (d.cryo) {
+        d.Ls = (int)L->FT_surf_day; d.Lb = (int)L->FT_sub_day;
+        d.surf_max = L->FT_surf_max; d.surf_min = L->FT_surf_min; d.sub_max = L->FT_sub_max; d.sub_min = L->FT_sub_min;
+        d.tacc = dev_alloc<double>(c, ld); d.acc_s = dev_alloc<double>(c, ld); d.acc_b = dev_alloc<double>(c, ld);
+        d.ring_s = dev_alloc<double>(c, ld * d.Ls); d.ring_b = dev_alloc<double>(c, ld * d.Lb);
+        if (!d.tacc || !d.acc_s || !d.acc_b || !d.ring_s || !d.ring_b) return SHUD_ERR_CUDA;
+        CK(cudaMemset(d.tacc, 0, sizeof(double) * ld)); CK(cudaMemset(d.acc_s, 0, sizeof(double) * ld));
+        CK(cudaMemset(d.acc_b, 0, sizeof(double) * ld));
+        CK(cudaMemset(d.ring_s, 0, sizeof(double) * ld * d.Ls)); CK(cudaMemset(d.ring_b, 0, sizeof(double) * ld * d.Lb));
+        c->cryo_tstart = -9999.; c->cryo_nday = 0.;
+        c->cryo_size_s = c->cryo_head_s = c->cryo_size_b = c->cryo_head_b = 0;
     }
     d.tsr_cap = 256;
     const size_t ntab = 5 * (size_t)d.nforc + d.nlc + d.nmf + 4 * (size_t)d.tsr_cap;
@@ -269,7 +303,25 @@ int shud_b200_land_step(shud_ctx *c, const shud_land_step *S) {
         o += d.tsr_cap;
     }
     CK(cudaMemcpyAsync(d.tab, h, sizeof(double) * o, cudaMemcpyHostToDevice, c->stream));
-    k_land<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, d, S->tsr_n, S->tsr_den, S->dt_min);
+    CryoStep cs = {};
+    cs.size_s = cs.size_b = 1.;
+    if (d.cryo) {
+        // _AccTemp::push(x, tnow): N_of_day++, and once >= 1440 min have passed the day's mean enters the queue; a
+        // full queue drops its oldest value (ring: the new value takes the slot of the one it displaces)
+        c->cryo_nday += 1.;
+        cs.nday = c->cryo_nday;
+        cs.do_push = (S->t - c->cryo_tstart) >= 1440.;
+        if (cs.do_push) {
+            if (c->cryo_size_s == d.Ls) { cs.pop_s = 1; cs.slot_s = c->cryo_head_s; c->cryo_head_s = (c->cryo_head_s + 1) % d.Ls; }
+            else { cs.slot_s = (c->cryo_head_s + c->cryo_size_s) % d.Ls; c->cryo_size_s++; }
+            if (c->cryo_size_b == d.Lb) { cs.pop_b = 1; cs.slot_b = c->cryo_head_b; c->cryo_head_b = (c->cryo_head_b + 1) % d.Lb; }
+            else { cs.slot_b = (c->cryo_head_b + c->cryo_size_b) % d.Lb; c->cryo_size_b++; }
+            c->cryo_tstart = S->t;
+            c->cryo_nday = 0.;
+        }
+        cs.size_s = (double)c->cryo_size_s; cs.size_b = (double)c->cryo_size_b;
+    }
+    k_land<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, d, S->tsr_n, S->tsr_den, S->dt_min, cs);
     if (c->Nl > 0) k_lake_means<<<(c->Nl + 63) / 64, 64, 0, c->stream>>>(c->m, d);
     CK(cudaGetLastError());
     return SHUD_OK;

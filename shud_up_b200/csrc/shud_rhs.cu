@@ -96,6 +96,15 @@ struct DevLand {
     double *prep, *etp, *temp, *tmf, *factor;   // qElePrep, qEleETP, t_temp, t_mf, terrain factor
     const int *lk_ptr, *lk_cell;                // lake -> its cells (device ids), ascending reference id
     const double *lk_rnele;                     // lake -> (double)NumEleLake
+    // CRYOSPHERE = 1: the two _AccTemp accumulators of every cell (AccTemperature.hpp): day sum, running sums,
+    // rings of the last Ls / Lb daily means [slot][ld]
+    int cryo, Ls, Lb;
+    double surf_max, surf_min, sub_max, sub_min;
+    double *tacc, *acc_s, *acc_b, *ring_s, *ring_b;
+};
+struct CryoStep {  // per-step, uniform over the cells (the day clock of the accumulators lives on the host)
+    int do_push, pop_s, pop_b, slot_s, slot_b;
+    double nday, size_s, size_b;
 };
 
 __device__ __forceinline__ void raise_err(int *err, int code, int where) {
@@ -1162,6 +1171,8 @@ struct shud_ctx {
     DevLand land{};
     bool has_land = false;
     double *land_stage = nullptr;  // pinned staging of the per-step tables
+    double cryo_tstart = -9999., cryo_nday = 0.;  // _AccTemp::Time_start, N_of_day (identical for every cell)
+    int cryo_size_s = 0, cryo_head_s = 0, cryo_size_b = 0, cryo_head_b = 0;
     bool diag_alloc = false;
     DevDiag acc{};          // output accumulators (same shapes as diag) + effKH/satn/Qseg copies
     double *acc_effKH = nullptr, *acc_satn = nullptr, *acc_QsegSurf = nullptr, *acc_QsegSub = nullptr;

@@ -82,12 +82,20 @@ def oracle_land_seq(mesh_snap, land_snap):
     ics = np.array(land_snap["land_yEleIS0"], dtype=np.float64, copy=True)
     fn = lib().shud_oracle_land_step
     fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p] * 3 + [C.POINTER(C.c_double)] * 2 + [C.c_void_p]
+    fn.argtypes = [C.c_void_p] * 3 + [C.POINTER(C.c_double)] * 2 + [C.c_void_p, C.POINTER(C.c_double)]
+    cryo = None
+    if L.cryosphere:
+        lib().shud_oracle_cryo_size.restype = C.c_long
+        cryo = np.zeros(lib().shud_oracle_cryo_size(C.byref(mesh), C.byref(L)))
+        cryo[0] = -9999.0
+    kept = set(int(v) for v in land_snap["lseq_kept"]) if "lseq_kept" in land_snap else None
     res = {n: [] for n in abi.LAND_OUT}
     for k, S, keep3 in abi.land_steps(land_snap):
         o, arrs = abi.make_land_out(Ne)
-        rc = fn(C.byref(mesh), C.byref(L), C.byref(S), _pd(snow), _pd(ics), C.byref(o))
+        rc = fn(C.byref(mesh), C.byref(L), C.byref(S), _pd(snow), _pd(ics), C.byref(o), _pd(cryo) if cryo is not None else None)
         assert rc == 0, rc
+        if kept is not None and k not in kept:
+            continue
         for n in abi.LAND_OUT:
             res[n].append(arrs[n].copy())
     return {n: np.stack(v) for n, v in res.items()}

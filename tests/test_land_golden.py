@@ -30,6 +30,22 @@ def test_oracle_land_sequence_bit_exact(basin):
         assert np.array_equal(res[name], ref), name
 
 
+def test_oracle_frozen_soil_factors_bit_exact():
+    """CRYOSPHERE = 1: the running means of the daily mean temperature over 7 / 28 days (AccTemperature.hpp) and
+    the factors fu_Surf / fu_Sub they give, 800 hourly steps (both windows wrap), outputs every 40th step"""
+    mesh = dict(np.load(os.path.join(GOLD, "ccw.mesh.npz")))
+    land = dict(np.load(os.path.join(GOLD, "ccw.cryo.npz")))
+    Ne = int(mesh["Ne"][0])
+    assert int(land["land_cs"][2]) == 1 and land["lseq_t"].size == 800
+    res = oracle_lib.oracle_land_seq(mesh, land)
+    nkept = land["lseq_kept"].size
+    for name in ("fu_Surf", "fu_Sub", "t_temp", "yEleSnow", "qEleNetPrep"):
+        ref = land["lseq_" + name].reshape(nkept, Ne)
+        assert np.array_equal(res[name], ref), name
+    fs, fb = land["lseq_fu_Surf"], land["lseq_fu_Sub"]
+    assert fs.min() == 0.0 and fs.max() == 1.0 and ((fs > 0) & (fs < 1)).any() and ((fb > 0) & (fb < 1)).any()
+
+
 def test_sequences_cover_the_branches():
     """the fixtures exercise what they claim: rain, snow accumulation, melt, interception, night and day, terrain
     factors above and below 1, lake cells"""

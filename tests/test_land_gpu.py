@@ -44,6 +44,32 @@ def test_land_sequence_matches_reference(basin):
             assert not bad.any(), (basin, k, name, int(bad.sum()), float(np.abs(got[name] - ref).max()))
 
 
+def test_frozen_soil_factors_match_reference():
+    """CRYOSPHERE = 1 over 800 hourly steps (both running-mean windows wrap), outputs every 40th step"""
+    from shud_up_b200.api import ShudRHS
+    snap, _ = load("ccw")
+    land = dict(np.load(os.path.join(GOLD, "ccw.cryo.npz")))
+    Ne = int(snap["Ne"][0])
+    rhs = ShudRHS(snap)
+    L, keep = abi.make_land(land)
+    assert L.cryosphere == 1
+    rhs.land_create(L)
+    rhs.land_set_state(land["land_yEleSnow0"], land["land_yEleIS0"])
+    kept = {int(v): j for j, v in enumerate(land["lseq_kept"])}
+    nk = len(kept)
+    for k, S, keep2 in abi.land_steps(land):
+        rhs.land_step(S)
+        if k not in kept:
+            continue
+        got = rhs.land_get()
+        for name in ("fu_Surf", "fu_Sub", "t_temp", "yEleSnow", "qEleNetPrep"):
+            ref = land["lseq_" + name].reshape(nk, Ne)[kept[k]]
+            scale = np.maximum(np.abs(ref), np.abs(ref).max())
+            bad = np.abs(got[name] - ref) > 1e-11 * np.maximum(scale, 1e-30)
+            assert not bad.any(), (k, name, float(np.abs(got[name] - ref).max()))
+    assert rhs.check()[0] == 0
+
+
 def test_land_step_feeds_the_rhs():
     """after land_step the RHS runs on the device-made forcing: same ydot as with the reference's arrays uploaded
     through set_forcing (qhh: lake means of qPotEvap / qElePrep included)"""

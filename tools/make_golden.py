@@ -116,6 +116,22 @@ def main():
         keep = {k: v for k, v in snap.items() if k.startswith("land_") or k.startswith("lseq_")}
         keep["_cmd"] = np.array(" ".join(cmd[1:]))
         np.savez_compressed(os.path.join(OUT, f"{basin}.land.npz"), **keep)
+    # frozen-soil factors (CRYOSPHERE = 1, switched on in memory with a -6 K temperature offset: no shipped basin
+    # uses them): 800 hourly steps = 33 days, so that both running-mean windows (7 and 28 days) wrap; outputs kept
+    # every 40th step, and only the ones the switch affects
+    binf = os.path.join(WORK, "ccw.cryo.bin")
+    cmd = [EXE, "ccw", binf, "--land-seq", "800", "--land-t0", "4254000", "--land-stride", "40", "--mutate", "cryo"]
+    r = subprocess.run(cmd, cwd=WORK, capture_output=True, text=True, errors="replace")
+    if r.returncode != 0:
+        sys.exit(f"reference run failed: {cmd}\n{r.stdout[-2000:]}")
+    snap = snapshot.read_bin(binf)
+    kept_out = {"lseq_fu_Surf", "lseq_fu_Sub", "lseq_t_temp", "lseq_yEleSnow", "lseq_qEleNetPrep"}
+    all_out = {"lseq_" + n for n in ("qElePrep", "qPotEvap", "qPotTran", "qEleETP", "t_lai", "t_temp", "t_mf", "qEleNetPrep",
+                                     "qEleE_IC", "yEleSnow", "yEleIS", "fu_Surf", "fu_Sub", "rn_factor")}
+    keep = {k: v for k, v in snap.items()
+            if (k.startswith("land_") or k.startswith("lseq_")) and (k not in all_out or k in kept_out)}
+    keep["_cmd"] = np.array(" ".join(cmd[1:]))
+    np.savez_compressed(os.path.join(OUT, "ccw.cryo.npz"), **keep)
     sz = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {len(os.listdir(OUT))} files, {sz/1e6:.2f} MB")
 
