@@ -38,7 +38,9 @@ def run(model, fseq, y0, n_steps, solver_step=10.0, et_step=60.0, rtol=1e-4, ato
 class GpuModel:
     """adapter: ShudRHS + device N_Vector (everything stays on the device, device order)"""
 
-    def __init__(self, mesh, fseq, device=0):
+    def __init__(self, mesh, fseq, device=0, land=None):
+        """land: a --land-seq snapshot (abi.make_land / abi.land_steps inputs): the land-surface step then runs on
+        the device (shud_b200_land_step) instead of uploading the forcing arrays of `fseq` every ET step"""
         import torch
         from .api import ShudRHS
         from .nvector import NVectorOps
@@ -52,6 +54,14 @@ class GpuModel:
         self.Ne, self.Nr = self.shud.Ne, self.shud.Nr
         self.outlets = np.nonzero(np.asarray(mesh["riv_down"]) < 0)[0]
         self._scratch = self.new_vector()
+        self.land_steps = None
+        if land is not None:
+            from . import abi
+            L, self._land_keep = abi.make_land(land)
+            self.shud.set_forcing(mesh, qEleE_IC=np.zeros(self.Ne))  # BC arrays once; the rest is rewritten per step
+            self.shud.land_create(L)
+            self.shud.land_set_state(land["land_yEleSnow0"], land["land_yEleIS0"])
+            self.land_steps = [(S, keep) for _, S, keep in abi.land_steps(land)]
 
     def close(self):
         self.torch.cuda.synchronize()
@@ -67,6 +77,9 @@ class GpuModel:
         self.shud.f_dev(t, y, ydot)
 
     def set_forcing(self, k):
+        if self.land_steps is not None:
+            self.shud.land_step(self.land_steps[k][0])
+            return
         f = {n: self.fseq["fseq_" + n][k] for n in ("qEleNetPrep", "qPotEvap", "qPotTran", "t_lai", "qElePrep")}
         f["fu_Surf"] = np.ones(self.Ne); f["fu_Sub"] = np.ones(self.Ne)
         self.shud.set_forcing(f, qEleE_IC=self.fseq["fseq_qEleE_IC"][k])

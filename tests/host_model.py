@@ -30,8 +30,15 @@ class HostOps:
 
 
 class OracleModel:
-    def __init__(self, mesh, fseq):
+    def __init__(self, mesh, fseq, land=None):
+        """land: a --land-seq snapshot; the oracle's land-surface step then makes the forcing of each ET step"""
         self.mesh, self.fseq = dict(mesh), fseq
+        self.land = None
+        if land is not None:
+            res = oracle_lib.oracle_land_seq(mesh, land)
+            Ne = int(mesh["Ne"][0])
+            self.land = {n: res[n] for n in ("qEleNetPrep", "qPotEvap", "qPotTran", "t_lai", "qElePrep", "fu_Surf", "fu_Sub",
+                                             "qEleE_IC")}
         self.ops = HostOps()
         self.Ne, self.NY = int(mesh["Ne"][0]), int(np.asarray(mesh["y"]).size)
         self.satn = np.zeros(self.Ne)
@@ -43,6 +50,11 @@ class OracleModel:
         return np.zeros(self.NY)
 
     def set_forcing(self, k):
+        if self.land is not None:
+            for n in ("qEleNetPrep", "qPotEvap", "qPotTran", "t_lai", "qElePrep", "fu_Surf", "fu_Sub"):
+                self.cur[n] = self.land[n][k]
+            self.eic = np.array(self.land["qEleE_IC"][k], copy=True)
+            return
         for n in ("qEleNetPrep", "qPotEvap", "qPotTran", "t_lai", "qElePrep"):
             self.cur[n] = self.fseq["fseq_" + n][k]
         self.cur["fu_Surf"] = np.ones(self.Ne); self.cur["fu_Sub"] = np.ones(self.Ne)
