@@ -214,6 +214,21 @@ int shud_b200_land_create(shud_ctx *ctx, const shud_land *L);
 int shud_b200_land_set_state(shud_ctx *ctx, const double *yEleSnow, const double *yEleIS); /* host [Ne] */
 int shud_b200_land_step(shud_ctx *ctx, const shud_land_step *S); /* asynchronous on the context stream */
 int shud_b200_land_get(shud_ctx *ctx, const shud_land_out *out);  /* synchronises */
+/* ---- ingest and checkpoint, host side ----
+ * shud_b200_mesh_save / _load: the shud_mesh SoA as ONE binary file (header + 64-byte aligned arrays) instead of the
+ * reference's ~10 text files parsed with strtold per field (src/classes/TabularData.cpp:27-55,
+ * src/ModelData/MD_readin.cpp:192-236).  _load reads the payload with a single read into one block (returned in
+ * *block, release with shud_b200_mesh_free after shud_b200_create) and points *out into it.
+ * shud_b200_format_ic: Model_Data::PrintInit (src/ModelData/MD_update.cpp:268-299), byte-identical text
+ * ("<prj>.cfg.ic.update"); y in the reference's blocked order, yEleIS / yEleSnow may be NULL (zeros).
+ * shud_b200_write_ic: the same from a DEVICE vector in device order; the canopy / snow buckets come from the
+ * device land-surface step when it is in use, else zeros. */
+int shud_b200_mesh_save(const char *path, const shud_mesh *m);
+int shud_b200_mesh_load(const char *path, shud_mesh *out, void **block);
+void shud_b200_mesh_free(void *block);
+int shud_b200_format_ic(const char *path, double t, int32_t Ne, int32_t Nr, int32_t Nl, const double *yEleIS,
+                        const double *yEleSnow, const double *y);
+int shud_b200_write_ic(shud_ctx *ctx, const char *path, double t, const double *y_dev);
 /* number of 128-cell tiles in each part (interior + boundary = ceil(Ne/128)) */
 int shud_b200_tile_counts(const shud_ctx *ctx, int *n_interior, int *n_boundary);
 int shud_b200_rhs_boundary_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev, void *halo_stream);

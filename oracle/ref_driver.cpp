@@ -18,6 +18,9 @@
  *
  * usage: shud_ref <prj> <out.bin> [--t MIN] [--state ic|rand:<seed>]
  *                 [--mutate a,b,..] [--time REPS] [--forcing-seq NSTEPS]
+ *   --print-init FILE: write the state of this run with the reference's own checkpoint writer
+ *   (Model_Data::PrintInit, src/ModelData/MD_update.cpp:268-299) after giving the canopy / snow buckets random
+ *   values; the buckets are dumped as ic_yEleIS / ic_yEleSnow (pin of shud_b200_format_ic).
  *   --land-seq N [--land-t0 MIN] [--land-stride K] [--mutate cryo]: replay N consecutive land-surface steps (updateAllTimeSeries + updateforcing + ET) on a fresh
  *   model and dump, per step, everything the per-cell part consumes (station rows, LAI / melt-factor class
  *   values, the terrain-radiation solar samples of the forcing interval) and produces: the pin of the
@@ -154,7 +157,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "usage: %s <prj> <out.bin> [--t MIN] [--state ic|rand:<seed>] [--mutate a,b] [--time REPS]\n", argv[0]);
         return 2;
     }
-    std::string prj = argv[1], outfn = argv[2], state = "ic", mutate = "";
+    std::string prj = argv[1], outfn = argv[2], state = "ic", mutate = "", print_init = "";
     double t_arg = NAN, land_t0 = NAN;
     int reps = 0, fseq = 0, lseq = 0, lstride = 1;
     for (int a = 3; a < argc; a++) {
@@ -164,6 +167,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[a], "--time") && a + 1 < argc) reps = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--forcing-seq") && a + 1 < argc) fseq = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--land-seq") && a + 1 < argc) lseq = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--print-init") && a + 1 < argc) print_init = argv[++a];
         else if (!strcmp(argv[a], "--land-t0") && a + 1 < argc) land_t0 = atof(argv[++a]);
         else if (!strcmp(argv[a], "--land-stride") && a + 1 < argc) lstride = atoi(argv[++a]);
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
@@ -423,6 +427,17 @@ int main(int argc, char **argv) {
         }
         for (int a = 0; a < 8; a++) putd((std::string("fseq_") + names[a]).c_str(), seq[a]);
         putd("fseq_t", tt);
+    }
+    if (!print_init.empty()) {
+        for (int i = 0; i < Ne; i++) {
+            MD->yEleIS[i] = (urand() < 0.3) ? 0. : 2e-3 * urand();
+            MD->yEleSnow[i] = (urand() < 0.5) ? 0. : 0.4 * urand();
+        }
+        putd("ic_yEleIS", MD->yEleIS, Ne); putd("ic_yEleSnow", MD->yEleSnow, Ne);
+        put1d("ic_t", t + 1440.);
+        MD->summary(udata);
+        MD->CS.UpdateICStep = 1;
+        MD->PrintInit(print_init.c_str(), t + 1440.);
     }
     if (lseq > 0) {
         Model_Data *M3 = new Model_Data(fin, fout);

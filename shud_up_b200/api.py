@@ -62,6 +62,11 @@ def lib():
         "shud_b200_rhs_interior_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_boundary_dev": (C.c_int, [vp, C.c_double, vp, vp, vp]),
         "shud_b200_tile_counts": (C.c_int, [vp, _PI, _PI]),
+        "shud_b200_mesh_save": (C.c_int, [C.c_char_p, C.POINTER(abi.ShudMesh)]),
+        "shud_b200_mesh_load": (C.c_int, [C.c_char_p, C.POINTER(abi.ShudMesh), C.POINTER(C.c_void_p)]),
+        "shud_b200_mesh_free": (None, [C.c_void_p]),
+        "shud_b200_format_ic": (C.c_int, [C.c_char_p, C.c_double, C.c_int32, C.c_int32, C.c_int32, _PD, _PD, _PD]),
+        "shud_b200_write_ic": (C.c_int, [vp, C.c_char_p, C.c_double, vp]),
         "shud_b200_land_create": (C.c_int, [vp, C.POINTER(abi.ShudLand)]),
         "shud_b200_land_set_state": (C.c_int, [vp, _PD, _PD]),
         "shud_b200_land_step": (C.c_int, [vp, C.POINTER(abi.ShudLandStep)]),
@@ -106,7 +111,10 @@ class ShudRHS:
         """mesh: dict of the static SoA arrays; if it carries halo_* arrays it is one partition of a
         larger mesh (shud_up_b200/partition.py) and nabr may name halo cells Ne+1..Ne+Nhalo."""
         L = lib()
-        self._mesh_struct, self._keep = abi.make_mesh(mesh)
+        if isinstance(mesh, LoadedMesh):  # a binary container read by shud_b200_mesh_load (no halo: whole domain)
+            self._mesh_struct, self._keep, mesh = mesh.mesh, [mesh], {}
+        else:
+            self._mesh_struct, self._keep = abi.make_mesh(mesh)
         self.Ne, self.Nr, self.Ns, self.Nl = (self._mesh_struct.Ne, self._mesh_struct.Nr, self._mesh_struct.Ns,
                                               self._mesh_struct.Nl)
         h = C.c_void_p()
@@ -265,6 +273,10 @@ class ShudRHS:
         """one f() of a partition: pack, NCCL sends/receives, interior part beside them, boundary part"""
         _chk(lib().shud_b200_rhs_exchange_dev(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "rhs_exchange_dev")
 
+    def write_ic(self, path, t, y_dev):
+        """checkpoint in the reference's <prj>.cfg.ic.update format, straight from the device vector"""
+        _chk(lib().shud_b200_write_ic(self._h, str(path).encode(), float(t), _ptr(y_dev)), "write_ic")
+
     def tile_counts(self):
         """(interior, boundary) 128-cell tiles of this partition"""
         a, b = C.c_int(0), C.c_int(0)
@@ -294,3 +306,38 @@ class ShudRHS:
         d, arrs = abi.make_diag(self.Ne, self.Nr, self.Ns, self.Nl)
         _chk(lib().shud_b200_get_diag(self._h, C.byref(d)), "shud_b200_get_diag")
         return arrs
+
+
+# ---- host-side ingest / checkpoint helpers (no device needed) ----
+def mesh_save(path, snap):
+    """write the shud_mesh SoA of a snapshot dict as one binary container"""
+    m, keep = abi.make_mesh(snap)
+    _chk(lib().shud_b200_mesh_save(str(path).encode(), C.byref(m)), "mesh_save")
+
+
+class LoadedMesh:
+    """a mesh container read back: .mesh is the abi.ShudMesh pointing into one block (freed by close())"""
+
+    def __init__(self, path):
+        self.mesh, self._block = abi.ShudMesh(), C.c_void_p()
+        _chk(lib().shud_b200_mesh_load(str(path).encode(), C.byref(self.mesh), C.byref(self._block)), "mesh_load")
+
+    def array(self, name, count, dtype=np.float64):
+        p = getattr(self.mesh, name)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(count,)).copy()
+
+    def close(self):
+        if self._block:
+            lib().shud_b200_mesh_free(self._block)
+            self._block = C.c_void_p()
+
+
+def format_ic(path, t, Ne, Nr, Nl, y, yEleIS=None, yEleSnow=None):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    a = None if yEleIS is None else np.ascontiguousarray(yEleIS, dtype=np.float64)
+    b = None if yEleSnow is None else np.ascontiguousarray(yEleSnow, dtype=np.float64)
+    _chk(lib().shud_b200_format_ic(str(path).encode(), float(t), int(Ne), int(Nr), int(Nl),
+                                   a.ctypes.data_as(_PD) if a is not None else None,
+                                   b.ctypes.data_as(_PD) if b is not None else None, y.ctypes.data_as(_PD)), "format_ic")

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libshud_b200.so")
-SOURCES = ["shud_rhs.cu", "shud_nvec.cu"]
+SOURCES = ["shud_rhs.cu", "shud_nvec.cu", "shud_io.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               # the x86-64 reference build contracts no product-sums; neither do we (parity first)
               "-fmad=false",

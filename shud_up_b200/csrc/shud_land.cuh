@@ -346,4 +346,24 @@ int shud_b200_land_get(shud_ctx *c, const shud_land_out *out) {
     return SHUD_OK;
 }
 
+// checkpoint in the reference's initial-condition format, straight from the device (shud_io.cu has the formatter)
+int shud_b200_write_ic(shud_ctx *c, const char *path, double t, const double *y_dev) {
+    if (!c || !path || !y_dev) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int rc = shud_b200_from_device_order(c, y_dev, c->y_stage);  // device order -> reference order (on the device)
+    if (rc) return rc;
+    std::vector<double> y(c->NY), is, sn;
+    CK(cudaMemcpyAsync(y.data(), c->y_stage, sizeof(double) * c->NY, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->has_land) {
+        is.resize(c->Ne); sn.resize(c->Ne);
+        shud_land_out o = {};
+        o.yEleIS = is.data(); o.yEleSnow = sn.data();
+        rc = shud_b200_land_get(c, &o);
+        if (rc) return rc;
+    }
+    return shud_b200_format_ic(path, t, c->Ne, c->Nr, c->Nl, c->has_land ? is.data() : nullptr,
+                               c->has_land ? sn.data() : nullptr, y.data());
+}
+
 }  // extern "C"

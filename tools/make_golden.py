@@ -132,6 +132,16 @@ def main():
             if (k.startswith("land_") or k.startswith("lseq_")) and (k not in all_out or k in kept_out)}
     keep["_cmd"] = np.array(" ".join(cmd[1:]))
     np.savez_compressed(os.path.join(OUT, "ccw.cryo.npz"), **keep)
+    # the reference's own checkpoint writer (Model_Data::PrintInit) on a random qhh state: pin of shud_b200_format_ic
+    binf, txtf = os.path.join(WORK, "qhh.ic.bin"), os.path.join(WORK, "qhh.ic.txt")
+    cmd = [EXE, "qhh", binf, "--state", "rand:4", "--print-init", txtf]
+    r = subprocess.run(cmd, cwd=WORK, capture_output=True, text=True, errors="replace")
+    if r.returncode != 0:
+        sys.exit(f"reference run failed: {cmd}\n{r.stdout[-2000:]}")
+    snap = snapshot.read_bin(binf)
+    np.savez_compressed(os.path.join(OUT, "qhh.icfile.npz"), y=snap["y"], ic_yEleIS=snap["ic_yEleIS"],
+                        ic_yEleSnow=snap["ic_yEleSnow"], ic_t=snap["ic_t"],
+                        text=np.frombuffer(open(txtf, "rb").read(), dtype=np.uint8), _cmd=np.array(" ".join(cmd[1:])))
     sz = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {len(os.listdir(OUT))} files, {sz/1e6:.2f} MB")
 
