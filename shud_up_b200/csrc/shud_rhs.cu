@@ -1180,6 +1180,9 @@ struct shud_ctx {
     bool acc_alloc = false;
     int num_update = 0;
     std::vector<void *> allocs;
+    char *arena = nullptr;          // one block for the lateral role's statics (optional persisting-L2 window)
+    size_t arena_off = 0, arena_cap = 0;
+    bool arena_on = false;
     std::vector<int> cperm, rperm, sperm;  // device id -> reference id (0-based)
     std::vector<int> cinv, rinv;           // reference id -> device id
     int *d_cperm = nullptr, *d_rperm = nullptr;
@@ -1233,6 +1236,14 @@ template <class T>
 T *dev_alloc(shud_ctx *c, size_t n) {
     void *p = nullptr;
     if (n == 0) n = 1;
+    if (c->arena_on) {
+        const size_t b = (n * sizeof(T) + 255) & ~(size_t)255;
+        if (c->arena_off + b <= c->arena_cap) {
+            p = c->arena + c->arena_off;
+            c->arena_off += b;
+            return (T *)p;
+        }
+    }
     if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
     c->allocs.push_back(p);
     return (T *)p;
@@ -1383,7 +1394,16 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     }
 
     // ---- static per-cell arrays ----
+    {
+        // the statics the lateral role streams every call, contiguous: SHUD_L2_PERSIST=1 pins them in L2
+        c->arena_cap = (size_t)12 * ((size_t)c->ld * sizeof(double) + 256);
+        void *a = nullptr;
+        if (cudaMalloc(&a, c->arena_cap) == cudaSuccess) { c->arena = (char *)a; c->allocs.push_back(a); }
+        else { cudaGetLastError(); c->arena_cap = 0; }
+    }
+    c->arena_on = c->arena != nullptr;
     m.area = up_cell(c, M->area, true); m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom);
+    c->arena_on = false;
     m.depression = up_cell(c, M->depression); m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy, true);
     m.infD = up_cell(c, M->infD); m.infKsatV = up_cell(c, M->infKsatV); m.macKsatV = up_cell(c, M->macKsatV);
     m.hAreaF = up_cell(c, M->hAreaF); m.thetaS = up_cell(c, M->ThetaS); m.thetaR = up_cell(c, M->ThetaR);
@@ -1392,8 +1412,30 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     m.vAreaF = up_cell(c, M->geo_vAreaF); m.vegFrac = up_cell(c, M->VegFrac); m.impAF = up_cell(c, M->ImpAF);
     m.wetland = up_cell(c, M->WetlandLevel); m.rootReach = up_cell(c, M->RootReachLevel);
     m.rough = up_cell(c, M->Rough); m.qss = up_cell(c, M->QSS);
-    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor, true); m.dist2edge = up_edge(c, M->Dist2Edge);
+    c->arena_on = c->arena != nullptr;
+    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor, true);
     m.avgRough = up_edge(c, M->avgRough, true);
+    c->arena_on = false;
+    m.dist2edge = up_edge(c, M->Dist2Edge);
+    if (c->arena && getenv("SHUD_L2_PERSIST") && atoi(getenv("SHUD_L2_PERSIST")) > 0) {
+        int max_persist = 0, max_win = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t setaside = std::min((size_t)max_persist, c->arena_off);
+        const size_t win = std::min((size_t)max_win, c->arena_off);
+        if (setaside > 0 && win > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess) {
+            cudaStreamAttrValue av = {};
+            av.accessPolicyWindow.base_ptr = c->arena;
+            av.accessPolicyWindow.num_bytes = win;
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setaside / (double)win);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaError_t e = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            fprintf(stderr, "[shud_b200] L2 persisting window: %zu MB of %zu MB, set-aside %zu MB (max %d MB): %s\n",
+                    win >> 20, c->arena_off >> 20, setaside >> 20, max_persist >> 20, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+    }
 
     // ---- topology, flags, bank edges ----
     const bool lakeon = M->lakeon != 0 && Nl > 0;

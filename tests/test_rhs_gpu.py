@@ -202,3 +202,40 @@ def test_synthetic_meshes_match_oracle(nx, ny, lake):
         assert parity.mismatches(got[name], ref[name]).size == 0, name
     if lake:
         assert int(mesh["Nl"][0]) == 1 and (mesh["ele_lakenabr"] > 0).sum() > 20
+
+
+def _subset(snap, n):
+    """the first n cells of a basin as a mesh of their own: neighbours outside become boundary edges, rivers dropped"""
+    Ne = int(snap["Ne"][0])
+    s = {}
+    for k, v in snap.items():
+        v = np.asarray(v)
+        if k.startswith("riv_") or k.startswith("seg_"):
+            s[k] = v[:0]
+        elif v.ndim == 1 and v.size == Ne:
+            s[k] = v[:n].copy()
+        elif v.ndim == 1 and v.size == 3 * Ne:
+            s[k] = v.reshape(3, Ne)[:, :n].copy().reshape(-1)
+        else:
+            s[k] = v
+    nab = s["ele_nabr"].reshape(3, n)
+    nab[nab > n] = 0
+    s["ele_nabr"] = nab.reshape(-1)
+    s["Ne"] = np.array([n], dtype=np.int32); s["Nr"] = np.array([0], dtype=np.int32); s["Ns"] = np.array([0], dtype=np.int32)
+    y = np.asarray(snap["y"])
+    s["y"] = np.concatenate([y[:n], y[Ne:Ne + n], y[2 * Ne:2 * Ne + n]])
+    return s
+
+
+@pytest.mark.parametrize("n", [1147, 100, 1])
+def test_ragged_and_riverless_meshes(n):
+    """edge cases of the launch geometry: no reaches and no segments at all (every river kernel launch is empty), a
+    mesh smaller than one 128-cell tile, a single cell (all three edges on the boundary)"""
+    snap = _subset(oracle_lib.load_case("ccw", "rand1"), n)
+    ref = oracle_lib.oracle_rhs(snap)
+    assert ref["err"] == 0
+    rhs, got = _run_gpu(snap)
+    assert got["code"] == 0, got
+    assert got["ydot"].size == 3 * n
+    bad = parity.mismatches(got["ydot"], ref["ydot"], parity.ydot_scale(snap, ref))
+    assert bad.size == 0, (n, bad[:5], got["ydot"][bad[:5]], ref["ydot"][bad[:5]])
