@@ -158,7 +158,7 @@ def main():
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
                           "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "synthetic-1M: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
+                          "config": {"workload": "synthetic-1M per GPU: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
                                      "seed": 20240611},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncpu, "kind": "port",
                                            "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP"},
