@@ -469,6 +469,34 @@ struct FAxpyDevNeg {  // w -= h[0] * v
     const double *h, *v; double *w;
     __device__ void operator()(int64_t i) const { w[i] = w[i] + (-h[0]) * v[i]; }
 };
+// fused passes of the modified Gram-Schmidt sweep (same arithmetic and the same reduction tree as the separate
+// kernels: results are bit-identical; one read of w and one launch less per Krylov basis vector)
+struct TDqCombineDot {  // out = S (I - gamma J) S^-1 v (FDqCombine);  term = out * u
+    double sigma, gamma; const double *vs, *ewt, *fp, *fy; double *out; const double *u;
+    __device__ double term(int, int64_t i) const {
+        const double w = ewt[i], v = vs[i] / w;
+        const double jv = (1.0 / sigma) * fp[i] + (-1.0 / sigma) * fy[i];
+        const double o = w * (v + (-gamma) * jv);
+        out[i] = o;
+        return o * u[i];
+    }
+};
+struct TAxpyNegDot {  // w -= h[0] * v (FAxpyDevNeg);  term = w_new * u
+    const double *h, *v; double *w; const double *u;
+    __device__ double term(int, int64_t i) const {
+        const double wn = w[i] + (-h[0]) * v[i];
+        w[i] = wn;
+        return wn * u[i];
+    }
+};
+struct TAxpyNegSq {  // w -= h[0] * v;  term = w_new^2
+    const double *h, *v; double *w;
+    __device__ double term(int, int64_t i) const {
+        const double wn = w[i] + (-h[0]) * v[i];
+        w[i] = wn;
+        return wn * wn;
+    }
+};
 struct FNormalizeDev {  // w /= sqrt(n2[0])  (left untouched when the norm is 0)
     const double *n2; double *w;
     __device__ void operator()(int64_t i) const {
@@ -560,13 +588,14 @@ int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, con
         // w = S (I - gamma J) S^-1 v_k, J by difference quotient: 1 RHS call
         if ((rc = shud_nv_dq_perturb(ws, n, sig, s->V[k], ewt, y, s->ytemp))) return rc;
         if ((rc = shud_b200_rhs_dev(s->gpu, t, s->ytemp, s->ftemp))) return rc;
-        if ((rc = shud_nv_dq_combine(ws, n, sig, gamma, s->V[k], ewt, s->ftemp, fy, s->V[k + 1]))) return rc;
-        // modified Gram-Schmidt, coefficients stay on the device
-        for (int i = 0; i <= k; i++) {
-            if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[k + 1], s->V[i]}, s->dH + i))) return rc;
-            if ((rc = run_map(ws, n, FAxpyDevNeg{s->dH + i, s->V[i], s->V[k + 1]}))) return rc;
-        }
-        if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[k + 1], s->V[k + 1]}, s->dH + k + 1))) return rc;
+        // ... fused with the first dot product of the modified Gram-Schmidt sweep; every later pass subtracts the
+        // previous projection and forms the next dot product (the last one the squared norm) in one read of w.
+        // Coefficients stay on the device: h_i is written by the reduction's last block and read by the next pass.
+        double *w = s->V[k + 1];
+        if ((rc = run_reduce_dev<R_SUM>(ws, n, TDqCombineDot{sig, gamma, s->V[k], ewt, s->ftemp, fy, w, s->V[0]}, s->dH))) return rc;
+        for (int i = 0; i < k; i++)
+            if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegDot{s->dH + i, s->V[i], w, s->V[i + 1]}, s->dH + i + 1))) return rc;
+        if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegSq{s->dH + k, s->V[k], w}, s->dH + k + 1))) return rc;
         if ((rc = run_map(ws, n, FNormalizeDev{s->dH + k + 1, s->V[k + 1]}))) return rc;
         CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, ws->stream));
         CKN(cudaStreamSynchronize(ws->stream));  // the one host synchronisation of this Krylov iteration
