@@ -523,7 +523,8 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                 double nsf, ygw_n, zs_n, zb_n, kh_n;
                 const unsigned r = (unsigned)(k - i0);
 #ifndef SHUD_NBR_GLOBAL
-                if (r < (unsigned)TILE) {  // neighbour inside the tile: shared memory
+                if (r < (unsigned)TILE && k < Ne) {  // neighbour inside the tile: shared memory (in the ragged last
+                                                      // tile a halo id Ne+h also falls into [i0, i0+TILE): not a cell)
                     nsf = t_sf[r]; ygw_n = t_gw[r]; zs_n = t_zs[r]; zb_n = t_zb[r]; kh_n = t_kh[r];
                 } else
 #endif
@@ -879,7 +880,7 @@ __global__ void __launch_bounds__(2 * TILE + 32, MINB) k_pipe(DevMesh m, DevDiag
                     if (kk >= 0) {
                         double nsf, ygw_n, zs_n, zb_n, kh_n;
                         const unsigned r = (unsigned)(kk - i0);
-                        if (r < (unsigned)TILE) {
+                        if (r < (unsigned)TILE && k < Ne) {
                             nsf = sd[A_YSF * TILE + r]; ygw_n = sd[A_YGW * TILE + r]; zs_n = sd[A_ZS * TILE + r];
                             zb_n = sd[A_ZB * TILE + r]; kh_n = sd[A_KH * TILE + r];
                         } else if (kk < Ne) {

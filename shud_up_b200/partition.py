@@ -78,6 +78,23 @@ def extract(mesh, owned_mask, gid=None, part_of_cell=None, keep_full_halo=False)
         np.logical_and.at(riv_all, seg_r, seg_owned)
     if np.any(riv_any & ~riv_all):
         raise NotImplementedError("a reach has segments in two partitions")
+    if Nr:
+        # a river tree is owned as a whole (reaches without segments follow the tree they belong to)
+        comp = _reach_components(mesh["riv_down"])
+        c_any = np.zeros(Nr, dtype=bool); c_all = np.ones(Nr, dtype=bool)
+        has_seg = np.zeros(Nr, dtype=bool)
+        if Ns:
+            has_seg[seg_r] = True
+        np.logical_or.at(c_any, comp, riv_any)
+        np.logical_and.at(c_all, comp[has_seg], riv_any[has_seg])
+        if np.any(c_any & ~c_all):
+            raise NotImplementedError("a reach and its downstream reach are in different partitions")
+        riv_any = c_any[comp]
+        # trees without any segment are owned by the partition that owns cell 0 of the mesh
+        orphan = ~has_seg
+        c_has = np.zeros(Nr, dtype=bool)
+        np.logical_or.at(c_has, comp, has_seg)
+        riv_any = riv_any | (~c_has[comp] & bool(owned_mask[0]))
     rown = np.nonzero(riv_any)[0]
     down = np.asarray(mesh["riv_down"])
     dn = down[rown]
@@ -119,6 +136,123 @@ def extract(mesh, owned_mask, gid=None, part_of_cell=None, keep_full_halo=False)
         loc["halo_state_expected"] = np.stack([y[halo], y[2 * Ne + halo]], 1).ravel()
     loc["_own_ref"], loc["_riv_ref"] = own, rown
     return loc
+
+
+def _reach_components(down):
+    """component id of every reach of the river forest (reaches linked by riv_down > 0)"""
+    down = np.asarray(down).astype(np.int64)
+    n = down.size
+    par = np.arange(n, dtype=np.int64)
+
+    def find(a):
+        while par[a] != a:
+            par[a] = par[par[a]]
+            a = par[a]
+        return a
+
+    for r in range(n):
+        if down[r] > 0:
+            a, b = find(r), find(down[r] - 1)
+            if a != b:
+                par[max(a, b)] = min(a, b)
+    return np.array([find(r) for r in range(n)], dtype=np.int64)
+
+
+def _hilbert_key(x, y, order=16):
+    """Hilbert-curve index of points scaled into a 2^order grid (numpy, vectorised)"""
+    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    span = max(x.max() - x.min(), y.max() - y.min(), 1e-30)
+    n = (1 << order) - 1
+    xi = np.minimum(n, (x - x.min()) / span * n).astype(np.int64)
+    yi = np.minimum(n, (y - y.min()) / span * n).astype(np.int64)
+    d = np.zeros(xi.shape, dtype=np.int64)
+    s = 1 << (order - 1)
+    while s > 0:
+        rx = (xi & s) > 0
+        ry = (yi & s) > 0
+        d += s * s * ((3 * rx.astype(np.int64)) ^ ry.astype(np.int64))
+        flip = ~ry & rx
+        xi = np.where(flip, n - xi, xi); yi = np.where(flip, n - yi, yi)
+        swap = ~ry
+        xi, yi = np.where(swap, yi, xi), np.where(swap, xi, yi)
+        s >>= 1
+    return d
+
+
+def assign(mesh, nparts):
+    """Owner rank of every cell for `nparts` partitions that `extract` accepts (Hilbert-range
+    split on cell centroids, with the river and lake constraints of this version built in).  Cells that must stay
+    together are merged into atoms first: the cells on the segments of one reach, a reach with its downstream reach
+    (so a river tree and its banks form one atom), a lake with its cells, its bank cells and the reaches flowing
+    into it, and a head-BC cell with its neighbours (a halo cell may not carry a head BC).  Atoms are then laid along
+    the Hilbert curve of their centroids and cut into `nparts` runs of about Ne / nparts cells.
+    Returns part_of_cell [Ne] (int32).  Balance is limited by the largest atom (one river tree = one partition)."""
+    Ne, Nr, Ns, Nl = (int(np.asarray(mesh[k]).reshape(-1)[0]) for k in ("Ne", "Nr", "Ns", "Nl"))
+    parent = np.arange(Ne, dtype=np.int64)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    def union(a, b):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+
+    seg_e = np.asarray(mesh["seg_iEle"]).astype(np.int64) - 1
+    seg_r = np.asarray(mesh["seg_iRiv"]).astype(np.int64) - 1
+    comp = _reach_components(mesh["riv_down"]) if Nr else np.zeros(0, dtype=np.int64)
+    rep = np.full(Nr, -1, dtype=np.int64)               # a representative cell of every river tree (by component id)
+    for e, r in zip(seg_e, seg_r):
+        c = comp[r]
+        if rep[c] < 0:
+            rep[c] = e
+        else:
+            union(e, rep[c])
+    rep = rep[comp] if Nr else rep                      # ... seen from every reach of the tree (with or without segments)
+    nabr = np.asarray(mesh["ele_nabr"]).reshape(3, Ne).astype(np.int64)
+    ilake = np.asarray(mesh["ele_iLake"]).astype(np.int64)
+    if Nl:
+        lrep = np.full(Nl, -1, dtype=np.int64)
+        for i in np.nonzero(ilake > 0)[0]:
+            l = ilake[i] - 1
+            if lrep[l] < 0:
+                lrep[l] = i
+            else:
+                union(i, lrep[l])
+        lnab = np.asarray(mesh["ele_lakenabr"]).reshape(3, Ne).astype(np.int64)
+        for j in range(3):
+            for i in np.nonzero(lnab[j] > 0)[0]:       # bank cells
+                if lrep[lnab[j, i] - 1] >= 0:
+                    union(i, lrep[lnab[j, i] - 1])
+        tolake = np.asarray(mesh["riv_toLake"]).astype(np.int64) if "riv_toLake" in mesh else np.full(Nr, -1)
+        for r in range(Nr):
+            l = tolake[r]
+            if 0 <= l < Nl and rep[r] >= 0 and lrep[l] >= 0:   # toLake is 0-based, -1 = none (ref_driver dump)
+                union(rep[r], lrep[l])
+    ibc = np.asarray(mesh["ele_iBC"])
+    for i in np.nonzero(ibc > 0)[0]:
+        for j in range(3):
+            if nabr[j, i] > 0:
+                union(i, nabr[j, i] - 1)
+    root = np.array([find(i) for i in range(Ne)], dtype=np.int64)
+    atoms, inv = np.unique(root, return_inverse=True)
+    size = np.bincount(inv, minlength=atoms.size)
+    x = np.asarray(mesh["ele_x"], dtype=np.float64); y = np.asarray(mesh["ele_y"], dtype=np.float64)
+    ax = np.bincount(inv, weights=x, minlength=atoms.size) / size
+    ay = np.bincount(inv, weights=y, minlength=atoms.size) / size
+    order = np.argsort(_hilbert_key(ax, ay), kind="stable")
+    part_of_atom = np.zeros(atoms.size, dtype=np.int32)
+    target, acc, p = Ne / float(nparts), 0.0, 0
+    for a in order:
+        # move on when this partition is full, keeping at least one atom for every remaining partition
+        if p < nparts - 1 and acc + 0.5 * size[a] > target * (p + 1):
+            p += 1
+        part_of_atom[a] = p
+        acc += size[a]
+    return part_of_atom[inv].astype(np.int32)
 
 
 def exchange_plan(own_gid, halo_gid, all_halo_gid):

@@ -57,7 +57,10 @@ def _extended(mesh, loc):
             ext[k] = v[cells]
     nab = np.asarray(mesh["ele_nabr"]).reshape(3, Ne)[:, cells]
     ext["ele_nabr"] = np.where(nab > 0, new[np.maximum(nab - 1, 0)], 0).astype(np.int32).ravel()
-    ext["ele_lakenabr"] = np.zeros(3 * cells.size, dtype=np.int32)
+    # lake banks are never cut (partition.extract refuses): owned cells keep their lake neighbours, halo cells have none
+    lk = np.zeros((3, cells.size), dtype=np.int32)
+    lk[:, :own.size] = np.asarray(loc["ele_lakenabr"]).reshape(3, own.size)
+    ext["ele_lakenabr"] = lk.ravel()
     ext["Ne"] = np.array([cells.size], dtype=np.int32)
     return ext, own.size, cells.size
 
@@ -94,6 +97,38 @@ def test_partitioned_rhs_equals_single_domain_bitwise(whole):
             assert np.array_equal(out[b * ntot:b * ntot + nown], ref[b * Ne + own]), (p, b)
         nr = int(loc["Nr"][0])
         assert np.array_equal(out[3 * ntot:3 * ntot + nr], ref[3 * Ne + loc["_riv_ref"]])
+
+
+@pytest.mark.parametrize("basin,case,nparts", [("ccw", "rand1", 2), ("ccw", "rand1", 3), ("heihe", "rand3", 2),
+                                               ("qhh", "rand4", 2), ("qhh", "rand4", 3)])
+def test_assigned_partitions_of_real_basins_equal_single_domain_bitwise(basin, case, nparts):
+    """partition.assign keeps river trees, lakes with their banks and head-BC cells whole, so partition.extract
+    accepts its partitions; each partition (owned + halo, halo state as the exchange delivers it) reproduces the
+    single-domain RHS bit for bit on its cells, reaches and lakes; every cell, reach and lake has exactly one owner"""
+    whole = oracle_lib.load_case(basin, case)
+    Ne, Nr, Nl = int(whole["Ne"][0]), int(whole["Nr"][0]), int(whole["Nl"][0])
+    ref = oracle_lib.oracle_rhs(whole, want_diag=False)["ydot"]
+    part = partition.assign(whole, nparts)
+    assert part.shape == (Ne,) and set(np.unique(part)) == set(range(nparts))
+    seen_cells, seen_riv, seen_lakes = np.zeros(Ne, int), np.zeros(Nr, int), 0
+    y = np.asarray(whole["y"])
+    for p in range(nparts):
+        loc = partition.extract(whole, part == p, part_of_cell=part, keep_full_halo=True)
+        ne, nr, nl = int(loc["Ne"][0]), int(loc["Nr"][0]), int(loc["Nl"][0])
+        own, halo = loc["_own_ref"], loc["_halo_ref"]
+        seen_cells[own] += 1; seen_riv[loc["_riv_ref"]] += 1; seen_lakes += nl
+        ext, nown, ntot = _extended(whole, loc)
+        nh = ntot - nown
+        ext["y"] = np.concatenate([np.r_[loc["y"][0:ne], y[halo]], np.r_[loc["y"][ne:2 * ne], np.zeros(nh)],
+                                   np.r_[loc["y"][2 * ne:3 * ne], y[2 * Ne + halo]], loc["y"][3 * ne:]])
+        ext["ele_u_satn"] = np.r_[loc["ele_u_satn"], np.zeros(nh)]
+        out = oracle_lib.oracle_rhs(ext, want_diag=False)["ydot"]
+        for b in range(3):
+            assert np.array_equal(out[b * ntot:b * ntot + nown], ref[b * Ne + own]), (p, b)
+        assert np.array_equal(out[3 * ntot:3 * ntot + nr], ref[3 * Ne + loc["_riv_ref"]])
+        if nl:
+            assert np.array_equal(out[3 * ntot + nr:], ref[3 * Ne + Nr:])
+    assert np.all(seen_cells == 1) and np.all(seen_riv == 1) and seen_lakes == Nl
 
 
 def test_cut_river_is_refused(whole):

@@ -97,3 +97,50 @@ def test_two_partitions_equal_single_domain_bitwise():
     nr0 = ctxs[0][0].Nr
     assert np.array_equal(np.r_[ctxs[0][4].cpu().numpy()[3 * ctxs[0][0].Ne:], ctxs[1][4].cpu().numpy()[3 * ctxs[1][0].Ne:]],
                           ref[3 * Ne:])
+
+
+@pytest.mark.parametrize("basin,case,nparts", [("qhh", "rand4", 2), ("ccw", "rand1", 3), ("heihe", "rand3", 2)])
+def test_assigned_partitions_of_real_basins_on_the_gpu(basin, case, nparts):
+    """partition.assign -> partition.extract -> one context per partition (all on cuda:0), halo state taken from the
+    whole state as the exchange delivers it: the owned cells, reaches and lakes get the bits of the single-domain
+    CUDA RHS (qhh: the lake and its banks live in one partition; heihe: reaches without segments follow their tree)"""
+    import torch
+    whole = oracle_lib.load_case(basin, case)
+    Ne, Nr, Nl = int(whole["Ne"][0]), int(whole["Nr"][0]), int(whole["Nl"][0])
+
+    def run(mesh, halo_pairs=None):
+        from shud_up_b200.api import ShudRHS
+        r = ShudRHS(mesh)
+        r.set_forcing(mesh, qEleE_IC=mesh["qEleE_IC_in"])
+        r.set_carried(mesh["ele_u_satn"])
+        s = r.torch_stream()
+        if halo_pairs is not None:
+            hb = torch.from_numpy(np.ascontiguousarray(halo_pairs)).cuda()
+            r.set_halo_state(hb)
+        with torch.cuda.stream(s):
+            yr = torch.from_numpy(np.ascontiguousarray(mesh["y"])).cuda()
+            yd, ydd, out = torch.empty_like(yr), torch.empty_like(yr), torch.empty_like(yr)
+            r.to_device_order(yr, yd)
+            r.f_dev(0.0, yd, ydd)
+            r.from_device_order(ydd, out)
+        s.synchronize()
+        assert r.check()[0] == 0
+        res = out.cpu().numpy()
+        r.close()
+        return res
+
+    ref = run(whole)
+    y = np.asarray(whole["y"])
+    part = partition.assign(whole, nparts)
+    for p in range(nparts):
+        loc = partition.extract(whole, part == p, part_of_cell=part, keep_full_halo=True)
+        ne, nr, nl = int(loc["Ne"][0]), int(loc["Nr"][0]), int(loc["Nl"][0])
+        halo = loc["_halo_ref"]
+        pairs = np.stack([y[halo], y[2 * Ne + halo]], 1).ravel()
+        got = run(loc, pairs)
+        own = loc["_own_ref"]
+        for b in range(3):
+            assert np.array_equal(got[b * ne:(b + 1) * ne], ref[b * Ne + own]), (p, b)
+        assert np.array_equal(got[3 * ne:3 * ne + nr], ref[3 * Ne + loc["_riv_ref"]])
+        if nl:
+            assert np.array_equal(got[3 * ne + nr:], ref[3 * Ne + Nr:])
