@@ -147,6 +147,17 @@ def _gloo_worker(rank, world, port, q):
     y = torch.from_numpy(loc["y"].copy())
     got = hx.exchange(y)[:2 * hx.nr].numpy().copy()
     ok = bool(np.array_equal(got, loc["halo_state_expected"])) and hx.in_place and hx.nr == NX
+    # the start()/finish() form that overlaps the exchange with the interior tiles gives the same halo state
+    hx.start(y)
+    hx.finish()
+    ok = ok and bool(np.array_equal(hx.halo_state[:2 * hx.nr].numpy(), loc["halo_state_expected"]))
+    # plan handed to the library-driven exchange (shud_b200_exchange_plan): one peer, NX cells each way, the cells
+    # sent are owned cells whose global ids are exactly the peer's halo ids
+    peers, sc, rc, cells = hx.native_plan()
+    ok = ok and peers.tolist() == [1 - rank] and sc.tolist() == [NX] and rc.tolist() == [NX] and cells.size == NX
+    all_halo = [None, None]
+    dist.all_gather_object(all_halo, np.asarray(loc["halo_gid"]))
+    ok = ok and bool(np.array_equal(np.asarray(loc["own_gid"])[cells], np.sort(all_halo[1 - rank])))
     # the distributed WRMS norm: local sum of squares + allreduce + global length
     w = torch.full_like(y, 0.5)
     s = torch.tensor([float(((y * w) ** 2).sum())], dtype=torch.float64)
