@@ -320,17 +320,21 @@ __global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const 
 
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised fused cell kernel.  A 256-thread block owns a tile of 128 consecutive cells
-// (consecutive along the Hilbert curve, so a compact patch of the mesh):
-//   warps 0-3 ("lateral" role, one thread per cell): stage the tile's Ysurf, Ygw, z_surf, z_bottom and
-//       effKH in shared memory, take the neighbour values of the 3 edges from there (global memory only
-//       for the ~10 % of neighbours outside the tile), compute the 3 overland + 3 groundwater edge
-//       fluxes, then - once the vertical role has handed over - the river segments and the surface and
-//       groundwater balance equations;
-//   warps 4-7 ("vertical" role, one thread per cell): ET partition, updateElement, infiltration,
-//       recharge; store the carried state and ydot[unsat]; hand P1, Es, G1, Eg, Tg and the ponding left
-//       for the river weir to the lateral role through shared memory.
-// Each role keeps about half of the cell's ~45 inputs live, so twice as many warps are resident as in
-// the one-thread-per-cell form, with no extra HBM traffic.  No atomics; every sum in a fixed order.
+// (consecutive along the Hilbert curve, so a compact patch of the mesh), two threads per cell:
+//   warps 0-3 ("lateral" role): every own value and edge static of the cell lands in shared memory by cp.async;
+//       the tile's Ysurf, Ygw, z_surf, z_bottom, effKH double as the neighbour table (global memory only for
+//       the ~15 % of neighbours outside the tile / in the halo); 3 overland + 3 groundwater edge fluxes (one
+//       copy of the edge code, three trips); the tile's river segments, one lane per segment slot (groundwater
+//       exchange before the hand-over, weir after it); Qe2r + Q0 + Q1 + Q2 and the first two terms of dYsf, dYgw;
+//   warps 4-7 ("vertical" role): its 26 inputs by cp.async, then in steps that re-read what they need from the
+//       staged slots (nothing held in a register across a pow()): updateElement -> infiltration / recharge ->
+//       hand P1, G1 and the ponding left for the weir to the lateral role -> ET partition while the lateral role
+//       finishes -> the three balance equations, ydot stores, carried state.
+// 64 registers, 48 KB of shared memory, 4 blocks (32 warps) per SM, no local-memory spills in the hot path, no
+// extra HBM traffic against the one-thread-per-cell form.  No atomics; every sum in a fixed order.
+// Named barriers: 1 lateral-internal, 2 vertical -> lateral hand-over, 3 lateral -> vertical hand-back.
+// Programmatic dependent launch: starts under k_effkh (the lateral role waits before its effKH copy) and lets
+// k_river_lake start in its last wave.
 // ---------------------------------------------------------------------------------------------
 constexpr int TILE = 128;
 constexpr int V_NIN = 26;     // per-cell inputs of the vertical role
