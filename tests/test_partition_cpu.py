@@ -105,7 +105,20 @@ def test_assigned_partitions_of_real_basins_equal_single_domain_bitwise(basin, c
     """partition.assign keeps river trees, lakes with their banks and head-BC cells whole, so partition.extract
     accepts its partitions; each partition (owned + halo, halo state as the exchange delivers it) reproduces the
     single-domain RHS bit for bit on its cells, reaches and lakes; every cell, reach and lake has exactly one owner"""
-    whole = oracle_lib.load_case(basin, case)
+    _check_assigned(oracle_lib.load_case(basin, case), nparts)
+
+
+@pytest.mark.parametrize("kw,nparts", [(dict(nx=40, ny=30, ntree=3, reaches_per_tree=30, lake_frac=0.02), 3),
+                                       (dict(nx=24, ny=24, ntree=1, reaches_per_tree=40, lake_frac=0.05), 5),
+                                       (dict(nx=50, ny=20, ntree=5, reaches_per_tree=20), 4)])
+def test_assigned_partitions_of_synthetic_meshes_with_lakes(kw, nparts):
+    kw = dict(kw)
+    whole = synth.make(kw.pop("nx"), kw.pop("ny"), **kw)
+    whole["ele_u_satn"] = oracle_lib.oracle_prime(whole, whole["y"])
+    _check_assigned(whole, nparts)
+
+
+def _check_assigned(whole, nparts):
     Ne, Nr, Nl = int(whole["Ne"][0]), int(whole["Nr"][0]), int(whole["Nl"][0])
     ref = oracle_lib.oracle_rhs(whole, want_diag=False)["ydot"]
     part = partition.assign(whole, nparts)
