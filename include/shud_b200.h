@@ -229,6 +229,10 @@ void shud_b200_mesh_free(void *block);
 int shud_b200_format_ic(const char *path, double t, int32_t Ne, int32_t Nr, int32_t Nl, const double *yEleIS,
                         const double *yEleSnow, const double *y);
 int shud_b200_write_ic(shud_ctx *ctx, const char *path, double t, const double *y_dev);
+/* the reverse of shud_b200_format_ic (restart): y [3 Ne + Nr + Nl] blocked, reference order; t, yEleIS, yEleSnow may
+ * be NULL.  SHUD_ERR_ARG when the file does not match the sizes. */
+int shud_b200_read_ic(const char *path, int32_t Ne, int32_t Nr, int32_t Nl, double *t, double *yEleIS, double *yEleSnow,
+                      double *y);
 /* number of 128-cell tiles in each part (interior + boundary = ceil(Ne/128)) */
 int shud_b200_tile_counts(const shud_ctx *ctx, int *n_interior, int *n_boundary);
 int shud_b200_rhs_boundary_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev, void *halo_stream);

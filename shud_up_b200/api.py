@@ -67,6 +67,7 @@ def lib():
         "shud_b200_mesh_free": (None, [C.c_void_p]),
         "shud_b200_format_ic": (C.c_int, [C.c_char_p, C.c_double, C.c_int32, C.c_int32, C.c_int32, _PD, _PD, _PD]),
         "shud_b200_write_ic": (C.c_int, [vp, C.c_char_p, C.c_double, vp]),
+        "shud_b200_read_ic": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, _PD, _PD, _PD, _PD]),
         "shud_b200_land_create": (C.c_int, [vp, C.POINTER(abi.ShudLand)]),
         "shud_b200_land_set_state": (C.c_int, [vp, _PD, _PD]),
         "shud_b200_land_step": (C.c_int, [vp, C.POINTER(abi.ShudLandStep)]),
@@ -341,3 +342,11 @@ def format_ic(path, t, Ne, Nr, Nl, y, yEleIS=None, yEleSnow=None):
     _chk(lib().shud_b200_format_ic(str(path).encode(), float(t), int(Ne), int(Nr), int(Nl),
                                    a.ctypes.data_as(_PD) if a is not None else None,
                                    b.ctypes.data_as(_PD) if b is not None else None, y.ctypes.data_as(_PD)), "format_ic")
+
+
+def read_ic(path, Ne, Nr, Nl):
+    """-> (t, y, yEleIS, yEleSnow) from a <prj>.cfg.ic(.update) file"""
+    y = np.empty(3 * Ne + Nr + Nl); a = np.empty(Ne); b = np.empty(Ne); t = C.c_double(0.0)
+    _chk(lib().shud_b200_read_ic(str(path).encode(), int(Ne), int(Nr), int(Nl), C.byref(t), a.ctypes.data_as(_PD),
+                                 b.ctypes.data_as(_PD), y.ctypes.data_as(_PD)), "read_ic")
+    return t.value, y, a, b

@@ -182,4 +182,47 @@ int shud_b200_format_ic(const char *path, double t, int32_t Ne, int32_t Nr, int3
     return fclose(fp) == 0 ? SHUD_OK : SHUD_ERR_CUDA;
 }
 
+// The reverse of shud_b200_format_ic: read "<prj>.cfg.ic" / ".cfg.ic.update" (the %lf text of PrintInit) back into the
+// blocked state vector and the two land-surface buckets.  Sizes must match the mesh the file was written for.
+int shud_b200_read_ic(const char *path, int32_t Ne, int32_t Nr, int32_t Nl, double *t, double *yEleIS, double *yEleSnow,
+                      double *y) {
+    if (!path || !y || Ne <= 0 || Nr < 0 || Nl < 0) return SHUD_ERR_ARG;
+    FILE *fp = fopen(path, "r");
+    if (!fp) return SHUD_ERR_ARG;
+    char line[512];
+    int n = 0, ncol = 0, idx = 0;
+    double tt = 0.;
+    bool ok = fgets(line, sizeof line, fp) && sscanf(line, "%d %d %lf", &n, &ncol, &tt) == 3 && n == Ne && ncol == 6 &&
+              fgets(line, sizeof line, fp);  // column names
+    for (int i = 0; ok && i < Ne; i++) {
+        double is, sn, sf, us, gw;
+        ok = fgets(line, sizeof line, fp) && sscanf(line, "%d %lf %lf %lf %lf %lf", &idx, &is, &sn, &sf, &us, &gw) == 6 &&
+             idx == i + 1;
+        if (ok) {
+            if (yEleIS) yEleIS[i] = is;
+            if (yEleSnow) yEleSnow[i] = sn;
+            y[i] = sf; y[(size_t)Ne + i] = us; y[2 * (size_t)Ne + i] = gw;
+        }
+    }
+    ok = ok && fgets(line, sizeof line, fp) && sscanf(line, "%d %d", &n, &ncol) == 2 && n == Nr && ncol == 2 &&
+         fgets(line, sizeof line, fp);
+    for (int i = 0; ok && i < Nr; i++) {
+        double v;
+        ok = fgets(line, sizeof line, fp) && sscanf(line, "%d %lf", &idx, &v) == 2 && idx == i + 1;
+        if (ok) y[3 * (size_t)Ne + i] = v;
+    }
+    if (ok && Nl > 0) {
+        ok = fgets(line, sizeof line, fp) && sscanf(line, "%d %d", &n, &ncol) == 2 && n == Nl && ncol == 2 &&
+             fgets(line, sizeof line, fp);
+        for (int i = 0; ok && i < Nl; i++) {
+            double v;
+            ok = fgets(line, sizeof line, fp) && sscanf(line, "%d %lf", &idx, &v) == 2 && idx == i + 1;
+            if (ok) y[3 * (size_t)Ne + Nr + i] = v;
+        }
+    }
+    fclose(fp);
+    if (ok && t) *t = tt;
+    return ok ? SHUD_OK : SHUD_ERR_ARG;
+}
+
 }  // extern "C"

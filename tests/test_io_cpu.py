@@ -22,6 +22,25 @@ def test_ic_file_is_byte_identical_to_the_reference_writer(tmp_path):
     assert open(out, "rb").read() == g["text"].tobytes()
 
 
+def test_ic_file_reads_back(tmp_path):
+    """restart: the reference-written file parses to the printed (6-decimal) values; a file of another mesh is refused"""
+    g = np.load(os.path.join(GOLD, "qhh.icfile.npz"))
+    mesh = np.load(os.path.join(GOLD, "qhh.mesh.npz"))
+    Ne, Nr, Nl = int(mesh["Ne"][0]), int(mesh["Nr"][0]), int(mesh["Nl"][0])
+    path = tmp_path / "qhh.cfg.ic"
+    open(path, "wb").write(g["text"].tobytes())
+    t, y, ics, snow = api.read_ic(path, Ne, Nr, Nl)
+    assert t == float(g["ic_t"][0])
+    assert np.allclose(y, g["y"], rtol=0, atol=5.0000001e-7) and np.allclose(ics, g["ic_yEleIS"], rtol=0, atol=5.0000001e-7)
+    assert np.allclose(snow, g["ic_yEleSnow"], rtol=0, atol=5.0000001e-7)
+    # writing what was read reproduces the file byte for byte (the text is a fixed point of read -> format)
+    again = tmp_path / "again.ic"
+    api.format_ic(again, t, Ne, Nr, Nl, y, ics, snow)
+    assert open(again, "rb").read() == g["text"].tobytes()
+    with pytest.raises(RuntimeError):
+        api.read_ic(path, Ne - 1, Nr, Nl)
+
+
 def _fields(mesh):
     m, keep = abi.make_mesh(mesh)
     Ne, Nr, Ns, Nl = m.Ne, m.Nr, m.Ns, m.Nl
