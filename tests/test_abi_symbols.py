@@ -81,3 +81,19 @@ def test_abi_struct_layout_matches_header():
             decl = re.sub(r"^(const\s+)?(double|int32_t)\s*", "", decl)
             fields += [x.strip().lstrip("*").strip() for x in decl.split(",")]
         assert fields == [f[0] for f in cls._fields_], cname
+
+
+def test_headers_are_plain_c_and_cxx(tmp_path):
+    """the boundary headers compile on their own as C99 and as C++14 (the reference's language level)"""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    src_c = tmp_path / "t.c"
+    src_c.write_text('#include "shud_b200.h"\n#include "shud_nvector.h"\nint main(void) { return SHUD_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src_c)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src_cc = tmp_path / "t.cpp"
+    src_cc.write_text('#include "shud_nvector.h"\n#include "shud_b200.h"\nint main() { return SHUD_OK; }\n')
+    r = subprocess.run(["g++", "-std=c++14", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src_cc)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
