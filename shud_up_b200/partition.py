@@ -255,6 +255,63 @@ def assign(mesh, nparts):
     return part_of_atom[inv].astype(np.int32)
 
 
+def cut_river_closure(mesh, part_of_cell, rank):
+    """DESIGN of the next step (cut river trees) stated as data: for partition `rank` of an
+    arbitrary cell partition, which cells and reaches it must hold so that owner-computes reproduces the single-domain
+    result on what it owns, with no flux exchanged:
+      own cells; halo cells (edge neighbours owned elsewhere: state Ysurf, Ygw);
+      own reaches (a reach belongs to the partition owning most of its bank cells, ties to the lowest rank; a reach
+      without segments follows its downstream reach, a tree without any segment goes to rank 0);
+      replica cells (bank cells of own reaches that live elsewhere: full vertical parameters + Ysurf, Yunsat, Ygw; only
+      their vertical role and segment fluxes are evaluated);
+      halo reaches (reaches with a segment on an own cell, and the downstream / upstream reaches of own reaches that
+      are owned elsewhere: statics + stage).
+    Returns dict(own, halo, replica, riv_own, riv_halo, seg) of 0-based reference ids; `seg` = the segments between the
+    held cells and the held reaches.  tests/test_partition_cut_design.py checks the closure with the CPU oracle; the
+    CUDA path does not consume it yet (partition.extract still refuses cut reaches)."""
+    Ne, Nr, Ns = (int(np.asarray(mesh[k]).reshape(-1)[0]) for k in ("Ne", "Nr", "Ns"))
+    part = np.asarray(part_of_cell).astype(np.int64)
+    nparts = int(part.max()) + 1
+    seg_e = np.asarray(mesh["seg_iEle"]).astype(np.int64) - 1
+    seg_r = np.asarray(mesh["seg_iRiv"]).astype(np.int64) - 1
+    down = np.asarray(mesh["riv_down"]).astype(np.int64)
+    # ---- owner of every reach ----
+    votes = np.zeros((Nr, nparts), dtype=np.int64)
+    np.add.at(votes, (seg_r, part[seg_e]), 1)
+    has_seg = votes.sum(1) > 0
+    riv_owner = np.where(has_seg, votes.argmax(1), -1)          # argmax: ties to the lowest rank
+    for _ in range(Nr):                                         # segment-less reaches follow their downstream reach
+        todo = np.nonzero((riv_owner < 0) & (down > 0))[0]
+        if todo.size == 0:
+            break
+        new = riv_owner[down[todo] - 1]
+        if np.all(new < 0):
+            break
+        riv_owner[todo] = np.where(new >= 0, new, -1)
+    riv_owner[riv_owner < 0] = 0
+    own = np.nonzero(part == rank)[0]
+    nabr = np.asarray(mesh["ele_nabr"]).reshape(3, Ne).astype(np.int64)
+    nb = nabr[:, own]
+    nb0 = nb[nb > 0] - 1
+    halo = np.unique(nb0[part[nb0] != rank])
+    riv_own = np.nonzero(riv_owner == rank)[0]
+    is_riv_own = np.zeros(Nr, dtype=bool); is_riv_own[riv_own] = True
+    # replica cells: bank cells of own reaches that are not own cells
+    bank = seg_e[is_riv_own[seg_r]]
+    replica = np.unique(bank[part[bank] != rank])
+    # halo reaches: reaches touching own cells, plus downstream / upstream neighbours of own reaches
+    touch = np.unique(seg_r[part[seg_e] == rank])
+    dn = down[riv_own]
+    dn = dn[dn > 0] - 1
+    ups = np.nonzero((down > 0) & is_riv_own[np.maximum(down - 1, 0)])[0]
+    cand = np.unique(np.concatenate([touch, dn, ups]))
+    riv_halo = cand[~is_riv_own[cand]]
+    held_c = np.zeros(Ne, dtype=bool); held_c[own] = True; held_c[halo] = True; held_c[replica] = True
+    held_r = np.zeros(Nr, dtype=bool); held_r[riv_own] = True; held_r[riv_halo] = True
+    seg = np.nonzero(held_c[seg_e] & held_r[seg_r])[0] if Ns else np.zeros(0, dtype=np.int64)
+    return dict(own=own, halo=halo, replica=replica, riv_own=riv_own, riv_halo=riv_halo, seg=seg, riv_owner=riv_owner)
+
+
 def exchange_plan(own_gid, halo_gid, all_halo_gid):
     """Which of my cells each peer needs, and where what each peer sends lands in my halo arrays.
     all_halo_gid[q] = halo_gid of rank q (from an all_gather).  Both sides order a message by global id.
