@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built library (it is git-ignored): build it once, in-tree (nvcc cross-compiles without
+    # a GPU).  The product itself never builds or falls back on its own - a missing library is an error there.
+    from shud_up_b200 import build
+    if not os.path.exists(build.LIB):
+        build.build(force=True)
 
 
 def pytest_collection_modifyitems(config, items):
