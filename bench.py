@@ -154,6 +154,7 @@ def main():
         mesh = stripe_mesh(1, 0)
         Ne = int(mesh["Ne"][0])
         per, n = cpu_oracle_time(mesh, ncpu, budget_s=max(5.0, min(60.0, 0.1 * steps)), max_calls=max(steps, 3))
+        per1, _n1 = cpu_oracle_time(mesh, 1, budget_s=3.0, max_calls=3)  # the reference's serial order, one core
         v = Ne / per
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
                           "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -161,7 +162,8 @@ def main():
                           "config": {"workload": "synthetic-1M per GPU: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
                                      "seed": 20240611},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncpu, "kind": "port",
-                                           "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP"},
+                                           "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP",
+                                           "serial_value": Ne / per1},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -477,9 +479,12 @@ def main():
             out["land_surface_step"] = land_rec
         if world == 1:
             per, n = cpu_oracle_time(mesh, ncpu, budget_s=a.cpu_budget)
+            per1, n1 = cpu_oracle_time(mesh, 1, budget_s=min(4.0, a.cpu_budget), max_calls=5)
             out["cpu_baseline"] = {"value": Ne / per, "unit": UNIT, "cores": ncpu, "kind": "port",
                                    "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP on {ncpu} threads",
-                                   "ms_per_step": per * 1e3}
+                                   "ms_per_step": per * 1e3,
+                                   # the reference's serial order exactly (SURVEY.md 8(d) build 1), one core
+                                   "serial_value": Ne / per1, "serial_ms_per_step": per1 * 1e3, "serial_calls": n1}
         print(json.dumps(out), flush=True)
     # orderly teardown while the CUDA context is still alive, then leave without running interpreter-exit
     # destructors (torch's event/stream destructors otherwise race the context teardown under torchrun)
