@@ -29,6 +29,16 @@ UNIT = "cell-updates/s"
 B_CELL, B_RIV, B_SEG = 392, 124, 72  # algorithmic bytes per unit and f() call
 
 
+WORKLOAD = "synthetic-1M per GPU: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step"
+
+
+def config_for(world):
+    """the workload description both arms print (identical dicts: the driver compares them)"""
+    return {"workload": WORKLOAD, "seed": 20240611, "l2": "inputs 400 MB per rank > 126 MB L2, no flush needed",
+            "multi_gpu": (f"{world} stripes of 1M cells of the {world}M-cell mesh, per-f() halo exchange of the boundary "
+                          "cells' (Ysurf, Ygw)") if world > 1 else "single GPU"}
+
+
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None"""
     try:
@@ -104,7 +114,7 @@ def stripe_mesh(world, rank):
                       rows=(rank * rows, (rank + 1) * rows), stripe_rows=rows)
 
 
-def cpu_oracle_time(mesh, nthreads, budget_s=15.0, max_calls=50):
+def cpu_oracle_time(mesh, nthreads, budget_s=15.0, max_calls=50, warm_calls=1, want_ydot=False):
     """time the CPU restatement of the reference f() (oracle/, the checker) on the host cores"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import ctypes as C
@@ -119,7 +129,11 @@ def cpu_oracle_time(mesh, nthreads, budget_s=15.0, max_calls=50):
     ydot = np.empty_like(y)
     pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     call = lambda: L.shud_oracle_rhs(C.byref(ms), C.byref(fs), pd(satn), pd(eic), pd(y), pd(ydot), None, nthreads)
-    call()  # warm-up (first touch of the workspace)
+    ydot0 = None
+    for k in range(max(1, warm_calls)):  # warm-up (first touch of the workspace)
+        call()
+        if k == 0 and want_ydot:  # the first call after priming: what the parity block compares the GPU with
+            ydot0 = ydot.copy()
     n, t0 = 0, time.perf_counter()
     while True:
         rc = call()
@@ -128,45 +142,103 @@ def cpu_oracle_time(mesh, nthreads, budget_s=15.0, max_calls=50):
         if el > budget_s or n >= max_calls:
             break
     assert rc == 0
+    if want_ydot:
+        return el / n, n, ydot0
     return el / n, n
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
-    a = ap.parse_args()
+def extended_for_oracle(loc):
+    """A partition ('owned + halo', shud_up_b200.partition.extract) as one ordinary mesh the CPU oracle can run:
+    every halo cell becomes a cell of its own at index Ne+h carrying what the partition knows about it - its statics
+    z_surf, z_bottom and effKH parameters (halo_*) and its exchanged state (Ysurf, Ygw) - with no neighbours of its
+    own; its remaining parameters are copies of cell 0 (its ydot is garbage and ignored).  ydot of the owned cells,
+    reaches and lakes of this mesh is what the partition must produce.  Checker-side only."""
+    from shud_up_b200 import partition
+    Ne, Nr, Nl = (int(np.asarray(loc[k]).reshape(-1)[0]) for k in ("Ne", "Nr", "Nl"))
+    nh = int(np.asarray(loc["halo_z_surf"]).shape[0])
+    ext = {}
+    for k, v in loc.items():
+        v = np.asarray(v)
+        if k.startswith(("halo_", "_", "own_")) or k == "y":
+            continue
+        if k in partition.EDGE_KEYS or k in ("ele_nabr", "ele_lakenabr"):
+            a = v.reshape(3, Ne)
+            fill = np.zeros((3, nh), dtype=a.dtype) if k in ("ele_nabr", "ele_lakenabr") else np.repeat(a[:, :1], nh, axis=1)
+            ext[k] = np.ascontiguousarray(np.concatenate([a, fill], axis=1)).ravel()
+        elif (k.startswith("ele_") or k in partition.CELL_DYN) and v.ndim == 1 and v.shape[0] == Ne:
+            fill = np.zeros(nh, dtype=v.dtype) if k in ("ele_iLake", "ele_iBC", "ele_iSS") else np.repeat(v[:1], nh)
+            ext[k] = np.concatenate([v, fill])
+        else:
+            ext[k] = v
+    for k in partition.HALO_KEYS:
+        ext["ele_" + k][Ne:] = np.asarray(loc["halo_" + k])
+    hs = np.asarray(loc["halo_state_expected"]).reshape(nh, 2)
+    y = np.asarray(loc["y"])
+    aq = ext["ele_AquiferDepth"][Ne:]
+    ext["y"] = np.concatenate([y[:Ne], hs[:, 0], y[Ne:2 * Ne], 0.1 * np.maximum(aq - hs[:, 1], 0.02), y[2 * Ne:3 * Ne], hs[:, 1],
+                               y[3 * Ne:]])
+    ext["Ne"] = np.array([Ne + nh], dtype=np.int32)
+    return ext, Ne, nh
+
+
+def oracle_parity(mesh, ydot_gpu, nthreads):
+    """the GPU ydot of THIS bench mesh (first f() after set_forcing + prime, reference order) against the CPU oracle
+    on the same inputs, at the tolerance of the parity tests: |d| <= 1e-12 max(|ydot_ref|, sum |terms|)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    import parity
+    if "halo_z_surf" in mesh and int(np.asarray(mesh["halo_z_surf"]).shape[0]) > 0:
+        ext, Ne, nh = extended_for_oracle(mesh)
+    else:
+        ext, Ne, nh = mesh, int(mesh["Ne"][0]), 0
+    satn = oracle_lib.oracle_prime(ext, ext["y"])
+    o = oracle_lib.oracle_rhs(ext, u_satn=satn, qEleE_IC=ext["qEleE_IC_in"], nthreads=nthreads)
+    assert o["err"] == 0
+    sc = parity.ydot_scale(ext, o)
+    NE = Ne + nh
+    keep = np.r_[0:Ne, NE:NE + Ne, 2 * NE:2 * NE + Ne, 3 * NE:o["ydot"].size]  # owned cells x3, reaches, lakes
+    ref, sc = o["ydot"][keep], sc[keep]
+    bad = parity.mismatches(ydot_gpu, ref, sc)
+    rel = np.abs(ydot_gpu - ref) / np.maximum(np.maximum(np.abs(ref), sc), 1e-300)
+    return {"n": int(ref.size), "n_bad": int(bad.size), "max_rel": float(rel.max()), "rtol": parity.RTOL,
+            "max_abs": float(np.abs(ydot_gpu - ref).max()),
+            "against": "oracle/shud_oracle.c (bit-exact to the reference f() on the golden cases), same mesh, forcing, "
+                       "carried state and y; scale = max(|ydot_ref|, sum |terms| of the balance equation)"}
+
+
+def reference_arm(a):
+    """the reference's own algorithm for this path on the host cores: the serial f() physics with `omp parallel for`
+    on its cell / segment / reach loops (oracle port; the as-shipped OpenMP build drops ET and lakes - SURVEY.md 2.1 -
+    and needs the basin text inputs, which do not exist on this box).  Rank 0 alone works."""
+    rank = int(os.environ.get("RANK", "0"))
+    steps, warm = a.steps, max(a.warmup, 3)
+    ncpu = os.cpu_count() or 1
+    if rank != 0:
+        return
+    mesh = stripe_mesh(1, 0)
+    Ne = int(mesh["Ne"][0])
+    # W untimed calls, then exactly K timed calls (one call = one step = one f() over the whole 1M-cell mesh)
+    per, n = cpu_oracle_time(mesh, ncpu, budget_s=1e9, max_calls=steps, warm_calls=warm)
+    per1, _n1 = cpu_oracle_time(mesh, 1, budget_s=3.0, max_calls=3)  # the reference's serial order, one core
+    v = Ne / per
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
+                      "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": config_for(a.gpus),
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncpu, "kind": "port",
+                                       "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP",
+                                       "serial_value": Ne / per1},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return
+
+
+
+def gpu_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     steps, warm = a.steps, max(a.warmup, 3)
     ncpu = os.cpu_count() or 1
-
-    if a.impl == "reference":
-        # the reference's own algorithm for this path on the host cores: the serial f() physics with
-        # `omp parallel for` on its cell / segment / reach loops (oracle port; the as-shipped OpenMP build
-        # drops ET and lakes - SURVEY.md 2.1 - and needs the basin text inputs, which do not exist on this box)
-        if rank != 0:
-            return
-        mesh = stripe_mesh(1, 0)
-        Ne = int(mesh["Ne"][0])
-        per, n = cpu_oracle_time(mesh, ncpu, budget_s=max(5.0, min(60.0, 0.1 * steps)), max_calls=max(steps, 3))
-        per1, _n1 = cpu_oracle_time(mesh, 1, budget_s=3.0, max_calls=3)  # the reference's serial order, one core
-        v = Ne / per
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
-                          "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "synthetic-1M per GPU: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
-                                     "seed": 20240611},
-                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncpu, "kind": "port",
-                                           "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP",
-                                           "serial_value": Ne / per1},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-
     import torch
     import torch.distributed as dist
     from shud_up_b200.api import ShudRHS
@@ -174,7 +246,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # never overrides the caller's setting (the driver reads NCCL's rank lines)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     mesh = stripe_mesh(world, rank)
     Ne, Nr, Ns, Nl = (int(mesh[k][0]) for k in ("Ne", "Nr", "Ns", "Nl"))
@@ -207,6 +279,22 @@ def main():
                 rhs.f_boundary_dev(0.0, y, ydot, halo_stream=hx.finish())
         else:
             rhs.f_dev(0.0, y, ydot)
+
+    # ---------------- parity of THIS mesh: the first f() after set_forcing + prime against the CPU oracle -----------
+    step()
+    with torch.cuda.stream(st):
+        rhs.from_device_order(ydot, y_ref)
+        ydot_first = y_ref.cpu().numpy().copy()
+        y_ref.copy_(torch.from_numpy(np.ascontiguousarray(mesh["y"])))
+    st.synchronize()
+    par = oracle_parity(mesh, ydot_first, max(1, ncpu // max(world, 1)))
+    del ydot_first
+    if world > 1:
+        pt = torch.tensor([par["n_bad"], par["n"]], dtype=torch.float64, device=dev)
+        pm = torch.tensor([par["max_rel"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(pt); dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+        par.update(n_bad=int(pt[0]), n=int(pt[1]), max_rel=float(pm[0]), ranks=world)
+    assert par["n_bad"] == 0, par
 
     eager_step, step_mode, g, native = step, "eager", None, False
     if hx is not None and os.environ.get("SHUD_BENCH_GRAPH", "1") != "0":
@@ -458,11 +546,11 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": "synthetic-1M per GPU: 1,000,000 cells / 50,000 reaches / 150,000 segments, one f() per step",
-                          "seed": 20240611, "l2": "inputs 400 MB per rank > 126 MB L2, no flush needed",
-                          "multi_gpu": (f"{world} stripes of 1M cells of the {world}M-cell mesh, NCCL all_to_all halo exchange of "
-                                        f"{hx.bytes_per_exchange} B per rank and f(), overlapped with the interior tiles; "
-                                        f"step launched as: {step_mode}; per rank [ms/step, interior tiles, boundary tiles]: {per_rank}") if world > 1 else "single GPU"},
+               "config": config_for(world),
+               "multi_gpu_detail": (f"halo exchange of {hx.bytes_per_exchange} B per rank and f(), overlapped with the interior "
+                                    f"tiles; step launched as: {step_mode}; per rank [ms/step, interior tiles, boundary "
+                                    f"tiles]: {per_rank}") if world > 1 else None,
+               "parity": par,
                "gpu_launches": (nst + (3 if world > 1 else 0)) * steps,
                "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -486,24 +574,42 @@ def main():
                                    # the reference's serial order exactly (SURVEY.md 8(d) build 1), one core
                                    "serial_value": Ne / per1, "serial_ms_per_step": per1 * 1e3, "serial_calls": n1}
         print(json.dumps(out), flush=True)
-    # orderly teardown while the CUDA context is still alive, then leave without running interpreter-exit
-    # destructors (torch's event/stream destructors otherwise race the context teardown under torchrun)
-    # (the result line is out: a teardown that stalls must not hold the job, so a timer ends the process)
-    killer = threading.Timer(20.0, lambda: os._exit(0))
-    killer.daemon = True
-    killer.start()
+    return rhs, g, hx
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return reference_arm(a)
+    import gc
+    import torch
+    import torch.distributed as dist
+    rhs, g, hx = gpu_arm(a)
+    # Orderly teardown, then leave through the interpreter's normal exit path (no os._exit).  Everything gpu_arm
+    # allocated on the context's stream died with its frame; what is left goes in dependency order: graph ->
+    # exchange buffers -> cached blocks of that stream -> the context (its streams, NCCL communicator) -> process group.
     torch.cuda.synchronize()
     if g is not None:
         g.reset()
-        del g
-    del hx
+    del g, hx
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     rhs.close()
-    if world > 1:
+    del rhs
+    torch.cuda.synchronize()
+    if dist.is_initialized():
         dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 if __name__ == "__main__":
