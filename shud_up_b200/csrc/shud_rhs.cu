@@ -11,6 +11,7 @@
 //   * launches per RHS: effKH pre-pass, warp-specialised fused cell kernel, river+lake kernel.
 // Device vectors are in DEVICE ORDER (permuted); shud_b200_rhs() (host pointers, reference
 // order) permutes on the way in and out.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>
@@ -72,8 +73,11 @@ struct DevMesh {
     int Nhalo;
     const double *h_zs, *h_zb, *h_aqd, *h_macD, *h_macKsatH, *h_vAreaF, *h_ksatH;
     const double *h_state;        // [Nhalo][2] = (Ysurf, Ygw) of each halo cell, filled by the halo exchange
-    double *h_kh;                 // effKH of halo cells (k_effkh)
+    double *h_kh;                 // effKH of halo cells (k_effkh, three-launch form only)
     int *err;  // [0] code, [1] where (1-based reference id)
+    // single-kernel form (shud_tile.cuh)
+    const void *nbrec;               // rk::NbRec[Ne]: packed neighbour record of every cell
+    double *r_qdown;                 // Manning flux of every reach (phase A -> phase B)
 };
 
 struct DevDiag {
@@ -146,176 +150,6 @@ __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restri
         if (e) raise_err(m.err, e, i + 1);
     }
     m.effKH[i] = kh;
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1: everything a cell owns: ET partition, infiltration, recharge, its 3 overland and 3
-// groundwater edge fluxes, its river segments, and the three balance equations.
-// ---------------------------------------------------------------------------------------------
-template <bool DIAG, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_cell(DevMesh m, DevDiag d, const double *__restrict__ Y,
-                                                    double *__restrict__ DY) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int Ne = m.Ne;
-    const size_t NE = (size_t)Ne;
-    const size_t LD = (size_t)m.ld;  // padded leading dimension of the static [3][.] arrays
-    if (i >= Ne) return;
-    // ---- phase 0: every load this cell owns is issued before anything is consumed, so one warp keeps
-    //      ~45 coalesced 256-byte requests in flight (the kernel is latency-bound otherwise) ----
-    const unsigned fl = __ldg(m.flags + i);
-    const int seg0 = __ldg(m.cell_seg_first + i);
-    const int nb0 = __ldg(m.nbr + i), nb1 = __ldg(m.nbr + LD + i), nb2 = __ldg(m.nbr + 2 * LD + i);
-    const double ysf = Y[i], yus = Y[NE + i], ygw_raw = Y[2 * NE + i];
-    const double kh = m.effKH[i];
-    const double satn_prev = m.satn[i], eic_in = m.eic[i];
-    CellForc f;
-    f.netPrep = __ldg(m.netPrep + i); f.potEvap = __ldg(m.potEvap + i); f.potTran = __ldg(m.potTran + i);
-    f.lai = __ldg(m.lai + i); f.fuSurf = __ldg(m.fuSurf + i); f.fuSub = __ldg(m.fuSub + i);
-    CellParams p;
-    p.aqd = __ldg(m.aqd + i); p.sy = __ldg(m.sy + i); p.infD = __ldg(m.infD + i); p.infKsatV = __ldg(m.infKsatV + i);
-    p.macKsatV = __ldg(m.macKsatV + i); p.hAreaF = __ldg(m.hAreaF + i); p.thetaS = __ldg(m.thetaS + i);
-    p.thetaR = __ldg(m.thetaR + i); p.thetaFC = __ldg(m.thetaFC + i); p.beta = __ldg(m.beta + i);
-    p.ksatV = __ldg(m.ksatV + i); p.vegFrac = __ldg(m.vegFrac + i); p.impAF = __ldg(m.impAF + i);
-    p.wetland = __ldg(m.wetland + i); p.rootReach = __ldg(m.rootReach + i);
-    const double zs = __ldg(m.z_surf + i), zb = __ldg(m.z_bottom + i), depression = __ldg(m.depression + i);
-    const double area = __ldg(m.area + i);
-    double B[3], dist[3], arough[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        B[j] = __ldg(m.edge + j * LD + i);
-        dist[j] = __ldg(m.dist + j * LD + i);
-        arough[j] = __ldg(m.avgRough + j * LD + i);
-    }
-    // ---- phase 1: neighbour gathers, unconditional (index clamped to the cell itself where there is no
-    //      neighbour cell) so that all 15 go out together as soon as the indices land ----
-    const int nb[3] = {nb0, nb1, nb2};
-    double n_ysf[3], n_ygw[3], n_zs[3], n_zb[3], n_kh[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int k = (nb[j] >= 0 && nb[j] < Ne) ? nb[j] : i;
-        n_ysf[j] = Y[k];
-        n_ygw[j] = Y[2 * NE + k];
-        n_zs[j] = __ldg(m.z_surf + k);
-        n_zb[j] = __ldg(m.z_bottom + k);
-        n_kh[j] = m.effKH[k];
-        if (nb[j] >= Ne) {  // halo cell of a partition
-            const int h = nb[j] - Ne;
-            n_ysf[j] = m.h_state[2 * h]; n_ygw[j] = m.h_state[2 * h + 1]; n_zs[j] = m.h_zs[h]; n_zb[j] = m.h_zb[h]; n_kh[j] = m.h_kh[h];
-        }
-    }
-    const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : ygw_raw;
-    const double fuSub = f.fuSub;
-    int err = 0;
-
-    // ---- phase 2: vertical processes (own data only; the gathers are still in flight) ----
-    CellVert v;
-    if (fl & F_LAKE) {
-        // fun_Ele_lakeVertical, src/ModelData/MD_ElementFlux.cpp:2-17
-        v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
-        v.satn = 1.; v.infil = v.exfil = v.rech = 0.; v.err = 0;
-    } else {
-        v = cell_vertical(p, f, ysf, yus, ygw, satn_prev, eic_in);
-        if (v.err) err = v.err;
-    }
-    m.eic[i] = v.eic;
-    m.satn[i] = v.satn;
-    if (DIAG) {
-        if (fl & F_LAKE) {
-            d.qEleTrans[i] = 0.; d.qEleEvapo[i] = f.potEvap; d.qEleETA[i] = 0. + f.potEvap + 0.;
-        } else {
-            const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
-            d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
-            d.iBeta[i] = v.iBeta;
-        }
-    }
-
-    // ---- phase 3: lateral fluxes through the 3 edges (fun_Ele_surface / fun_Ele_sub) ----
-    double Qs[3] = {0., 0., 0.}, Qg[3] = {0., 0., 0.};
-    if (!(fl & F_LAKE)) {  // fun_Ele_lakeHorizon: a lake cell has no lateral flux of its own
-        const double isf = ysf < 0. ? 0. : ysf;
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double qs = 0., qg = 0.;
-            if (nb[j] >= 0) {
-                const double nsf = n_ysf[j] < 0. ? 0. : n_ysf[j];
-                double ygw_n = n_ygw[j];
-                if (m.has_headbc && nb[j] < Ne && (m.flags[nb[j]] & F_HEADBC)) ygw_n = m.ele_yBC[nb[j]];
-                qs = edge_surface(isf, zs, nsf, n_zs[j], depression, dist[j], B[j], arough[j]);
-                qg = edge_sub(ygw, zb, ygw_n, n_zb[j], kh, n_kh[j], dist[j], B[j]);
-            } else if (nb[j] <= -2) {
-                // bank of a lake: weir over the shore + Darcy against the lake stage (MD_ElementFlux.cpp:46-53,107-121)
-                const int slot = -2 - nb[j], l = m.bank_lake[slot];
-                const double yl = Y[3 * NE + m.Nr + l];
-                const double nsf = yl < 0. ? 0. : yl;
-                qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, B[j], 0.01);
-                qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], dist[j], B[j]);
-            } else if (!m.close_boundary) {
-                // open boundary (MD_ElementFlux.cpp:81-92,139-151)
-                const double d2e = m.dist2edge[j * LD + i];
-                if (isf > depression) {
-                    const double s = isf / d2e * 0.5;
-                    if (s > 0.) qs = sqrt(s) * cbrt(isf * isf * isf * isf * isf) * B[j] / m.rough[i];
-                }
-                if (ygw > depression * 10.) {
-                    const double grad = ygw / d2e * 0.5;
-                    if (grad > 0.) qg = kh * grad;
-                }
-            }
-            Qs[j] = qs;
-            Qg[j] = qg * fuSub;
-        }
-    }
-
-    // ---- river segments touching this cell (fun_Seg_surface / fun_Seg_sub, MD_RiverFlux.cpp:100-126;
-    //      PassValue's element side, MD_f.cpp:228-235) ----
-    double e2rS = 0., e2rG = 0.;
-    const int nseg = (int)(fl >> NSEG_SHIFT);
-    if (nseg) {
-        double isf2 = ysf - v.infil + v.exfil;
-        isf2 = dmax(0., isf2);
-        for (int k = 0; k < nseg; k++) {
-            const int q = seg0 + k;
-            const int s = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
-            const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
-            const double zr = zs - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
-            const double qs = weir_jtoi(zs, isf2, zr, yr, zs + __ldg(m.cs_zbank + q), __ldg(m.cs_cwr + q), len, depression);
-            const double qg = flux_r2e_gw(yr, zr, ygw, zb, kh, __ldg(m.cs_ksatH + q), len, __ldg(m.cs_bed + q)) * fuSub;
-            m.QsegSurf[s] = qs;
-            m.QsegSub[s] = qg;
-            e2rS += -qs;
-            e2rG += -qg;
-        }
-    }
-
-    // ---- f_applyDY, cell part (MD_f.cpp:65-156) ----
-    double surfTot = e2rS, subTot = e2rG;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        surfTot += Qs[j];
-        subTot += Qg[j];
-        if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
-    }
-    double dsf = f.netPrep - v.infil + v.exfil - SHUD_DIVS(surfTot, area) - v.Es;
-    double dus = v.infil - v.rech - v.Eu - v.Tu;
-    double dgw = v.rech - v.exfil - SHUD_DIVS(subTot, area) - v.Eg - v.Tg;
-    if (fl & F_HEADBC) dgw = 0;
-    else if (fl & F_FLUXBC) dgw += SHUD_DIVS(m.ele_QBC[i], area);
-    if (fl & F_SS_SURF) dsf += SHUD_DIVS(m.qss[i], area);
-    else if (fl & F_SS_GW) dgw += SHUD_DIVS(m.qss[i], area);
-    dus = SHUD_DIVS(dus, p.sy);
-    dgw = SHUD_DIVS(dgw, p.sy);
-    if (fl & F_LAKE) { dsf = 0.; dus = 0.; dgw = 0.; }
-    DY[i] = dsf;
-    DY[NE + i] = dus;
-    DY[2 * NE + i] = dgw;
-    if (err) raise_err(m.err, err, i + 1);
-    if (DIAG) {
-        d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech;
-        d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
-#pragma unroll
-        for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
-        d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -645,344 +479,29 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Persistent, TMA-pipelined form of the warp-specialised cell kernel (the default when Ne is even).
-// One block per resident slot (2 per SM) walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-// A producer warp streams every per-cell input slice of the NEXT tile (40 x 1 KB doubles + 5 x 512 B ints)
-// into a 2-stage shared-memory ring with cp.async.bulk (TMA) and mbarrier transaction counts, while the
-// 4 lateral + 4 vertical warps compute the CURRENT tile out of shared memory: HBM latency is off the
-// critical path, no input is parked in registers (no spills), and the staged slices double as the
-// in-tile neighbour table.  Arithmetic and evaluation order are those of k_fused.
-// ---------------------------------------------------------------------------------------------
-enum {
-    A_YSF = 0, A_YUS, A_YGW, A_SATN, A_EIC, A_NETP, A_PE, A_PT, A_LAI, A_FUS, A_FUB, A_AQD, A_SY, A_INFD, A_INFK,
-    A_MACKV, A_HAF, A_THS, A_THR, A_THFC, A_BETA, A_KSV, A_VEG, A_IMP, A_WET, A_ROOT,
-    A_KH, A_ZS, A_ZB, A_DEP, A_AREA, A_E0, A_E1, A_E2, A_D0, A_D1, A_D2, A_R0, A_R1, A_R2,
-    A_ND
-};
-enum { I_NB0 = 0, I_NB1, I_NB2, I_FL, I_SEG0, I_NI };
-constexpr int STAGE_DBL = A_ND * TILE;                                   // doubles per stage
-constexpr int STAGE_BYTES = STAGE_DBL * 8 + I_NI * TILE * 4;             // 43520
-constexpr int PIPE_XCH_DBL = 6 * TILE + 2 * SEGCAP;                      // hand-over + segment slots
-constexpr int pipe_smem(int stages) { return stages * STAGE_BYTES + PIPE_XCH_DBL * 8 + 64; }
+#include "shud_tile.cuh"
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *b, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+// shapes of the persistent kernel (SHUD_TILE_CFG): cells per tile, teams per block, shared-memory stages
+using TileCfg0 = rk::Cfg<96, 5, 6>;
+using TileCfg1 = rk::Cfg<64, 7, 9>;
+using TileCfg2 = rk::Cfg<32, 15, 19>;
+using TileCfg3 = rk::Cfg<96, 4, 6>;
+using TileCfg4 = rk::Cfg<64, 6, 9>;
+static int tile_cfg_rt(int cfg) { return cfg == 2 ? 32 : ((cfg == 1 || cfg == 4) ? 64 : 96); }
+template <class CF>
+static cudaError_t tile_attr_one() {
+    cudaError_t e = cudaFuncSetAttribute(k_rhs<false, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_rhs<true, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES);
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity) {
-    unsigned ok = 0;
-    const unsigned a = smem_u32(b);
-    while (!ok) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+static cudaError_t tile_kernel_attrs(int cfg) {
+    switch (cfg) {
+        case 1: return tile_attr_one<TileCfg1>();
+        case 2: return tile_attr_one<TileCfg2>();
+        case 3: return tile_attr_one<TileCfg3>();
+        case 4: return tile_attr_one<TileCfg4>();
+        default: return tile_attr_one<TileCfg0>();
     }
-}
-// TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <bool DIAG, int PIPE_STAGES, int MINB>
-__global__ void __launch_bounds__(2 * TILE + 32, MINB) k_pipe(DevMesh m, DevDiag d, const double *__restrict__ Y,
-                                                              double *__restrict__ DY, int ntiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *xch = reinterpret_cast<double *>(smem_raw + PIPE_STAGES * STAGE_BYTES);
-    double *x_P1 = xch, *x_Es = xch + TILE, *x_G1 = xch + 2 * TILE, *x_Eg = xch + 3 * TILE, *x_Tg = xch + 4 * TILE,
-           *x_isf2 = xch + 5 * TILE, *sq_s = xch + 6 * TILE, *sq_g = xch + 6 * TILE + SEGCAP;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(xch + PIPE_XCH_DBL);
-    uint64_t *full = bars, *empty = bars + PIPE_STAGES;
-    const int Ne = m.Ne;
-    const size_t NE = (size_t)Ne, LD = (size_t)m.ld;
-    const bool y_staged = (Ne & 1) == 0;  // Y blocks are 16-byte aligned only then
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (threadIdx.x >= 2 * TILE) {
-        // =============================== producer warp ===============================
-        // all 32 lanes issue copies (one or two each); lane 0 arms the transaction count
-        const int lane = threadIdx.x - 2 * TILE;
-        int k = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
-            const int s = k % PIPE_STAGES;
-            if (k >= PIPE_STAGES) mbar_wait(&empty[s], ((k / PIPE_STAGES) - 1) & 1);
-            const size_t i0 = (size_t)tile * TILE;
-            double *sd = reinterpret_cast<double *>(smem_raw + (size_t)s * STAGE_BYTES);
-            int *si = reinterpret_cast<int *>(sd + STAGE_DBL);
-            const bool ytile = y_staged && (i0 + TILE <= NE);
-            if (lane == 0) mbar_expect_tx(&full[s], (unsigned)(STAGE_BYTES - (ytile ? 0 : 3 * TILE * 8)));
-            // copy table: slot a of the stage <- source pointer
-            for (int a = lane; a < A_ND + I_NI; a += 32) {
-                const void *src = nullptr;
-                void *dst;
-                unsigned bytes = TILE * 8;
-                if (a < A_ND) dst = sd + a * TILE; else { dst = si + (a - A_ND) * TILE; bytes = TILE * 4; }
-                switch (a) {
-                    case A_YSF: src = ytile ? Y + i0 : nullptr; break;
-                    case A_YUS: src = ytile ? Y + NE + i0 : nullptr; break;
-                    case A_YGW: src = ytile ? Y + 2 * NE + i0 : nullptr; break;
-                    case A_SATN: src = m.satn + i0; break;
-                    case A_EIC: src = m.eic + i0; break;
-                    case A_NETP: src = m.netPrep + i0; break;
-                    case A_PE: src = m.potEvap + i0; break;
-                    case A_PT: src = m.potTran + i0; break;
-                    case A_LAI: src = m.lai + i0; break;
-                    case A_FUS: src = m.fuSurf + i0; break;
-                    case A_FUB: src = m.fuSub + i0; break;
-                    case A_AQD: src = m.aqd + i0; break;
-                    case A_SY: src = m.sy + i0; break;
-                    case A_INFD: src = m.infD + i0; break;
-                    case A_INFK: src = m.infKsatV + i0; break;
-                    case A_MACKV: src = m.macKsatV + i0; break;
-                    case A_HAF: src = m.hAreaF + i0; break;
-                    case A_THS: src = m.thetaS + i0; break;
-                    case A_THR: src = m.thetaR + i0; break;
-                    case A_THFC: src = m.thetaFC + i0; break;
-                    case A_BETA: src = m.beta + i0; break;
-                    case A_KSV: src = m.ksatV + i0; break;
-                    case A_VEG: src = m.vegFrac + i0; break;
-                    case A_IMP: src = m.impAF + i0; break;
-                    case A_WET: src = m.wetland + i0; break;
-                    case A_ROOT: src = m.rootReach + i0; break;
-                    case A_KH: src = m.effKH + i0; break;
-                    case A_ZS: src = m.z_surf + i0; break;
-                    case A_ZB: src = m.z_bottom + i0; break;
-                    case A_DEP: src = m.depression + i0; break;
-                    case A_AREA: src = m.area + i0; break;
-                    case A_E0: case A_E1: case A_E2: src = m.edge + (a - A_E0) * LD + i0; break;
-                    case A_D0: case A_D1: case A_D2: src = m.dist + (a - A_D0) * LD + i0; break;
-                    case A_R0: case A_R1: case A_R2: src = m.avgRough + (a - A_R0) * LD + i0; break;
-                    case A_ND + I_NB0: case A_ND + I_NB1: case A_ND + I_NB2: src = m.nbr + (a - A_ND - I_NB0) * LD + i0; break;
-                    case A_ND + I_FL: src = m.flags + i0; break;
-                    case A_ND + I_SEG0: src = m.cell_seg_first + i0; break;
-                }
-                if (src) tma_load(dst, src, bytes, &full[s]);
-            }
-        }
-        return;
-    }
-
-    const int lane_cell = threadIdx.x & (TILE - 1);
-    const bool vertical = threadIdx.x >= TILE;
-    int k = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
-        const int s = k % PIPE_STAGES;
-        const double *sd = reinterpret_cast<const double *>(smem_raw + (size_t)s * STAGE_BYTES);
-        double *sdw = reinterpret_cast<double *>(smem_raw + (size_t)s * STAGE_BYTES);
-        const int *si = reinterpret_cast<const int *>(sd + STAGE_DBL);
-        const int i0 = tile * TILE;
-        const int i = i0 + lane_cell;
-        const bool valid = i < Ne;
-        const int ic = valid ? i : Ne - 1;
-        const bool ytile = y_staged && (i0 + TILE <= Ne);
-        mbar_wait(&full[s], (k / PIPE_STAGES) & 1);
-        const unsigned fl = valid ? (unsigned)si[I_FL * TILE + lane_cell] : 0u;
-#define SD(a) sd[(a) * TILE + lane_cell]
-        if (vertical) {
-            // =============================== vertical role ===============================
-            const double ysf = ytile ? SD(A_YSF) : Y[ic], yus = ytile ? SD(A_YUS) : Y[NE + ic];
-            const double ygw_raw = ytile ? SD(A_YGW) : Y[2 * NE + ic];
-            CellForc f;
-            f.netPrep = SD(A_NETP); f.potEvap = SD(A_PE); f.potTran = SD(A_PT); f.lai = SD(A_LAI);
-            f.fuSurf = SD(A_FUS); f.fuSub = SD(A_FUB);
-            CellParams p;
-            p.aqd = SD(A_AQD); p.sy = SD(A_SY); p.infD = SD(A_INFD); p.infKsatV = SD(A_INFK); p.macKsatV = SD(A_MACKV);
-            p.hAreaF = SD(A_HAF); p.thetaS = SD(A_THS); p.thetaR = SD(A_THR); p.thetaFC = SD(A_THFC); p.beta = SD(A_BETA);
-            p.ksatV = SD(A_KSV); p.vegFrac = SD(A_VEG); p.impAF = SD(A_IMP); p.wetland = SD(A_WET); p.rootReach = SD(A_ROOT);
-            const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
-            CellVert v;
-            if (fl & F_LAKE) {
-                v.Es = v.Eu = v.Eg = v.Tu = v.Tg = 0.; v.eic = 0.; v.iBeta = 0.;
-                v.satn = 1.; v.infil = v.exfil = v.rech = 0.; v.err = 0;
-            } else {
-                v = cell_vertical(p, f, ysf, yus, ygw, SD(A_SATN), SD(A_EIC));
-            }
-            double isf2 = ysf - v.infil + v.exfil;
-            x_P1[lane_cell] = f.netPrep - v.infil + v.exfil;
-            x_Es[lane_cell] = v.Es;
-            x_G1[lane_cell] = v.rech - v.exfil;
-            x_Eg[lane_cell] = v.Eg;
-            x_Tg[lane_cell] = v.Tg;
-            x_isf2[lane_cell] = dmax(0., isf2);
-            bar_sync(3, 2 * TILE);  // lateral role has fixed up the staged tile; every x_isf2 is written
-            {
-                const int q0 = si[I_SEG0 * TILE];
-                const int q1 = __ldg(m.cell_seg_first + (i0 + TILE < Ne ? i0 + TILE : Ne));
-                for (int tq = lane_cell; tq < q1 - q0; tq += TILE) {
-                    const int q = q0 + tq;
-                    const int lc = __ldg(m.cs_cell + q) - i0, sgm = __ldg(m.cs_seg + q), r = __ldg(m.cs_riv + q);
-                    const double yr = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : Y[3 * NE + r];
-                    const double zs_c = sd[A_ZS * TILE + lc];
-                    const double zr = zs_c - __ldg(m.cs_depth + q), len = __ldg(m.cs_len + q);
-                    const double qs = weir_jtoi(zs_c, x_isf2[lc], zr, yr, zs_c + __ldg(m.cs_zbank + q),
-                                                __ldg(m.cs_cwr + q), len, sd[A_DEP * TILE + lc]);
-                    const double ygw_c = ytile ? sd[A_YGW * TILE + lc] : sdw[A_YGW * TILE + lc];
-                    const double qg = flux_r2e_gw(yr, zr, ygw_c, sd[A_ZB * TILE + lc], sd[A_KH * TILE + lc],
-                                                  __ldg(m.cs_ksatH + q), len, __ldg(m.cs_bed + q)) * sd[A_FUB * TILE + lc];
-                    m.QsegSurf[sgm] = qs;
-                    m.QsegSub[sgm] = qg;
-                    if (tq < SEGCAP) { sq_s[tq] = qs; sq_g[tq] = qg; }
-                }
-            }
-            bar_arrive(2, 2 * TILE);
-            if (valid) {
-                m.eic[i] = v.eic;
-                m.satn[i] = v.satn;
-                double dus = v.infil - v.rech - v.Eu - v.Tu;
-                dus = SHUD_DIVS(dus, p.sy);
-                if (fl & F_LAKE) dus = 0.;
-                DY[NE + i] = dus;
-                if (v.err) raise_err(m.err, v.err, i + 1);
-                if (DIAG) {
-                    if (fl & F_LAKE) {
-                        d.qEleTrans[i] = 0.; d.qEleEvapo[i] = f.potEvap; d.qEleETA[i] = 0. + f.potEvap + 0.;
-                    } else {
-                        const double trans = v.Tg + v.Tu, evapo = v.Eu + v.Eg + v.Es;
-                        d.qEleTrans[i] = trans; d.qEleEvapo[i] = evapo; d.qEleETA[i] = v.eic + evapo + trans;
-                        d.iBeta[i] = v.iBeta;
-                    }
-                    d.qEleInfil[i] = v.infil; d.qEleExfil[i] = v.exfil; d.qEleRecharge[i] = v.rech;
-                    d.qEs[i] = v.Es; d.qEu[i] = v.Eu; d.qEg[i] = v.Eg; d.qTu[i] = v.Tu; d.qTg[i] = v.Tg;
-                }
-            }
-        } else {
-            // =============================== lateral role ===============================
-            const int seg0 = si[I_SEG0 * TILE + lane_cell];
-            const int nb[3] = {si[I_NB0 * TILE + lane_cell], si[I_NB1 * TILE + lane_cell], si[I_NB2 * TILE + lane_cell]};
-            const double ysf = ytile ? SD(A_YSF) : Y[ic];
-            const double ygw_raw = ytile ? SD(A_YGW) : Y[2 * NE + ic];
-            const double kh = SD(A_KH), zs = SD(A_ZS), zb = SD(A_ZB);
-            const double ygw = (fl & F_HEADBC) ? m.ele_yBC[ic] : ygw_raw;
-            // the staged slices are the in-tile neighbour table: make them hold what a neighbour must see
-            // (clamped tail cells, head-BC groundwater, Y of a tile whose Y was not TMA-staged)
-            if (!ytile) { sdw[A_YSF * TILE + lane_cell] = ysf; }
-            if (!ytile || (fl & F_HEADBC)) sdw[A_YGW * TILE + lane_cell] = ygw;
-            const double fuSub = SD(A_FUB), depression = SD(A_DEP);
-            const double area = SD(A_AREA), sy = SD(A_SY);
-            bar_sync(1, TILE);
-            bar_arrive(3, 2 * TILE);
-            int err = 0;
-            double Qs[3] = {0., 0., 0.}, Qg[3] = {0., 0., 0.};
-            if (valid && !(fl & F_LAKE)) {
-                const double isf = ysf < 0. ? 0. : ysf;
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    double qs = 0., qg = 0.;
-                    const int kk = nb[j];
-                    const double Bj = SD(A_E0 + j), distj = SD(A_D0 + j), roughj = SD(A_R0 + j);
-                    if (kk >= 0) {
-                        double nsf, ygw_n, zs_n, zb_n, kh_n;
-                        const unsigned r = (unsigned)(kk - i0);
-                        if (r < (unsigned)TILE && k < Ne) {
-                            nsf = sd[A_YSF * TILE + r]; ygw_n = sd[A_YGW * TILE + r]; zs_n = sd[A_ZS * TILE + r];
-                            zb_n = sd[A_ZB * TILE + r]; kh_n = sd[A_KH * TILE + r];
-                        } else if (kk < Ne) {
-                            nsf = Y[kk]; ygw_n = Y[2 * NE + kk]; zs_n = __ldg(m.z_surf + kk); zb_n = __ldg(m.z_bottom + kk);
-                            kh_n = m.effKH[kk];
-                            if (m.has_headbc && (m.flags[kk] & F_HEADBC)) ygw_n = m.ele_yBC[kk];
-                        } else {
-                            const int h = kk - Ne;
-                            nsf = m.h_state[2 * h]; ygw_n = m.h_state[2 * h + 1]; zs_n = m.h_zs[h]; zb_n = m.h_zb[h];
-                            kh_n = m.h_kh[h];
-                        }
-                        nsf = nsf < 0. ? 0. : nsf;
-                        qs = edge_surface(isf, zs, nsf, zs_n, depression, distj, Bj, roughj);
-                        qg = edge_sub(ygw, zb, ygw_n, zb_n, kh, kh_n, distj, Bj);
-                    } else if (kk <= -2) {
-                        const int slot = -2 - kk, l = m.bank_lake[slot];
-                        const double yl = Y[3 * NE + m.Nr + l];
-                        const double nsf = yl < 0. ? 0. : yl;
-                        qs = weir_jtoi(m.l_zmin[l], nsf, zs, isf, zs, 0.6, Bj, 0.01);
-                        qg = edge_sub(ygw, zb, yl, m.l_yi0[l], kh, m.bank_kh[slot], distj, Bj);
-                    } else if (!m.close_boundary) {
-                        const double d2e = m.dist2edge[j * LD + ic];
-                        if (isf > depression) {
-                            const double sl = isf / d2e * 0.5;
-                            if (sl > 0.) qs = sqrt(sl) * cbrt(isf * isf * isf * isf * isf) * Bj / m.rough[ic];
-                        }
-                        if (ygw > depression * 10.) {
-                            const double grad = ygw / d2e * 0.5;
-                            if (grad > 0.) qg = kh * grad;
-                        }
-                    }
-                    Qs[j] = qs;
-                    Qg[j] = qg * fuSub;
-                }
-            }
-            bar_sync(2, 2 * TILE);  // vertical role has handed over (and finished the segment pass)
-            if (valid) {
-                const double P1 = x_P1[lane_cell], Es = x_Es[lane_cell], G1 = x_G1[lane_cell], Eg = x_Eg[lane_cell],
-                             Tg = x_Tg[lane_cell];
-                double e2rS = 0., e2rG = 0.;
-                const int nseg = (int)(fl >> NSEG_SHIFT);
-                if (nseg) {
-                    const int tq0 = seg0 - si[I_SEG0 * TILE];
-                    for (int kq = 0; kq < nseg; kq++) {
-                        const int tq = tq0 + kq;
-                        double qs, qg;
-                        if (tq < SEGCAP) { qs = sq_s[tq]; qg = sq_g[tq]; }
-                        else { const int sgm = __ldg(m.cs_seg + seg0 + kq); qs = m.QsegSurf[sgm]; qg = m.QsegSub[sgm]; }
-                        e2rS += -qs;
-                        e2rG += -qg;
-                    }
-                }
-                double surfTot = e2rS, subTot = e2rG;
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    surfTot += Qs[j];
-                    subTot += Qg[j];
-                    if (not_finite(Qs[j]) || not_finite(Qg[j])) err = err > 10 ? err : 10;
-                }
-                double dsf = P1 - SHUD_DIVS(surfTot, area) - Es;
-                double dgw = G1 - SHUD_DIVS(subTot, area) - Eg - Tg;
-                if (fl & F_HEADBC) dgw = 0;
-                else if (fl & F_FLUXBC) dgw += SHUD_DIVS(m.ele_QBC[i], area);
-                if (fl & F_SS_SURF) dsf += SHUD_DIVS(m.qss[i], area);
-                else if (fl & F_SS_GW) dgw += SHUD_DIVS(m.qss[i], area);
-                dgw = SHUD_DIVS(dgw, sy);
-                if (fl & F_LAKE) { dsf = 0.; dgw = 0.; }
-                DY[i] = dsf;
-                DY[2 * NE + i] = dgw;
-                if (err) raise_err(m.err, err, i + 1);
-                if (DIAG) {
-#pragma unroll
-                    for (int j = 0; j < 3; j++) { d.QeleSurf[j * NE + i] = Qs[j]; d.QeleSub[j * NE + i] = Qg[j]; }
-                    d.QeleSurfTot[i] = surfTot; d.QeleSubTot[i] = subTot; d.Qe2r_Surf[i] = e2rS; d.Qe2r_Sub[i] = e2rG;
-                }
-            }
-        }
-#undef SD
-        // every reader of stage s and of the hand-over arrays is done: release the stage to the producer
-        bar_sync(4, 2 * TILE);
-        if (threadIdx.x == 0) mbar_arrive(&empty[s]);
-    }
-}
-
-// Manning flux of reach r towards its downstream end, everything gathered from global memory
-__device__ __forceinline__ double reach_down_flux(const DevMesh &m, const double *__restrict__ Yr, int r, int *err) {
-    const double yraw = Yr[r];
-    const double ystg = (m.r_bc[r] > 0) ? m.r_yBC[r] : yraw;
-    const int down = m.r_down[r];
-    double y_dn = 0., depth_dn = 0., slope_dn = 0.;
-    if (down >= 0) {
-        y_dn = (m.r_bc[down] > 0) ? m.r_yBC[down] : Yr[down];
-        depth_dn = m.r_depth[down];
-        slope_dn = m.r_slope[down];
-    }
-    // r_down device coding: >=0 downstream reach (device id); <0 the reference's outlet code
-    return river_down(yraw, ystg, m.r_w0[r], m.r_bank[r], m.r_len[r], m.r_slope[r], m.r_depth[r], m.r_rough[r],
-                      m.r_dist[r], down >= 0 ? 1 : down, m.r_toLake[r], y_dn, depth_dn, slope_dn, err);
 }
 
 // fixed-shape block sum (deterministic): warp shuffle tree, then warp 0 over the warp partials
@@ -1185,9 +704,12 @@ struct shud_ctx {
     bool acc_alloc = false;
     int num_update = 0;
     std::vector<void *> allocs;
-    char *arena = nullptr;          // one block for the lateral role's statics (optional persisting-L2 window)
+    // the three [slice][ld] families of per-cell arrays the persistent kernel stages with one TMA box copy each
+    // (shud_tile.cuh): consecutive allocations from `arena` are contiguous, slice after slice
+    char *arena = nullptr;
     size_t arena_off = 0, arena_cap = 0;
     bool arena_on = false;
+    CUtensorMap map_dyn{}, map_stat{}, map_int{};
     std::vector<int> cperm, rperm, sperm;  // device id -> reference id (0-based)
     std::vector<int> cinv, rinv;           // reference id -> device id
     int *d_cperm = nullptr, *d_rperm = nullptr;
@@ -1215,15 +737,17 @@ struct shud_ctx {
     double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
     int x_nsend = 0;
     int use_xgraph = 1;               // SHUD_XGRAPH: rhs_exchange_dev replayed as one CUDA graph per (y, ydot)
-    int pipe_grid = 296;  // persistent blocks of k_pipe: 2 per SM (2 stages) or 4 per SM (1 stage)
-    int pipe_stages = 2;
+    // single-kernel form (shud_tile.cuh): one persistent block per SM
+    int legacy = 0;        // SHUD_LEGACY=1: the three-launch form (k_effkh, k_fused, k_river_lake), A/B only
+    int cfg = 0;           // SHUD_TILE_CFG: shape of the persistent kernel (tile size / teams / stages), see tile_cfgs
+    int tile = 96;         // cells per tile of the form in use (three-launch form: 128)
+    int nsm = 148;
+    int *sync_words = nullptr;  // 3 sets of rk::W_NWORDS ints: whole / interior launch, boundary launch, phase-B launch
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
     int use_graph = 1;
     int use_pdl = 1;   // programmatic dependent launch of the cell kernel behind k_effkh (SHUD_PDL)
     struct GraphEntry { const double *y; double *yd; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs, xgraphs;
-    int split = 2;      // 2: warp-specialised fused cell kernel (default); 0: one-thread-per-cell k_cell (SHUD_SPLIT, A/B only)
-    int cell_minb = 4;  // resident blocks per SM the cell kernel is compiled for (tuning knob)
 };
 
 #define CK(call)                                                                                         \
@@ -1308,7 +832,11 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     c->device = device;
     const int Ne = c->Ne = M->Ne, Nr = c->Nr = M->Nr, Ns = c->Ns = M->Ns, Nl = c->Nl = M->Nl;
     c->NY = 3 * (int64_t)Ne + Nr + Nl;
-    c->ld = ((Ne + 127) / 128) * 128;
+    c->ld = ((Ne + 383) / 384) * 384;  // a multiple of both tile sizes (96, 128)
+    if (getenv("SHUD_LEGACY")) c->legacy = atoi(getenv("SHUD_LEGACY"));
+    if (getenv("SHUD_TILE_CFG")) c->cfg = std::max(0, std::min(4, atoi(getenv("SHUD_TILE_CFG"))));
+    c->tile = c->legacy ? TILE : tile_cfg_rt(c->cfg);
+    cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, device);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
     // ---- cell order: Hilbert curve over centroids (if given) ----
@@ -1333,6 +861,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     //      [interior tiles | boundary tiles (+ the ragged last tile)], so each part of the RHS is one contiguous
     //      tile range (shud_b200_rhs_interior_dev / _boundary_dev) ----
     {
+        const int TILE = c->tile;
         const int ntile = (Ne + TILE - 1) / TILE, nfull = Ne / TILE;
         c->n_int_tiles = ntile; c->n_bnd_tiles = 0;
         if (Nhalo > 0) {
@@ -1388,59 +917,40 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     const int LDh = c->ld;
     m.close_boundary = M->close_boundary;
     {
-        const char *e1 = getenv("SHUD_CELL_MINB");
-        if (e1) c->cell_minb = atoi(e1);
-        if (getenv("SHUD_SPLIT")) c->split = atoi(getenv("SHUD_SPLIT"));
-        if (getenv("SHUD_PIPE_GRID")) c->pipe_grid = atoi(getenv("SHUD_PIPE_GRID"));
         if (getenv("SHUD_PDL")) c->use_pdl = atoi(getenv("SHUD_PDL"));
         if (getenv("SHUD_GRAPH")) c->use_graph = atoi(getenv("SHUD_GRAPH"));
         if (getenv("SHUD_XGRAPH")) c->use_xgraph = atoi(getenv("SHUD_XGRAPH"));
         if (getenv("SHUD_FUSED_MINB")) c->fused_minb = atoi(getenv("SHUD_FUSED_MINB"));
     }
 
-    // ---- static per-cell arrays ----
-    {
-        // the statics the lateral role streams every call, contiguous: SHUD_L2_PERSIST=1 pins them in L2
-        c->arena_cap = (size_t)12 * ((size_t)c->ld * sizeof(double) + 256);
+    // ---- static per-cell arrays: the 32 slices of the static family first, in the order of the S_* enum of
+    //      shud_tile.cuh, from one block (so that they form one [32][ld] array), then the others ----
+    auto open_arena = [&](size_t bytes) -> bool {
         void *a = nullptr;
-        if (cudaMalloc(&a, c->arena_cap) == cudaSuccess) { c->arena = (char *)a; c->allocs.push_back(a); }
-        else { cudaGetLastError(); c->arena_cap = 0; }
-    }
-    c->arena_on = c->arena != nullptr;
-    m.area = up_cell(c, M->area, true); m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom);
+        if (cudaMalloc(&a, bytes) != cudaSuccess) return false;
+        c->allocs.push_back(a);
+        c->arena = (char *)a; c->arena_off = 0; c->arena_cap = bytes; c->arena_on = true;
+        return true;
+    };
+    const size_t slice_d = (size_t)c->ld * sizeof(double), slice_i = (size_t)c->ld * sizeof(int);
+    if (!open_arena(rk::N_STAT * slice_d)) { delete c; return SHUD_ERR_CUDA; }
+    char *const stat_base = c->arena;
+    m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy, true); m.infD = up_cell(c, M->infD);
+    m.infKsatV = up_cell(c, M->infKsatV); m.macKsatV = up_cell(c, M->macKsatV); m.hAreaF = up_cell(c, M->hAreaF);
+    m.thetaS = up_cell(c, M->ThetaS); m.thetaR = up_cell(c, M->ThetaR); m.thetaFC = up_cell(c, M->ThetaFC);
+    m.beta = up_cell(c, M->Beta); m.ksatV = up_cell(c, M->KsatV); m.vegFrac = up_cell(c, M->VegFrac);
+    m.impAF = up_cell(c, M->ImpAF); m.wetland = up_cell(c, M->WetlandLevel); m.rootReach = up_cell(c, M->RootReachLevel);
+    m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom); m.depression = up_cell(c, M->depression);
+    m.area = up_cell(c, M->area, true);
+    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor, true); m.avgRough = up_edge(c, M->avgRough, true);
+    m.macD = up_cell(c, M->macD); m.macKsatH = up_cell(c, M->macKsatH); m.vAreaF = up_cell(c, M->geo_vAreaF);
+    m.ksatH = up_cell(c, M->KsatH);
+    if (c->arena_off != rk::N_STAT * slice_d || (const char *)m.aqd != stat_base ||
+        (const char *)m.ksatH != stat_base + (rk::S_KSH - rk::S_STAT0) * slice_d ||
+        (const char *)m.edge != stat_base + (rk::S_E0 - rk::S_STAT0) * slice_d) { delete c; return SHUD_ERR_CUDA; }
     c->arena_on = false;
-    m.depression = up_cell(c, M->depression); m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy, true);
-    m.infD = up_cell(c, M->infD); m.infKsatV = up_cell(c, M->infKsatV); m.macKsatV = up_cell(c, M->macKsatV);
-    m.hAreaF = up_cell(c, M->hAreaF); m.thetaS = up_cell(c, M->ThetaS); m.thetaR = up_cell(c, M->ThetaR);
-    m.thetaFC = up_cell(c, M->ThetaFC); m.beta = up_cell(c, M->Beta); m.ksatH = up_cell(c, M->KsatH);
-    m.ksatV = up_cell(c, M->KsatV); m.macKsatH = up_cell(c, M->macKsatH); m.macD = up_cell(c, M->macD);
-    m.vAreaF = up_cell(c, M->geo_vAreaF); m.vegFrac = up_cell(c, M->VegFrac); m.impAF = up_cell(c, M->ImpAF);
-    m.wetland = up_cell(c, M->WetlandLevel); m.rootReach = up_cell(c, M->RootReachLevel);
     m.rough = up_cell(c, M->Rough); m.qss = up_cell(c, M->QSS);
-    c->arena_on = c->arena != nullptr;
-    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor, true);
-    m.avgRough = up_edge(c, M->avgRough, true);
-    c->arena_on = false;
     m.dist2edge = up_edge(c, M->Dist2Edge);
-    if (c->arena && getenv("SHUD_L2_PERSIST") && atoi(getenv("SHUD_L2_PERSIST")) > 0) {
-        int max_persist = 0, max_win = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
-        const size_t setaside = std::min((size_t)max_persist, c->arena_off);
-        const size_t win = std::min((size_t)max_win, c->arena_off);
-        if (setaside > 0 && win > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess) {
-            cudaStreamAttrValue av = {};
-            av.accessPolicyWindow.base_ptr = c->arena;
-            av.accessPolicyWindow.num_bytes = win;
-            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setaside / (double)win);
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaError_t e = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-            fprintf(stderr, "[shud_b200] L2 persisting window: %zu MB of %zu MB, set-aside %zu MB (max %d MB): %s\n",
-                    win >> 20, c->arena_off >> 20, setaside >> 20, max_persist >> 20, cudaGetErrorString(e));
-        }
-        cudaGetLastError();
-    }
 
     // ---- topology, flags, bank edges ----
     const bool lakeon = M->lakeon != 0 && Nl > 0;
@@ -1498,7 +1008,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     m.has_headbc = has_headbc;
 
     // ---- cell -> segments (ascending reference segment id) ----
-    std::vector<int> nseg(Ne, 0), cell_seg_first(LDh + 1, 0), cell_seg_idx(Ns), cs_cell_h(Ns);
+    std::vector<int> nseg(Ne, 0), cell_seg_first(LDh + 4, 0), cell_seg_idx(Ns), cs_cell_h(Ns);
     for (int s = 0; s < Ns; s++) nseg[c->cinv[M->seg_iEle[s] - 1]]++;
     {
         int acc = 0;
@@ -1507,7 +1017,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             for (int k = 0; k < nseg[i]; k++) cs_cell_h[acc + k] = i;
             acc += nseg[i];
         }
-        for (int i = Ne; i <= LDh; i++) cell_seg_first[i] = acc;
+        for (int i = Ne; i < LDh + 4; i++) cell_seg_first[i] = acc;
         std::vector<int> fill(Ne, 0);
         for (int s = 0; s < Ns; s++) {  // ascending reference id
             const int i = c->cinv[M->seg_iEle[s] - 1];
@@ -1518,8 +1028,19 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             flags[i] |= (unsigned)nseg[i] << NSEG_SHIFT;
         }
     }
-    m.flags = dev_upload(c, flags); m.nbr = dev_upload(c, nbr);
-    m.cell_seg_first = dev_upload(c, cell_seg_first);
+    // the int family [6][ld]: nbr (3 rows), flags, cell_seg_first, and cell_seg_first shifted by one cell
+    if (!open_arena(rk::I_NI * slice_i)) { delete c; return SHUD_ERR_CUDA; }
+    char *const int_base = c->arena;
+    m.nbr = dev_upload(c, nbr); m.flags = dev_upload(c, flags);
+    {
+        std::vector<int> first(cell_seg_first.begin(), cell_seg_first.begin() + LDh);
+        std::vector<int> next(cell_seg_first.begin() + 1, cell_seg_first.begin() + LDh + 1);
+        const int *f_ = dev_upload(c, first), *n_ = dev_upload(c, next);
+        if ((const char *)f_ != int_base + rk::I_SEG0 * slice_i || (const char *)n_ != int_base + rk::I_SEGN * slice_i ||
+            (const char *)m.flags != int_base + rk::I_FL * slice_i) { delete c; return SHUD_ERR_CUDA; }
+    }
+    c->arena_on = false;
+    m.cell_seg_first = dev_upload(c, cell_seg_first);   // [ld + 4]: flat copy for everything else
     {
         std::vector<int> cs_seg(Ns), cs_riv(Ns), cs_bc(Ns);
         std::vector<double> cs_len(Ns), cs_cwr(Ns), cs_depth(Ns), cs_zbank(Ns), cs_ksatH(Ns), cs_bed(Ns);
@@ -1629,9 +1150,14 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         CK(cudaMemset(m.h_kh, 0, sizeof(double) * Nhalo));
     }
     // ---- dynamic arrays ----
+    // the dyn family [8][ld] (forcing step + carried state), in the order of the S_* enum
+    if (!open_arena(rk::N_DYN * slice_d)) { delete c; return SHUD_ERR_CUDA; }
+    char *const dyn_base = c->arena;
     m.netPrep = dev_alloc<double>(c, LDh); m.potEvap = dev_alloc<double>(c, LDh); m.potTran = dev_alloc<double>(c, LDh);
     m.lai = dev_alloc<double>(c, LDh); m.fuSurf = dev_alloc<double>(c, LDh); m.fuSub = dev_alloc<double>(c, LDh);
-    m.eic = dev_alloc<double>(c, LDh); m.satn = dev_alloc<double>(c, LDh);
+    m.satn = dev_alloc<double>(c, LDh); m.eic = dev_alloc<double>(c, LDh);
+    if ((char *)m.eic != dyn_base + rk::S_EIC * slice_d) { delete c; return SHUD_ERR_CUDA; }
+    c->arena_on = false;
     m.ele_yBC = dev_alloc<double>(c, LDh); m.ele_QBC = dev_alloc<double>(c, LDh);
     m.r_yBC = dev_alloc<double>(c, Nr); m.r_qBC = dev_alloc<double>(c, Nr);
     m.effKH = dev_alloc<double>(c, LDh); m.QsegSurf = dev_alloc<double>(c, Ns); m.QsegSub = dev_alloc<double>(c, Ns);
@@ -1647,15 +1173,46 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     c->ydot_dev = dev_alloc<double>(c, c->NY);
     c->h_pinned_n = (size_t)std::max(Ne, Nr);
     CK(cudaMallocHost(&c->h_pinned, sizeof(double) * c->h_pinned_n));
+    // ---- single-kernel form: copy table of a tile, packed neighbour records, synchronisation words ----
     {
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-        if (getenv("SHUD_PIPE_STAGES")) c->pipe_stages = atoi(getenv("SHUD_PIPE_STAGES"));
-        if (!getenv("SHUD_PIPE_GRID")) c->pipe_grid = (c->pipe_stages == 1 ? 4 : 2) * nsm;
-        CK(cudaFuncSetAttribute(k_pipe<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(2)));
-        CK(cudaFuncSetAttribute(k_pipe<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(2)));
-        CK(cudaFuncSetAttribute(k_pipe<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(1)));
-        CK(cudaFuncSetAttribute(k_pipe<true, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(1)));
+        // tensor maps of the three families: a tile = the box {tile cells, all slices} at column i0
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            delete c; return SHUD_ERR_CUDA;
+        }
+        auto encode = [&](CUtensorMap *map, CUtensorMapDataType dt, size_t elem, void *base, int rows) -> bool {
+            const cuuint64_t gdim[2] = {(cuuint64_t)c->ld, (cuuint64_t)rows};
+            const cuuint64_t gstr[1] = {(cuuint64_t)c->ld * elem};
+            const cuuint32_t box[2] = {(cuuint32_t)c->tile, (cuuint32_t)rows};
+            const cuuint32_t estr[2] = {1, 1};
+            return ((encode_fn)fn)(map, dt, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        if (!c->legacy &&
+            (!encode(&c->map_dyn, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, dyn_base, rk::N_DYN) ||
+             !encode(&c->map_stat, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, stat_base, rk::N_STAT) ||
+             !encode(&c->map_int, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, int_base, rk::I_NI))) {
+            fprintf(stderr, "[shud_b200] cuTensorMapEncodeTiled failed\n");
+            delete c; return SHUD_ERR_CUDA;
+        }
+        std::vector<rk::NbRec> rec(Ne);
+        for (int i = 0; i < Ne; i++) {
+            const int o = c->cperm[i];
+            rk::NbRec &r = rec[i];
+            r.zs = M->z_surf[o]; r.zb = M->z_bottom[o]; r.aqd = M->AquiferDepth[o];
+            r.macD = (M->iLake[o] > 0) ? 0.0 : M->macD[o];
+            r.kmac = M->macKsatH[o]; r.af = M->geo_vAreaF[o]; r.kmx = M->KsatH[o]; r.pad = 0.;
+        }
+        m.nbrec = dev_upload(c, rec);
+        m.r_qdown = dev_alloc<double>(c, Nr);
+        c->sync_words = dev_alloc<int>(c, 3 * rk::W_NWORDS);
+        CK(cudaMemset(c->sync_words, 0, sizeof(int) * 3 * rk::W_NWORDS));
+        CK(tile_kernel_attrs(c->cfg));
     }
     CK(cudaDeviceSynchronize());
     *out = c;
@@ -1682,7 +1239,11 @@ void shud_b200_destroy(shud_ctx *c) {
 
 int64_t shud_b200_ny(const shud_ctx *c) { return c ? c->NY : 0; }
 void *shud_b200_stream(shud_ctx *c) { return c ? (void *)c->stream : nullptr; }
-int shud_b200_launches_per_rhs(const shud_ctx *c) { return (c && (c->Nr > 0 || c->Nl > 0)) ? 3 : 2; }
+int shud_b200_launches_per_rhs(const shud_ctx *c) {
+    if (!c) return 0;
+    if (!c->legacy) return 1;
+    return (c->Nr > 0 || c->Nl > 0) ? 3 : 2;
+}
 
 static int upload_perm(shud_ctx *c, double *dst, const double *src, const std::vector<int> &perm) {
     // gather on the host into pinned memory, then one async copy (stream-ordered)
@@ -1939,25 +1500,22 @@ static int ensure_diag(shud_ctx *c) {
 }
 
 }  // extern "C"
-template <bool DIAG>
-static void launch_cell(shud_ctx *c, const double *y, double *ydot) {
-    const int nb = (c->Ne + 127) / 128;
-    switch (c->cell_minb) {
-        case 3: k_cell<DIAG, 3><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
-        case 5: k_cell<DIAG, 5><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
-        case 6: k_cell<DIAG, 6><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
-        case 8: k_cell<DIAG, 8><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
-        default: k_cell<DIAG, 4><<<nb, 128, 0, c->stream>>>(c->m, c->diag, y, ydot); break;
-    }
+// the whole f() (or a part of it) as one launch of the persistent kernel: tiles [t0, t1), phases, word set
+template <bool DIAG, class CF>
+static void launch_tile_cfg(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, int t0, int t1, int phases, int set) {
+    k_rhs<DIAG, CF><<<c->nsm, CF::NTHREADS, CF::SMEM_BYTES, st>>>(c->m, c->diag, c->map_dyn, c->map_stat, c->map_int, y, ydot,
+                                                                  t0, t1, phases, c->sync_words + set * rk::W_NWORDS);
 }
 template <bool DIAG>
-static void launch_pipe(shud_ctx *c, const double *y, double *ydot) {
-    const int ntiles = (c->Ne + TILE - 1) / TILE;
-    const int grid = std::min(ntiles, c->pipe_grid);
-    if (c->pipe_stages == 1)
-        k_pipe<DIAG, 1, 4><<<grid, 2 * TILE + 32, pipe_smem(1), c->stream>>>(c->m, c->diag, y, ydot, ntiles);
-    else
-        k_pipe<DIAG, 2, 2><<<grid, 2 * TILE + 32, pipe_smem(2), c->stream>>>(c->m, c->diag, y, ydot, ntiles);
+static void launch_tile_kernel(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, int t0, int t1, int phases,
+                               int set) {
+    switch (c->cfg) {
+        case 1: launch_tile_cfg<DIAG, TileCfg1>(c, st, y, ydot, t0, t1, phases, set); break;
+        case 2: launch_tile_cfg<DIAG, TileCfg2>(c, st, y, ydot, t0, t1, phases, set); break;
+        case 3: launch_tile_cfg<DIAG, TileCfg3>(c, st, y, ydot, t0, t1, phases, set); break;
+        case 4: launch_tile_cfg<DIAG, TileCfg4>(c, st, y, ydot, t0, t1, phases, set); break;
+        default: launch_tile_cfg<DIAG, TileCfg0>(c, st, y, ydot, t0, t1, phases, set); break;
+    }
 }
 template <bool DIAG>
 static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = false) {
@@ -1983,20 +1541,17 @@ static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = 
 template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     const int Ne = c->Ne;
-    if (c->split == 3) {
-        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
-        launch_pipe<DIAG>(c, y, ydot);
-    } else if (c->split == 2) {
-        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
-        launch_fused<DIAG>(c, y, ydot, true);
-    } else {
-        k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
-        launch_cell<DIAG>(c, y, ydot);
+    if (!c->legacy) {
+        launch_tile_kernel<DIAG>(c, c->stream, y, ydot, 0, (Ne + c->tile - 1) / c->tile, rk::PH_A | rk::PH_TILES | rk::PH_B, 0);
+        CK(cudaGetLastError());
+        return SHUD_OK;
     }
+    k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
+    launch_fused<DIAG>(c, y, ydot, true);
     const int nb_riv = (c->Nr + 127) / 128;
     if (nb_riv + c->Nl > 0) {
         bool done = false;
-        if (c->use_pdl && c->split == 2) {
+        if (c->use_pdl) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(nb_riv + c->Nl); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
             cudaLaunchAttribute at[1];
@@ -2059,11 +1614,17 @@ int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
 int shud_b200_rhs_interior_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     (void)t;
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
-    k_effkh<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
     if (!c->ev_kh) {
         CK(cudaEventCreateWithFlags(&c->ev_kh, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
     }
+    if (!c->legacy) {
+        // phase A (reaches' Manning flux, lakes) + every tile that sees no halo cell
+        launch_tile_kernel<false>(c, c->stream, y, ydot, 0, c->n_int_tiles, rk::PH_A | rk::PH_TILES, 0);
+        CK(cudaGetLastError());
+        return SHUD_OK;
+    }
+    k_effkh<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
     CK(cudaEventRecord(c->ev_kh, c->stream));
     if (c->n_int_tiles > 0)
         k_fused<false, 4><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
@@ -2076,6 +1637,19 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
     // the halo-dependent tiles go on the stream the exchange completes on: they run beside the interior tiles of
     // the context stream (a few hundred blocks in the gaps of ~8000) instead of as a short serial pass behind them
     cudaStream_t hs = halo_stream ? (cudaStream_t)halo_stream : c->stream;
+    if (!c->legacy) {
+        // the tiles that see a halo cell, on the stream the exchange completes on; then phase B behind both parts
+        const bool side2 = hs != c->stream;
+        if (c->n_bnd_tiles > 0)
+            launch_tile_kernel<false>(c, hs, y, ydot, c->n_int_tiles, c->n_int_tiles + c->n_bnd_tiles, rk::PH_TILES, 1);
+        if (side2) {
+            CK(cudaEventRecord(c->ev_bnd, hs));
+            CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
+        }
+        if (c->Nr > 0) launch_tile_kernel<false>(c, c->stream, y, ydot, 0, 0, rk::PH_B, 2);
+        CK(cudaGetLastError());
+        return SHUD_OK;
+    }
     const bool side = hs != c->stream && c->ev_kh;
     if (side) CK(cudaStreamWaitEvent(hs, c->ev_kh, 0));
     if (c->Nhalo > 0) k_effkh<<<(c->Nhalo + 255) / 256, 256, 0, hs>>>(c->m, y, c->Ne);
@@ -2102,10 +1676,17 @@ int shud_b200_tile_counts(const shud_ctx *c, int *n_interior, int *n_boundary) {
 int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydot) {
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
-    if (c->split == 3 && stage == 1) launch_pipe<false>(c, y, ydot);
-    else if (c->split == 2 && stage == 1) launch_fused<false>(c, y, ydot);
+    if (!c->legacy) {
+        // stage 0: the whole f(); 1: phase A alone; 2: the tiles alone; 3: phase B alone (profiling)
+        const int nt = (Ne + c->tile - 1) / c->tile;
+        const int ph[4] = {rk::PH_A | rk::PH_TILES | rk::PH_B, rk::PH_A, rk::PH_TILES, rk::PH_B};
+        if (stage < 0 || stage > 3) return SHUD_ERR_ARG;
+        launch_tile_kernel<false>(c, c->stream, y, ydot, 0, (ph[stage] & rk::PH_TILES) ? nt : 0, ph[stage], 0);
+        CK(cudaGetLastError());
+        return SHUD_OK;
+    }
+    if (stage == 1) launch_fused<false>(c, y, ydot);
     else if (stage == 0) k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
-    else if (stage == 1) launch_cell<false>(c, y, ydot);
     else if (stage == 2 && nb_riv + c->Nl > 0)
         k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
     else return SHUD_ERR_ARG;

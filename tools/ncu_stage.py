@@ -16,8 +16,9 @@ with torch.cuda.stream(st):
     y_ref = torch.from_numpy(np.ascontiguousarray(mesh["y"])).cuda()
     y = torch.empty_like(y_ref); ydot = torch.empty_like(y_ref)
     rhs.to_device_order(y_ref, y)
+    stages = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else list(range(rhs.launches_per_rhs))
     for _ in range(6):
-        for s in range(rhs.launches_per_rhs):
+        for s in stages:
             rhs.f_stage_dev(s, y, ydot)
 st.synchronize()
 print("ok", rhs.check())
