@@ -8,7 +8,7 @@ import oracle_lib
 from shud_up_b200 import abi
 
 CASES = [("ccw", "ic"), ("ccw", "rand1"), ("ccw", "mut2"), ("heihe", "ic"), ("heihe", "rand3"),
-         ("qhh", "ic"), ("qhh", "rand4"), ("qhh", "mut5")]
+         ("qhh", "ic"), ("qhh", "rand4"), ("qhh", "mut5"), ("qhh", "lakes6")]
 
 # reference-side names of the flux arrays in the snapshots
 REF_NAMES = {"u_satn": "u_satn_out"}

@@ -10,7 +10,7 @@ from shud_up_b200 import abi
 pytestmark = pytest.mark.gpu
 
 CASES = [("ccw", "ic"), ("ccw", "rand1"), ("ccw", "mut2"), ("heihe", "ic"), ("heihe", "rand3"),
-         ("qhh", "ic"), ("qhh", "rand4"), ("qhh", "mut5")]
+         ("qhh", "ic"), ("qhh", "rand4"), ("qhh", "mut5"), ("qhh", "lakes6")]
 # flux arrays compared at 1e-12 relative on their own (no cancellation inside them)
 FLUX = ["qEleInfil", "qEleExfil", "qEleRecharge", "qEs", "qEu", "qEg", "qTu", "qTg", "qEleTrans", "qEleEvapo",
         "qEleETA", "u_effKH", "u_satn", "QeleSurf", "QeleSub", "QsegSurf", "QsegSub", "QrivDown", "y2LakeArea",
