@@ -481,29 +481,6 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
 
 #include "shud_tile.cuh"
 
-// shapes of the persistent kernel (SHUD_TILE_CFG): cells per tile, teams per block, shared-memory stages
-using TileCfg0 = rk::Cfg<96, 5, 6>;
-using TileCfg1 = rk::Cfg<64, 7, 9>;
-using TileCfg2 = rk::Cfg<32, 15, 19>;
-using TileCfg3 = rk::Cfg<96, 4, 6>;
-using TileCfg4 = rk::Cfg<64, 6, 9>;
-static int tile_cfg_rt(int cfg) { return cfg == 2 ? 32 : ((cfg == 1 || cfg == 4) ? 64 : 96); }
-template <class CF>
-static cudaError_t tile_attr_one() {
-    cudaError_t e = cudaFuncSetAttribute(k_rhs<false, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_rhs<true, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES);
-}
-static cudaError_t tile_kernel_attrs(int cfg) {
-    switch (cfg) {
-        case 1: return tile_attr_one<TileCfg1>();
-        case 2: return tile_attr_one<TileCfg2>();
-        case 3: return tile_attr_one<TileCfg3>();
-        case 4: return tile_attr_one<TileCfg4>();
-        default: return tile_attr_one<TileCfg0>();
-    }
-}
-
 // fixed-shape block sum (deterministic): warp shuffle tree, then warp 0 over the warp partials
 template <int NT>
 __device__ __forceinline__ double block_sum(double v, double *sm) {
@@ -737,12 +714,9 @@ struct shud_ctx {
     double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
     int x_nsend = 0;
     int use_xgraph = 1;               // SHUD_XGRAPH: rhs_exchange_dev replayed as one CUDA graph per (y, ydot)
-    // single-kernel form (shud_tile.cuh): one persistent block per SM
-    int legacy = 0;        // SHUD_LEGACY=1: the three-launch form (k_effkh, k_fused, k_river_lake), A/B only
-    int cfg = 0;           // SHUD_TILE_CFG: shape of the persistent kernel (tile size / teams / stages), see tile_cfgs
-    int tile = 96;         // cells per tile of the form in use (three-launch form: 128)
+    int legacy = 0;        // SHUD_LEGACY=1: the round-1 three-launch form (k_effkh, k_fused, k_river_lake), A/B only
+    int tile = 128;        // cells per tile
     int nsm = 148;
-    int *sync_words = nullptr;  // 3 sets of rk::W_NWORDS ints: whole / interior launch, boundary launch, phase-B launch
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
     int use_graph = 1;
     int use_pdl = 1;   // programmatic dependent launch of the cell kernel behind k_effkh (SHUD_PDL)
@@ -834,8 +808,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     c->NY = 3 * (int64_t)Ne + Nr + Nl;
     c->ld = ((Ne + 383) / 384) * 384;  // a multiple of both tile sizes (96, 128)
     if (getenv("SHUD_LEGACY")) c->legacy = atoi(getenv("SHUD_LEGACY"));
-    if (getenv("SHUD_TILE_CFG")) c->cfg = std::max(0, std::min(4, atoi(getenv("SHUD_TILE_CFG"))));
-    c->tile = c->legacy ? TILE : tile_cfg_rt(c->cfg);
+    c->tile = TILE;
     cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, device);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
@@ -1210,9 +1183,8 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         }
         m.nbrec = dev_upload(c, rec);
         m.r_qdown = dev_alloc<double>(c, Nr);
-        c->sync_words = dev_alloc<int>(c, 3 * rk::W_NWORDS);
-        CK(cudaMemset(c->sync_words, 0, sizeof(int) * 3 * rk::W_NWORDS));
-        CK(tile_kernel_attrs(c->cfg));
+        CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rk::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rk::SMEM_BYTES));
     }
     CK(cudaDeviceSynchronize());
     *out = c;
@@ -1241,7 +1213,7 @@ int64_t shud_b200_ny(const shud_ctx *c) { return c ? c->NY : 0; }
 void *shud_b200_stream(shud_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int shud_b200_launches_per_rhs(const shud_ctx *c) {
     if (!c) return 0;
-    if (!c->legacy) return 1;
+    if (!c->legacy) return c->Nr > 0 ? 2 : 1;
     return (c->Nr > 0 || c->Nl > 0) ? 3 : 2;
 }
 
@@ -1500,22 +1472,26 @@ static int ensure_diag(shud_ctx *c) {
 }
 
 }  // extern "C"
-// the whole f() (or a part of it) as one launch of the persistent kernel: tiles [t0, t1), phases, word set
-template <bool DIAG, class CF>
-static void launch_tile_cfg(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, int t0, int t1, int phases, int set) {
-    k_rhs<DIAG, CF><<<c->nsm, CF::NTHREADS, CF::SMEM_BYTES, st>>>(c->m, c->diag, c->map_dyn, c->map_stat, c->map_int, y, ydot,
-                                                                  t0, t1, phases, c->sync_words + set * rk::W_NWORDS);
+// tiles [t0, t0 + nt) of the cell kernel on stream `st`; `river`: these blocks also do the state-only river work
+// (Manning flux of every reach, lakes).  pdl: launched under the kernel in front of it.
+template <bool DIAG>
+static cudaError_t launch_tiles(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, int t0, int nt, bool river) {
+    if (nt <= 0) return cudaSuccess;
+    const int share = river ? std::max(1, (c->Nr + nt - 1) / nt) : 0;
+    if (share > rk::RT) return cudaErrorInvalidValue;  // more reaches than threads to deal them to (never: Nr << Ne)
+    k_tile<DIAG><<<nt, 2 * rk::RT, rk::SMEM_BYTES, st>>>(c->m, c->diag, c->map_dyn, c->map_stat, c->map_int, y, ydot, t0, share);
+    return cudaGetLastError();
 }
 template <bool DIAG>
-static void launch_tile_kernel(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, int t0, int t1, int phases,
-                               int set) {
-    switch (c->cfg) {
-        case 1: launch_tile_cfg<DIAG, TileCfg1>(c, st, y, ydot, t0, t1, phases, set); break;
-        case 2: launch_tile_cfg<DIAG, TileCfg2>(c, st, y, ydot, t0, t1, phases, set); break;
-        case 3: launch_tile_cfg<DIAG, TileCfg3>(c, st, y, ydot, t0, t1, phases, set); break;
-        case 4: launch_tile_cfg<DIAG, TileCfg4>(c, st, y, ydot, t0, t1, phases, set); break;
-        default: launch_tile_cfg<DIAG, TileCfg0>(c, st, y, ydot, t0, t1, phases, set); break;
-    }
+static cudaError_t launch_river_tail(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, bool pdl) {
+    if (c->Nr <= 0) return cudaSuccess;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((c->Nr + 255) / 256); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl && c->use_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_river_tail<DIAG>, c->m, c->diag, y, ydot);
 }
 template <bool DIAG>
 static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = false) {
@@ -1542,8 +1518,8 @@ template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     const int Ne = c->Ne;
     if (!c->legacy) {
-        launch_tile_kernel<DIAG>(c, c->stream, y, ydot, 0, (Ne + c->tile - 1) / c->tile, rk::PH_A | rk::PH_TILES | rk::PH_B, 0);
-        CK(cudaGetLastError());
+        CK(launch_tiles<DIAG>(c, c->stream, y, ydot, 0, (Ne + TILE - 1) / TILE, true));
+        CK(launch_river_tail<DIAG>(c, c->stream, y, ydot, true));
         return SHUD_OK;
     }
     k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
@@ -1619,9 +1595,9 @@ int shud_b200_rhs_interior_dev(shud_ctx *c, double t, const double *y, double *y
         CK(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
     }
     if (!c->legacy) {
-        // phase A (reaches' Manning flux, lakes) + every tile that sees no halo cell
-        launch_tile_kernel<false>(c, c->stream, y, ydot, 0, c->n_int_tiles, rk::PH_A | rk::PH_TILES, 0);
-        CK(cudaGetLastError());
+        // every tile that sees no halo cell; its blocks also do the state-only river work.  (A partition whose tiles
+        // all see a halo cell has no interior part: the boundary part then does the river work.)
+        CK(launch_tiles<false>(c, c->stream, y, ydot, 0, c->n_int_tiles, true));
         return SHUD_OK;
     }
     k_effkh<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
@@ -1640,14 +1616,12 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
     if (!c->legacy) {
         // the tiles that see a halo cell, on the stream the exchange completes on; then phase B behind both parts
         const bool side2 = hs != c->stream;
-        if (c->n_bnd_tiles > 0)
-            launch_tile_kernel<false>(c, hs, y, ydot, c->n_int_tiles, c->n_int_tiles + c->n_bnd_tiles, rk::PH_TILES, 1);
+        CK(launch_tiles<false>(c, hs, y, ydot, c->n_int_tiles, c->n_bnd_tiles, c->n_int_tiles == 0));
         if (side2) {
             CK(cudaEventRecord(c->ev_bnd, hs));
             CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
         }
-        if (c->Nr > 0) launch_tile_kernel<false>(c, c->stream, y, ydot, 0, 0, rk::PH_B, 2);
-        CK(cudaGetLastError());
+        CK(launch_river_tail<false>(c, c->stream, y, ydot, !side2));
         return SHUD_OK;
     }
     const bool side = hs != c->stream && c->ev_kh;
@@ -1677,12 +1651,10 @@ int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydo
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
     if (!c->legacy) {
-        // stage 0: the whole f(); 1: phase A alone; 2: the tiles alone; 3: phase B alone (profiling)
-        const int nt = (Ne + c->tile - 1) / c->tile;
-        const int ph[4] = {rk::PH_A | rk::PH_TILES | rk::PH_B, rk::PH_A, rk::PH_TILES, rk::PH_B};
-        if (stage < 0 || stage > 3) return SHUD_ERR_ARG;
-        launch_tile_kernel<false>(c, c->stream, y, ydot, 0, (ph[stage] & rk::PH_TILES) ? nt : 0, ph[stage], 0);
-        CK(cudaGetLastError());
+        // stage 0: the cell kernel (with its share of the river work); 1: the river tail
+        if (stage == 0) CK(launch_tiles<false>(c, c->stream, y, ydot, 0, (Ne + TILE - 1) / TILE, true));
+        else if (stage == 1) CK(launch_river_tail<false>(c, c->stream, y, ydot, false));
+        else return SHUD_ERR_ARG;
         return SHUD_OK;
     }
     if (stage == 1) launch_fused<false>(c, y, ydot);

@@ -72,7 +72,7 @@ def test_two_partitions_equal_single_domain_bitwise():
             assert np.array_equal(got[b * ne:(b + 1) * ne], ref[b * Ne + sel]), (p, b)
         # the interior / boundary split (what overlaps the NCCL exchange) gives the same bits
         n_int, n_bnd = r.tile_counts()
-        assert n_int > 0 and n_bnd > 0 and n_int + n_bnd == (ne + 95) // 96
+        assert n_int > 0 and n_bnd > 0 and n_int + n_bnd == (ne + 127) // 128
         r.prime(loc["y"]); r.set_forcing(loc, qEleE_IC=loc["qEleE_IC_in"])
         yd2 = torch.full_like(ydd, float("nan"))
         with torch.cuda.stream(s):

@@ -32,7 +32,7 @@ def timeit(fn, n):
     e1.record(st); st.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 res = {"rhs_us": timeit(lambda: rhs.f_dev(0.0, y, ydot), steps)}
-for s in range(4 if rhs.launches_per_rhs == 1 else rhs.launches_per_rhs):  # single-kernel form: whole, phase A, tiles, phase B
+for s in range(rhs.launches_per_rhs):
     res[f"stage{s}_us"] = timeit(lambda: rhs.f_stage_dev(s, y, ydot), steps)
 Ne, Nr, Ns = rhs.Ne, rhs.Nr, rhs.Ns
 b = 392 * Ne + 124 * Nr + 72 * Ns
