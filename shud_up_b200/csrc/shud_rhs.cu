@@ -11,7 +11,6 @@
 //   * launches per RHS: effKH pre-pass, warp-specialised fused cell kernel, river+lake kernel.
 // Device vectors are in DEVICE ORDER (permuted); shud_b200_rhs() (host pointers, reference
 // order) permutes on the way in and out.
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>
@@ -73,11 +72,8 @@ struct DevMesh {
     int Nhalo;
     const double *h_zs, *h_zb, *h_aqd, *h_macD, *h_macKsatH, *h_vAreaF, *h_ksatH;
     const double *h_state;        // [Nhalo][2] = (Ysurf, Ygw) of each halo cell, filled by the halo exchange
-    double *h_kh;                 // effKH of halo cells (k_effkh, three-launch form only)
+    double *h_kh;                 // effKH of halo cells (k_effkh)
     int *err;  // [0] code, [1] where (1-based reference id)
-    // single-kernel form (shud_tile.cuh)
-    const void *nbrec;               // rk::NbRec[Ne]: packed neighbour record of every cell
-    double *r_qdown;                 // Manning flux of every reach (phase A -> phase B)
 };
 
 struct DevDiag {
@@ -479,7 +475,21 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     }
 }
 
-#include "shud_tile.cuh"
+// Manning flux of reach r towards its downstream end, everything gathered from global memory
+__device__ __forceinline__ double reach_down_flux(const DevMesh &m, const double *__restrict__ Yr, int r, int *err) {
+    const double yraw = Yr[r];
+    const double ystg = (m.r_bc[r] > 0) ? m.r_yBC[r] : yraw;
+    const int down = m.r_down[r];
+    double y_dn = 0., depth_dn = 0., slope_dn = 0.;
+    if (down >= 0) {
+        y_dn = (m.r_bc[down] > 0) ? m.r_yBC[down] : Yr[down];
+        depth_dn = m.r_depth[down];
+        slope_dn = m.r_slope[down];
+    }
+    // r_down device coding: >=0 downstream reach (device id); <0 the reference's outlet code
+    return river_down(yraw, ystg, m.r_w0[r], m.r_bank[r], m.r_len[r], m.r_slope[r], m.r_depth[r], m.r_rough[r],
+                      m.r_dist[r], down >= 0 ? 1 : down, m.r_toLake[r], y_dn, depth_dn, slope_dn, err);
+}
 
 // fixed-shape block sum (deterministic): warp shuffle tree, then warp 0 over the warp partials
 template <int NT>
@@ -681,12 +691,9 @@ struct shud_ctx {
     bool acc_alloc = false;
     int num_update = 0;
     std::vector<void *> allocs;
-    // the three [slice][ld] families of per-cell arrays the persistent kernel stages with one TMA box copy each
-    // (shud_tile.cuh): consecutive allocations from `arena` are contiguous, slice after slice
-    char *arena = nullptr;
+    char *arena = nullptr;          // one block for the lateral role's statics (optional persisting-L2 window)
     size_t arena_off = 0, arena_cap = 0;
     bool arena_on = false;
-    CUtensorMap map_dyn{}, map_stat{}, map_int{};
     std::vector<int> cperm, rperm, sperm;  // device id -> reference id (0-based)
     std::vector<int> cinv, rinv;           // reference id -> device id
     int *d_cperm = nullptr, *d_rperm = nullptr;
@@ -714,9 +721,6 @@ struct shud_ctx {
     double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
     int x_nsend = 0;
     int use_xgraph = 1;               // SHUD_XGRAPH: rhs_exchange_dev replayed as one CUDA graph per (y, ydot)
-    int legacy = 0;        // SHUD_LEGACY=1: the round-1 three-launch form (k_effkh, k_fused, k_river_lake), A/B only
-    int tile = 128;        // cells per tile
-    int nsm = 148;
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
     int use_graph = 1;
     int use_pdl = 1;   // programmatic dependent launch of the cell kernel behind k_effkh (SHUD_PDL)
@@ -806,10 +810,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     c->device = device;
     const int Ne = c->Ne = M->Ne, Nr = c->Nr = M->Nr, Ns = c->Ns = M->Ns, Nl = c->Nl = M->Nl;
     c->NY = 3 * (int64_t)Ne + Nr + Nl;
-    c->ld = ((Ne + 383) / 384) * 384;  // a multiple of both tile sizes (96, 128)
-    if (getenv("SHUD_LEGACY")) c->legacy = atoi(getenv("SHUD_LEGACY"));
-    c->tile = TILE;
-    cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, device);
+    c->ld = ((Ne + 127) / 128) * 128;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
     // ---- cell order: Hilbert curve over centroids (if given) ----
@@ -834,7 +835,6 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     //      [interior tiles | boundary tiles (+ the ragged last tile)], so each part of the RHS is one contiguous
     //      tile range (shud_b200_rhs_interior_dev / _boundary_dev) ----
     {
-        const int TILE = c->tile;
         const int ntile = (Ne + TILE - 1) / TILE, nfull = Ne / TILE;
         c->n_int_tiles = ntile; c->n_bnd_tiles = 0;
         if (Nhalo > 0) {
@@ -896,34 +896,49 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         if (getenv("SHUD_FUSED_MINB")) c->fused_minb = atoi(getenv("SHUD_FUSED_MINB"));
     }
 
-    // ---- static per-cell arrays: the 32 slices of the static family first, in the order of the S_* enum of
-    //      shud_tile.cuh, from one block (so that they form one [32][ld] array), then the others ----
-    auto open_arena = [&](size_t bytes) -> bool {
+    // ---- static per-cell arrays ----
+    {
+        // the statics the lateral role streams every call, contiguous: SHUD_L2_PERSIST=1 pins them in L2
+        c->arena_cap = (size_t)12 * ((size_t)c->ld * sizeof(double) + 256);
         void *a = nullptr;
-        if (cudaMalloc(&a, bytes) != cudaSuccess) return false;
-        c->allocs.push_back(a);
-        c->arena = (char *)a; c->arena_off = 0; c->arena_cap = bytes; c->arena_on = true;
-        return true;
-    };
-    const size_t slice_d = (size_t)c->ld * sizeof(double), slice_i = (size_t)c->ld * sizeof(int);
-    if (!open_arena(rk::N_STAT * slice_d)) { delete c; return SHUD_ERR_CUDA; }
-    char *const stat_base = c->arena;
-    m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy, true); m.infD = up_cell(c, M->infD);
-    m.infKsatV = up_cell(c, M->infKsatV); m.macKsatV = up_cell(c, M->macKsatV); m.hAreaF = up_cell(c, M->hAreaF);
-    m.thetaS = up_cell(c, M->ThetaS); m.thetaR = up_cell(c, M->ThetaR); m.thetaFC = up_cell(c, M->ThetaFC);
-    m.beta = up_cell(c, M->Beta); m.ksatV = up_cell(c, M->KsatV); m.vegFrac = up_cell(c, M->VegFrac);
-    m.impAF = up_cell(c, M->ImpAF); m.wetland = up_cell(c, M->WetlandLevel); m.rootReach = up_cell(c, M->RootReachLevel);
-    m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom); m.depression = up_cell(c, M->depression);
-    m.area = up_cell(c, M->area, true);
-    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor, true); m.avgRough = up_edge(c, M->avgRough, true);
-    m.macD = up_cell(c, M->macD); m.macKsatH = up_cell(c, M->macKsatH); m.vAreaF = up_cell(c, M->geo_vAreaF);
-    m.ksatH = up_cell(c, M->KsatH);
-    if (c->arena_off != rk::N_STAT * slice_d || (const char *)m.aqd != stat_base ||
-        (const char *)m.ksatH != stat_base + (rk::S_KSH - rk::S_STAT0) * slice_d ||
-        (const char *)m.edge != stat_base + (rk::S_E0 - rk::S_STAT0) * slice_d) { delete c; return SHUD_ERR_CUDA; }
+        if (cudaMalloc(&a, c->arena_cap) == cudaSuccess) { c->arena = (char *)a; c->allocs.push_back(a); }
+        else { cudaGetLastError(); c->arena_cap = 0; }
+    }
+    c->arena_on = c->arena != nullptr;
+    m.area = up_cell(c, M->area, true); m.z_surf = up_cell(c, M->z_surf); m.z_bottom = up_cell(c, M->z_bottom);
     c->arena_on = false;
+    m.depression = up_cell(c, M->depression); m.aqd = up_cell(c, M->AquiferDepth); m.sy = up_cell(c, M->Sy, true);
+    m.infD = up_cell(c, M->infD); m.infKsatV = up_cell(c, M->infKsatV); m.macKsatV = up_cell(c, M->macKsatV);
+    m.hAreaF = up_cell(c, M->hAreaF); m.thetaS = up_cell(c, M->ThetaS); m.thetaR = up_cell(c, M->ThetaR);
+    m.thetaFC = up_cell(c, M->ThetaFC); m.beta = up_cell(c, M->Beta); m.ksatH = up_cell(c, M->KsatH);
+    m.ksatV = up_cell(c, M->KsatV); m.macKsatH = up_cell(c, M->macKsatH); m.macD = up_cell(c, M->macD);
+    m.vAreaF = up_cell(c, M->geo_vAreaF); m.vegFrac = up_cell(c, M->VegFrac); m.impAF = up_cell(c, M->ImpAF);
+    m.wetland = up_cell(c, M->WetlandLevel); m.rootReach = up_cell(c, M->RootReachLevel);
     m.rough = up_cell(c, M->Rough); m.qss = up_cell(c, M->QSS);
+    c->arena_on = c->arena != nullptr;
+    m.edge = up_edge(c, M->edge); m.dist = up_edge(c, M->Dist2Nabor, true);
+    m.avgRough = up_edge(c, M->avgRough, true);
+    c->arena_on = false;
     m.dist2edge = up_edge(c, M->Dist2Edge);
+    if (c->arena && getenv("SHUD_L2_PERSIST") && atoi(getenv("SHUD_L2_PERSIST")) > 0) {
+        int max_persist = 0, max_win = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t setaside = std::min((size_t)max_persist, c->arena_off);
+        const size_t win = std::min((size_t)max_win, c->arena_off);
+        if (setaside > 0 && win > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess) {
+            cudaStreamAttrValue av = {};
+            av.accessPolicyWindow.base_ptr = c->arena;
+            av.accessPolicyWindow.num_bytes = win;
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setaside / (double)win);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaError_t e = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            fprintf(stderr, "[shud_b200] L2 persisting window: %zu MB of %zu MB, set-aside %zu MB (max %d MB): %s\n",
+                    win >> 20, c->arena_off >> 20, setaside >> 20, max_persist >> 20, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+    }
 
     // ---- topology, flags, bank edges ----
     const bool lakeon = M->lakeon != 0 && Nl > 0;
@@ -981,7 +996,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     m.has_headbc = has_headbc;
 
     // ---- cell -> segments (ascending reference segment id) ----
-    std::vector<int> nseg(Ne, 0), cell_seg_first(LDh + 4, 0), cell_seg_idx(Ns), cs_cell_h(Ns);
+    std::vector<int> nseg(Ne, 0), cell_seg_first(LDh + 1, 0), cell_seg_idx(Ns), cs_cell_h(Ns);
     for (int s = 0; s < Ns; s++) nseg[c->cinv[M->seg_iEle[s] - 1]]++;
     {
         int acc = 0;
@@ -990,7 +1005,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             for (int k = 0; k < nseg[i]; k++) cs_cell_h[acc + k] = i;
             acc += nseg[i];
         }
-        for (int i = Ne; i < LDh + 4; i++) cell_seg_first[i] = acc;
+        for (int i = Ne; i <= LDh; i++) cell_seg_first[i] = acc;
         std::vector<int> fill(Ne, 0);
         for (int s = 0; s < Ns; s++) {  // ascending reference id
             const int i = c->cinv[M->seg_iEle[s] - 1];
@@ -1001,19 +1016,8 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
             flags[i] |= (unsigned)nseg[i] << NSEG_SHIFT;
         }
     }
-    // the int family [6][ld]: nbr (3 rows), flags, cell_seg_first, and cell_seg_first shifted by one cell
-    if (!open_arena(rk::I_NI * slice_i)) { delete c; return SHUD_ERR_CUDA; }
-    char *const int_base = c->arena;
-    m.nbr = dev_upload(c, nbr); m.flags = dev_upload(c, flags);
-    {
-        std::vector<int> first(cell_seg_first.begin(), cell_seg_first.begin() + LDh);
-        std::vector<int> next(cell_seg_first.begin() + 1, cell_seg_first.begin() + LDh + 1);
-        const int *f_ = dev_upload(c, first), *n_ = dev_upload(c, next);
-        if ((const char *)f_ != int_base + rk::I_SEG0 * slice_i || (const char *)n_ != int_base + rk::I_SEGN * slice_i ||
-            (const char *)m.flags != int_base + rk::I_FL * slice_i) { delete c; return SHUD_ERR_CUDA; }
-    }
-    c->arena_on = false;
-    m.cell_seg_first = dev_upload(c, cell_seg_first);   // [ld + 4]: flat copy for everything else
+    m.flags = dev_upload(c, flags); m.nbr = dev_upload(c, nbr);
+    m.cell_seg_first = dev_upload(c, cell_seg_first);
     {
         std::vector<int> cs_seg(Ns), cs_riv(Ns), cs_bc(Ns);
         std::vector<double> cs_len(Ns), cs_cwr(Ns), cs_depth(Ns), cs_zbank(Ns), cs_ksatH(Ns), cs_bed(Ns);
@@ -1123,14 +1127,9 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         CK(cudaMemset(m.h_kh, 0, sizeof(double) * Nhalo));
     }
     // ---- dynamic arrays ----
-    // the dyn family [8][ld] (forcing step + carried state), in the order of the S_* enum
-    if (!open_arena(rk::N_DYN * slice_d)) { delete c; return SHUD_ERR_CUDA; }
-    char *const dyn_base = c->arena;
     m.netPrep = dev_alloc<double>(c, LDh); m.potEvap = dev_alloc<double>(c, LDh); m.potTran = dev_alloc<double>(c, LDh);
     m.lai = dev_alloc<double>(c, LDh); m.fuSurf = dev_alloc<double>(c, LDh); m.fuSub = dev_alloc<double>(c, LDh);
-    m.satn = dev_alloc<double>(c, LDh); m.eic = dev_alloc<double>(c, LDh);
-    if ((char *)m.eic != dyn_base + rk::S_EIC * slice_d) { delete c; return SHUD_ERR_CUDA; }
-    c->arena_on = false;
+    m.eic = dev_alloc<double>(c, LDh); m.satn = dev_alloc<double>(c, LDh);
     m.ele_yBC = dev_alloc<double>(c, LDh); m.ele_QBC = dev_alloc<double>(c, LDh);
     m.r_yBC = dev_alloc<double>(c, Nr); m.r_qBC = dev_alloc<double>(c, Nr);
     m.effKH = dev_alloc<double>(c, LDh); m.QsegSurf = dev_alloc<double>(c, Ns); m.QsegSub = dev_alloc<double>(c, Ns);
@@ -1146,46 +1145,6 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     c->ydot_dev = dev_alloc<double>(c, c->NY);
     c->h_pinned_n = (size_t)std::max(Ne, Nr);
     CK(cudaMallocHost(&c->h_pinned, sizeof(double) * c->h_pinned_n));
-    // ---- single-kernel form: copy table of a tile, packed neighbour records, synchronisation words ----
-    {
-        // tensor maps of the three families: a tile = the box {tile cells, all slices} at column i0
-        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-            delete c; return SHUD_ERR_CUDA;
-        }
-        auto encode = [&](CUtensorMap *map, CUtensorMapDataType dt, size_t elem, void *base, int rows) -> bool {
-            const cuuint64_t gdim[2] = {(cuuint64_t)c->ld, (cuuint64_t)rows};
-            const cuuint64_t gstr[1] = {(cuuint64_t)c->ld * elem};
-            const cuuint32_t box[2] = {(cuuint32_t)c->tile, (cuuint32_t)rows};
-            const cuuint32_t estr[2] = {1, 1};
-            return ((encode_fn)fn)(map, dt, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-        };
-        if (!c->legacy &&
-            (!encode(&c->map_dyn, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, dyn_base, rk::N_DYN) ||
-             !encode(&c->map_stat, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, stat_base, rk::N_STAT) ||
-             !encode(&c->map_int, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, int_base, rk::I_NI))) {
-            fprintf(stderr, "[shud_b200] cuTensorMapEncodeTiled failed\n");
-            delete c; return SHUD_ERR_CUDA;
-        }
-        std::vector<rk::NbRec> rec(Ne);
-        for (int i = 0; i < Ne; i++) {
-            const int o = c->cperm[i];
-            rk::NbRec &r = rec[i];
-            r.zs = M->z_surf[o]; r.zb = M->z_bottom[o]; r.aqd = M->AquiferDepth[o];
-            r.macD = (M->iLake[o] > 0) ? 0.0 : M->macD[o];
-            r.kmac = M->macKsatH[o]; r.af = M->geo_vAreaF[o]; r.kmx = M->KsatH[o]; r.pad = 0.;
-        }
-        m.nbrec = dev_upload(c, rec);
-        m.r_qdown = dev_alloc<double>(c, Nr);
-        CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rk::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rk::SMEM_BYTES));
-    }
     CK(cudaDeviceSynchronize());
     *out = c;
     return SHUD_OK;
@@ -1211,11 +1170,7 @@ void shud_b200_destroy(shud_ctx *c) {
 
 int64_t shud_b200_ny(const shud_ctx *c) { return c ? c->NY : 0; }
 void *shud_b200_stream(shud_ctx *c) { return c ? (void *)c->stream : nullptr; }
-int shud_b200_launches_per_rhs(const shud_ctx *c) {
-    if (!c) return 0;
-    if (!c->legacy) return c->Nr > 0 ? 2 : 1;
-    return (c->Nr > 0 || c->Nl > 0) ? 3 : 2;
-}
+int shud_b200_launches_per_rhs(const shud_ctx *c) { return (c && (c->Nr > 0 || c->Nl > 0)) ? 3 : 2; }
 
 static int upload_perm(shud_ctx *c, double *dst, const double *src, const std::vector<int> &perm) {
     // gather on the host into pinned memory, then one async copy (stream-ordered)
@@ -1472,27 +1427,6 @@ static int ensure_diag(shud_ctx *c) {
 }
 
 }  // extern "C"
-// tiles [t0, t0 + nt) of the cell kernel on stream `st`; `river`: these blocks also do the state-only river work
-// (Manning flux of every reach, lakes).  pdl: launched under the kernel in front of it.
-template <bool DIAG>
-static cudaError_t launch_tiles(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, int t0, int nt, bool river) {
-    if (nt <= 0) return cudaSuccess;
-    const int share = river ? std::max(1, (c->Nr + nt - 1) / nt) : 0;
-    if (share > rk::RT) return cudaErrorInvalidValue;  // more reaches than threads to deal them to (never: Nr << Ne)
-    k_tile<DIAG><<<nt, 2 * rk::RT, rk::SMEM_BYTES, st>>>(c->m, c->diag, c->map_dyn, c->map_stat, c->map_int, y, ydot, t0, share);
-    return cudaGetLastError();
-}
-template <bool DIAG>
-static cudaError_t launch_river_tail(shud_ctx *c, cudaStream_t st, const double *y, double *ydot, bool pdl) {
-    if (c->Nr <= 0) return cudaSuccess;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((c->Nr + 255) / 256); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (pdl && c->use_pdl) ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_river_tail<DIAG>, c->m, c->diag, y, ydot);
-}
 template <bool DIAG>
 static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = false) {
     const int nb = (c->Ne + TILE - 1) / TILE;
@@ -1517,11 +1451,6 @@ static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = 
 template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     const int Ne = c->Ne;
-    if (!c->legacy) {
-        CK(launch_tiles<DIAG>(c, c->stream, y, ydot, 0, (Ne + TILE - 1) / TILE, true));
-        CK(launch_river_tail<DIAG>(c, c->stream, y, ydot, true));
-        return SHUD_OK;
-    }
     k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
     launch_fused<DIAG>(c, y, ydot, true);
     const int nb_riv = (c->Nr + 127) / 128;
@@ -1590,17 +1519,11 @@ int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
 int shud_b200_rhs_interior_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     (void)t;
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    k_effkh<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
     if (!c->ev_kh) {
         CK(cudaEventCreateWithFlags(&c->ev_kh, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
     }
-    if (!c->legacy) {
-        // every tile that sees no halo cell; its blocks also do the state-only river work.  (A partition whose tiles
-        // all see a halo cell has no interior part: the boundary part then does the river work.)
-        CK(launch_tiles<false>(c, c->stream, y, ydot, 0, c->n_int_tiles, true));
-        return SHUD_OK;
-    }
-    k_effkh<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
     CK(cudaEventRecord(c->ev_kh, c->stream));
     if (c->n_int_tiles > 0)
         k_fused<false, 4><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
@@ -1613,17 +1536,6 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
     // the halo-dependent tiles go on the stream the exchange completes on: they run beside the interior tiles of
     // the context stream (a few hundred blocks in the gaps of ~8000) instead of as a short serial pass behind them
     cudaStream_t hs = halo_stream ? (cudaStream_t)halo_stream : c->stream;
-    if (!c->legacy) {
-        // the tiles that see a halo cell, on the stream the exchange completes on; then phase B behind both parts
-        const bool side2 = hs != c->stream;
-        CK(launch_tiles<false>(c, hs, y, ydot, c->n_int_tiles, c->n_bnd_tiles, c->n_int_tiles == 0));
-        if (side2) {
-            CK(cudaEventRecord(c->ev_bnd, hs));
-            CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
-        }
-        CK(launch_river_tail<false>(c, c->stream, y, ydot, !side2));
-        return SHUD_OK;
-    }
     const bool side = hs != c->stream && c->ev_kh;
     if (side) CK(cudaStreamWaitEvent(hs, c->ev_kh, 0));
     if (c->Nhalo > 0) k_effkh<<<(c->Nhalo + 255) / 256, 256, 0, hs>>>(c->m, y, c->Ne);
@@ -1650,15 +1562,8 @@ int shud_b200_tile_counts(const shud_ctx *c, int *n_interior, int *n_boundary) {
 int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydot) {
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     const int Ne = c->Ne, nb_riv = (c->Nr + 127) / 128;
-    if (!c->legacy) {
-        // stage 0: the cell kernel (with its share of the river work); 1: the river tail
-        if (stage == 0) CK(launch_tiles<false>(c, c->stream, y, ydot, 0, (Ne + TILE - 1) / TILE, true));
-        else if (stage == 1) CK(launch_river_tail<false>(c, c->stream, y, ydot, false));
-        else return SHUD_ERR_ARG;
-        return SHUD_OK;
-    }
-    if (stage == 1) launch_fused<false>(c, y, ydot);
-    else if (stage == 0) k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
+    if (stage == 0) k_effkh<<<(Ne + c->Nhalo + 255) / 256, 256, 0, c->stream>>>(c->m, y, 0);
+    else if (stage == 1) launch_fused<false>(c, y, ydot);
     else if (stage == 2 && nb_riv + c->Nl > 0)
         k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
     else return SHUD_ERR_ARG;

@@ -139,21 +139,6 @@ def test_device_error_word_mirrors_reference_exit_codes():
         rhs.f(0.0, y, np.empty_like(y))
 
 
-@pytest.mark.parametrize("basin,case", [("qhh", "mut5"), ("ccw", "mut2"), ("heihe", "rand3")])
-def test_single_kernel_equals_three_launch_form(basin, case, monkeypatch):
-    """the persistent single-kernel f() (shud_tile.cuh: TMA-staged 96-cell tiles, effKH evaluated in place, reaches and
-    lakes in the same launch) computes the same ydot and carried state, bit for bit, as the three-launch form it
-    replaces (SHUD_LEGACY=1: effKH pre-pass, 128-cell cell kernel, river/lake kernel)"""
-    snap = oracle_lib.load_case(basin, case)
-    rhs, a = _run_gpu(snap, diag=False)
-    monkeypatch.setenv("SHUD_LEGACY", "1")
-    rhs2, b = _run_gpu(snap, diag=False)
-    assert rhs.launches_per_rhs <= 2 and rhs2.launches_per_rhs >= 2
-    assert a["code"] == 0 and b["code"] == 0
-    assert np.array_equal(a["ydot"], b["ydot"])
-    assert np.array_equal(a["u_satn_out"], b["u_satn_out"]) and np.array_equal(a["qEleE_IC_out"], b["qEleE_IC_out"])
-
-
 def test_device_side_output_accumulation():
     """Print_Ctrl::PrintData semantics (src/classes/Model_Control.cpp:930-962): buffer += value per SolverStep,
     buffer *= tau/NumUpdate at the interval end, reset - done on the device, one download per interval."""
