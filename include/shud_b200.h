@@ -135,6 +135,14 @@ int shud_b200_get_carried(shud_ctx *ctx, double *u_satn_host, double *qEleE_IC_h
  * device, src != dst); shud_b200_perm() exposes the maps (device id -> 0-based reference id). */
 int shud_b200_to_device_order(shud_ctx *ctx, const double *ref_order_dev, double *dev_order_dev);
 int shud_b200_from_device_order(shud_ctx *ctx, const double *dev_order_dev, double *ref_order_dev);
+/* host vector in the reference's blocked order <-> device vector in device order (one copy + one permutation kernel;
+ * both synchronise): the host mirror of the device N_Vector (SetIC2Y writes, src/ModelData/MD_initialize.cpp:117-135) */
+int shud_b200_upload_ref(shud_ctx *ctx, const double *y_host_ref, double *y_dev);
+int shud_b200_download_ref(shud_ctx *ctx, const double *y_dev, double *y_host_ref);
+/* Model_Data::summary(N_Vector) (src/ModelData/MD_update.cpp:190-216), the read-back the driver does every SolverStep:
+ * the device vector (device order) lands in y_host_ref [NY] in the reference's blocked order, with the groundwater
+ * head of iBC > 0 cells and the stage of BC > 0 reaches replaced by their boundary values.  Synchronises. */
+int shud_b200_summary_dev(shud_ctx *ctx, const double *y_dev, double *y_host_ref);
 int shud_b200_perm(const shud_ctx *ctx, int32_t *cell_perm /*[Ne]*/, int32_t *reach_perm /*[Nr]*/);
 
 /* The RHS.  Replaces int f(double t, N_Vector y, N_Vector ydot, void *MD)
@@ -222,7 +230,8 @@ int shud_b200_land_get(shud_ctx *ctx, const shud_land_out *out);  /* synchronise
  * shud_b200_format_ic: Model_Data::PrintInit (src/ModelData/MD_update.cpp:268-299), byte-identical text
  * ("<prj>.cfg.ic.update"); y in the reference's blocked order, yEleIS / yEleSnow may be NULL (zeros).
  * shud_b200_write_ic: the same from a DEVICE vector in device order; the canopy / snow buckets come from the
- * device land-surface step when it is in use, else zeros. */
+ * device land-surface step when it is in use, else zeros; like PrintInit after summary(), head-BC cells and
+ * stage-BC reaches print their boundary value (shud_b200_summary_dev). */
 int shud_b200_mesh_save(const char *path, const shud_mesh *m);
 int shud_b200_mesh_load(const char *path, shud_mesh *out, void **block);
 void shud_b200_mesh_free(void *block);

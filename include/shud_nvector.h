@@ -26,6 +26,8 @@ typedef struct shud_nvws shud_nvws; /* reduction workspace bound to one device +
 /* `stream` is a cudaStream_t (e.g. shud_b200_stream()); NULL = the legacy default stream */
 int shud_nv_ws_create(int device, void *stream, shud_nvws **out);
 void shud_nv_ws_destroy(shud_nvws *ws);
+void *shud_nv_ws_stream(const shud_nvws *ws); /* the cudaStream_t the workspace was created on */
+int shud_nv_ws_device(const shud_nvws *ws);
 
 /* ---- streaming operations (return 0 or a negative SHUD_ERR_* code) ---- */
 int shud_nv_linearsum(shud_nvws *ws, int64_t n, double a, const double *x, double b, const double *y, double *z); /* nvlinearsum  z = a x + b y */

@@ -55,6 +55,7 @@ def lib():
         "shud_b200_get_carried": (C.c_int, [vp, _PD, _PD]),
         "shud_b200_to_device_order": (C.c_int, [vp, vp, vp]),
         "shud_b200_from_device_order": (C.c_int, [vp, vp, vp]),
+        "shud_b200_summary_dev": (C.c_int, [vp, vp, _PD]),
         "shud_b200_perm": (C.c_int, [vp, _PI, _PI]),
         "shud_b200_rhs_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs": (C.c_int, [vp, C.c_double, vp, vp]),
@@ -164,6 +165,13 @@ class ShudRHS:
 
     def from_device_order(self, dev_dev, out_ref):
         _chk(lib().shud_b200_from_device_order(self._h, _ptr(dev_dev), _ptr(out_ref)), "from_device_order")
+
+    def summary(self, y_dev):
+        """Model_Data::summary (MD_update.cpp:190-216): the device vector as a host array in reference order, BC heads
+        and BC stages in place of the solver's frozen rows"""
+        out = np.empty(self.NY)
+        _chk(lib().shud_b200_summary_dev(self._h, _ptr(y_dev), out.ctypes.data_as(_PD)), "summary")
+        return out
 
     # ---- halo exchange plumbing (multi-GPU) ----
     def set_halo_state(self, halo_state_dev):

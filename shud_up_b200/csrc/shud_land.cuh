@@ -350,11 +350,11 @@ int shud_b200_land_get(shud_ctx *c, const shud_land_out *out) {
 int shud_b200_write_ic(shud_ctx *c, const char *path, double t, const double *y_dev) {
     if (!c || !path || !y_dev) return SHUD_ERR_ARG;
     CK(cudaSetDevice(c->device));
-    int rc = shud_b200_from_device_order(c, y_dev, c->y_stage);  // device order -> reference order (on the device)
-    if (rc) return rc;
+    // the reference prints what summary() left in yEle*/yRivStg (shud.cpp:137-157): BC heads / stages, not the
+    // solver's frozen rows; device order -> reference order on the device, one D2H
     std::vector<double> y(c->NY), is, sn;
-    CK(cudaMemcpyAsync(y.data(), c->y_stage, sizeof(double) * c->NY, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    int rc = shud_b200_summary_dev(c, y_dev, y.data());
+    if (rc) return rc;
     if (c->has_land) {
         is.resize(c->Ne); sn.resize(c->Ne);
         shud_land_out o = {};

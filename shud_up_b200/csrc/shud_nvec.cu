@@ -333,6 +333,9 @@ void shud_nv_ws_destroy(shud_nvws *ws) {
     delete ws;
 }
 
+void *shud_nv_ws_stream(const shud_nvws *ws) { return ws ? (void *)ws->stream : nullptr; }
+int shud_nv_ws_device(const shud_nvws *ws) { return ws ? ws->device : -1; }
+
 int shud_nv_linearsum(shud_nvws *ws, int64_t n, double a, const double *x, double b, const double *y, double *z) {
     if (b == 1.0 && z == y) return run_map(ws, n, FAxpy{a, x, z});   // y += a x
     if (a == 1.0 && z == x) return run_map(ws, n, FAxpy{b, y, z});   // x += b y

@@ -615,7 +615,24 @@ __global__ void k_scale_copy(double *__restrict__ dst, double *__restrict__ acc,
 __global__ void k_prime(DevMesh m, const double *__restrict__ Y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.Ne) return;
-    m.satn[i] = cell_satn(m.aqd[i], m.thetaS[i], m.thetaR[i], Y[(size_t)m.Ne + i], Y[2 * (size_t)m.Ne + i]);
+    // updateforcing reads uYgw, which f_update set to the BC head for iBC > 0 cells (MD_update.cpp:114-118)
+    const double ygw = (m.flags[i] & F_HEADBC) ? m.ele_yBC[i] : Y[2 * (size_t)m.Ne + i];
+    m.satn[i] = cell_satn(m.aqd[i], m.thetaS[i], m.thetaR[i], Y[(size_t)m.Ne + i], ygw);
+}
+
+// Model_Data::summary (MD_update.cpp:190-216): the state the host prints / checkpoints is the solver vector with the
+// groundwater head of head-BC cells and the stage of stage-BC reaches replaced by their BC values (device order)
+__global__ void k_summary(DevMesh m, const double *__restrict__ Y, double *__restrict__ out, size_t NY) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= NY) return;
+    const size_t NE = (size_t)m.Ne;
+    double v = Y[k];
+    if (k >= 2 * NE && k < 3 * NE) {
+        if (m.flags[k - 2 * NE] & F_HEADBC) v = m.ele_yBC[k - 2 * NE];
+    } else if (k >= 3 * NE && k < 3 * NE + (size_t)m.Nr) {
+        if (m.r_bc[k - 3 * NE] > 0) v = m.r_yBC[k - 3 * NE];
+    }
+    out[k] = v;
 }
 
 // reference order <-> device order (cells x3 blocks, reaches; lakes keep their order)
@@ -719,7 +736,7 @@ struct shud_ctx {
     std::vector<int> x_peer, x_scount, x_rcount;  // per neighbour partition: rank, cells sent, halo cells received
     int *x_sidx = nullptr;            // device-order ids of the cells sent, concatenated by peer
     double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
-    int x_nsend = 0;
+    int x_nsend = 0, x_cap_send = 0;
     int use_xgraph = 1;               // SHUD_XGRAPH: rhs_exchange_dev replayed as one CUDA graph per (y, ydot)
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
     int use_graph = 1;
@@ -1156,12 +1173,12 @@ void shud_b200_destroy(shud_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->land_stage) cudaFreeHost(c->land_stage);
     if (c->xstream) cudaStreamSynchronize(c->xstream);
+    drop_graphs(c);  // the captured exchange graphs hold NCCL nodes: gone before the communicator
     if (c->nccl_comm && c->nccl_comm_destroy) c->nccl_comm_destroy(c->nccl_comm);
     if (c->xstream) cudaStreamDestroy(c->xstream);
     if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ev_kh) cudaEventDestroy(c->ev_kh);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
-    for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->stream);
@@ -1248,6 +1265,26 @@ int shud_b200_from_device_order(shud_ctx *c, const double *dev_dev, double *ref_
     return SHUD_OK;
 }
 
+// host vector in the reference's blocked order <-> device vector in device order (the host mirror of the N_Vector)
+int shud_b200_upload_ref(shud_ctx *c, const double *y_host_ref, double *y_dev) {
+    if (!c || !y_host_ref || !y_dev) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->y_stage, y_host_ref, sizeof(double) * c->NY, cudaMemcpyHostToDevice, c->stream));
+    int rc = shud_b200_to_device_order(c, c->y_stage, y_dev);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));  // y_host_ref may be pageable / reused by the caller
+    return SHUD_OK;
+}
+int shud_b200_download_ref(shud_ctx *c, const double *y_dev, double *y_host_ref) {
+    if (!c || !y_host_ref || !y_dev) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int rc = shud_b200_from_device_order(c, y_dev, c->y_stage);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(y_host_ref, c->y_stage, sizeof(double) * c->NY, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SHUD_OK;
+}
+
 int shud_b200_set_halo_state_dev(shud_ctx *c, const double *state) {
     if (!c || (c->Nhalo > 0 && !state)) return SHUD_ERR_ARG;
     c->m.h_state = state;
@@ -1319,9 +1356,14 @@ int shud_b200_exchange_plan(shud_ctx *c, int npeers, const int32_t *peer_rank, c
         idx[k] = c->cinv[send_cells[k]];
     }
     c->x_nsend = ns;
-    c->x_sidx = dev_upload(c, idx);
-    c->x_sbuf = dev_alloc<double>(c, 2 * (size_t)std::max(ns, 1));
-    c->x_hstate = dev_alloc<double>(c, 2 * (size_t)std::max(nr, 1));
+    drop_graphs(c);  // captured exchanges point at the previous plan
+    if (ns > c->x_cap_send || !c->x_sidx) {  // a repeated plan reuses the buffers of the previous one
+        c->x_cap_send = std::max(ns, 1);
+        c->x_sidx = dev_alloc<int>(c, (size_t)c->x_cap_send);
+        c->x_sbuf = dev_alloc<double>(c, 2 * (size_t)c->x_cap_send);
+    }
+    if (ns > 0) CK(cudaMemcpy(c->x_sidx, idx.data(), sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice));
+    if (!c->x_hstate) c->x_hstate = dev_alloc<double>(c, 2 * (size_t)std::max(nr, 1));  // nr == Nhalo: fixed per context
     CK(cudaMemset(c->x_hstate, 0, sizeof(double) * 2 * (size_t)std::max(nr, 1)));
     return shud_b200_set_halo_state_dev(c, c->x_hstate);
 }
@@ -1389,6 +1431,18 @@ int shud_b200_perm(const shud_ctx *c, int32_t *cp, int32_t *rp) {
     if (!c) return SHUD_ERR_ARG;
     if (cp) std::copy(c->cperm.begin(), c->cperm.end(), cp);
     if (rp) std::copy(c->rperm.begin(), c->rperm.end(), rp);
+    return SHUD_OK;
+}
+
+int shud_b200_summary_dev(shud_ctx *c, const double *y_dev, double *y_host_ref) {
+    if (!c || !y_dev || !y_host_ref) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    k_summary<<<(unsigned)((c->NY + 255) / 256), 256, 0, c->stream>>>(c->m, y_dev, c->ydot_dev, (size_t)c->NY);
+    CK(cudaGetLastError());
+    int rc = shud_b200_from_device_order(c, c->ydot_dev, c->y_stage);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(y_host_ref, c->y_stage, sizeof(double) * c->NY, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return SHUD_OK;
 }
 

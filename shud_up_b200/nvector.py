@@ -278,8 +278,15 @@ class DistributedOps:
         import torch
         self._l, self._dist, self._torch, self._dev, self.n_global = local, dist, torch, device, int(n_global)
 
-    def __getattr__(self, name):          # streaming and fused streaming ops: purely local
-        return getattr(self._l, name)
+    _LOCAL_OK = ("N_VLinearSum", "N_VConst", "N_VProd", "N_VDiv", "N_VScale", "N_VAbs", "N_VInv", "N_VAddConst",
+                 "N_VCompare", "N_VLinearCombination", "N_VScaleAddMulti", "N_VLinearSumVectorArray",
+                 "N_VScaleVectorArray", "N_VConstVectorArray", "EwtSet", "NewtonResid", "DQPerturb", "DQCombine",
+                 "close", "sync")
+
+    def __getattr__(self, name):          # streaming and fused streaming ops only: purely local, no reduction inside
+        if name in DistributedOps._LOCAL_OK:
+            return getattr(self._l, name)
+        raise AttributeError(f"DistributedOps has no op {name} (reductions must be overridden with an allreduce)")
 
     def _allreduce(self, vals, op):
         t = self._torch.tensor(vals, dtype=self._torch.float64, device=self._dev)
@@ -311,3 +318,32 @@ class DistributedOps:
 
     def N_VWL2Norm(self, x, w):
         return self._allreduce([self._l.N_VWSqrSumLocal(x, w)], self._dist.ReduceOp.SUM)[0] ** 0.5
+
+    def N_VWSqrSumMaskLocal(self, x, w, idv):
+        return self._l.N_VWSqrSumMaskLocal(x, w, idv)
+
+    def N_VWrmsNormMask(self, x, w, idv):
+        s = self._allreduce([self._l.N_VWSqrSumMaskLocal(x, w, idv)], self._dist.ReduceOp.SUM)[0]
+        return (s / self.n_global) ** 0.5
+
+    def N_VMinQuotient(self, num, den):
+        return self._allreduce([self._l.N_VMinQuotient(num, den)], self._dist.ReduceOp.MIN)[0]
+
+    def N_VInvTest(self, x, z):
+        return bool(self._allreduce([1.0 if self._l.N_VInvTest(x, z) else 0.0], self._dist.ReduceOp.MIN)[0])
+
+    def N_VConstrMask(self, c, x, m):
+        return bool(self._allreduce([1.0 if self._l.N_VConstrMask(c, x, m) else 0.0], self._dist.ReduceOp.MIN)[0])
+
+    def N_VWrmsNormVectorArray(self, X, W):
+        import numpy as np
+        s = self._allreduce([self._l.N_VWSqrSumLocal(x, w) for x, w in zip(X, W)], self._dist.ReduceOp.SUM)
+        return np.sqrt(np.array(s) / self.n_global)
+
+    def NewtonUpdate(self, x, ewt, y, acor):
+        """y += x; acor += x locally, ||x||_WRMS over the WHOLE vector: every rank gets the same convergence norm
+        (the local table would return sqrt(local sum / n_global))"""
+        s = self._l.N_VWSqrSumLocal(x, ewt)
+        self._l.N_VLinearSum(1.0, y, 1.0, x, y)
+        self._l.N_VLinearSum(1.0, acor, 1.0, x, acor)
+        return (self._allreduce([s], self._dist.ReduceOp.SUM)[0] / self.n_global) ** 0.5

@@ -21,6 +21,19 @@ class HostOps:
     def N_VL1Norm(self, x): return float(np.abs(x).sum())
     def N_VWSqrSumLocal(self, x, w): return float(np.sum((x * w) ** 2))
     def N_VDotProdMulti(self, x, Y): return np.array([float(np.dot(x, y)) for y in Y])
+    def N_VWSqrSumMaskLocal(self, x, w, idv): return float(np.sum(((x * w) ** 2)[idv > 0]))
+    def N_VWrmsNormMask(self, x, w, idv): return float(np.sqrt(self.N_VWSqrSumMaskLocal(x, w, idv) / x.size))
+    def N_VMinQuotient(self, num, den): return float((num[den != 0] / den[den != 0]).min()) if (den != 0).any() else 1.7976931348623157e308
+
+    def N_VInvTest(self, x, z):
+        nz = x != 0
+        z[nz] = 1.0 / x[nz]
+        return bool(nz.all())
+
+    def N_VConstrMask(self, c, x, m):
+        bad = ((np.abs(c) > 1.5) & (x * c <= 0)) | ((np.abs(c) > 0.5) & (x * c < 0))
+        m[:] = bad.astype(np.float64)
+        return not bool(bad.any())
 
     def N_VLinearCombination(self, c, X, z):
         s = c[0] * X[0]

@@ -198,7 +198,45 @@ def _gloo_nvec_worker(rank, world, port, q):
     ref = dict(dot=float(xg @ yg), wrms=float(np.sqrt(np.sum((xg * wg) ** 2) / 1001)), mx=float(np.abs(xg).max()),
                mn=float(xg.min()), l1=float(np.abs(xg).sum()), multi=[float(xg @ yg), float(xg @ wg)])
     ok = all(np.allclose(res[k], ref[k], rtol=1e-13) for k in ref)
-    q.put((rank, ok, res["dot"]))
+    # the reducing ops the local table would answer with a per-rank value: masks, quotients, tests, Newton
+    idg = (rng.uniform(size=1001) > 0.3).astype(np.float64)
+    deng = np.where(rng.uniform(size=1001) > 0.2, rng.uniform(0.5, 2, 1001), 0.0)
+    cg = rng.integers(-2, 3, 1001).astype(np.float64)
+    zg = xg.copy(); zg[17] = 0.0                       # one zero, on rank 0 only
+    host = HostOps()
+    z1, z2, m1, m2 = np.zeros(1001), np.zeros_like(x), np.zeros(1001), np.zeros_like(x)
+    res2 = dict(wm=ops.N_VWrmsNormMask(x, w, idg[sl].copy()), mq=ops.N_VMinQuotient(x, deng[sl].copy()),
+                it=ops.N_VInvTest(zg[sl].copy(), z2), cm=ops.N_VConstrMask(cg[sl].copy(), x, m2),
+                va=ops.N_VWrmsNormVectorArray([x, y], [w, w]).tolist())
+    ref2 = dict(wm=host.N_VWrmsNormMask(xg, wg, idg), mq=host.N_VMinQuotient(xg, deng), it=host.N_VInvTest(zg, z1),
+                cm=host.N_VConstrMask(cg, xg, m1), va=[host.N_VWrmsNorm(xg, wg), host.N_VWrmsNorm(yg, wg)])
+    ok = ok and all(np.allclose(res2[k], ref2[k], rtol=1e-13) for k in ref2) and np.array_equal(m2, m1[sl])
+    yy, ac = y.copy(), np.zeros_like(y)
+    dele = ops.NewtonUpdate(x, w, yy, ac)
+    ok = ok and np.isclose(dele, ref["wrms"], rtol=1e-13) and np.array_equal(yy, y + x) and np.array_equal(ac, x)
+    try:
+        ops.N_VSomethingNew
+        ok = False                                     # unknown ops must not fall through to the local table
+    except AttributeError:
+        pass
+    # the integrator on the distributed table takes the same steps on every rank and the same steps as one domain
+    from shud_up_b200.integrator import BDFKrylov
+    lam = np.linspace(0.01, 2.0, 1001)
+
+    def run(o, sl_):
+        lm = lam[sl_]
+        integ = BDFKrylov(o, lambda: np.zeros(lm.size), lambda t, yv, yd: np.copyto(yd, -lm * yv), lm.size, rtol=1e-6,
+                          atol=1e-8, max_step=1.0, init_step=1e-3, n_global=1001)
+        integ.init(0.0, np.ones(lm.size))
+        hs = []
+        while integ.t < 3.0 - 1e-12:
+            integ.step(3.0); hs.append(integ.t)
+        return hs, integ.hist[0].copy()
+    hs_d, y_d = run(ops, sl)
+    hs_1, y_1 = run(host, slice(0, 1001))
+    ok = ok and len(hs_d) == len(hs_1) and np.allclose(hs_d, hs_1, rtol=1e-9) and np.allclose(y_d, y_1[sl], rtol=1e-8)
+    ok = ok and np.allclose(y_1, np.exp(-lam * 3.0), atol=1e-4)
+    q.put((rank, ok, res["dot"], hs_d))
     dist.destroy_process_group()
 
 
@@ -214,8 +252,9 @@ def test_distributed_nvector_reductions_over_gloo():
     for p in ps:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert all(ok for _, ok, _ in res), res
+    assert all(r[1] for r in res), res
     assert res[0][2] == res[1][2]          # every rank holds the same global value
+    assert res[0][3] == res[1][3]          # ... and takes the same time steps
 
 
 def test_halo_exchange_over_gloo_world_size_2():
