@@ -178,6 +178,9 @@ int shud_b200_comm_init(shud_ctx *ctx, const char *nccl_lib, const void *id128, 
 int shud_b200_exchange_plan(shud_ctx *ctx, int npeers, const int32_t *peer_rank, const int32_t *send_count,
                             const int32_t *recv_count, const int32_t *send_cells);
 int shud_b200_rhs_exchange_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+/* Scalar allreduce over the same communicator for the distributed N_Vector reductions:
+ * `vals` are n HOST doubles reduced in place over all ranks; op 0 sum, 1 max, 2 min.  Synchronises the context stream. */
+int shud_b200_allreduce(shud_ctx *ctx, double *vals, int n, int op);
 /* ---- land-surface step on the device ----
  * Replaces the per-cell loops of Model_Data::updateforcing / tReadForcing (src/ModelData/MD_ET.cpp:14-281:
  * lapse-rate temperature, terrain-radiation factor, Penman-Monteith potential evaporation / transpiration) and

@@ -21,7 +21,7 @@
  *   --print-init FILE: write the state of this run with the reference's own checkpoint writer
  *   (Model_Data::PrintInit, src/ModelData/MD_update.cpp:268-299) after giving the canopy / snow buckets random
  *   values; the buckets are dumped as ic_yEleIS / ic_yEleSnow (pin of shud_b200_format_ic).
- *   --land-seq N [--land-t0 MIN] [--land-stride K] [--mutate cryo]: replay N consecutive land-surface steps (updateAllTimeSeries + updateforcing + ET) on a fresh
+ *   --land-seq N [--land-t0 MIN] [--land-dt MIN] [--land-stride K] [--mutate cryo]: replay N consecutive land-surface steps (updateAllTimeSeries + updateforcing + ET) on a fresh
  *   model and dump, per step, everything the per-cell part consumes (station rows, LAI / melt-factor class
  *   values, the terrain-radiation solar samples of the forcing interval) and produces: the pin of the
  *   land-surface step.
@@ -158,7 +158,7 @@ int main(int argc, char **argv) {
         return 2;
     }
     std::string prj = argv[1], outfn = argv[2], state = "ic", mutate = "", print_init = "";
-    double t_arg = NAN, land_t0 = NAN;
+    double t_arg = NAN, land_t0 = NAN, land_dt = 60.;
     int reps = 0, fseq = 0, lseq = 0, lstride = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--t") && a + 1 < argc) t_arg = atof(argv[++a]);
@@ -167,6 +167,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[a], "--time") && a + 1 < argc) reps = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--forcing-seq") && a + 1 < argc) fseq = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--land-seq") && a + 1 < argc) lseq = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--land-dt") && a + 1 < argc) land_dt = atof(argv[++a]);
         else if (!strcmp(argv[a], "--print-init") && a + 1 < argc) print_init = argv[++a];
         else if (!strcmp(argv[a], "--land-t0") && a + 1 < argc) land_t0 = atof(argv[++a]);
         else if (!strcmp(argv[a], "--land-stride") && a + 1 < argc) lstride = atoi(argv[++a]);
@@ -482,10 +483,10 @@ int main(int argc, char **argv) {
         std::vector<double> tt, frows, lai, mf, sx, sy, sz, wdt, den;
         std::vector<int> sn, kept;
         double tf = std::isnan(land_t0) ? M3->CS.StartTime : land_t0;
-        for (int k = 0; k < lseq; k++, tf += 60.) {
+        for (int k = 0; k < lseq; k++, tf += land_dt) {
             M3->updateAllTimeSeries(tf);
             M3->updateforcing(tf);
-            M3->ET(tf, tf + 60.);
+            M3->ET(tf, tf + land_dt);
             for (int st = 0; st < nf; st++)
                 for (int col = 1; col <= 5; col++)
                     frows.push_back(M3->forcing ? M3->forcing->get(st, col) : M3->tsd_weather[st].getX(tf, col));
@@ -507,6 +508,7 @@ int main(int argc, char **argv) {
             tt.push_back(tf);
         }
         put1i("land_nforc", nf); put1i("land_nlc", nlc); put1i("land_nmf", nmf);
+        put1d("lseq_dt", land_dt);
         putd("lseq_t", tt); putd("lseq_forc", frows); putd("lseq_lai", lai); putd("lseq_mf", mf);
         puti("lseq_tsr_n", sn); putd("lseq_tsr_den", den); puti("lseq_kept", kept);
         putd("lseq_tsr_sx", sx); putd("lseq_tsr_sy", sy); putd("lseq_tsr_sz", sz); putd("lseq_tsr_wdt", wdt);

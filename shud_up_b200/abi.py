@@ -218,6 +218,7 @@ def land_steps(snap):
     """iterate the per-step inputs of a --land-seq snapshot: yields (k, ShudLandStep, keepalive)"""
     nf, nlc, nmf = int(snap["land_nforc"][0]), int(snap["land_nlc"][0]), int(snap["land_nmf"][0])
     n = np.asarray(snap["lseq_tsr_n"]); off = np.concatenate([[0], np.cumsum(n)])
+    dt = float(snap["lseq_dt"][0]) if "lseq_dt" in snap else 60.0   # ET(t, tnext): tnext - t (MD_ET.cpp:286)
     for k in range(n.size):
         S, keep = ShudLandStep(), []
         for name, src in (("forc", snap["lseq_forc"][5 * nf * k:5 * nf * (k + 1)]), ("lai", snap["lseq_lai"][nlc * k:nlc * (k + 1)]),
@@ -225,7 +226,7 @@ def land_steps(snap):
             a, p = _d(src); keep.append(a); setattr(S, name, p)
         for name in ("sx", "sy", "sz", "wdt"):
             a, p = _d(np.asarray(snap["lseq_tsr_" + name][off[k]:off[k + 1]])); keep.append(a); setattr(S, "tsr_" + name, p)
-        S.tsr_n, S.tsr_den, S.dt_min, S.t = int(n[k]), float(snap["lseq_tsr_den"][k]), 60.0, float(snap["lseq_t"][k])
+        S.tsr_n, S.tsr_den, S.dt_min, S.t = int(n[k]), float(snap["lseq_tsr_den"][k]), dt, float(snap["lseq_t"][k])
         yield k, S, keep
 
 

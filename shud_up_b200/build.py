@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libshud_b200.so")
-SOURCES = ["shud_rhs.cu", "shud_nvec.cu", "shud_io.cu"]
+SOURCES = ["shud_rhs.cu", "shud_nvec.cu", "shud_io.cu", "shud_nvector_sundials.cu", "shud_nvector_generic.cpp",
+           "shud_cvode.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               # the x86-64 reference build contracts no product-sums; neither do we (parity first)
               "-fmad=false",
@@ -21,7 +22,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "shud_b200.h"),
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", h) for h in os.listdir(os.path.join(ROOT, "include"))] + [
                                                                  os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -731,6 +731,8 @@ struct shud_ctx {
     int (*nccl_recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*nccl_group_start)() = nullptr, (*nccl_group_end)() = nullptr;
     int (*nccl_comm_destroy)(void *) = nullptr;
+    int (*nccl_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    double *ar_dev = nullptr;         // scratch of the scalar allreduce (SHUD_AR_MAX doubles)
     cudaStream_t xstream = nullptr;   // the exchange (and the boundary tiles) run here, beside the interior tiles
     cudaEvent_t ev_pack = nullptr;
     std::vector<int> x_peer, x_scount, x_rcount;  // per neighbour partition: rank, cells sent, halo cells received
@@ -1329,6 +1331,7 @@ int shud_b200_comm_init(shud_ctx *c, const char *nccl_lib, const void *id128, in
     c->nccl_group_start = (int (*)())dlsym(c->nccl_dl, "ncclGroupStart");
     c->nccl_group_end = (int (*)())dlsym(c->nccl_dl, "ncclGroupEnd");
     c->nccl_comm_destroy = (int (*)(void *))dlsym(c->nccl_dl, "ncclCommDestroy");
+    c->nccl_allreduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(c->nccl_dl, "ncclAllReduce");
     if (!init || !c->nccl_send || !c->nccl_recv || !c->nccl_group_start || !c->nccl_group_end) return SHUD_ERR_CUDA;
     nccl_uid id;
     memcpy(&id, id128, sizeof(id));
@@ -1337,6 +1340,28 @@ int shud_b200_comm_init(shud_ctx *c, const char *nccl_lib, const void *id128, in
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+    return SHUD_OK;
+}
+
+// Scalar allreduce of the distributed N_Vector reductions ("local partial + ncclAllReduce", batched:
+// all the dot products of a Gram-Schmidt sweep travel in one call).  vals: host doubles, reduced in place over the
+// ranks of the communicator; op 0 sum, 1 max, 2 min.  Runs on the context stream; synchronises.
+constexpr int SHUD_AR_MAX = 64;
+int shud_b200_allreduce(shud_ctx *c, double *vals, int n, int op) {
+    if (!c || !vals || n < 0 || op < 0 || op > 2) return SHUD_ERR_ARG;
+    if (n == 0) return SHUD_OK;
+    if (!c->nccl_comm || !c->nccl_allreduce) return SHUD_ERR_ARG;  // shud_b200_comm_init first
+    CK(cudaSetDevice(c->device));
+    if (!c->ar_dev) c->ar_dev = dev_alloc<double>(c, SHUD_AR_MAX);
+    static const int nccl_op[3] = {0 /*ncclSum*/, 2 /*ncclMax*/, 3 /*ncclMin*/};
+    for (int k0 = 0; k0 < n; k0 += SHUD_AR_MAX) {
+        const int m = std::min(SHUD_AR_MAX, n - k0);
+        CK(cudaMemcpyAsync(c->ar_dev, vals + k0, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        if (c->nccl_allreduce(c->ar_dev, c->ar_dev, (size_t)m, 8 /*ncclFloat64*/, nccl_op[op], c->nccl_comm, c->stream) != 0)
+            return SHUD_ERR_CUDA;
+        CK(cudaMemcpyAsync(vals + k0, c->ar_dev, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     return SHUD_OK;
 }
 

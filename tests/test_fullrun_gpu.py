@@ -1,0 +1,52 @@
+"""Full runs of the three shipped basins (north_star: outlet hydrograph + water balance within a stated tolerance):
+the reference's time loop (src/Model/shud.cpp:91-155) with the library's CVODE-shaped integrator (BDF order 1-5,
+Newton, SPGMR(5), the settings of each basin's cfg.para) drives
+  (a) the GPU arm: device land-surface step + CUDA RHS + SHUD B200 N_Vector (device-fused Newton-Krylov), and
+  (b) the checker arm: oracle land step + oracle RHS + host serial N_Vector under the same integrator source,
+over the first days of tests/golden/<basin>.run.npz (the land-surface inputs of a 30-day window replayed by the
+unmodified reference at the SolverStep cadence).  tools/fullrun_report.py runs the whole 30 days and writes
+profiles/r02_fullrun_*.jsonl; here a shorter window keeps the GPU suite quick.
+Stated tolerance: Nash-Sutcliffe efficiency of the outlet hydrograph >= 0.999, relative volume
+error <= 1e-3, basin water-balance residual within 1.1 x the checker arm's (+ 1e-6 of the precipitation volume)."""
+import os
+
+import numpy as np
+import pytest
+
+import host_cv
+import oracle_lib
+from shud_up_b200 import driver
+
+pytestmark = pytest.mark.gpu
+
+
+def nse(sim, obs):
+    den = float(np.sum((obs - obs.mean()) ** 2))
+    return 1.0 - float(np.sum((sim - obs) ** 2)) / den if den > 0 else 1.0
+
+
+def compare(gpu, ref):
+    qg, qr = gpu["q_out"].sum(axis=1), ref["q_out"].sum(axis=1)
+    vol = abs(qg.sum() - qr.sum()) / max(abs(qr.sum()), 1e-300)
+    return dict(nse=nse(qg, qr), vol_err=vol, resid_gpu=gpu["budget"]["resid_m3"], resid_ref=ref["budget"]["resid_m3"],
+                P=ref["budget"]["P_m3"])
+
+
+@pytest.mark.parametrize("basin,days", [("ccw", 5), ("heihe", 4), ("qhh", 2)])
+def test_outlet_hydrograph_and_water_balance(basin, days):
+    mesh = oracle_lib.load_case(basin, "ic")
+    run = dict(np.load(os.path.join(oracle_lib.GOLDEN, f"{basin}.run.npz")))
+    n = int(round(days * 1440.0 / float(run["run_cfg"][3])))
+    ref = driver.run_cv(host_cv.OracleArm(mesh, run), run, n_steps=n)
+    arm = driver.GpuArm(mesh, run)
+    gpu = driver.run_cv(arm, run, n_steps=n)
+    arm.close()
+    c = compare(gpu, ref)
+    print(basin, c, "gpu", gpu["stats"], "ref", ref["stats"], "sim-days/s gpu", gpu["sim_days_per_wall_s"], "ref",
+          ref["sim_days_per_wall_s"])
+    assert gpu["stats"]["nst"] >= n
+    assert c["nse"] >= 0.999 and c["vol_err"] <= 1e-3, c
+    assert abs(c["resid_gpu"]) <= 1.1 * abs(c["resid_ref"]) + 1e-6 * abs(c["P"]), c
+    ewt = 1e-4 * np.abs(ref["y_end"]) + 1e-4
+    wrms = np.sqrt(np.mean(((gpu["y_end"] - ref["y_end"]) / ewt) ** 2))
+    assert wrms < 1.0, wrms
