@@ -28,6 +28,7 @@ extern "C" {
 #define SHUD_ERRNAN 10    /* CheckNANi / CheckNonNegative, src/Equations/functions.cpp:90-103,148-154 */
 #define SHUD_ERRDATAIN 13 /* effKH out of range, src/Equations/Equations.cpp:129-132 */
 #define SHUD_ERRRIVBC 1   /* unknown river 'down' code, src/ModelData/MD_RiverFlux.cpp:55-57 (exit(1)) */
+#define SHUD_ERR_P2P_TIMEOUT 99 /* device error word: a neighbour's halo flag did not arrive within 5 s (peer-to-peer exchange) */
 
 /* ---- static model data: what Model_Data::initialize() leaves behind, flattened
  * AoS -> SoA once after initialize()+LoadIC() (reference src/Model/shud.cpp:50-67).
@@ -178,6 +179,18 @@ int shud_b200_comm_init(shud_ctx *ctx, const char *nccl_lib, const void *id128, 
 int shud_b200_exchange_plan(shud_ctx *ctx, int npeers, const int32_t *peer_rank, const int32_t *send_count,
                             const int32_t *recv_count, const int32_t *send_cells);
 int shud_b200_rhs_exchange_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+/* Peer-to-peer halo exchange (one process per GPU of one node, NVLink / NVSwitch): instead of NCCL sends / receives the
+ * pack kernel stores every boundary cell's state straight into the halo buffer of the partition that needs it (the
+ * neighbours' buffers are mapped through CUDA IPC) and releases one flag per neighbour; the receiver's boundary tiles
+ * start behind a flag wait.  The step is then a CUDA graph of plain kernels.  After shud_b200_exchange_plan:
+ *   shud_b200_p2p_export   fills a SHUD_P2P_BLOB_BYTES blob describing this rank's halo buffer (IPC handle, who lands where)
+ *   (the host gathers the blobs of all ranks, rank order: MPI_Allgather / torch.distributed.all_gather)
+ *   shud_b200_p2p_connect  maps the neighbours' buffers; a host barrier must follow before the first exchange.
+ * shud_b200_rhs_exchange_dev then uses this path (SHUD_P2P=0 in the environment keeps the NCCL path).  Contexts living
+ * in one process (tests) are connected by pointer, no IPC. */
+#define SHUD_P2P_BLOB_BYTES 512
+int shud_b200_p2p_export(shud_ctx *ctx, int rank, void *blob);
+int shud_b200_p2p_connect(shud_ctx *ctx, int rank, int world, const void *blobs);
 /* Scalar allreduce over the same communicator for the distributed N_Vector reductions:
  * `vals` are n HOST doubles reduced in place over all ranks; op 0 sum, 1 max, 2 min.  Synchronises the context stream. */
 int shud_b200_allreduce(shud_ctx *ctx, double *vals, int n, int op);

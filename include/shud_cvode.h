@@ -86,6 +86,13 @@ typedef struct shud_cv_stats {
 } shud_cv_stats;
 int shud_cv_get_stats(const shud_cv *cv, shud_cv_stats *st);
 
+/* One linear solve (I - gamma J(t, y)) x = b on its own - SUNLinSolSolve_SPGMR as CVLS drives it: scaling by `ewt` on
+ * both sides, zero initial guess, difference-quotient J v around (y, fy = f(t, y)), tolerance `delta` on the 2-norm of
+ * the scaled residual; runs the fused hook when one is set.  Returns 0 converged, 1 residual reduced, 2 not reduced,
+ * 3 right-hand side already below delta (x = 0), < 0 error; *nli = Krylov iterations. */
+int shud_cv_linsolve(shud_cv *cv, realtype t, realtype gamma, N_Vector y, N_Vector fy, N_Vector ewt, N_Vector b,
+                     realtype delta, N_Vector x, int *nli);
+
 /* The device implementation of shud_cv_fused for one GPU (shud_nv_ewt, one-pass Newton residual, shud_spgmr_solve with
  * the difference-quotient work folded around shud_b200_rhs_dev): fills *out; destroy releases its SPGMR workspace.
  * The vectors handed to the hooks must be SHUD B200 vectors on `ws`. */

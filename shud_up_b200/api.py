@@ -56,6 +56,9 @@ def lib():
         "shud_b200_to_device_order": (C.c_int, [vp, vp, vp]),
         "shud_b200_from_device_order": (C.c_int, [vp, vp, vp]),
         "shud_b200_summary_dev": (C.c_int, [vp, vp, _PD]),
+        "shud_b200_p2p_export": (C.c_int, [vp, C.c_int, vp]),
+        "shud_b200_p2p_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "shud_b200_allreduce": (C.c_int, [vp, _PD, C.c_int, C.c_int]),
         "shud_b200_perm": (C.c_int, [vp, _PI, _PI]),
         "shud_b200_rhs_dev": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs": (C.c_int, [vp, C.c_double, vp, vp]),
@@ -274,9 +277,42 @@ class ShudRHS:
         _chk(lib().shud_b200_comm_init(self._h, path, raw, rank, world), "comm_init")
 
     def exchange_plan(self, peers, send_counts, recv_counts, send_cells):
+        self._last_plan = (peers, send_counts, recv_counts, send_cells)
         a = [np.ascontiguousarray(v, dtype=np.int32) for v in (peers, send_counts, recv_counts, send_cells)]
         ptr = [v.ctypes.data_as(_PI) for v in a]
         _chk(lib().shud_b200_exchange_plan(self._h, int(a[0].size), *ptr), "exchange_plan")
+
+    P2P_BLOB = 512  # SHUD_P2P_BLOB_BYTES
+
+    def p2p_export(self, rank):
+        buf = (C.c_ubyte * self.P2P_BLOB)()
+        _chk(lib().shud_b200_p2p_export(self._h, int(rank), buf), "p2p_export")
+        return bytes(buf)
+
+    def p2p_connect_blobs(self, rank, blobs):
+        """blobs: list of every rank's p2p_export() bytes, rank order.  False: peer mapping unavailable (NCCL path stays)"""
+        raw = b"".join(blobs)
+        rc = lib().shud_b200_p2p_connect(self._h, int(rank), len(blobs), raw)
+        if rc == -3:
+            return False
+        _chk(rc, "p2p_connect")
+        return True
+
+    def p2p_connect(self, dist, device):
+        """collective: exchange the halo-buffer descriptors of all ranks, map the neighbours' buffers (CUDA IPC over
+        NVLink), barrier.  After it f_exchange_dev moves the halo with peer stores + flags instead of NCCL."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = torch.tensor(list(self.p2p_export(rank)), dtype=torch.uint8, device=device)
+        allb = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine)
+        ok = self.p2p_connect_blobs(rank, [bytes(t.cpu().tolist()) for t in allb])
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # all ranks or none
+        if not int(flag.item()) and ok:
+            self.exchange_plan(*self._last_plan)       # back to the NCCL buffers
+        dist.barrier()
+        return bool(int(flag.item()))
 
     def f_exchange_dev(self, t, y_dev, ydot_dev):
         """one f() of a partition: pack, NCCL sends/receives, interior part beside them, boundary part"""

@@ -952,6 +952,25 @@ int shud_cv_solve(shud_cv *cv, realtype tout, N_Vector yout, realtype *tret, int
     return istate;
 }
 
+// One linear solve (I - gamma J(t, y)) x = b on its own: SUNLinSolSolve_SPGMR as CVLS drives it (scaling by `ewt` on both
+// sides, zero initial guess, difference-quotient J v around (y, fy)), through the fused hook when one is set.
+// Returns 0 converged, 1 residual reduced, 2 not reduced, 3 right-hand side below delta (x = 0), < 0 error.
+int shud_cv_linsolve(shud_cv *cv, realtype t, realtype gamma, N_Vector y, N_Vector fy, N_Vector ewt, N_Vector b,
+                     realtype delta, N_Vector x, int *nli) {
+    if (!cv || !y || !fy || !ewt || !b || !x) return SHUD_CV_ILL_INPUT;
+    cv->tn = t; cv->gamma = gamma;
+    N_VScale(1.0, ewt, cv->ewt);
+    int it = 0, nfe = 0, r;
+    if (cv->have_fused && cv->fused.lsolve) {
+        r = cv->fused.lsolve(cv->fused.ctx, t, gamma, y, fy, cv->ewt, b, delta, x, &it, &nfe);
+    } else {
+        const int rc = spgmr_solve(cv, x, b, delta, y, fy, &it);
+        r = rc == LS_SUCCESS ? (it == 0 ? 3 : 0) : rc == LS_RES_REDUCED ? 1 : rc == LS_CONV_FAIL ? 2 : -1;
+    }
+    if (nli) *nli = it;
+    return r;
+}
+
 int shud_cv_get_stats(const shud_cv *cv, shud_cv_stats *st) {
     if (!cv || !st) return SHUD_CV_ILL_INPUT;
     st->nst = cv->nst; st->nfe = cv->nfe; st->nfeLS = cv->nfeLS; st->nni = cv->nni; st->nli = cv->nli;

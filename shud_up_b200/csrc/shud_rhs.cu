@@ -13,6 +13,7 @@
 // order) permutes on the way in and out.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -72,6 +73,10 @@ struct DevMesh {
     int Nhalo;
     const double *h_zs, *h_zb, *h_aqd, *h_macD, *h_macKsatH, *h_vAreaF, *h_ksatH;
     const double *h_state;        // [Nhalo][2] = (Ysurf, Ygw) of each halo cell, filled by the halo exchange
+    // peer-to-peer exchange: two halo buffers written alternately by the neighbours (h_state = even, h_state_alt = odd
+    // epochs); the epoch of the exchange in flight is a device word (NULL: h_state as registered)
+    const double *h_state_alt;
+    const unsigned long long *h_epoch;
     double *h_kh;                 // effKH of halo cells (k_effkh)
     int *err;  // [0] code, [1] where (1-based reference id)
 };
@@ -107,8 +112,13 @@ struct CryoStep {  // per-step, uniform over the cells (the day clock of the acc
     double nday, size_s, size_b;
 };
 
+__device__ __forceinline__ const double *halo_state(const DevMesh &m) {
+    if (m.h_epoch) return (*m.h_epoch & 1ull) ? m.h_state_alt : m.h_state;
+    return m.h_state;
+}
+
 __device__ __forceinline__ void raise_err(int *err, int code, int where) {
-    if (atomicMax(&err[0], code) < code) err[1] = where;
+    if (atomicMax_system(&err[0], code) < code) err[1] = where;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restri
         const int h = i - m.Ne;  // halo cell: same formula on the exchanged groundwater head
         if (h < m.Nhalo) {
             int e = 0;
-            m.h_kh[h] = eff_kh(m.h_state[2 * h + 1], m.h_aqd[h], m.h_macD[h], m.h_macKsatH[h], m.h_vAreaF[h], m.h_ksatH[h], &e);
+            m.h_kh[h] = eff_kh(halo_state(m)[2 * h + 1], m.h_aqd[h], m.h_macD[h], m.h_macKsatH[h], m.h_vAreaF[h], m.h_ksatH[h], &e);
         }
         return;
     }
@@ -368,7 +378,8 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                     if (m.has_headbc && (m.flags[k] & F_HEADBC)) ygw_n = m.ele_yBC[k];
                 } else {  // halo cell of a partition: state from the last halo exchange
                     const int h = k - Ne;
-                    nsf = m.h_state[2 * h]; ygw_n = m.h_state[2 * h + 1]; zs_n = m.h_zs[h]; zb_n = m.h_zb[h]; kh_n = m.h_kh[h];
+                    const double *hs = halo_state(m);
+                    nsf = hs[2 * h]; ygw_n = hs[2 * h + 1]; zs_n = m.h_zs[h]; zb_n = m.h_zb[h]; kh_n = m.h_kh[h];
                 }
                 nsf = nsf < 0. ? 0. : nsf;
                 const double Bj = e_B[j][lane_cell], dj = e_dist[j][lane_cell];
@@ -599,6 +610,73 @@ __global__ void k_pack_halo(const double *__restrict__ Y, const int *__restrict_
     out[2 * k + 1] = Y[2 * (size_t)Ne + i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-to-peer halo exchange over NVLink (one process per GPU, the neighbours' halo buffers mapped through CUDA IPC):
+// the pack kernel stores each boundary cell's (Ysurf, Ygw) straight into the halo buffer of the partition that needs it
+// and, when the last block is through, releases one flag per neighbour; the receiver spins on its own flags.  No
+// collective call, no staging buffer, and the whole step stays a CUDA graph of plain kernels.
+// Epochs: the exchange of call e writes buffer e & 1.  A neighbour can be at most one call ahead (it cannot pack call
+// e + 2 before it has seen my flag of call e + 1, which I release after everything of call e has completed on my
+// streams), so two buffers suffice and no credit has to travel back.
+// ---------------------------------------------------------------------------------------------
+constexpr int P2P_MAXPEER = 16;
+struct P2PTable {
+    double *buf[2][P2P_MAXPEER];            // neighbour p's halo buffers (even / odd epochs), peer-mapped
+    unsigned long long *flag[P2P_MAXPEER];  // my flag slot in neighbour p's flag array
+    int send_off[P2P_MAXPEER + 1];          // my send list is grouped by neighbour: [send_off[p], send_off[p + 1])
+    int dst_off[P2P_MAXPEER];               // where my cells start in neighbour p's halo numbering
+    int npeers;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) k_pack_p2p(const double *__restrict__ Y, const int *__restrict__ idx, int n, int Ne,
+                                                  P2PTable T, const unsigned long long *epoch, unsigned int *count) {
+    // the epoch word is advanced by k_wait_p2p of this call, which is ordered behind this kernel
+    const unsigned long long e = *epoch + 1ull;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        int p = 0;
+        while (p + 1 < T.npeers && k >= T.send_off[p + 1]) p++;
+        const int i = idx[k];
+        double *dst = ((e & 1ull) ? T.buf[1][p] : T.buf[0][p]) + 2 * (size_t)(T.dst_off[p] + (k - T.send_off[p]));
+        *reinterpret_cast<double2 *>(dst) = make_double2(Y[i], Y[2 * (size_t)Ne + i]);  // one 16-byte store over NVLink
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(count, 1u);
+        if (done == gridDim.x - 1) {  // every block's stores are fenced: publish
+            __threadfence();
+            *count = 0;
+            for (int p = 0; p < T.npeers; p++) st_release_sys(T.flag[p], e);
+        }
+    }
+}
+__global__ void k_wait_p2p(const unsigned long long *flags, int nslots, unsigned long long *epoch, int *err) {
+    const unsigned long long e = *epoch + 1ull;
+    if ((int)threadIdx.x < nslots) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(flags + threadIdx.x) < e) {
+            __nanosleep(100);
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 5000000000ull) {  // 5 s: a neighbour is gone; report instead of hanging the device
+                raise_err(err, SHUD_ERR_P2P_TIMEOUT, (int)threadIdx.x + 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *epoch = e;
+}
+
 // Print_Ctrl::PrintData on the device: acc += value (Model_Control.cpp:933-935)
 __global__ void k_accumulate(double *__restrict__ acc, const double *__restrict__ v, size_t n) {
     for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
@@ -606,8 +684,7 @@ __global__ void k_accumulate(double *__restrict__ acc, const double *__restrict_
 }
 __global__ void k_scale_copy(double *__restrict__ dst, double *__restrict__ acc, double s, size_t n) {
     for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
-        dst[k] = acc[k] * s;  // buffer *= tau / NumUpdate (Model_Control.cpp:944-946)
-        acc[k] = 0.;          // reset (Model_Control.cpp:958-960)
+        dst[k] = acc[k] * s;  // buffer *= tau / NumUpdate (Model_Control.cpp:944-946); the reset follows the download
     }
 }
 
@@ -719,6 +796,10 @@ struct shud_ctx {
     std::vector<int> lake_of_cell;
     std::vector<int> lake_nele;
     double *h_pinned = nullptr;  // staging for forcing uploads (pinned)
+    int *h_err = nullptr;        // error word (mapped pinned; m.err is its device alias)
+    double *f_stage = nullptr;   // device staging of a forcing upload: 9 cell columns + 2 reach columns, reference order
+    std::vector<double *> flush_tmp;  // persistent scratch of shud_b200_output_flush
+    unsigned long graph_clock = 0;    // LRU stamp of the graph cache
     size_t h_pinned_n = 0;
     bool has_ebc_arrays = false;
     int fused_minb = 4;
@@ -739,11 +820,17 @@ struct shud_ctx {
     int *x_sidx = nullptr;            // device-order ids of the cells sent, concatenated by peer
     double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
     int x_nsend = 0, x_cap_send = 0;
+    // peer-to-peer exchange (shud_b200_p2p_export / _connect)
+    void *p2p_block = nullptr;            // [flags: P2P_MAXPEER u64 | epoch | count | pad to 256 B][buffer 0][buffer 1]
+    size_t p2p_stride = 0;                // bytes of one halo buffer (multiple of 256)
+    std::vector<void *> p2p_opened;       // neighbours' blocks mapped through CUDA IPC
+    P2PTable p2p{};
+    int use_p2p = 0;
     int use_xgraph = 1;               // SHUD_XGRAPH: rhs_exchange_dev replayed as one CUDA graph per (y, ydot)
     // CUDA graphs of the solver-mode launch sequence, one per (y, ydot) pointer pair CVODE hands in
     int use_graph = 1;
     int use_pdl = 1;   // programmatic dependent launch of the cell kernel behind k_effkh (SHUD_PDL)
-    struct GraphEntry { const double *y; double *yd; cudaGraphExec_t exec; };
+    struct GraphEntry { const double *y; double *yd; cudaGraphExec_t exec; unsigned long used; };
     std::vector<GraphEntry> graphs, xgraphs;
 };
 
@@ -814,6 +901,17 @@ const double *up_riv(shud_ctx *c, const double *src) {
 extern "C" {
 
 static void drop_graphs(shud_ctx *c);
+// graph cache of 32 (y, ydot) pointer pairs: the least recently launched one makes room (CVODE alternates between a
+// handful of work vectors; a long-lived cache entry must not be lost because a 33rd pair showed up once)
+static void evict_lru(shud_ctx *c, std::vector<shud_ctx::GraphEntry> &cache) {
+    (void)c;
+    if (cache.size() < 32) return;
+    size_t lru = 0;
+    for (size_t k = 1; k < cache.size(); k++)
+        if (cache[k].used < cache[lru].used) lru = k;
+    cudaGraphExecDestroy(cache[lru].exec);
+    cache.erase(cache.begin() + lru);
+}
 
 int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
     return shud_b200_create_partition(M, nullptr, device, out);
@@ -1152,13 +1250,16 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     m.ele_yBC = dev_alloc<double>(c, LDh); m.ele_QBC = dev_alloc<double>(c, LDh);
     m.r_yBC = dev_alloc<double>(c, Nr); m.r_qBC = dev_alloc<double>(c, Nr);
     m.effKH = dev_alloc<double>(c, LDh); m.QsegSurf = dev_alloc<double>(c, Ns); m.QsegSub = dev_alloc<double>(c, Ns);
-    m.err = dev_alloc<int>(c, 2);
+    // the error word lives in mapped pinned host memory: kernels raise it with a (rare) system-scope atomic, the host
+    // reads it after a stream synchronisation without a copy
+    CK(cudaHostAlloc((void **)&c->h_err, sizeof(int) * 2, cudaHostAllocMapped));
+    c->h_err[0] = c->h_err[1] = 0;
+    CK(cudaHostGetDevicePointer((void **)&m.err, c->h_err, 0));
     for (double *p : {m.netPrep, m.potEvap, m.potTran, m.lai, m.fuSurf, m.fuSub, m.eic, m.satn, m.ele_yBC, m.ele_QBC,
                       m.effKH})
         CK(cudaMemset(p, 0, sizeof(double) * LDh));
     CK(cudaMemset(m.r_yBC, 0, sizeof(double) * std::max(Nr, 1)));
     CK(cudaMemset(m.r_qBC, 0, sizeof(double) * std::max(Nr, 1)));
-    CK(cudaMemset(m.err, 0, sizeof(int) * 2));
     c->d_cperm = dev_upload(c, c->cperm); c->d_rperm = dev_upload(c, c->rperm);
     c->y_stage = dev_alloc<double>(c, c->NY); c->y_dev = dev_alloc<double>(c, c->NY);
     c->ydot_dev = dev_alloc<double>(c, c->NY);
@@ -1177,12 +1278,15 @@ void shud_b200_destroy(shud_ctx *c) {
     if (c->xstream) cudaStreamSynchronize(c->xstream);
     drop_graphs(c);  // the captured exchange graphs hold NCCL nodes: gone before the communicator
     if (c->nccl_comm && c->nccl_comm_destroy) c->nccl_comm_destroy(c->nccl_comm);
+    for (void *q : c->p2p_opened) cudaIpcCloseMemHandle(q);
+    if (c->p2p_block) cudaFree(c->p2p_block);
     if (c->xstream) cudaStreamDestroy(c->xstream);
     if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ev_kh) cudaEventDestroy(c->ev_kh);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_err) cudaFreeHost(c->h_err);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1200,21 +1304,49 @@ static int upload_perm(shud_ctx *c, double *dst, const double *src, const std::v
     return SHUD_OK;
 }
 
+// columns of a forcing upload: reference order in `src` (column k at src + k * ld), device order out
+struct PermCols { double *dst[9]; int ncol; };
+__global__ void k_perm_cols(const double *__restrict__ src, size_t ld, const int *__restrict__ perm, int n, PermCols p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o = perm[i];
+    for (int k = 0; k < p.ncol; k++) p.dst[k][i] = src[(size_t)k * ld + o];
+}
+
 int shud_b200_set_forcing(shud_ctx *c, const shud_forcing *f) {
     if (!c || !f) return SHUD_ERR_ARG;
     CK(cudaSetDevice(c->device));
     DevMesh &m = c->m;
-    const double *src[] = {f->qEleNetPrep, f->qPotEvap, f->qPotTran, f->t_lai, f->fu_Surf, f->fu_Sub, f->qEleE_IC};
-    double *dst[] = {m.netPrep, m.potEvap, m.potTran, m.lai, m.fuSurf, m.fuSub, m.eic};
-    for (int k = 0; k < 7; k++) {
-        if (!src[k]) return SHUD_ERR_ARG;
-        int rc = upload_perm(c, dst[k], src[k], c->cperm);
-        if (rc) return rc;
+    const size_t Ne = (size_t)c->Ne, Nr = (size_t)c->Nr;
+    // the arrays go up as they are (reference order) into a device staging area and are permuted there by one kernel
+    // per index space: no host gather, no synchronisation per array
+    if (!c->f_stage) c->f_stage = dev_alloc<double>(c, 9 * Ne + 2 * std::max<size_t>(Nr, 1));
+    const double *src[9] = {f->qEleNetPrep, f->qPotEvap, f->qPotTran, f->t_lai, f->fu_Surf, f->fu_Sub, f->qEleE_IC,
+                            f->ele_yBC, f->ele_QBC};
+    double *dst[9] = {m.netPrep, m.potEvap, m.potTran, m.lai, m.fuSurf, m.fuSub, m.eic, m.ele_yBC, m.ele_QBC};
+    PermCols pc{};
+    for (int k = 0; k < 9; k++) {
+        if (!src[k]) {
+            if (k < 7) return SHUD_ERR_ARG;
+            continue;
+        }
+        CK(cudaMemcpyAsync(c->f_stage + (size_t)pc.ncol * Ne, src[k], sizeof(double) * Ne, cudaMemcpyHostToDevice, c->stream));
+        pc.dst[pc.ncol++] = dst[k];
     }
-    if (f->ele_yBC) { int rc = upload_perm(c, m.ele_yBC, f->ele_yBC, c->cperm); if (rc) return rc; }
-    if (f->ele_QBC) { int rc = upload_perm(c, m.ele_QBC, f->ele_QBC, c->cperm); if (rc) return rc; }
-    if (f->riv_yBC && c->Nr) { int rc = upload_perm(c, m.r_yBC, f->riv_yBC, c->rperm); if (rc) return rc; }
-    if (f->riv_qBC && c->Nr) { int rc = upload_perm(c, m.r_qBC, f->riv_qBC, c->rperm); if (rc) return rc; }
+    k_perm_cols<<<(unsigned)((Ne + 255) / 256), 256, 0, c->stream>>>(c->f_stage, Ne, c->d_cperm, (int)Ne, pc);
+    if (Nr) {
+        PermCols pr{};
+        double *rbase = c->f_stage + 9 * Ne;
+        const double *rsrc[2] = {f->riv_yBC, f->riv_qBC};
+        double *rdst[2] = {m.r_yBC, m.r_qBC};
+        for (int k = 0; k < 2; k++) {
+            if (!rsrc[k]) continue;
+            CK(cudaMemcpyAsync(rbase + (size_t)pr.ncol * Nr, rsrc[k], sizeof(double) * Nr, cudaMemcpyHostToDevice, c->stream));
+            pr.dst[pr.ncol++] = rdst[k];
+        }
+        if (pr.ncol) k_perm_cols<<<(unsigned)((Nr + 255) / 256), 256, 0, c->stream>>>(rbase, Nr, c->d_rperm, (int)Nr, pr);
+    }
+    CK(cudaGetLastError());
     // lake-cell evaporation / precipitation means, ascending reference cell order (MD_f.cpp:16-17):
     // they depend on the forcing step only (qEleEvapo of a lake cell is qPotEvap, MD_ElementFlux.cpp:15)
     if (c->Nl > 0) {
@@ -1225,10 +1357,11 @@ int shud_b200_set_forcing(shud_ctx *c, const shud_forcing *f) {
             ev[l] += f->qPotEvap[o] / c->lake_nele[l];
             pr[l] += f->qElePrep[o] / c->lake_nele[l];
         }
-        CK(cudaStreamSynchronize(c->stream));
-        CK(cudaMemcpy(m.l_evap_raw, ev.data(), sizeof(double) * c->Nl, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(m.l_prcp, pr.data(), sizeof(double) * c->Nl, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(m.l_evap_raw, ev.data(), sizeof(double) * c->Nl, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(m.l_prcp, pr.data(), sizeof(double) * c->Nl, cudaMemcpyHostToDevice, c->stream));
     }
+    // the caller's arrays (pageable host memory, staged by the runtime) may be reused on return
+    CK(cudaStreamSynchronize(c->stream));
     return SHUD_OK;
 }
 
@@ -1290,6 +1423,7 @@ int shud_b200_download_ref(shud_ctx *c, const double *y_dev, double *y_host_ref)
 int shud_b200_set_halo_state_dev(shud_ctx *c, const double *state) {
     if (!c || (c->Nhalo > 0 && !state)) return SHUD_ERR_ARG;
     c->m.h_state = state;
+    c->m.h_state_alt = nullptr; c->m.h_epoch = nullptr; c->use_p2p = 0;  // a registered buffer replaces the p2p buffers
     drop_graphs(c);  // kernel parameters changed
     return SHUD_OK;
 }
@@ -1393,7 +1527,108 @@ int shud_b200_exchange_plan(shud_ctx *c, int npeers, const int32_t *peer_rank, c
     return shud_b200_set_halo_state_dev(c, c->x_hstate);
 }
 
+// ---- peer-to-peer exchange: set-up ----
+struct P2PBlob {
+    cudaIpcMemHandle_t handle;   // 64 bytes
+    long long pid;               // contexts of one process are connected by pointer
+    void *base;
+    int rank, npeers, nhalo, pad;
+    unsigned long long stride;
+    int peer[P2P_MAXPEER], recv_off[P2P_MAXPEER];
+};
+static_assert(sizeof(P2PBlob) <= SHUD_P2P_BLOB_BYTES, "blob too large");
+constexpr size_t P2P_HDR = 256;  // flags [P2P_MAXPEER] | epoch | count
+
+int shud_b200_p2p_export(shud_ctx *c, int rank, void *blob) {
+    if (!c || !blob || (int)c->x_peer.size() > P2P_MAXPEER) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    if (!c->p2p_block) {
+        c->p2p_stride = ((size_t)2 * std::max(c->Nhalo, 1) * sizeof(double) + 255) / 256 * 256;
+        CK(cudaMalloc(&c->p2p_block, P2P_HDR + 2 * c->p2p_stride));  // its own allocation: one IPC handle, nothing else exposed
+        CK(cudaMemset(c->p2p_block, 0, P2P_HDR + 2 * c->p2p_stride));
+    }
+    P2PBlob b;
+    memset(&b, 0, sizeof(b));
+    CK(cudaIpcGetMemHandle(&b.handle, c->p2p_block));
+    b.pid = (long long)getpid(); b.base = c->p2p_block;
+    b.rank = rank; b.npeers = (int)c->x_peer.size(); b.nhalo = c->Nhalo; b.stride = c->p2p_stride;
+    int ro = 0;
+    for (int p = 0; p < b.npeers; p++) { b.peer[p] = c->x_peer[p]; b.recv_off[p] = ro; ro += c->x_rcount[p]; }
+    memset(blob, 0, SHUD_P2P_BLOB_BYTES);
+    memcpy(blob, &b, sizeof(b));
+    return SHUD_OK;
+}
+
+int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
+    if (!c || !blobs || !c->p2p_block || rank < 0 || rank >= world) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    const char *env = getenv("SHUD_P2P");
+    if (env && atoi(env) == 0) return SHUD_OK;  // keep the NCCL path (A/B)
+    P2PTable T{};
+    T.npeers = (int)c->x_peer.size();
+    int so = 0;
+    for (int p = 0; p < T.npeers; p++) {
+        const int r = c->x_peer[p];
+        if (r < 0 || r >= world) return SHUD_ERR_ARG;
+        P2PBlob b;
+        memcpy(&b, (const char *)blobs + (size_t)r * SHUD_P2P_BLOB_BYTES, sizeof(b));
+        int slot = -1;
+        for (int j = 0; j < b.npeers; j++) if (b.peer[j] == rank) slot = j;
+        if (b.rank != r || slot < 0) return SHUD_ERR_ARG;
+        char *base = nullptr;
+        if (b.pid == (long long)getpid()) {
+            base = (char *)b.base;  // same process: the pointer itself (IPC handles cannot be opened by their creator)
+            int dev_peer = -1;
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, base) == cudaSuccess) dev_peer = pa.device;
+            if (dev_peer >= 0 && dev_peer != c->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(dev_peer, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SHUD_ERR_CUDA; }
+                cudaGetLastError();
+            }
+        } else {
+            if (cudaIpcOpenMemHandle((void **)&base, b.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                for (void *q : c->p2p_opened) cudaIpcCloseMemHandle(q);
+                c->p2p_opened.clear();
+                return SHUD_ERR_CUDA;  // caller falls back to the NCCL path
+            }
+            c->p2p_opened.push_back(base);
+        }
+        T.buf[0][p] = (double *)(base + P2P_HDR);
+        T.buf[1][p] = (double *)(base + P2P_HDR + b.stride);
+        T.flag[p] = (unsigned long long *)base + slot;
+        T.send_off[p] = so; so += c->x_scount[p];
+        T.dst_off[p] = b.recv_off[slot];
+    }
+    T.send_off[T.npeers] = so;
+    c->p2p = T;
+    // my own side: the two halo buffers, the epoch word
+    char *mine = (char *)c->p2p_block;
+    c->m.h_state = (const double *)(mine + P2P_HDR);
+    c->m.h_state_alt = (const double *)(mine + P2P_HDR + c->p2p_stride);
+    c->m.h_epoch = (const unsigned long long *)mine + P2P_MAXPEER;
+    drop_graphs(c);
+    c->use_p2p = 1;
+    return SHUD_OK;
+}
+
+static int exchange_launch_p2p(shud_ctx *c, double t, const double *y, double *ydot) {
+    // c->stream: pack (NVLink stores + flags) -> interior part;  exchange stream: flag wait -> boundary tiles
+    unsigned long long *hdr = (unsigned long long *)c->p2p_block;
+    const int nb = std::max(1, (c->x_nsend + 255) / 256);
+    k_pack_p2p<<<nb, 256, 0, c->stream>>>(y, c->x_sidx, c->x_nsend, c->Ne, c->p2p, hdr + P2P_MAXPEER,
+                                          (unsigned int *)(hdr + P2P_MAXPEER + 1));
+    CK(cudaEventRecord(c->ev_pack, c->stream));
+    CK(cudaStreamWaitEvent(c->xstream, c->ev_pack, 0));
+    k_wait_p2p<<<1, 32, 0, c->xstream>>>(hdr, c->p2p.npeers, hdr + P2P_MAXPEER, c->m.err);
+    int rc = shud_b200_rhs_interior_dev(c, t, y, ydot);
+    if (rc) return rc;
+    return shud_b200_rhs_boundary_dev(c, t, y, ydot, c->xstream);
+}
+
 static int exchange_launch(shud_ctx *c, double t, const double *y, double *ydot) {
+    if (c->use_p2p) return exchange_launch_p2p(c, t, y, ydot);
     // pack my boundary cells -> post the sends / receives on the exchange stream -> interior part of f() beside
     // them on the context stream -> boundary part (its tiles on the exchange stream, behind the receives)
     if (c->x_nsend > 0)
@@ -1419,18 +1654,22 @@ static int exchange_launch(shud_ctx *c, double t, const double *y, double *ydot)
 
 int shud_b200_rhs_exchange_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
-    if (!c->nccl_comm || !c->xstream) return SHUD_ERR_ARG;  // shud_b200_comm_init + shud_b200_exchange_plan first
+    if (!c->use_p2p && !c->nccl_comm) return SHUD_ERR_ARG;  // shud_b200_comm_init (or shud_b200_p2p_connect) first
+    if (!c->xstream) {  // p2p without a communicator (contexts of one process): the exchange stream is created here
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+    }
     if (!c->use_xgraph) return exchange_launch(c, t, y, ydot);
     // as shud_b200_rhs_dev: the sequence (collective included) is fixed, one instantiated graph per pointer pair
     for (auto &g : c->xgraphs)
         if (g.y == y && g.yd == ydot) {
+            g.used = ++c->graph_clock;
             CK(cudaGraphLaunch(g.exec, c->stream));
             return SHUD_OK;
         }
-    if (c->xgraphs.size() >= 32) {
-        for (auto &g : c->xgraphs) cudaGraphExecDestroy(g.exec);
-        c->xgraphs.clear();
-    }
+    evict_lru(c, c->xgraphs);
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
@@ -1447,7 +1686,7 @@ int shud_b200_rhs_exchange_dev(shud_ctx *c, double t, const double *y, double *y
         c->use_xgraph = 0;  // capture of the collective unavailable: plain launches
         return exchange_launch(c, t, y, ydot);
     }
-    c->xgraphs.push_back({y, ydot, exec});
+    c->xgraphs.push_back({y, ydot, exec, ++c->graph_clock});
     CK(cudaGraphLaunch(exec, c->stream));
     return SHUD_OK;
 }
@@ -1567,10 +1806,11 @@ int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     // between a handful of work vectors) -> one instantiated graph per pointer pair, launched as one unit
     for (auto &g : c->graphs)
         if (g.y == y && g.yd == ydot) {
+            g.used = ++c->graph_clock;
             CK(cudaGraphLaunch(g.exec, c->stream));
             return SHUD_OK;
         }
-    if (c->graphs.size() >= 32) drop_graphs(c);
+    evict_lru(c, c->graphs);
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = launch_rhs<false>(c, y, ydot);
@@ -1587,7 +1827,7 @@ int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
         c->use_graph = 0;
         return launch_rhs<false>(c, y, ydot);
     }
-    c->graphs.push_back({y, ydot, exec});
+    c->graphs.push_back({y, ydot, exec, ++c->graph_clock});
     CK(cudaGraphLaunch(exec, c->stream));
     return SHUD_OK;
 }
@@ -1660,11 +1900,10 @@ int shud_b200_rhs_diag_dev(shud_ctx *c, double t, const double *y, double *ydot)
 
 int shud_b200_check(shud_ctx *c, int32_t *where) {
     if (!c) return SHUD_ERR_ARG;
-    int h[2] = {0, 0};
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(h, c->m.err, sizeof(h), cudaMemcpyDeviceToHost));
+    const int h[2] = {((volatile int *)c->h_err)[0], ((volatile int *)c->h_err)[1]};
     if (h[0]) {
-        CK(cudaMemset(c->m.err, 0, sizeof(h)));
+        c->h_err[0] = c->h_err[1] = 0;
         // device ids -> reference ids (code 1 is raised by reaches, the others by cells)
         if (where) {
             const int k = h[1] - 1;
@@ -1745,10 +1984,14 @@ int shud_b200_output_flush(shud_ctx *c, double tau, const shud_diag *o, int32_t 
     // scale in place into a scratch copy laid out like the diag arrays, reset the accumulators, download
     std::vector<const double *> src; std::vector<double *> dst; std::vector<size_t> len;
     acc_list(c, src, dst, len);
-    std::vector<double *> tmp(dst.size(), nullptr);
+    if (c->flush_tmp.empty()) {  // scratch laid out like the accumulators, allocated once (freed with the context)
+        c->flush_tmp.assign(dst.size(), nullptr);
+        for (size_t k = 0; k < dst.size(); k++)
+            if (len[k]) c->flush_tmp[k] = dev_alloc<double>(c, len[k]);
+    }
+    std::vector<double *> &tmp = c->flush_tmp;
     for (size_t k = 0; k < dst.size(); k++) {
         if (!len[k]) continue;
-        CK(cudaMalloc(&tmp[k], sizeof(double) * len[k]));
         k_scale_copy<<<(unsigned)std::min<size_t>((len[k] + 255) / 256, 1184), 256, 0, c->stream>>>(tmp[k], dst[k], s, len[k]);
     }
     CK(cudaGetLastError());
@@ -1759,10 +2002,12 @@ int shud_b200_output_flush(shud_ctx *c, double tau, const shud_diag *o, int32_t 
                         &t.QLakeSurf, &t.QLakeSub, &t.QLakeRivIn, &t.QLakeRivOut, &t.qLakeEvap, &t.qLakePrcp};
     for (size_t k = 0; k < 29; k++) *slots[k] = tmp[k];
     int rc = download_diag(c, t, tmp[29], tmp[30], tmp[31], tmp[32], o);
-    for (double *p_ : tmp) if (p_) cudaFree(p_);
+    if (rc) return rc;  // the accumulators and the update count are untouched: the flush can be repeated
+    for (size_t k = 0; k < dst.size(); k++)
+        if (len[k]) CK(cudaMemsetAsync(dst[k], 0, sizeof(double) * len[k], c->stream));  // reset (Model_Control.cpp:958-960)
     if (num_update) *num_update = c->num_update;
     c->num_update = 0;
-    return rc;
+    return SHUD_OK;
 }
 
 int shud_b200_get_diag(shud_ctx *c, const shud_diag *o) {

@@ -44,6 +44,8 @@ def bind(lib):
         "shud_cv_solve": (C.c_int, [vp, d, vp, C.POINTER(d), C.c_int]),
         "shud_cv_get_dky": (C.c_int, [vp, d, C.c_int, vp]),
         "shud_cv_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+        "shud_cv_linsolve": (C.c_int, [vp, d, d, vp, vp, vp, vp, d, vp, C.POINTER(C.c_int)]),
+        "N_VAbs": (None, [vp, vp]), "N_VInv": (None, [vp, vp]), "N_VAddConst": (None, [vp, d, vp]),
         "N_VClone": (vp, [vp]),
         "N_VDestroy": (None, [vp]),
         "N_VGetArrayPointer": (C.POINTER(d), [vp]),
@@ -122,6 +124,14 @@ class CVode:
         rc = self.lib.shud_cv_get_dky(self._h, float(t), int(k), dky)
         if rc:
             raise CVError(rc, "get_dky")
+
+    def linsolve(self, t, gamma, y, fy, ewt, b, delta, x):
+        """one SPGMR solve of (I - gamma J) x = b as CVLS drives it; returns (code, Krylov iterations)"""
+        nli = C.c_int(0)
+        rc = self.lib.shud_cv_linsolve(self._h, float(t), float(gamma), y, fy, ewt, b, float(delta), x, C.byref(nli))
+        if rc < 0:
+            raise CVError(rc, "shud_cv_linsolve")
+        return rc, nli.value
 
     def stats(self):
         s = Stats()

@@ -7,7 +7,17 @@ over the first days of tests/golden/<basin>.run.npz (the land-surface inputs of 
 unmodified reference at the SolverStep cadence).  tools/fullrun_report.py runs the whole 30 days and writes
 profiles/r02_fullrun_*.jsonl; here a shorter window keeps the GPU suite quick.
 Stated tolerance: Nash-Sutcliffe efficiency of the outlet hydrograph >= 0.999, relative volume
-error <= 1e-3, basin water-balance residual within 1.1 x the checker arm's (+ 1e-6 of the precipitation volume)."""
+error <= 1e-3 (heihe 4e-3), basin water-balance residual within 1.1 x the checker arm's (+ 1e-6 of the precipitation
+volume), end state within WRMS_BAR in the solver's own error-weight norm.  The bars for the end state and heihe's volume
+are calibrated on the CHECKER ARM'S OWN round-off spread (y0 perturbed by 1e-13 relative, two perturbations, CPU):
+  ccw  5 d: same 750 steps, 7-8 Newton convergence failures, WRMS 0.40 / 0.44, volume 2.6e-5
+  heihe 4 d: the perturbed runs take 589 steps instead of 623 (4 convergence failures fewer) - the very trajectory the
+             GPU arm takes - WRMS 2.5 / 2.2, volume 8.8e-4 / 3e-5
+  qhh  2 d: same 482 steps, WRMS 1e-7
+i.e. after a Newton convergence failure the step sequence is chaotic at round-off level and two correct runs differ by
+a few local tolerances; bar = 4 x the larger spread (qhh: 1e-2)."""
+WRMS_BAR = {"ccw": 2.0, "heihe": 10.0, "qhh": 1e-2}
+VOL_BAR = {"ccw": 1e-3, "heihe": 4e-3, "qhh": 1e-3}
 import os
 
 import numpy as np
@@ -45,8 +55,8 @@ def test_outlet_hydrograph_and_water_balance(basin, days):
     print(basin, c, "gpu", gpu["stats"], "ref", ref["stats"], "sim-days/s gpu", gpu["sim_days_per_wall_s"], "ref",
           ref["sim_days_per_wall_s"])
     assert gpu["stats"]["nst"] >= n
-    assert c["nse"] >= 0.999 and c["vol_err"] <= 1e-3, c
+    assert c["nse"] >= 0.999 and c["vol_err"] <= VOL_BAR[basin], c
     assert abs(c["resid_gpu"]) <= 1.1 * abs(c["resid_ref"]) + 1e-6 * abs(c["P"]), c
     ewt = 1e-4 * np.abs(ref["y_end"]) + 1e-4
     wrms = np.sqrt(np.mean(((gpu["y_end"] - ref["y_end"]) / ewt) ** 2))
-    assert wrms < 1.0, wrms
+    assert wrms < WRMS_BAR[basin], wrms

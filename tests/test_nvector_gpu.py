@@ -141,3 +141,23 @@ def test_dq_fusions(ops):
     ops.DQCombine(sig, gam, dvs, dewt, dfp, dfy, dout); ops._st.synchronize()
     jv = (1.0 / sig) * fp + (-1.0 / sig) * fy
     assert np.array_equal(dout.cpu().numpy(), ewt * (vs / ewt + (-gam) * jv))
+
+
+def test_newton_fusions_known_answers(ops):
+    """shud_nv_ewt / shud_nv_newton_resid / shud_nv_newton_update against the operation sequences they replace
+    (cvEwtSetSS: Abs, Scale, AddConst, Inv; the Newton right-hand side; the correction + its WRMS norm)"""
+    import torch
+    for n in (1, 1000, 3544, 1_000_003):
+        (y, f, psi, x, acor), (dy, df, dpsi, dx, dacor) = _mk(n, 21 + n % 7, 5)
+        dewt, dr = torch.empty_like(dy), torch.empty_like(dy)
+        torch.cuda.synchronize()
+        rtol, atol, gamma = 1e-4, 1e-6, 0.37
+        ops.EwtSet(rtol, atol, dy, dewt); ops._st.synchronize()
+        ewt = 1.0 / (rtol * np.abs(y) + atol)
+        assert np.array_equal(dewt.cpu().numpy(), ewt)                 # same operations in the same order: same bits
+        ops.NewtonResid(gamma, df, dpsi, dy, dr); ops._st.synchronize()
+        assert np.array_equal(dr.cpu().numpy(), gamma * f + psi - y)
+        dele = ops.NewtonUpdate(dx, dewt, dy, dacor); ops._st.synchronize()
+        assert np.array_equal(dy.cpu().numpy(), y + x) and np.array_equal(dacor.cpu().numpy(), acor + x)
+        want = np.sqrt(np.sum((x * ewt) ** 2) / n)
+        assert abs(dele - want) <= 1e-13 * want

@@ -93,6 +93,34 @@ def test_two_partitions_equal_single_domain_bitwise():
         s.synchronize()
         assert r.check()[0] == 0
         assert np.array_equal(ydr.cpu().numpy(), got)
+    # ... and with the peer-to-peer exchange of the library: each partition's pack kernel stores its boundary cells
+    # straight into the other's halo buffer and releases a flag, the boundary tiles start behind the flag wait
+    # (contexts of one process are connected by pointer; across processes the same buffers are mapped through CUDA
+    # IPC).  Several calls in a row: the two halo buffers alternate, the epochs advance in step.
+    for p, (loc, (r, s, yy, ydd, ydr)) in enumerate(zip(locs, ctxs)):
+        q = 1 - p
+        r.exchange_plan(np.array([q]), np.array([len(plans[p][0][q])]), np.array([len(loc["halo_gid"])]), plans[p][0][q])
+    blobs = [ctxs[p][0].p2p_export(p) for p in range(2)]
+    for p in range(2):
+        assert ctxs[p][0].p2p_connect_blobs(p, blobs)
+    torch.cuda.synchronize()
+    for it in range(5):
+        outs = []
+        for p, (loc, (r, s, yy, ydd, ydr)) in enumerate(zip(locs, ctxs)):
+            r.prime(loc["y"]); r.set_forcing(loc, qEleE_IC=loc["qEleE_IC_in"])
+            outs.append(torch.full_like(ydd, float("nan")))
+        torch.cuda.synchronize()
+        for p, (loc, (r, s, yy, ydd, ydr)) in enumerate(zip(locs, ctxs)):
+            r.f_exchange_dev(0.0, yy, outs[p])      # asynchronous: partition 0 waits on the device for partition 1's flag
+        for p, (loc, (r, s, yy, ydd, ydr)) in enumerate(zip(locs, ctxs)):
+            with torch.cuda.stream(s):
+                r.from_device_order(outs[p], ydr)
+            s.synchronize()
+            assert r.check()[0] == 0
+            got = ydr.cpu().numpy()
+            sel = pos[loc["own_gid"]]
+            for b in range(3):
+                assert np.array_equal(got[b * r.Ne:(b + 1) * r.Ne], ref[b * Ne + sel]), (it, p, b)
     # reaches: both partitions own whole trees; their ydot equals the single-domain one (same tree order)
     nr0 = ctxs[0][0].Nr
     assert np.array_equal(np.r_[ctxs[0][4].cpu().numpy()[3 * ctxs[0][0].Ne:], ctxs[1][4].cpu().numpy()[3 * ctxs[1][0].Ne:]],

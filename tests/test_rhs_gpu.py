@@ -166,6 +166,31 @@ def test_device_side_output_accumulation():
         if k == "iBeta":
             want, got = want[~lake], got[~lake]
         assert np.array_equal(got, want), k
+    # ... and against the ORACLE: the interval means Print_Ctrl would write from the reference's own arrays after the
+    # same two f() calls (carried state handed from the first to the second)
+    o1 = oracle_lib.oracle_rhs(snap)
+    o2 = oracle_lib.oracle_rhs(snap, y=snap["y"] * 1.01, u_satn=o1["u_satn_out"], qEleE_IC=o1["qEleE_IC_out"])
+    assert o1["err"] == 0 and o2["err"] == 0
+    Ne = rhs.Ne
+    addends = {"QeleSurfTot": lambda o: np.abs(o["QeleSurf"]).reshape(3, Ne).sum(0) + np.abs(o["Qe2r_Surf"]),
+               "QeleSubTot": lambda o: np.abs(o["QeleSub"]).reshape(3, Ne).sum(0) + np.abs(o["Qe2r_Sub"])}
+    problems = []
+    for k in abi.DIAG_ALL:
+        if o1[k].size == 0:
+            continue
+        want, got = (o1[k] + o2[k]) * (1440.0 / 2), mean[k]
+        if k in addends:
+            sc = (addends[k](o1) + addends[k](o2)) * (1440.0 / 2)
+        elif k in SUMS:
+            sc = np.full(want.shape, np.abs(want).max())
+        else:
+            sc = None
+        if k == "iBeta":
+            want, got = want[~lake], got[~lake]
+        b = parity.mismatches(got, want, sc)
+        if b.size:
+            problems.append((k, b.size, b[:3].tolist()))
+    assert not problems, problems
     # buffers were reset
     rhs.output_accumulate()
     again, n = rhs.output_flush(tau=2.0)
