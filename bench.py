@@ -296,7 +296,7 @@ def gpu_arm(a):
         par.update(n_bad=int(pt[0]), n=int(pt[1]), max_rel=float(pm[0]), ranks=world)
     assert par["n_bad"] == 0, par
 
-    eager_step, step_mode, g, native = step, "eager", None, False
+    eager_step, step_mode, g, native, p2p = step, "eager", None, False, False
     if hx is not None and os.environ.get("SHUD_BENCH_GRAPH", "1") != "0":
         # N>1: the step is 7 short launches + one NCCL call from Python; capture it (collective included) into one
         # CUDA graph so that the host does one launch per f(), as the single-GPU path does inside the library
@@ -330,29 +330,32 @@ def gpu_arm(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t[0])
         t_eager, t_graph = probe(eager_step), probe(graph_step)
-        # third candidate, the product path: the C library drives the exchange itself (own NCCL communicator,
-        # grouped ncclSend/ncclRecv per neighbour, one C call per f(): shud_b200_rhs_exchange_dev)
-        t_native = float("inf")
-        if os.environ.get("SHUD_BENCH_NATIVE", "1") != "0":
-            rhs.comm_init(dist, dev)
-            rhs.exchange_plan(*hx.native_plan())
-            def native_step():
-                rhs.f_exchange_dev(0.0, y, ydot)
-            t_native = probe(native_step)
-            # the two exchange implementations must give the same bits (the state is stationary after warm-up)
-            native_step(); torch.cuda.synchronize(); yd_native = ydot.clone()
-            rhs.set_halo_state(hx.halo_state); eager_step(); torch.cuda.synchronize()
-            assert torch.equal(yd_native, ydot), "library-driven exchange differs from the torch.distributed one"
-            rhs.exchange_plan(*hx.native_plan())
-        probes = f"probe: library-NCCL {t_native * 1e3:.0f} us, torch graph {t_graph * 1e3:.0f} us, torch eager {t_eager * 1e3:.0f} us"
-        if t_native <= min(t_graph, t_eager):
-            step, step_mode, native = native_step, "one C call per f(), NCCL sends/receives issued by the library (" + probes + ")", True
-        else:
-            rhs.set_halo_state(hx.halo_state)  # back to the buffer the torch collective fills
-            if t_graph <= t_eager:
-                step, step_mode = graph_step, "cuda-graph incl. the torch NCCL collective (" + probes + ")"
-            else:
-                step, step_mode = eager_step, "eager torch collective (" + probes + ")"
+        eager_step(); torch.cuda.synchronize(); yd_torch = ydot.clone()   # the state is stationary after warm-up
+        # The product path - and the one that is timed: the C library drives the exchange itself, one C call per f()
+        # (shud_b200_rhs_exchange_dev), replayed as one CUDA graph.  Two transports: grouped ncclSend / ncclRecv per
+        # neighbour over the library's own communicator, and - when the neighbours' buffers can be mapped (CUDA IPC over
+        # NVLink) - peer stores + flags with no collective call at all.  Both must give the bits of the torch exchange.
+        rhs.comm_init(dist, dev)
+        rhs.exchange_plan(*hx.native_plan())
+        def native_step():
+            rhs.f_exchange_dev(0.0, y, ydot)
+        t_nccl = probe(native_step)
+        native_step(); torch.cuda.synchronize()
+        assert torch.equal(ydot, yd_torch), "library-driven NCCL exchange differs from the torch.distributed one"
+        t_p2p, p2p = float("inf"), False
+        if os.environ.get("SHUD_P2P", "1") != "0":
+            p2p = rhs.p2p_connect(dist, dev)
+            if p2p:
+                t_p2p = probe(native_step)
+                native_step(); torch.cuda.synchronize()
+                assert torch.equal(ydot, yd_torch), "peer-to-peer exchange differs from the torch.distributed one"
+        del yd_torch
+        native = True
+        step = native_step
+        step_mode = (f"one C call per f() (shud_b200_rhs_exchange_dev) replayed as a CUDA graph; halo transport: "
+                     f"{'peer stores + flags over NVLink (CUDA IPC)' if p2p else 'NCCL send/recv issued by the library'}; "
+                     f"probes: library p2p {t_p2p * 1e3:.0f} us, library NCCL {t_nccl * 1e3:.0f} us, torch graph "
+                     f"{t_graph * 1e3:.0f} us, torch eager {t_eager * 1e3:.0f} us")
 
     def barrier():
         if world > 1:
@@ -479,41 +482,78 @@ def gpu_arm(a):
                             "algorithmic (96 read, 112 written); replaces_upload_ms = shud_b200_set_forcing of the 7 per-cell "
                             "arrays the reference's host loop would hand over each ET step"}
 
-    # ---------------- RHS + SPGMR together (configs[3]): BDF/Newton steps with the device N_Vector ----------------
+    # ---------------- RHS + SPGMR together (configs[3]): BDF / Newton / SPGMR steps of the library's integrator ------
+    # The CVODE-shaped integrator (include/shud_cvode.h) runs in C on SHUD B200 N_Vectors: the time loop, the Newton
+    # iteration, SPGMR and every vector operation are library code; Python only starts each step.  One GPU: the
+    # device-fused Newton-Krylov pieces (shud_b200_cv_fused_create).  N > 1: the generic operations table on distributed
+    # vectors - every reduction is a local kernel + one ncclAllReduce inside the library (all dot products of a
+    # Gram-Schmidt sweep in one call) - and f() = halo exchange + RHS (shud_b200_f_exchange).
     nk = None
-    if world == 1:
-        from shud_up_b200.integrator import BDFKrylov
-        from shud_up_b200.nvector import DeviceSPGMR, NVectorOps
-        ops = NVectorOps(local_rank, rhs.stream_ptr, owner=rhs)
-        ls = DeviceSPGMR(ops, rhs, maxl=5)
-
-        def newv():
-            with torch.cuda.stream(st):
-                return torch.zeros(rhs.NY, dtype=torch.float64, device=dev)
-        integ = BDFKrylov(ops, newv, lambda t_, a_, b_: rhs.f_dev(t_, a_, b_), rhs.NY, rtol=1e-4, atol=1e-4,
-                          max_step=10.0, init_step=1e-3, linear_solver=ls)
-        integ.init(0.0, y)
+    if world == 1 or native:
+        import ctypes as C
+        from shud_up_b200 import cvode as _cv
+        from shud_up_b200.api import lib as _lib
+        L = _cv.bind(_lib())
+        L.N_VNew_ShudB200.restype = C.c_void_p
+        L.N_VNew_ShudB200.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.N_VCopyToDevice_ShudB200.argtypes = [C.c_void_p]
+        L.N_VSetDistributed_ShudB200.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        ws = C.c_void_p()
+        assert L.shud_nv_ws_create(local_rank, C.c_void_p(rhs.stream_ptr), C.byref(ws)) == 0
+        yv = C.c_void_p(L.N_VNew_ShudB200(rhs.NY, ws, rhs._h, None))
+        np.ctypeslib.as_array(L.N_VGetArrayPointer(yv), shape=(rhs.NY,))[:] = mesh["y"]
+        assert L.N_VCopyToDevice_ShudB200(yv) == 0
+        n_glob = rhs.NY
+        if world > 1:
+            ng = torch.tensor([float(rhs.NY)], dtype=torch.float64, device=dev)
+            dist.all_reduce(ng)
+            n_glob = int(ng[0])
+            L.N_VSetDistributed_ShudB200(yv, n_glob, C.c_void_p(_cv.fn_address(L, "shud_b200_nv_allreduce")), rhs._h)
+        rhs.prime(mesh["y"])
+        cvi = _cv.CVode(L, _cv.fn_address(L, "shud_b200_f_exchange" if world > 1 else "shud_b200_f"), rhs._h.value, 0.0, yv)
+        cvi.configure(rtol=1e-4, atol=1e-4, init_step=1e-3, max_step=10.0)
+        fz = None
+        if world == 1:
+            fz = _cv.Fused()
+            L.shud_b200_cv_fused_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_cv.Fused)]
+            L.shud_b200_cv_fused_destroy.argtypes = [C.POINTER(_cv.Fused)]
+            assert L.shud_b200_cv_fused_create(rhs._h, ws, 5, C.byref(fz)) == 0
+            cvi.set_fused(fz)
         for _ in range(3):
-            integ.step(1e9)
-        st.synchronize()
-        s0 = dict(integ.stats)
-        t_sim0 = float(integ.t)
+            cvi.solve(1e9, yv, itask=_cv.CV_ONE_STEP)
+        barrier()
+        s0 = cvi.stats()
+        t_sim0 = cvi.t
         t0 = time.perf_counter()
         for _ in range(20):
-            integ.step(1e9)
-        st.synchronize()
+            cvi.solve(1e9, yv, itask=_cv.CV_ONE_STEP)
+        barrier()
         w_nk = time.perf_counter() - t0
-        dlt = {k_: integ.stats[k_] - s0[k_] for k_ in s0}
-        sim_min = float(integ.t) - t_sim0
-        nk = {"bdf_steps": 20, "rhs_calls": dlt["nfe"], "newton_iters": dlt["nni"], "krylov_iters": dlt["nli"],
-              "wall_ms": w_nk * 1e3, "cell_updates_per_s": dlt["nfe"] * Ne / w_nk,
-              # BASELINE.json's second metric on this mesh: simulated time advanced by these 20 steps (start-up phase of
-              # the integration: the step size is still growing from init_step) per wall second
+        s1 = cvi.stats()
+        nrhs = (s1["nfe"] + s1["nfeLS"]) - (s0["nfe"] + s0["nfeLS"])
+        sim_min = cvi.t - t_sim0
+        tot_cells = Ne
+        if world > 1:
+            tc = torch.tensor([float(Ne)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tc)
+            tot_cells = int(tc[0])
+        nk = {"bdf_steps": s1["nst"] - s0["nst"], "rhs_calls": nrhs, "newton_iters": s1["nni"] - s0["nni"],
+              "krylov_iters": s1["nli"] - s0["nli"], "order": s1["qlast"], "wall_ms": w_nk * 1e3,
+              "cell_updates_per_s": nrhs * tot_cells / w_nk,
+              # BASELINE.json's second metric on this mesh: simulated time advanced by these steps (start-up phase of the
+              # integration: the step size is still growing from init_step) per wall second
               "sim_minutes": sim_min, "sim_days_per_wall_s": sim_min / 1440.0 / w_nk,
-              "ms_per_rhs_call_incl_vector_ops": w_nk * 1e3 / max(dlt["nfe"], 1),
-              "what": "variable-step BDF + modified Newton + device-resident SPGMR(5) with difference-quotient Jv "
-                      "(shud_up_b200/integrator.py, shud_spgmr_solve); every vector op on the device N_Vector"}
-        ls.close(); ops.close()
+              "ms_per_rhs_call_incl_vector_ops": w_nk * 1e3 / max(nrhs, 1),
+              "what": ("CVODE-shaped integrator of the library (BDF 1-5, Newton, SPGMR(5), difference-quotient Jv; "
+                       "csrc/shud_cvode.cpp) on SHUD B200 N_Vectors, "
+                       + ("device-fused Newton-Krylov pieces (shud_spgmr_solve)" if world == 1 else
+                          f"{world} partitions: distributed vectors, reductions = local kernel + ncclAllReduce in the "
+                          "library, f() = halo exchange + RHS"))}
+        cvi.close()
+        if fz is not None:
+            L.shud_b200_cv_fused_destroy(C.byref(fz))
+        L.N_VDestroy(yv)
+        L.shud_nv_ws_destroy(ws)
         with torch.cuda.stream(st):
             rhs.to_device_order(y_ref, y)
         st.synchronize()
@@ -551,7 +591,7 @@ def gpu_arm(a):
                                     f"tiles; step launched as: {step_mode}; per rank [ms/step, interior tiles, boundary "
                                     f"tiles]: {per_rank}") if world > 1 else None,
                "parity": par,
-               "gpu_launches": (nst + (3 if world > 1 else 0)) * steps,
+               "gpu_launches": (nst + ((4 if p2p else 3) if world > 1 else 0)) * steps,
                "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,
