@@ -178,6 +178,18 @@ def extended_for_oracle(loc):
     ext["y"] = np.concatenate([y[:Ne], hs[:, 0], y[Ne:2 * Ne], 0.1 * np.maximum(aq - hs[:, 1], 0.02), y[2 * Ne:3 * Ne], hs[:, 1],
                                y[3 * Ne:]])
     ext["Ne"] = np.array([Ne + nh], dtype=np.int32)
+    if "riv_toLake" in ext and np.any(np.asarray(ext["riv_toLake"]) >= Nl):
+        # reaches flowing into a lake held by another partition (partition.extract_cut marks them with index Nl): the
+        # oracle gets one dummy lake to pour them into (its ydot is ignored)
+        ptr = np.asarray(ext["lake_bathy_ptr"]).astype(np.int32)
+        ext["lake_zmin"] = np.concatenate([np.asarray(ext["lake_zmin"], dtype=np.float64), [0.0]])
+        ext["lake_NumEleLake"] = np.concatenate([np.asarray(ext["lake_NumEleLake"]).astype(np.int32), [1]]).astype(np.int32)
+        ext["lake_bathy_yi"] = np.concatenate([np.asarray(ext["lake_bathy_yi"], dtype=np.float64), [0.0, 1.0, 2.0]])
+        ext["lake_bathy_ai"] = np.concatenate([np.asarray(ext["lake_bathy_ai"], dtype=np.float64), [1.0, 1.0, 1.0]])
+        ext["lake_bathy_ptr"] = np.concatenate([ptr, [ptr[-1] + 3]]).astype(np.int32)
+        ext["y"] = np.concatenate([ext["y"], [1.0]])
+        ext["Nl"] = np.array([Nl + 1], dtype=np.int32)
+        ext["lakeon"] = np.array([1], dtype=np.int32)
     return ext, Ne, nh
 
 
@@ -221,6 +233,14 @@ def reference_arm(a):
     per, n = cpu_oracle_time(mesh, ncpu, budget_s=1e9, max_calls=steps, warm_calls=warm)
     per1, _n1 = cpu_oracle_time(mesh, 1, budget_s=3.0, max_calls=3)  # the reference's serial order, one core
     v = Ne / per
+    # where the reference tree and its compiled builds exist (the build container), time the reference's own serial
+    # and as-shipped OpenMP f() on the three shipped basins beside the port (builds a / b)
+    ref_builds = None
+    try:
+        from tools import time_reference
+        ref_builds = time_reference.run(200)
+    except Exception:
+        ref_builds = None
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
                       "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -228,6 +248,7 @@ def reference_arm(a):
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncpu, "kind": "port",
                                        "sample": f"{n} f() calls on the full 1M-cell mesh, oracle/shud_oracle.c with OpenMP",
                                        "serial_value": Ne / per1},
+                      "reference_builds": ref_builds,
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return
 

@@ -243,7 +243,9 @@ __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src) {
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <bool DIAG, int MINB>
+// HALO: the context is a partition (halo cells, flag acquire of the peer-to-peer exchange); a single domain compiles
+// neither (the cell kernel is sensitive to its instruction footprint: 106.4 vs 102.6 us with the halo code present)
+template <bool DIAG, int MINB, bool HALO>
 __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, const double *__restrict__ Y,
                                                           double *__restrict__ DY, int tile0) {
     __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE], t_area[TILE];
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     const unsigned fl = __ldg(m.flags + ic);  // issued behind the copies, not ahead of them
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (fl & F_HEADBC) t_gw[lane_cell] = m.ele_yBC[ic];
-    if (m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles && lane_cell < m.h_nflags) {
+    if (HALO && m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles && lane_cell < m.h_nflags) {
         // a tile that sees halo cells: one lane per neighbour partition acquires that neighbour's flag of the exchange
         // in flight before anybody in the tile reads a halo value (the barrier below orders the others behind it)
         const unsigned long long e = *m.h_epoch + 1ull;
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                     nsf = t_sf[r]; ygw_n = t_gw[r]; zs_n = t_zs[r]; zb_n = t_zb[r]; kh_n = t_kh[r];
                 } else
 #endif
-                if (k < Ne) {
+                if (!HALO || k < Ne) {
                     nsf = Y[k]; ygw_n = Y[2 * NE + k]; zs_n = __ldg(m.z_surf + k); zb_n = __ldg(m.z_bottom + k);
                     kh_n = m.effKH[k];
                     if (m.has_headbc && (m.flags[k] & F_HEADBC)) ygw_n = m.ele_yBC[k];
@@ -813,7 +815,6 @@ struct shud_ctx {
     unsigned long graph_clock = 0;    // LRU stamp of the graph cache
     size_t h_pinned_n = 0;
     bool has_ebc_arrays = false;
-    int fused_minb = 4;
     // partition: tiles whose cells see no halo cell (interior) / the others (boundary) - overlap of the exchange
     int n_int_tiles = 0, n_bnd_tiles = 0;
     cudaEvent_t ev_kh = nullptr, ev_bnd = nullptr;  // effKH of the owned cells done / boundary tiles done (rhs_boundary_dev)
@@ -1021,7 +1022,6 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         if (getenv("SHUD_PDL")) c->use_pdl = atoi(getenv("SHUD_PDL"));
         if (getenv("SHUD_GRAPH")) c->use_graph = atoi(getenv("SHUD_GRAPH"));
         if (getenv("SHUD_XGRAPH")) c->use_xgraph = atoi(getenv("SHUD_XGRAPH"));
-        if (getenv("SHUD_FUSED_MINB")) c->fused_minb = atoi(getenv("SHUD_FUSED_MINB"));
     }
 
     // ---- static per-cell arrays ----
@@ -1755,7 +1755,7 @@ static void launch_prepass(shud_ctx *c, const double *y) {
 template <bool DIAG>
 static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = false) {
     const int nb = (c->Ne + TILE - 1) / TILE;
-    if (pdl && c->use_pdl && c->fused_minb == 4) {
+    if (pdl && c->use_pdl) {
         // launched while k_effkh is still running (programmatic stream serialisation)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nb); cfg.blockDim = dim3(2 * TILE); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
@@ -1763,15 +1763,14 @@ static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4>, c->m, c->diag, y, ydot, 0) == cudaSuccess) return;
+        const cudaError_t e = c->Nhalo > 0 ? cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, true>, c->m, c->diag, y, ydot, 0)
+                                           : cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, false>, c->m, c->diag, y, ydot, 0);
+        if (e == cudaSuccess) return;
         cudaGetLastError();
         c->use_pdl = 0;
     }
-    switch (c->fused_minb) {
-        case 2: k_fused<DIAG, 2><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0); break;
-        case 3: k_fused<DIAG, 3><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0); break;
-        default: k_fused<DIAG, 4><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0); break;
-    }
+    if (c->Nhalo > 0) k_fused<DIAG, 4, true><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
+    else k_fused<DIAG, 4, false><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
 }
 template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
@@ -1854,7 +1853,7 @@ int shud_b200_rhs_interior_dev(shud_ctx *c, double t, const double *y, double *y
     }
     CK(cudaEventRecord(c->ev_kh, c->stream));
     if (c->n_int_tiles > 0)
-        k_fused<false, 4><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
+        k_fused<false, 4, true><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
     CK(cudaGetLastError());
     return SHUD_OK;
 }
@@ -1867,7 +1866,7 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
     const bool side = hs != c->stream && c->ev_kh;
     if (side) CK(cudaStreamWaitEvent(hs, c->ev_kh, 0));
     if (c->n_bnd_tiles > 0)
-        k_fused<false, 4><<<c->n_bnd_tiles, 2 * TILE, 0, hs>>>(c->m, c->diag, y, ydot, c->n_int_tiles);
+        k_fused<false, 4, true><<<c->n_bnd_tiles, 2 * TILE, 0, hs>>>(c->m, c->diag, y, ydot, c->n_int_tiles);
     if (side) {
         CK(cudaEventRecord(c->ev_bnd, hs));
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));

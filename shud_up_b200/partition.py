@@ -458,3 +458,222 @@ class HaloExchange:
         if nr and not self.in_place:
             self.halo_state.view(-1, 2)[:nr].index_copy_(0, self.recv_pos, self.rbuf[:2 * nr].view(-1, 2))
         return self.halo_state
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Cut river trees: any cell partition that keeps a lake with its cells and
+# banks, and a head-BC cell with its neighbours, in one piece.  Owner-computes, nothing but STATES crosses a cut:
+#   halo cells    edge neighbours owned elsewhere                       (Ysurf, Ygw)            as before
+#   ghost cells   bank cells of my reaches that live elsewhere          (Ysurf, Yunsat, Ygw)    ordinary local cells, no
+#                 edges; their vertical role and segment fluxes are evaluated here, their ydot is 0
+#   ghost reaches reaches on my cells' banks / up- / downstream of my reaches / flowing into my lakes, owned elsewhere
+#                 (stage)                                                ordinary local reaches, ydot 0
+# ------------------------------------------------------------------------------------------------------------------
+def assign_cells(mesh, nparts):
+    """Hilbert-range owner of every cell with only the constraints the cut-river path still has: a lake stays with its
+    cells and bank cells, a head-BC cell with its neighbours.  River trees are cut wherever the ranges fall, so the
+    balance no longer depends on the size of the largest tree."""
+    Ne, Nl = (int(np.asarray(mesh[k]).reshape(-1)[0]) for k in ("Ne", "Nl"))
+    parent = np.arange(Ne, dtype=np.int64)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    def union(a, b):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+
+    nabr = np.asarray(mesh["ele_nabr"]).reshape(3, Ne).astype(np.int64)
+    ilake = np.asarray(mesh["ele_iLake"]).astype(np.int64)
+    if Nl:
+        lrep = np.full(Nl, -1, dtype=np.int64)
+        for i in np.nonzero(ilake > 0)[0]:
+            l = ilake[i] - 1
+            if lrep[l] < 0:
+                lrep[l] = i
+            else:
+                union(i, lrep[l])
+        lnab = np.asarray(mesh["ele_lakenabr"]).reshape(3, Ne).astype(np.int64)
+        for j in range(3):
+            for i in np.nonzero(lnab[j] > 0)[0]:
+                if lrep[lnab[j, i] - 1] >= 0:
+                    union(i, lrep[lnab[j, i] - 1])
+    for i in np.nonzero(np.asarray(mesh["ele_iBC"]) > 0)[0]:
+        for j in range(3):
+            if nabr[j, i] > 0:
+                union(i, nabr[j, i] - 1)
+    root = np.array([find(i) for i in range(Ne)], dtype=np.int64) if (Nl or np.any(np.asarray(mesh["ele_iBC"]) > 0)) \
+        else np.arange(Ne, dtype=np.int64)
+    atoms, inv = np.unique(root, return_inverse=True)
+    size = np.bincount(inv, minlength=atoms.size)
+    x = np.asarray(mesh["ele_x"], dtype=np.float64); y = np.asarray(mesh["ele_y"], dtype=np.float64)
+    ax = np.bincount(inv, weights=x, minlength=atoms.size) / size
+    ay = np.bincount(inv, weights=y, minlength=atoms.size) / size
+    order = np.argsort(_hilbert_key(ax, ay), kind="stable")
+    csum = np.cumsum(size[order]) - 0.5 * size[order]
+    part_of_atom = np.empty(atoms.size, dtype=np.int32)
+    part_of_atom[order] = np.minimum((csum * nparts / float(Ne)).astype(np.int64), nparts - 1)
+    return part_of_atom[inv].astype(np.int32)
+
+
+def _closure_with_lakes(mesh, part, rank):
+    cl = cut_river_closure(mesh, part, rank)
+    Nl = int(np.asarray(mesh["Nl"]).reshape(-1)[0])
+    if Nl and "riv_toLake" in mesh:
+        ilake = np.asarray(mesh["ele_iLake"]).astype(np.int64)
+        lake_owner = np.full(Nl, -1, dtype=np.int64)
+        for l in range(Nl):
+            cells = np.nonzero(ilake == l + 1)[0]
+            if cells.size:
+                lake_owner[l] = part[cells[0]]
+        tl = np.asarray(mesh["riv_toLake"]).astype(np.int64)
+        into_mine = np.nonzero((tl >= 0) & (tl < Nl) & (lake_owner[np.clip(tl, 0, Nl - 1)] == rank))[0]
+        extra = into_mine[cl["riv_owner"][into_mine] != rank]
+        cl["riv_halo"] = np.unique(np.concatenate([cl["riv_halo"], extra]))
+        cl["lake_owner"] = lake_owner
+    return cl
+
+
+def extract_cut(mesh, part_of_cell, rank, closures=None):
+    """Local mesh of partition `rank` of the cell partition `part_of_cell` with river trees cut (see above), and the
+    exchange lists.  Returns (loc, plan):
+      loc   snapshot-named local mesh: cells = own + ghost cells (the last loc['n_ghost_cells']), halo_* arrays as
+            `extract` makes them, reaches = own + ghost reaches (the last loc['n_ghost_reaches']), segments between held
+            cells and held reaches with an own cell or an own reach; y in the local blocked layout (ghost entries hold
+            the owners' values at extraction time; the kernels never read them - the exchange delivers them)
+      plan  dict(peers, send_counts [npeers][3], recv_counts [npeers][3], send_items): per neighbour and kind (0 halo
+            pairs, 1 ghost-cell triples, 2 ghost-reach stages) how many doubles travel, and the flat indices into MY
+            local blocked vector (reference-local order) of what I send, grouped by (peer, kind), each group in the
+            receiver's order (by global id)."""
+    Ne, Nr, Ns, Nl = (int(np.asarray(mesh[k]).reshape(-1)[0]) for k in ("Ne", "Nr", "Ns", "Nl"))
+    part = np.asarray(part_of_cell).astype(np.int64)
+    nparts = int(part.max()) + 1
+    if closures is None:
+        closures = [_closure_with_lakes(mesh, part, p) for p in range(nparts)]
+    cl = closures[rank]
+    riv_owner = cl["riv_owner"]
+    own = cl["own"]
+    rep = cl["replica"]
+    rep = rep[np.lexsort((rep, part[rep]))]                  # ghost cells by (owner, global id)
+    halo = cl["halo"]
+    halo = halo[np.lexsort((halo, part[halo]))]              # halo cells by (owner, global id)
+    rh = cl["riv_halo"]
+    rh = rh[np.lexsort((rh, riv_owner[rh]))]                 # ghost reaches by (owner, global id)
+    cells = np.concatenate([own, rep])
+    rivs = np.concatenate([cl["riv_own"], rh])
+    nown, nloc, nrown = own.size, cells.size, cl["riv_own"].size
+    ibc, ilake = np.asarray(mesh["ele_iBC"]), np.asarray(mesh["ele_iLake"])
+    if np.any(ibc[halo] > 0) or np.any(ilake[halo] > 0) or np.any(ilake[rep] > 0):
+        raise NotImplementedError("halo / ghost cells with a head BC or inside a lake (use assign_cells)")
+    cnew = np.zeros(Ne, dtype=np.int64); cnew[cells] = np.arange(1, nloc + 1)
+    hnew = np.zeros(Ne, dtype=np.int64); hnew[halo] = nloc + np.arange(1, halo.size + 1)
+    rnew = np.zeros(Nr, dtype=np.int64); rnew[rivs] = np.arange(1, rivs.size + 1)
+    nabr = np.asarray(mesh["ele_nabr"]).reshape(3, Ne).astype(np.int64)
+    lnab = np.asarray(mesh["ele_lakenabr"]).reshape(3, Ne).astype(np.int64)
+    nb = nabr[:, own]
+    nb0 = np.maximum(nb - 1, 0)
+    is_own_nb = (nb > 0) & (part[nb0] == rank)
+    nab_loc = np.where(nb > 0, np.where(is_own_nb, cnew[nb0], hnew[nb0]), 0)
+    if np.any(lnab[:, own][(nb > 0) & ~is_own_nb] > 0):
+        raise NotImplementedError("a lake bank is cut by the partition (use assign_cells)")
+    loc = {}
+    for k, v in mesh.items():
+        v = np.asarray(v)
+        if k in CELL_SKIP:
+            continue
+        if k in EDGE_KEYS:
+            loc[k] = np.ascontiguousarray(v.reshape(3, Ne)[:, cells]).ravel()
+        elif (k.startswith("ele_") or k in CELL_DYN) and v.ndim == 1 and v.shape[0] == Ne:
+            loc[k] = v[cells]
+        elif k.startswith("riv_") and v.ndim == 1 and v.shape[0] == Nr:
+            loc[k] = v[rivs]
+    loc["ele_nabr"] = np.concatenate([nab_loc, np.zeros((3, rep.size), dtype=np.int64)], axis=1).astype(np.int32).ravel()
+    loc["ele_lakenabr"] = np.concatenate([lnab[:, own], np.zeros((3, rep.size), dtype=np.int64)], axis=1).astype(np.int32).ravel()
+    for k in HALO_KEYS:
+        loc["halo_" + k] = np.asarray(mesh["ele_" + k])[halo]
+    # lakes: whole and local, or absent
+    lake_keep = np.zeros(Nl, dtype=bool)
+    if Nl:
+        lake_keep = cl["lake_owner"] == rank if "lake_owner" in cl else np.array([np.any(ilake[own] == l + 1) for l in range(Nl)])
+        if np.any((ilake > 0) & lake_keep[np.clip(ilake - 1, 0, Nl - 1)] & (part != rank)):
+            raise NotImplementedError("a lake is cut by the partition (use assign_cells)")
+    lnew = np.zeros(Nl, dtype=np.int64); lnew[lake_keep] = np.arange(1, int(lake_keep.sum()) + 1)
+    nl_loc = int(lake_keep.sum())
+    if Nl:
+        il = loc["ele_iLake"].astype(np.int64)
+        loc["ele_iLake"] = np.where(il > 0, lnew[np.clip(il - 1, 0, Nl - 1)], 0).astype(np.int32)
+        ln = loc["ele_lakenabr"].astype(np.int64)
+        loc["ele_lakenabr"] = np.where(ln > 0, lnew[np.clip(ln - 1, 0, Nl - 1)], 0).astype(np.int32)
+        ptr = np.asarray(mesh["lake_bathy_ptr"]).astype(np.int64)
+        keep = np.nonzero(lake_keep)[0]
+        loc["lake_zmin"] = np.asarray(mesh["lake_zmin"])[keep]
+        loc["lake_NumEleLake"] = np.asarray(mesh["lake_NumEleLake"])[keep]
+        yi, ai, p2 = [], [], [0]
+        for l in keep:
+            yi.append(np.asarray(mesh["lake_bathy_yi"])[ptr[l]:ptr[l + 1]]); ai.append(np.asarray(mesh["lake_bathy_ai"])[ptr[l]:ptr[l + 1]])
+            p2.append(p2[-1] + int(ptr[l + 1] - ptr[l]))
+        loc["lake_bathy_yi"] = np.concatenate(yi) if yi else np.zeros(0)
+        loc["lake_bathy_ai"] = np.concatenate(ai) if ai else np.zeros(0)
+        loc["lake_bathy_ptr"] = np.asarray(p2, dtype=np.int32)
+        if "riv_toLake" in mesh:
+            tl = np.asarray(mesh["riv_toLake"]).astype(np.int64)[rivs]
+            ok = (tl >= 0) & (tl < Nl)
+            # a lake held elsewhere keeps "flows into a lake" (the routing formula) under the index one past the local lakes
+            loc["riv_toLake"] = np.where(ok, np.where(lake_keep[np.clip(tl, 0, Nl - 1)], lnew[np.clip(tl, 0, Nl - 1)] - 1, nl_loc), tl).astype(np.int32)
+    else:
+        loc["lake_zmin"] = np.zeros(0); loc["lake_NumEleLake"] = np.zeros(0, dtype=np.int32)
+        loc["lake_bathy_ptr"] = np.zeros(1, dtype=np.int32); loc["lake_bathy_yi"] = np.zeros(0); loc["lake_bathy_ai"] = np.zeros(0)
+    down = np.asarray(mesh["riv_down"]).astype(np.int64)[rivs]
+    dn_new = np.where(down > 0, rnew[np.maximum(down - 1, 0)], down)
+    if np.any((down[:nrown] > 0) & (dn_new[:nrown] == 0)):
+        raise AssertionError("closure: the downstream reach of an own reach is not held")
+    loc["riv_down"] = np.where((down > 0) & (dn_new == 0), -3, dn_new).astype(np.int32)   # ghost reach, downstream not held
+    seg_e = np.asarray(mesh["seg_iEle"]).astype(np.int64) - 1
+    seg_r = np.asarray(mesh["seg_iRiv"]).astype(np.int64) - 1
+    is_own_c = part[seg_e] == rank
+    is_own_r = riv_owner[seg_r] == rank
+    sg = np.nonzero(is_own_c | is_own_r)[0] if Ns else np.zeros(0, dtype=np.int64)
+    if sg.size and (np.any(cnew[seg_e[sg]] == 0) or np.any(rnew[seg_r[sg]] == 0)):
+        raise AssertionError("closure: a needed segment touches a cell or reach that is not held")
+    loc["seg_iEle"] = cnew[seg_e[sg]].astype(np.int32)
+    loc["seg_iRiv"] = rnew[seg_r[sg]].astype(np.int32)
+    loc["seg_length"] = np.asarray(mesh["seg_length"])[sg]
+    loc["seg_Cwr"] = np.asarray(mesh["seg_Cwr"])[sg]
+    for k, v in (("Ne", nloc), ("Nr", rivs.size), ("Ns", sg.size), ("Nl", nl_loc),
+                 ("close_boundary", int(np.asarray(mesh["close_boundary"]).reshape(-1)[0])),
+                 ("lakeon", int(np.asarray(mesh["lakeon"]).reshape(-1)[0]) if (nl_loc or ("riv_toLake" in loc and np.any(loc["riv_toLake"] >= 0))) else 0),
+                 ("n_ghost_cells", rep.size), ("n_ghost_reaches", rh.size)):
+        loc[k] = np.array([v], dtype=np.int32)
+    lakes_kept = np.nonzero(lake_keep)[0]
+    if "y" in mesh:
+        y = np.asarray(mesh["y"])
+        loc["y"] = np.concatenate([y[cells], y[Ne + cells], y[2 * Ne + cells], y[3 * Ne + rivs], y[3 * Ne + Nr + lakes_kept]])
+        loc["halo_state_expected"] = np.stack([y[halo], y[2 * Ne + halo]], 1).ravel()
+    loc["_own_ref"], loc["_riv_ref"], loc["_lake_ref"] = own, cl["riv_own"], lakes_kept
+    loc["own_gid"], loc["halo_gid"] = own, halo
+    # ---- exchange lists ----
+    peers, send_counts, recv_counts, items = [], [], [], []
+    for q in range(nparts):
+        if q == rank:
+            continue
+        cq = closures[q]
+        # what q needs from me, in q's order (by global id within my ownership)
+        hq = np.sort(cq["halo"][part[cq["halo"]] == rank])
+        gq = np.sort(cq["replica"][part[cq["replica"]] == rank])
+        rq = np.sort(cq["riv_halo"][riv_owner[cq["riv_halo"]] == rank])
+        # what I receive from q
+        rc = [2 * int(np.sum(part[halo] == q)), 3 * int(np.sum(part[rep] == q)), int(np.sum(riv_owner[rh] == q))]
+        sc = [2 * hq.size, 3 * gq.size, rq.size]
+        if sum(rc) == 0 and sum(sc) == 0:
+            continue
+        hi = cnew[hq] - 1; gi = cnew[gq] - 1; ri = rnew[rq] - 1
+        it = [np.stack([hi, 2 * nloc + hi], 1).ravel(), np.stack([gi, nloc + gi, 2 * nloc + gi], 1).ravel(), 3 * nloc + ri]
+        peers.append(q); send_counts.append(sc); recv_counts.append(rc); items.append(np.concatenate(it))
+    plan = dict(peers=np.asarray(peers, dtype=np.int32), send_counts=np.asarray(send_counts, dtype=np.int32).reshape(-1, 3),
+                recv_counts=np.asarray(recv_counts, dtype=np.int32).reshape(-1, 3),
+                send_items=(np.concatenate(items) if items else np.zeros(0)).astype(np.int32))
+    return loc, plan

@@ -1,0 +1,85 @@
+"""Cut river trees, host side (shud_up_b200.partition.assign_cells / extract_cut): Hilbert-range cell partitions that cut
+the river network anywhere (lakes and head-BC neighbourhoods stay whole) give every rank a local mesh - own cells, ghost
+cells (bank cells of its reaches that live elsewhere), ghost reaches - on which the ORDINARY right-hand side reproduces
+the single-domain ydot of every own cell, own reach and own lake bit for bit (CPU oracle), and exchange lists that carry
+exactly the states the ghosts and halo cells need."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from shud_up_b200 import partition
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(bench)
+
+CASES = [("ccw", "rand1", 4), ("heihe", "rand3", 3), ("heihe", "rand3", 8), ("qhh", "rand4", 4), ("qhh", "lakes6", 3)]
+
+
+@pytest.mark.parametrize("basin,case,nparts", CASES)
+def test_cut_partitions_reproduce_the_single_domain(basin, case, nparts):
+    mesh = oracle_lib.load_case(basin, case)
+    Ne, Nr = int(mesh["Ne"][0]), int(mesh["Nr"][0])
+    ref = oracle_lib.oracle_rhs(mesh, want_diag=False)["ydot"]
+    part = partition.assign_cells(mesh, nparts)
+    closures = [partition._closure_with_lakes(mesh, part, p) for p in range(nparts)]
+    n_ghost, riv_owned, locs, plans = 0, np.zeros(Nr, dtype=int), [], []
+    for p in range(nparts):
+        loc, plan = partition.extract_cut(mesh, part, p, closures)
+        locs.append(loc); plans.append(plan)
+        ext, ne, nh = bench.extended_for_oracle(loc)
+        out = oracle_lib.oracle_rhs(ext, want_diag=False)
+        assert out["err"] == 0
+        o, NE = out["ydot"], ne + nh
+        nown, nro, nl = loc["_own_ref"].size, loc["_riv_ref"].size, loc["_lake_ref"].size
+        for b in range(3):
+            assert np.array_equal(o[b * NE:b * NE + nown], ref[b * Ne + loc["_own_ref"]]), (p, b)
+        assert np.array_equal(o[3 * NE:3 * NE + nro], ref[3 * Ne + loc["_riv_ref"]]), p
+        nr_loc = int(loc["Nr"][0])
+        assert np.array_equal(o[3 * NE + nr_loc:3 * NE + nr_loc + nl], ref[3 * Ne + Nr + loc["_lake_ref"]]), p
+        riv_owned[loc["_riv_ref"]] += 1
+        n_ghost += int(loc["n_ghost_cells"][0]) + int(loc["n_ghost_reaches"][0])
+    assert np.all(riv_owned == 1) and n_ghost > 0          # every reach has one owner; the partition cuts the network
+    # the exchange lists: what q sends to p is exactly what p's halo / ghost slots hold, in p's order
+    y = np.asarray(mesh["y"])
+    for p in range(nparts):
+        lp, pp = locs[p], plans[p]
+        nloc, nh = int(lp["Ne"][0]), lp["halo_gid"].size
+        ngc, ngr = int(lp["n_ghost_cells"][0]), int(lp["n_ghost_reaches"][0])
+        got = [[], [], []]
+        for j, q in enumerate(pp["peers"]):
+            lq, pq = locs[q], plans[q]
+            jq = list(pq["peers"]).index(p)
+            off = int(pq["send_counts"][:jq].sum())
+            sc = pq["send_counts"][jq]
+            assert list(sc) == list(pp["recv_counts"][j])
+            for kind in range(3):
+                it = pq["send_items"][off:off + sc[kind]]
+                got[kind].append(np.asarray(lq["y"])[it])
+                off += sc[kind]
+        halo_pairs = np.concatenate(got[0]) if got[0] else np.zeros(0)
+        assert np.array_equal(halo_pairs, lp["halo_state_expected"])
+        yl = np.asarray(lp["y"])
+        gc = np.concatenate(got[1]) if got[1] else np.zeros(0)
+        want_gc = np.stack([yl[nloc - ngc:nloc], yl[2 * nloc - ngc:2 * nloc], yl[3 * nloc - ngc:3 * nloc]], 1).ravel()
+        assert np.array_equal(gc, want_gc)
+        gr = np.concatenate(got[2]) if got[2] else np.zeros(0)
+        nr_loc = int(lp["Nr"][0])
+        assert np.array_equal(gr, yl[3 * nloc + nr_loc - ngr:3 * nloc + nr_loc])
+
+
+def test_balance_no_longer_depends_on_the_largest_river_tree():
+    for basin, case in (("heihe", "rand3"), ("qhh", "rand4")):
+        mesh = oracle_lib.load_case(basin, case)
+        for nparts in (8,):
+            old = np.bincount(partition.assign(mesh, nparts), minlength=nparts)
+            new = np.bincount(partition.assign_cells(mesh, nparts), minlength=nparts)
+            imb = lambda s: s.max() / s.mean() - 1.0
+            print(basin, nparts, "whole trees", imb(old), "cut rivers", imb(new))
+            assert imb(new) <= imb(old) + 1e-12
+            if basin == "heihe":
+                assert imb(new) <= 0.05
