@@ -98,6 +98,13 @@ typedef struct shud_halo {
     int32_t Nhalo;
     const double *z_surf, *z_bottom;                               /* [Nhalo] geometry of the far cell */
     const double *AquiferDepth, *macD, *macKsatH, *geo_vAreaF, *KsatH; /* [Nhalo] its effKH parameters */
+    /* Cut river trees: the LAST n_ghost_cells cells and the LAST n_ghost_reaches reaches of the shud_mesh are GHOSTS -
+     * bank cells of this partition's reaches that another partition owns (no edges; their vertical role and segment
+     * fluxes are evaluated here from the owner's (Ysurf, Yunsat, Ygw)), and reaches on this partition's banks / up- or
+     * downstream of its reaches / flowing into its lakes that another partition owns (stage from the owner).  Their
+     * states arrive with the halo exchange (shud_b200_exchange_plan_items), their entries of y are never read, their
+     * entries of ydot are 0.  Both 0: whole river trees per partition, as before. */
+    int32_t n_ghost_cells, n_ghost_reaches;
 } shud_halo;
 
 typedef struct shud_ctx shud_ctx;
@@ -179,6 +186,14 @@ int shud_b200_comm_init(shud_ctx *ctx, const char *nccl_lib, const void *id128, 
 int shud_b200_exchange_plan(shud_ctx *ctx, int npeers, const int32_t *peer_rank, const int32_t *send_count,
                             const int32_t *recv_count, const int32_t *send_cells);
 int shud_b200_rhs_exchange_dev(shud_ctx *ctx, double t, const double *y_dev, double *ydot_dev);
+/* The general exchange plan (peer-to-peer path; required when the partition has ghosts): per neighbour three groups of
+ * doubles travel - kind 0 halo-cell pairs (Ysurf, Ygw), kind 1 ghost-cell triples (Ysurf, Yunsat, Ygw), kind 2
+ * ghost-reach stages.  send_count / recv_count: [npeers][3] doubles per (neighbour, kind); the receives of a kind land
+ * in neighbour order, which must be the order the halo cells / ghost cells / ghost reaches are numbered in (by owner,
+ * then global id).  send_items: flat 0-based indices into THIS partition's blocked vector in reference-local order
+ * ([Ysurf | Yunsat | Ygw | Yriv | Ylake] over its local cells and reaches), grouped by (neighbour, kind). */
+int shud_b200_exchange_plan_items(shud_ctx *ctx, int npeers, const int32_t *peer_rank, const int32_t *send_count,
+                                  const int32_t *recv_count, const int32_t *send_items);
 /* Peer-to-peer halo exchange (one process per GPU of one node, NVLink / NVSwitch): instead of NCCL sends / receives the
  * pack kernel stores every boundary cell's state straight into the halo buffer of the partition that needs it (the
  * neighbours' buffers are mapped through CUDA IPC) and releases one flag per neighbour; the receiver's boundary tiles

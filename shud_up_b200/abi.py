@@ -45,7 +45,7 @@ HALO_D = ["z_surf", "z_bottom", "AquiferDepth", "macD", "macKsatH", "geo_vAreaF"
 
 
 class ShudHalo(C.Structure):
-    _fields_ = [("Nhalo", C.c_int32)] + [(n, _PD) for n in HALO_D]
+    _fields_ = [("Nhalo", C.c_int32)] + [(n, _PD) for n in HALO_D] + [("n_ghost_cells", C.c_int32), ("n_ghost_reaches", C.c_int32)]
 
 
 def make_halo(halo):
@@ -59,6 +59,9 @@ def make_halo(halo):
         assert a.shape[0] == n
         keep.append(a)
         setattr(h, name, p)
+    # cut river trees (partition.extract_cut): the last cells / reaches of the local mesh are ghosts
+    h.n_ghost_cells = int(np.asarray(halo["n_ghost_cells"]).reshape(-1)[0]) if "n_ghost_cells" in halo else 0
+    h.n_ghost_reaches = int(np.asarray(halo["n_ghost_reaches"]).reshape(-1)[0]) if "n_ghost_reaches" in halo else 0
     return h, keep
 
 

@@ -56,6 +56,7 @@ def lib():
         "shud_b200_to_device_order": (C.c_int, [vp, vp, vp]),
         "shud_b200_from_device_order": (C.c_int, [vp, vp, vp]),
         "shud_b200_summary_dev": (C.c_int, [vp, vp, _PD]),
+        "shud_b200_exchange_plan_items": (C.c_int, [vp, C.c_int, _PI, _PI, _PI, _PI]),
         "shud_b200_p2p_export": (C.c_int, [vp, C.c_int, vp]),
         "shud_b200_p2p_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "shud_b200_allreduce": (C.c_int, [vp, _PD, C.c_int, C.c_int]),
@@ -124,7 +125,8 @@ class ShudRHS:
                                               self._mesh_struct.Nl)
         h = C.c_void_p()
         self.Nhalo = 0
-        if "halo_z_surf" in mesh and len(mesh["halo_z_surf"]) > 0:
+        ghosts = any(int(np.asarray(mesh[k]).reshape(-1)[0]) > 0 for k in ("n_ghost_cells", "n_ghost_reaches") if k in mesh)
+        if "halo_z_surf" in mesh and (len(mesh["halo_z_surf"]) > 0 or ghosts):
             hs, keep = abi.make_halo(mesh)
             self._keep += keep
             self.Nhalo = hs.Nhalo
@@ -281,6 +283,14 @@ class ShudRHS:
         a = [np.ascontiguousarray(v, dtype=np.int32) for v in (peers, send_counts, recv_counts, send_cells)]
         ptr = [v.ctypes.data_as(_PI) for v in a]
         _chk(lib().shud_b200_exchange_plan(self._h, int(a[0].size), *ptr), "exchange_plan")
+
+    def exchange_plan_items(self, plan):
+        """plan: partition.extract_cut's dict (peers, send_counts [n][3], recv_counts [n][3], send_items): the general
+        exchange - halo pairs, ghost-cell triples, ghost-reach stages - of the peer-to-peer path"""
+        a = [np.ascontiguousarray(plan[k], dtype=np.int32).ravel() for k in ("peers", "send_counts", "recv_counts", "send_items")]
+        self._last_plan = None
+        _chk(lib().shud_b200_exchange_plan_items(self._h, int(a[0].size), *[v.ctypes.data_as(_PI) for v in a]),
+             "exchange_plan_items")
 
     P2P_BLOB = 512  # SHUD_P2P_BLOB_BYTES
 

@@ -30,7 +30,7 @@ namespace {
 
 using namespace shud;
 
-constexpr unsigned F_LAKE = 1u, F_HEADBC = 2u, F_FLUXBC = 4u, F_SS_SURF = 8u, F_SS_GW = 16u;
+constexpr unsigned F_LAKE = 1u, F_HEADBC = 2u, F_FLUXBC = 4u, F_SS_SURF = 8u, F_SS_GW = 16u, F_GHOST = 32u;
 constexpr int NSEG_SHIFT = 8;
 
 struct DevMesh {
@@ -77,8 +77,14 @@ struct DevMesh {
     // epochs); the epoch of the exchange in flight is a device word (NULL: h_state as registered)
     const double *h_state_alt;
     unsigned long long *h_epoch;           // completed exchanges; the one in flight is *h_epoch + 1
+    unsigned int *h_done;                  // blocks of the river / lake kernel through (the last one advances the epoch)
     const unsigned long long *h_flags;     // [h_nflags] epoch of the last halo each neighbour has delivered here
     int h_nflags, n_int_tiles;             // tiles >= n_int_tiles see halo cells: they wait for the flags
+    // cut river trees: ghost cells / ghost reaches (owned elsewhere, evaluated here from exchanged states; ydot 0)
+    const int *g_cslot;                    // [Ne] ghost-cell slot of a cell flagged F_GHOST
+    const int *r_gslot;                    // [Nr] ghost-reach slot, -1 = own reach (NULL: no ghost reach)
+    const int *cs_g;                       // [Ns] per cell-side segment slot: ghost-reach slot of its reach or -1
+    int g_coff, g_roff;                    // where the ghost-cell triples / ghost-reach stages start in a halo buffer
     int *err;  // [0] code, [1] where (1-based reference id)
 };
 
@@ -125,17 +131,19 @@ struct CryoStep {  // per-step, uniform over the cells (the day clock of the acc
 // buffers suffice and no credit has to travel back.  The epoch word advances at the end of the river / lake kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int P2P_MAXPEER = 16;
+constexpr int P2P_MAXSEG = 3 * P2P_MAXPEER;
 struct P2PTable {
     double *buf[2][P2P_MAXPEER];            // neighbour p's halo buffers (even / odd epochs), peer-mapped
     unsigned long long *flag[P2P_MAXPEER];  // my flag slot in neighbour p's flag array
-    int send_off[P2P_MAXPEER + 1];          // my send list is grouped by neighbour: [send_off[p], send_off[p + 1])
-    int dst_off[P2P_MAXPEER];               // where my cells start in neighbour p's halo numbering
-    int npeers;
+    int npeers, nseg;
+    // the doubles I send are grouped by (neighbour, kind): segment s = items [seg_start[s], seg_start[s + 1]) go to
+    // neighbour seg_peer[s], starting at double seg_dst[s] of its halo buffer
+    int seg_start[P2P_MAXSEG + 1], seg_peer[P2P_MAXSEG], seg_dst[P2P_MAXSEG];
 };
 struct PackArgs {
     P2PTable T;
-    const int *idx;        // device ids of the cells sent, grouped by neighbour
-    int n, nblk;           // cells sent, blocks of the pre-pass that carry them
+    const int *idx;        // flat device-order indices into the state vector of the doubles sent
+    int n, nblk;           // doubles sent, blocks of the pre-pass that carry them
     unsigned int *count;   // blocks through
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -192,13 +200,13 @@ __global__ void __launch_bounds__(256) k_effkh_pack(DevMesh m, const double *__r
     asm volatile("griddepcontrol.launch_dependents;");
     if ((int)blockIdx.x < P.nblk) {
         const unsigned long long e = *m.h_epoch + 1ull;  // the epoch word advances at the end of this call (k_river_lake)
-        const int k = blockIdx.x * blockDim.x + threadIdx.x;
-        if (k < P.n) {
-            int p = 0;
-            while (p + 1 < P.T.npeers && k >= P.T.send_off[p + 1]) p++;
-            const int i = P.idx[k];
-            double *dst = ((e & 1ull) ? P.T.buf[1][p] : P.T.buf[0][p]) + 2 * (size_t)(P.T.dst_off[p] + (k - P.T.send_off[p]));
-            *reinterpret_cast<double2 *>(dst) = make_double2(Y[i], Y[2 * (size_t)m.Ne + i]);  // one 16-byte store over NVLink
+        // (a small partition can have more doubles to send than pre-pass threads: the packing blocks stride over them)
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += P.nblk * blockDim.x) {
+            int sg = 0;
+            while (sg + 1 < P.T.nseg && k >= P.T.seg_start[sg + 1]) sg++;
+            const int p = P.T.seg_peer[sg];
+            double *dst = ((e & 1ull) ? P.T.buf[1][p] : P.T.buf[0][p]) + (size_t)(P.T.seg_dst[sg] + (k - P.T.seg_start[sg]));
+            *dst = Y[P.idx[k]];  // a store over NVLink into the neighbour's halo buffer
         }
         __threadfence_system();
         __syncthreads();
@@ -293,6 +301,26 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         // budget would spill it to local memory, i.e. to L2).  Order: soil first - the lateral role needs only its
         // results (P1, G1, ponding) - then the ET partition while the lateral role does the weir and the lateral
         // sums, then the three balance equations of the cell.
+        if (HALO && m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles) {
+            // a tile with ghost cells: this role reads exchanged states too - acquire the neighbours' flags (the lateral
+            // role does the same for itself), then the ghost cells take (Ysurf, Yunsat, Ygw) from the halo buffer
+            if (lane_cell < m.h_nflags) {
+                const unsigned long long e = *m.h_epoch + 1ull;
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+                while (ld_acquire_sys(m.h_flags + lane_cell) < e) {
+                    __nanosleep(200);
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 5000000000ull) { raise_err(m.err, SHUD_ERR_P2P_TIMEOUT, lane_cell + 1); break; }
+                }
+            }
+            bar_sync(4, TILE);
+            if (VFL() & F_GHOST) {
+                const double *g = halo_state(m) + m.g_coff + 3 * (size_t)m.g_cslot[ic];
+                VIN(0) = __ldcg(g); VIN(1) = __ldcg(g + 1); VIN(2) = __ldcg(g + 2);
+            }
+        }
         if (VFL() & F_HEADBC) VIN(2) = m.ele_yBC[ic];
         // ---- step 1: updateElement (2 pow) ----
         SoilState st;
@@ -370,7 +398,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             dgw = SHUD_DIVS(dgw, sy);
             double dus = VIN(15) - v.Eu - v.Tu;
             dus = SHUD_DIVS(dus, sy);
-            if (fl & F_LAKE) { dsf = 0.; dus = 0.; dgw = 0.; }
+            if (fl & (HALO ? (F_LAKE | F_GHOST) : F_LAKE)) { dsf = 0.; dus = 0.; dgw = 0.; }  // lake cell; ghost: its owner integrates it
             DY[i] = dsf;
             DY[NE + i] = dus;
             DY[2 * NE + i] = dgw;
@@ -426,6 +454,20 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         }
     }
     bar_sync(1, TILE);           // the tile's own values are in shared memory (lateral warps)
+    if (HALO && m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles) {
+        if (fl & F_GHOST) {
+            // ghost cell: state from the exchange, effKH evaluated here (the pre-pass saw its stale vector entry)
+            const double *g = halo_state(m) + m.g_coff + 3 * (size_t)m.g_cslot[ic];
+            const double gsf = __ldcg(g);
+            double ggw = __ldcg(g + 2);
+            if (fl & F_HEADBC) ggw = m.ele_yBC[ic];
+            int e2 = 0;
+            t_sf[lane_cell] = gsf; t_gw[lane_cell] = ggw;
+            t_kh[lane_cell] = (fl & F_LAKE) ? m.ksatH[ic]
+                                            : eff_kh(ggw, m.aqd[ic], m.macD[ic], m.macKsatH[ic], m.vAreaF[ic], m.ksatH[ic], &e2);
+        }
+        bar_sync(1, TILE);       // ... the segment pass below reads other lanes' slots
+    }
     const double ysf = t_sf[lane_cell], ygw = t_gw[lane_cell], zs = t_zs[lane_cell], zb = t_zb[lane_cell];
     const double kh = t_kh[lane_cell], depression = t_dep[lane_cell], fuSub = t_fus[lane_cell];
     int err = 0;
@@ -497,7 +539,9 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     if (has_seg) {
         const int q = q0 + lane_cell;
         s_lc = __ldg(m.cs_cell + q) - i0; s_sgm = __ldg(m.cs_seg + q);
-        s_yr = m.cs_yr[q]; s_zr = __ldg(m.cs_zr + q); s_zbk = __ldg(m.cs_zbk + q); s_cwr = __ldg(m.cs_cwr + q);
+        s_yr = m.cs_yr[q];
+        if (HALO && m.cs_g) { const int gs = __ldg(m.cs_g + q); if (gs >= 0) s_yr = __ldcg(halo_state(m) + m.g_roff + gs); }
+        s_zr = __ldg(m.cs_zr + q); s_zbk = __ldg(m.cs_zbk + q); s_cwr = __ldg(m.cs_cwr + q);
         s_len = __ldg(m.cs_len + q);
         const double qg = flux_r2e_gw(s_yr, s_zr, t_gw[s_lc], t_zb[s_lc], t_kh[s_lc], __ldg(m.cs_ksatH + q), s_len,
                                       __ldg(m.cs_bed + q)) * t_fus[s_lc];
@@ -513,7 +557,9 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     for (int tq = TILE + lane_cell; tq < nsq; tq += TILE) {  // tiles with more than 128 segments (rare)
         const int q = q0 + tq;
         const int lc = __ldg(m.cs_cell + q) - i0, sgm = __ldg(m.cs_seg + q);
-        const double yr = m.cs_yr[q], zr = __ldg(m.cs_zr + q), len = __ldg(m.cs_len + q);
+        double yr = m.cs_yr[q];
+        if (HALO && m.cs_g) { const int gs = __ldg(m.cs_g + q); if (gs >= 0) yr = __ldcg(halo_state(m) + m.g_roff + gs); }
+        const double zr = __ldg(m.cs_zr + q), len = __ldg(m.cs_len + q);
         const double qs = weir_jtoi(t_zs[lc], x_isf2[lc], zr, yr, __ldg(m.cs_zbk + q), __ldg(m.cs_cwr + q), len, t_dep[lc]);
         const double qg = flux_r2e_gw(yr, zr, t_gw[lc], t_zb[lc], t_kh[lc], __ldg(m.cs_ksatH + q), len,
                                       __ldg(m.cs_bed + q)) * t_fus[lc];
@@ -562,14 +608,22 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
     }
 }
 
+// stage of reach r as the solver sees it: the vector entry of an own reach, the exchanged stage of a ghost reach
+__device__ __forceinline__ double reach_y(const DevMesh &m, const double *__restrict__ Yr, int r) {
+    if (m.r_gslot) {
+        const int gs = m.r_gslot[r];
+        if (gs >= 0) return __ldcg(halo_state(m) + m.g_roff + gs);
+    }
+    return Yr[r];
+}
 // Manning flux of reach r towards its downstream end, everything gathered from global memory
 __device__ __forceinline__ double reach_down_flux(const DevMesh &m, const double *__restrict__ Yr, int r, int *err) {
-    const double yraw = Yr[r];
+    const double yraw = reach_y(m, Yr, r);
     const double ystg = (m.r_bc[r] > 0) ? m.r_yBC[r] : yraw;
     const int down = m.r_down[r];
     double y_dn = 0., depth_dn = 0., slope_dn = 0.;
     if (down >= 0) {
-        y_dn = (m.r_bc[down] > 0) ? m.r_yBC[down] : Yr[down];
+        y_dn = (m.r_bc[down] > 0) ? m.r_yBC[down] : reach_y(m, Yr, down);
         depth_dn = m.r_depth[down];
         slope_dn = m.r_slope[down];
     }
@@ -601,18 +655,33 @@ __device__ __forceinline__ double block_sum(double v, double *sm) {
 //     blocks [nb_riv, nb_riv+Nl) - one block per lake (MD_f.cpp:16-17,44-47,180-191).
 // ---------------------------------------------------------------------------------------------
 template <bool DIAG>
-__global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const double *__restrict__ Y,
-                                                    double *__restrict__ DY, int nb_riv) {
+__device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag &d, const double *__restrict__ Y,
+                                                double *__restrict__ DY, int nb_riv, double *sm) {
     const size_t NE = (size_t)m.Ne;
     const size_t LD = (size_t)m.ld;
     const double *Yr = Y + 3 * NE;
-    if (m.h_flags && blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
-        asm volatile("griddepcontrol.wait;" ::: "memory");  // the cell kernel (every halo read of this call) is complete
-        *m.h_epoch = *m.h_epoch + 1ull;
+    if (m.h_flags && m.r_gslot) {
+        // ghost reaches: this kernel reads exchanged stages too; one lane per neighbour acquires its flag (long set)
+        if ((int)threadIdx.x < m.h_nflags) {
+            const unsigned long long e = *m.h_epoch + 1ull;
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys(m.h_flags + threadIdx.x) < e) {
+                __nanosleep(200);
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 5000000000ull) { raise_err(m.err, SHUD_ERR_P2P_TIMEOUT, (int)threadIdx.x + 1); break; }
+            }
+        }
+        __syncthreads();
     }
     if ((int)blockIdx.x < nb_riv) {
         const int r = blockIdx.x * blockDim.x + threadIdx.x;
-        if (r >= m.Nr) return;
+        if (r >= m.Nr || (m.r_gslot && m.r_gslot[r] >= 0)) {
+            // past the end, or a ghost reach: its owner integrates it, its entry of ydot is 0 here
+            if (r < m.Nr) DY[3 * NE + r] = 0.;
+            return;
+        }
         const int s0 = m.r_seg_ptr[r], s1 = m.r_seg_ptr[r + 1], u0 = m.r_up_ptr[r], u1 = m.r_up_ptr[r + 1];
         const int bc = m.r_bc[r];
         const double yraw = Yr[r], w0 = m.r_w0[r], bank = m.r_bank[r], len = m.r_len[r];
@@ -645,7 +714,6 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
         return;
     }
     // ---- lake l ----
-    __shared__ double sm[8];
     const int l = blockIdx.x - nb_riv;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const double yl = Y[3 * NE + m.Nr + l];
@@ -677,6 +745,25 @@ __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const 
         if (DIAG) {
             d.y2LakeArea[l] = area; d.QLakeSurf[l] = qs; d.QLakeSub[l] = qg; d.QLakeRivIn[l] = qin;
             d.QLakeRivOut[l] = qout; d.qLakeEvap[l] = evap; d.qLakePrcp[l] = prcp;
+        }
+    }
+}
+template <bool DIAG>
+__global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const double *__restrict__ Y,
+                                                    double *__restrict__ DY, int nb_riv) {
+    __shared__ double sm[8];
+    river_lake_body<DIAG>(m, d, Y, DY, nb_riv, sm);
+    if (m.h_flags) {
+        // peer-to-peer exchange: the epoch word advances when the LAST block of this grid is through - every block reads
+        // it (parity of the halo buffer) - and the cell kernel, whose halo tiles read it too, has completed
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            __threadfence();
+            if (atomicAdd(m.h_done, 1u) == gridDim.x - 1) {
+                *m.h_done = 0u;
+                *m.h_epoch = *m.h_epoch + 1ull;
+            }
         }
     }
 }
@@ -832,6 +919,11 @@ struct shud_ctx {
     int *x_sidx = nullptr;            // device-order ids of the cells sent, concatenated by peer
     double *x_sbuf = nullptr, *x_hstate = nullptr;  // packed (Ysurf, Ygw) pairs out / halo state in
     int x_nsend = 0, x_cap_send = 0;
+    int n_ghost_cells = 0, n_ghost_reaches = 0;
+    // the exchange as doubles grouped by (neighbour, kind) - kinds: 0 halo pairs, 1 ghost-cell triples, 2 ghost-reach stages
+    std::vector<int> x_scount3, x_rcount3;   // [npeers][3]
+    int *x_items = nullptr;                  // flat device-order indices into the state vector of what I send
+    int x_nitems = 0;
     // peer-to-peer exchange (shud_b200_p2p_export / _connect)
     void *p2p_block = nullptr;            // [flags: P2P_MAXPEER u64 | epoch | count | pad to 256 B][buffer 0][buffer 1]
     size_t p2p_stride = 0;                // bytes of one halo buffer (multiple of 256)
@@ -932,6 +1024,8 @@ int shud_b200_create(const shud_mesh *M, int device, shud_ctx **out) {
 int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int device, shud_ctx **out) {
     if (!M || !out || M->Ne <= 0) return SHUD_ERR_ARG;
     const int Nhalo = (H && H->Nhalo > 0) ? H->Nhalo : 0;
+    const int ngc = H ? std::max(0, (int)H->n_ghost_cells) : 0, ngr = H ? std::max(0, (int)H->n_ghost_reaches) : 0;
+    if (ngc > M->Ne || ngr > M->Nr) return SHUD_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) return SHUD_ERR_NO_DEVICE;
     CK(cudaSetDevice(device));
@@ -966,10 +1060,15 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
     {
         const int ntile = (Ne + TILE - 1) / TILE, nfull = Ne / TILE;
         c->n_int_tiles = ntile; c->n_bnd_tiles = 0;
-        if (Nhalo > 0) {
+        if (Nhalo > 0 || ngc > 0 || ngr > 0) {
+            // tiles that read exchanged data: they see a halo cell, hold a ghost cell, or have a segment on a ghost reach
+            std::vector<char> on_ghost_reach(Ne, 0);
+            for (int sg = 0; sg < Ns; sg++)
+                if (M->seg_iRiv[sg] - 1 >= Nr - ngr && M->seg_iEle[sg] >= 1 && M->seg_iEle[sg] <= Ne) on_ghost_reach[M->seg_iEle[sg] - 1] = 1;
             std::vector<char> isb(ntile, 0);
             for (int i = 0; i < Ne; i++) {
                 const int o = c->cperm[i];
+                if (o >= Ne - ngc || on_ghost_reach[o]) isb[i / TILE] = 1;
                 for (int j = 0; j < 3; j++)
                     if (M->nabr[(size_t)j * Ne + o] - 1 >= Ne) isb[i / TILE] = 1;
             }
@@ -1089,6 +1188,7 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         else if (M->iBC[o] < 0) f |= F_FLUXBC;
         if (M->iSS[o] > 0) f |= F_SS_SURF;
         else if (M->iSS[o] < 0) f |= F_SS_GW;
+        if (o >= Ne - ngc) f |= F_GHOST;
         flags[i] = f;
         for (int j = 0; j < 3; j++) {
             const int nb = M->nabr[(size_t)j * Ne + o] - 1;
@@ -1168,6 +1268,23 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         m.cs_zbank = dev_upload(c, cs_zbank); m.cs_ksatH = dev_upload(c, cs_ksatH); m.cs_bed = dev_upload(c, cs_bed);
         m.cs_zr = dev_upload(c, cs_zr); m.cs_zbk = dev_upload(c, cs_zbk);
         m.cs_yr = dev_alloc<double>(c, Ns);
+        m.cs_g = nullptr; m.g_cslot = nullptr; m.r_gslot = nullptr;
+        m.g_coff = 2 * Nhalo; m.g_roff = 2 * Nhalo + 3 * ngc;
+        if (ngr > 0) {
+            std::vector<int> cs_g(std::max(Ns, 1), -1), rg(std::max(Nr, 1), -1);
+            for (int q = 0; q < Ns; q++) {
+                const int ro = M->seg_iRiv[c->sperm[cell_seg_idx[q]]] - 1;
+                if (ro >= Nr - ngr) cs_g[q] = ro - (Nr - ngr);
+            }
+            for (int o = Nr - ngr; o < Nr; o++) rg[c->rinv[o]] = o - (Nr - ngr);
+            m.cs_g = dev_upload(c, cs_g); m.r_gslot = dev_upload(c, rg);
+        }
+        if (ngc > 0) {
+            std::vector<int> gs(LDh, -1);
+            for (int o = Ne - ngc; o < Ne; o++) gs[c->cinv[o]] = o - (Ne - ngc);
+            m.g_cslot = dev_upload(c, gs);
+        }
+        c->n_ghost_cells = ngc; c->n_ghost_reaches = ngr;
     }
     m.bank_cell = dev_upload(c, bank_cell); m.bank_j = dev_upload(c, bank_j); m.bank_lake = dev_upload(c, bank_lake);
     m.bank_kh = dev_upload(c, bank_kh);
@@ -1183,9 +1300,11 @@ int shud_b200_create_partition(const shud_mesh *M, const shud_halo *H, int devic
         for (int o = 0; o < Nr; o++) {  // ascending reference id => upstream lists come out ascending
             const int r = c->rinv[o];
             const int dn = M->riv_down[o];
-            const int tl = (lakeon && M->riv_toLake) ? M->riv_toLake[o] : -9999;
+            // a partition may hold reaches that flow into a lake held elsewhere (index >= Nl): they keep the to-lake
+            // routing formula but feed no local lake
+            const int tl = (M->lakeon != 0 && M->riv_toLake) ? M->riv_toLake[o] : -9999;
             bc[r] = M->riv_BC[o];
-            toLake[r] = (tl >= 0 && tl < Nl) ? tl : -1;
+            toLake[r] = tl >= 0 ? std::min(tl, Nl) : -1;
             if (dn > 0 && dn <= Nr) {
                 down[r] = c->rinv[dn - 1];
                 // PassValue: iDownStrm >= 0 && toLake <= 0 (MD_f.cpp:237)
@@ -1432,7 +1551,7 @@ int shud_b200_download_ref(shud_ctx *c, const double *y_dev, double *y_host_ref)
 int shud_b200_set_halo_state_dev(shud_ctx *c, const double *state) {
     if (!c || (c->Nhalo > 0 && !state)) return SHUD_ERR_ARG;
     c->m.h_state = state;
-    c->m.h_state_alt = nullptr; c->m.h_epoch = nullptr; c->m.h_flags = nullptr; c->m.h_nflags = 0;
+    c->m.h_state_alt = nullptr; c->m.h_epoch = nullptr; c->m.h_flags = nullptr; c->m.h_done = nullptr; c->m.h_nflags = 0;
     c->use_p2p = 0;  // a registered buffer replaces the p2p buffers
     drop_graphs(c);  // kernel parameters changed
     return SHUD_OK;
@@ -1525,6 +1644,7 @@ int shud_b200_exchange_plan(shud_ctx *c, int npeers, const int32_t *peer_rank, c
         idx[k] = c->cinv[send_cells[k]];
     }
     c->x_nsend = ns;
+    c->x_scount3.clear(); c->x_rcount3.clear(); c->x_nitems = 0;  // rebuilt from the pair form by shud_b200_p2p_export
     drop_graphs(c);  // captured exchanges point at the previous plan
     if (ns > c->x_cap_send || !c->x_sidx) {  // a repeated plan reuses the buffers of the previous one
         c->x_cap_send = std::max(ns, 1);
@@ -1542,18 +1662,72 @@ struct P2PBlob {
     cudaIpcMemHandle_t handle;   // 64 bytes
     long long pid;               // contexts of one process are connected by pointer
     void *base;
-    int rank, npeers, nhalo, pad;
+    int rank, npeers;
     unsigned long long stride;
-    int peer[P2P_MAXPEER], recv_off[P2P_MAXPEER];
+    int peer[P2P_MAXPEER], recv_off[P2P_MAXPEER][3];  // where neighbour p's doubles of each kind land in my halo buffer
 };
 static_assert(sizeof(P2PBlob) <= SHUD_P2P_BLOB_BYTES, "blob too large");
 constexpr size_t P2P_HDR = 256;  // flags [P2P_MAXPEER] | epoch | count
 
+// device-order flat index of entry `k` (reference-local blocked order) of this partition's state vector
+static int flat_to_device(const shud_ctx *c, int k) {
+    const int Ne = c->Ne, Nr = c->Nr;
+    if (k < 0 || k >= c->NY) return -1;
+    if (k < 3 * Ne) return (k / Ne) * Ne + c->cinv[k % Ne];
+    if (k < 3 * Ne + Nr) return 3 * Ne + c->rinv[k - 3 * Ne];
+    return k;
+}
+
+int shud_b200_exchange_plan_items(shud_ctx *c, int npeers, const int32_t *peer_rank, const int32_t *send_count,
+                                  const int32_t *recv_count, const int32_t *send_items) {
+    if (!c || npeers < 0 || npeers > P2P_MAXPEER || (npeers > 0 && (!peer_rank || !send_count || !recv_count))) return SHUD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int ns = 0, nr[3] = {0, 0, 0};
+    for (int p = 0; p < npeers; p++)
+        for (int k = 0; k < 3; k++) {
+            if (send_count[3 * p + k] < 0 || recv_count[3 * p + k] < 0) return SHUD_ERR_ARG;
+            ns += send_count[3 * p + k]; nr[k] += recv_count[3 * p + k];
+        }
+    if (nr[0] != 2 * c->Nhalo || nr[1] != 3 * c->n_ghost_cells || nr[2] != c->n_ghost_reaches || (ns > 0 && !send_items))
+        return SHUD_ERR_ARG;
+    std::vector<int> idx(std::max(ns, 1), 0);
+    for (int k = 0; k < ns; k++) {
+        idx[k] = flat_to_device(c, send_items[k]);
+        if (idx[k] < 0) return SHUD_ERR_ARG;
+    }
+    drop_graphs(c);
+    c->x_peer.assign(peer_rank, peer_rank + npeers);
+    c->x_scount3.assign(send_count, send_count + 3 * npeers);
+    c->x_rcount3.assign(recv_count, recv_count + 3 * npeers);
+    c->x_nitems = ns;
+    c->x_items = dev_upload(c, idx);
+    // the pair form of the plan (NCCL path, shud_b200_exchange_plan) only exists without ghosts
+    c->x_scount.assign(npeers, 0); c->x_rcount.assign(npeers, 0);
+    for (int p = 0; p < npeers; p++) { c->x_scount[p] = send_count[3 * p] / 2; c->x_rcount[p] = recv_count[3 * p] / 2; }
+    c->use_p2p = 0;
+    return SHUD_OK;
+}
+
 int shud_b200_p2p_export(shud_ctx *c, int rank, void *blob) {
     if (!c || !blob || (int)c->x_peer.size() > P2P_MAXPEER) return SHUD_ERR_ARG;
     CK(cudaSetDevice(c->device));
+    const int npeers = (int)c->x_peer.size();
+    if (c->x_rcount3.empty() && npeers > 0) {
+        // plan given in the pair form (shud_b200_exchange_plan): halo pairs only
+        if (c->n_ghost_cells || c->n_ghost_reaches) return SHUD_ERR_ARG;
+        std::vector<int> items;
+        c->x_scount3.assign(3 * npeers, 0); c->x_rcount3.assign(3 * npeers, 0);
+        std::vector<int> sidx(std::max(c->x_nsend, 1));
+        if (c->x_nsend) CK(cudaMemcpy(sidx.data(), c->x_sidx, sizeof(int) * c->x_nsend, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < c->x_nsend; k++) { items.push_back(sidx[k]); items.push_back(2 * c->Ne + sidx[k]); }
+        for (int p = 0; p < npeers; p++) { c->x_scount3[3 * p] = 2 * c->x_scount[p]; c->x_rcount3[3 * p] = 2 * c->x_rcount[p]; }
+        c->x_nitems = (int)items.size();
+        if (items.empty()) items.push_back(0);
+        c->x_items = dev_upload(c, items);
+    }
+    const size_t ndbl = (size_t)2 * c->Nhalo + 3 * (size_t)c->n_ghost_cells + (size_t)c->n_ghost_reaches;
     if (!c->p2p_block) {
-        c->p2p_stride = ((size_t)2 * std::max(c->Nhalo, 1) * sizeof(double) + 255) / 256 * 256;
+        c->p2p_stride = (std::max<size_t>(ndbl, 1) * sizeof(double) + 255) / 256 * 256;
         CK(cudaMalloc(&c->p2p_block, P2P_HDR + 2 * c->p2p_stride));  // its own allocation: one IPC handle, nothing else exposed
         CK(cudaMemset(c->p2p_block, 0, P2P_HDR + 2 * c->p2p_stride));
     }
@@ -1561,9 +1735,13 @@ int shud_b200_p2p_export(shud_ctx *c, int rank, void *blob) {
     memset(&b, 0, sizeof(b));
     CK(cudaIpcGetMemHandle(&b.handle, c->p2p_block));
     b.pid = (long long)getpid(); b.base = c->p2p_block;
-    b.rank = rank; b.npeers = (int)c->x_peer.size(); b.nhalo = c->Nhalo; b.stride = c->p2p_stride;
-    int ro = 0;
-    for (int p = 0; p < b.npeers; p++) { b.peer[p] = c->x_peer[p]; b.recv_off[p] = ro; ro += c->x_rcount[p]; }
+    b.rank = rank; b.npeers = npeers; b.stride = c->p2p_stride;
+    // a kind's region is filled neighbour by neighbour, in the order the halo cells / ghosts are numbered
+    int ro[3] = {0, 2 * c->Nhalo, 2 * c->Nhalo + 3 * c->n_ghost_cells};
+    for (int p = 0; p < npeers; p++) {
+        b.peer[p] = c->x_peer[p];
+        for (int k = 0; k < 3; k++) { b.recv_off[p][k] = ro[k]; ro[k] += c->x_rcount3[3 * p + k]; }
+    }
     memset(blob, 0, SHUD_P2P_BLOB_BYTES);
     memcpy(blob, &b, sizeof(b));
     return SHUD_OK;
@@ -1608,17 +1786,23 @@ int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
         T.buf[0][p] = (double *)(base + P2P_HDR);
         T.buf[1][p] = (double *)(base + P2P_HDR + b.stride);
         T.flag[p] = (unsigned long long *)base + slot;
-        T.send_off[p] = so; so += c->x_scount[p];
-        T.dst_off[p] = b.recv_off[slot];
+        for (int k = 0; k < 3; k++) {
+            const int n = c->x_scount3[3 * p + k];
+            if (n == 0) continue;
+            T.seg_start[T.nseg] = so; T.seg_peer[T.nseg] = p; T.seg_dst[T.nseg] = b.recv_off[slot][k];
+            T.nseg++; so += n;
+        }
     }
-    T.send_off[T.npeers] = so;
+    T.seg_start[T.nseg] = so;
+    if (so != c->x_nitems) return SHUD_ERR_ARG;
     c->p2p = T;
-    // my own side: the two halo buffers, the epoch word
+    // my own side: the two halo buffers, the flags, the epoch word
     char *mine = (char *)c->p2p_block;
     c->m.h_state = (const double *)(mine + P2P_HDR);
     c->m.h_state_alt = (const double *)(mine + P2P_HDR + c->p2p_stride);
     c->m.h_epoch = (unsigned long long *)mine + P2P_MAXPEER;
     c->m.h_flags = (const unsigned long long *)mine;
+    c->m.h_done = (unsigned int *)((unsigned long long *)mine + P2P_MAXPEER + 1) + 1;  // beside the pack counter
     c->m.h_nflags = T.npeers;
     c->m.n_int_tiles = c->n_int_tiles;
     drop_graphs(c);
@@ -1744,8 +1928,8 @@ static void launch_prepass(shud_ctx *c, const double *y) {
     const int nb = (c->Ne + 255) / 256;
     if (c->use_p2p) {
         PackArgs P;
-        P.T = c->p2p; P.idx = c->x_sidx; P.n = c->x_nsend;
-        P.nblk = std::min(nb, std::max(1, (c->x_nsend + 255) / 256));
+        P.T = c->p2p; P.idx = c->x_items; P.n = c->x_nitems;
+        P.nblk = std::min(nb, std::max(1, (c->x_nitems + 255) / 256));
         P.count = (unsigned int *)((unsigned long long *)c->p2p_block + P2P_MAXPEER + 1);
         k_effkh_pack<<<nb, 256, 0, c->stream>>>(c->m, y, P);
     } else {

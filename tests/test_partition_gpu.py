@@ -172,3 +172,59 @@ def test_assigned_partitions_of_real_basins_on_the_gpu(basin, case, nparts):
         assert np.array_equal(got[3 * ne:3 * ne + nr], ref[3 * Ne + loc["_riv_ref"]])
         if nl:
             assert np.array_equal(got[3 * ne + nr:], ref[3 * Ne + Nr:])
+
+
+@pytest.mark.parametrize("basin,case,nparts", [("ccw", "rand1", 4), ("heihe", "rand3", 3), ("heihe", "rand3", 8),
+                                               ("qhh", "rand4", 4), ("qhh", "lakes6", 3)])
+def test_cut_river_trees_on_the_gpu(basin, case, nparts):
+    """Hilbert-range partitions that cut the river network anywhere (partition.assign_cells / extract_cut): every rank's
+    context holds own + ghost cells and own + ghost reaches, the peer-to-peer exchange delivers halo pairs, ghost-cell
+    triples and ghost-reach stages, and the owned cells, reaches and lakes get the bits of the single-domain CUDA RHS.
+    All contexts on cuda:0, connected by pointer; three calls in a row (alternating halo buffers, advancing epochs)."""
+    import torch
+    mesh = oracle_lib.load_case(basin, case)
+    Ne, Nr, Nl = int(mesh["Ne"][0]), int(mesh["Nr"][0]), int(mesh["Nl"][0])
+    mesh = dict(mesh); mesh["ele_u_satn"] = oracle_lib.oracle_prime(mesh, mesh["y"])
+    rhs, st, y, yd, yd_ref = _run(mesh)
+    with torch.cuda.stream(st):
+        rhs.f_dev(0.0, y, yd)
+        rhs.from_device_order(yd, yd_ref)
+    st.synchronize()
+    assert rhs.check()[0] == 0
+    ref = yd_ref.cpu().numpy()
+    part = partition.assign_cells(mesh, nparts)
+    closures = [partition._closure_with_lakes(mesh, part, p) for p in range(nparts)]
+    ex = [partition.extract_cut(mesh, part, p, closures) for p in range(nparts)]
+    ctxs = [_run(loc) for loc, _ in ex]
+    assert sum(int(loc["n_ghost_cells"][0]) + int(loc["n_ghost_reaches"][0]) for loc, _ in ex) > 0
+    for (loc, plan), c in zip(ex, ctxs):
+        c[0].exchange_plan_items(plan)
+    blobs = [ctxs[p][0].p2p_export(p) for p in range(nparts)]
+    for p in range(nparts):
+        assert ctxs[p][0].p2p_connect_blobs(p, blobs)
+    torch.cuda.synchronize()
+    for it in range(3):
+        outs = []
+        for (loc, plan), (r, s, yy, ydd, ydr) in zip(ex, ctxs):
+            r.prime(loc["y"]); r.set_forcing(loc, qEleE_IC=loc["qEleE_IC_in"])
+            outs.append(torch.full_like(ydd, float("nan")))
+        torch.cuda.synchronize()
+        for p, (r, s, yy, ydd, ydr) in enumerate(ctxs):
+            r.f_exchange_dev(0.0, yy, outs[p])
+        for p, ((loc, plan), (r, s, yy, ydd, ydr)) in enumerate(zip(ex, ctxs)):
+            with torch.cuda.stream(s):
+                r.from_device_order(outs[p], ydr)
+            s.synchronize()
+            assert r.check()[0] == 0
+            got = ydr.cpu().numpy()
+            nloc, nown, nro, nl = r.Ne, loc["_own_ref"].size, loc["_riv_ref"].size, loc["_lake_ref"].size
+            ngc, ngr = int(loc["n_ghost_cells"][0]), int(loc["n_ghost_reaches"][0])
+            for b in range(3):
+                assert np.array_equal(got[b * nloc:b * nloc + nown], ref[b * Ne + loc["_own_ref"]]), (it, p, b)
+                assert np.all(got[b * nloc + nown:(b + 1) * nloc] == 0.0)                       # ghost cells: ydot 0
+            assert np.array_equal(got[3 * nloc:3 * nloc + nro], ref[3 * Ne + loc["_riv_ref"]]), (it, p)
+            assert np.all(got[3 * nloc + nro:3 * nloc + r.Nr] == 0.0)                           # ghost reaches: ydot 0
+            assert np.array_equal(got[3 * nloc + r.Nr:3 * nloc + r.Nr + nl], ref[3 * Ne + Nr + loc["_lake_ref"]]), (it, p)
+    for c in ctxs:
+        c[0].close()
+    rhs.close()
