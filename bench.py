@@ -579,6 +579,49 @@ def gpu_arm(a):
             rhs.to_device_order(y_ref, y)
         st.synchronize()
 
+    # ---------------- strong-scaling anchor: the 8 x 1M cells of the N=8 weak-scaling run in ONE context -------------
+    # (N=1 only, driver-run and clock-sampled like the headline: SCALE's N=8 time against this one is the strong ratio)
+    anchor = None
+    if world == 1 and os.environ.get("SHUD_BENCH_ANCHOR", "1") != "0":
+        from shud_up_b200 import synth as _synth
+        try:
+            t_a0 = time.perf_counter()
+            m8 = _synth.make(**_synth.named("8M"))
+            r8 = ShudRHS(m8, device=local_rank)
+            r8.set_forcing(m8, qEleE_IC=m8["qEleE_IC_in"])
+            r8.prime(m8["y"])
+            s8 = r8.torch_stream()
+            with torch.cuda.stream(s8):
+                y8r = torch.from_numpy(np.ascontiguousarray(m8["y"])).to(dev)
+                y8, yd8 = torch.empty_like(y8r), torch.empty_like(y8r)
+                r8.to_device_order(y8r, y8)
+            s8.synchronize()
+            for _ in range(5):
+                r8.f_dev(0.0, y8, yd8)
+            s8.synchronize()
+            n8 = 60
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with ClockSampler(local_rank) as clk8:
+                a0.record(s8)
+                for _ in range(n8):
+                    r8.f_dev(0.0, y8, yd8)
+                a1.record(s8)
+                s8.synchronize()
+                for _ in range(1500):  # long enough for a few clock samples
+                    r8.f_dev(0.0, y8, yd8)
+                s8.synchronize()
+            assert r8.check()[0] == 0
+            ms8 = a0.elapsed_time(a1) / n8
+            ne8 = int(m8["Ne"][0])
+            anchor = {"workload": "synthetic-8M in one context: 8,000,000 cells / 400,000 reaches / 1,200,000 segments",
+                      "ms_per_step": ms8, "value": ne8 / (ms8 * 1e-3), "unit": UNIT, "steps": n8,
+                      "rhs_frac": (B_CELL * ne8 + B_RIV * r8.Nr + B_SEG * r8.Ns) / (ms8 * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                      "clocks": clk8.summary(), "setup_s": time.perf_counter() - t_a0 - ms8 * 1e-3 * (n8 + 1505)}
+            r8.close()
+            del m8, y8r, y8, yd8
+        except Exception as exc:  # the anchor must never cost the headline
+            anchor = {"unavailable": repr(exc)[:200]}
+
     # ---------------- reduce over ranks: max time ----------------
     tt = torch.tensor([ms_dev, s_e2e * 1e3], dtype=torch.float64, device=dev)
     cells = torch.tensor([float(Ne)], dtype=torch.float64, device=dev)
@@ -622,6 +665,8 @@ def gpu_arm(a):
                             "rhs_frac": b_rhs / (ms_step * 1e-3) / 1e9 / peak},
                "e2e": {"value": total_cells / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * rhs.NY * world,
                        "d2h_bytes_per_step": 8 * rhs.NY * world, "ms_per_step": ms_e2e_max}}
+        if anchor is not None:
+            out["strong_scaling_anchor"] = anchor
         if nk is not None:
             out["newton_krylov"] = nk
         if land_rec is not None:

@@ -209,6 +209,9 @@ int shud_b200_p2p_connect(shud_ctx *ctx, int rank, int world, const void *blobs)
 /* Scalar allreduce over the same communicator for the distributed N_Vector reductions:
  * `vals` are n HOST doubles reduced in place over all ranks; op 0 sum, 1 max, 2 min.  Synchronises the context stream. */
 int shud_b200_allreduce(shud_ctx *ctx, double *vals, int n, int op);
+/* The same on doubles already in DEVICE memory, enqueued on `stream` without copy or synchronisation (ctx = the shud_ctx):
+ * the allreduce hook of a distributed N_Vector workspace (shud_nv_ws_set_allreduce, include/shud_nvector.h). */
+int shud_b200_allreduce_dev(void *ctx, double *dev_vals, int n, int op, void *stream);
 /* ---- land-surface step on the device ----
  * Replaces the per-cell loops of Model_Data::updateforcing / tReadForcing (src/ModelData/MD_ET.cpp:14-281:
  * lapse-rate temperature, terrain-radiation factor, Penman-Monteith potential evaporation / transpiration) and

@@ -27,6 +27,14 @@ typedef struct shud_nvws shud_nvws; /* reduction workspace bound to one device +
 int shud_nv_ws_create(int device, void *stream, shud_nvws **out);
 void shud_nv_ws_destroy(shud_nvws *ws);
 void *shud_nv_ws_stream(const shud_nvws *ws); /* the cudaStream_t the workspace was created on */
+/* Distributed vectors (one partition per GPU): with an allreduce installed every reduction below returns the GLOBAL
+ * value - the per-rank partials stay in device memory, `fn(ctx, dev_vals, n, op, stream)` reduces them over the ranks
+ * in place on the workspace's stream (op 0 sum, 1 max, 2 min; shud_b200_allreduce_dev = ncclAllReduce over the context's
+ * communicator), and only the result crosses to the host: one synchronisation per reduction.  Every rank must issue the
+ * same reductions.  shud_nv_ws_local(ws, 1) ... shud_nv_ws_local(ws, 0) brackets calls that must stay local. */
+typedef int (*shud_nv_allreduce_dev_fn)(void *ctx, double *dev_vals, int n, int op, void *stream);
+int shud_nv_ws_set_allreduce(shud_nvws *ws, shud_nv_allreduce_dev_fn fn, void *ctx);
+void shud_nv_ws_local(shud_nvws *ws, int on);
 int shud_nv_ws_device(const shud_nvws *ws);
 
 /* ---- streaming operations (return 0 or a negative SHUD_ERR_* code) ---- */

@@ -135,6 +135,13 @@ int shud_b200_mesh_load(const char *path, shud_mesh *out, void **block) {
     }
     char *buf = nullptr;
     if (ok) {
+        // the payload must fit in what the file actually holds: a crafted header must not size the allocation
+        const size_t head = sizeof(h) + sizeof(Entry) * kNF;
+        ok = fseek(fp, 0, SEEK_END) == 0;
+        const long fsize = ok ? ftell(fp) : -1;
+        ok = ok && fsize >= 0 && (uint64_t)fsize >= align64(head) && h.payload_bytes <= (uint64_t)fsize - align64(head);
+    }
+    if (ok) {
         const size_t head = sizeof(h) + sizeof(Entry) * kNF;
         ok = fseek(fp, (long)align64(head), SEEK_SET) == 0;
         if (ok && posix_memalign((void **)&buf, 64, h.payload_bytes ? h.payload_bytes : 64) != 0) { buf = nullptr; ok = false; }
@@ -147,7 +154,9 @@ int shud_b200_mesh_load(const char *path, shud_mesh *out, void **block) {
     for (int k = 0; k < kNF; k++) {
         if (strncmp(ent[k].name, kFields[k].name, sizeof(ent[k].name)) != 0 || ent[k].is_int != (uint32_t)kFields[k].is_int ||
             ent[k].count != dim_len(out, kFields[k].dim, h.nbathy) ||
-            (ent[k].present && ent[k].offset + ent[k].count * (ent[k].is_int ? 4 : 8) > h.payload_bytes)) {
+            // offsets come from the file: no wrap-around, inside the payload, aligned for the element type
+            (ent[k].present && (ent[k].offset > h.payload_bytes || (ent[k].offset & 63) != 0 ||
+                                ent[k].count > (h.payload_bytes - ent[k].offset) / (ent[k].is_int ? 4 : 8)))) {
             free(buf);
             return SHUD_ERR_ARG;
         }

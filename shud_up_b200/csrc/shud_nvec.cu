@@ -250,6 +250,11 @@ struct shud_nvws {
     double *d_out;         // [SHUD_NV_MAXVEC]
     double *h_out;         // mapped pinned, [SHUD_NV_MAXVEC]
     double *h_out_dev;     // device alias of h_out
+    // distributed vector: the partial results of a reduction stay on the device, are reduced over the ranks in place
+    // (ncclAllReduce on the same stream) and only then copied to the host: one synchronisation per reduction
+    shud_nv_allreduce_dev_fn ar_dev = nullptr;
+    void *ar_ctx = nullptr;
+    int ar_off = 0;        // > 0: reductions are local for the moment (the *local members of the operations table)
 };
 
 #define CKN(call)                                                                                          \
@@ -275,6 +280,20 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
     if (!ws || !out || nv < 1 || nv > NV) return SHUD_ERR_ARG;
     if (n <= 0) {
         for (int k = 0; k < nv; k++) out[k] = (KIND == R_MIN) ? DBL_MAX : 0.0;
+        return SHUD_OK;
+    }
+    if (ws->ar_dev && !ws->ar_off) {
+        // every rank calls this with the same nv (SPMD): raw partials -> allreduce on the device -> host, post on the host
+        k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
+                                                                  ws->h_out_dev, 0, 1.0);
+        CKN(cudaGetLastError());
+        if (ws->ar_dev(ws->ar_ctx, ws->d_out, nv, KIND, (void *)ws->stream) != 0) return SHUD_ERR_CUDA;
+        CKN(cudaMemcpyAsync(ws->h_out, ws->d_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, ws->stream));
+        CKN(cudaStreamSynchronize(ws->stream));
+        for (int k = 0; k < nv; k++) {
+            const double v = ws->h_out[k];
+            out[k] = post == 1 ? sqrt(v / nglob) : (post == 2 ? sqrt(v) : v);
+        }
         return SHUD_OK;
     }
     k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
@@ -333,6 +352,12 @@ void shud_nv_ws_destroy(shud_nvws *ws) {
     delete ws;
 }
 
+int shud_nv_ws_set_allreduce(shud_nvws *ws, shud_nv_allreduce_dev_fn fn, void *ctx) {
+    if (!ws) return SHUD_ERR_ARG;
+    ws->ar_dev = fn; ws->ar_ctx = ctx; ws->ar_off = 0;
+    return SHUD_OK;
+}
+void shud_nv_ws_local(shud_nvws *ws, int on) { if (ws) ws->ar_off += on ? 1 : -1; }
 void *shud_nv_ws_stream(const shud_nvws *ws) { return ws ? (void *)ws->stream : nullptr; }
 int shud_nv_ws_device(const shud_nvws *ws) { return ws ? ws->device : -1; }
 

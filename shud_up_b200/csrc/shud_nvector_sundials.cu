@@ -165,51 +165,79 @@ void nv_compare(realtype c, N_Vector x, N_Vector z) {
     fail(shud_nv_compare(WS(z), LEN(z), c, D(x), D(z)), "N_VCompare"); wrote(z);
 }
 
-// local reductions
-realtype nv_dotprodlocal(N_Vector x, N_Vector y) { double r; fail(shud_nv_dotprod(WS(x), LEN(x), D(x), D(y), &r), "N_VDotProd"); return r; }
-realtype nv_maxnormlocal(N_Vector x) { double r; fail(shud_nv_maxnorm(WS(x), LEN(x), D(x), &r), "N_VMaxNorm"); return r; }
-realtype nv_minlocal(N_Vector x) { double r; fail(shud_nv_min(WS(x), LEN(x), D(x), &r), "N_VMin"); return r; }
-realtype nv_l1normlocal(N_Vector x) { double r; fail(shud_nv_l1norm(WS(x), LEN(x), D(x), &r), "N_VL1Norm"); return r; }
-realtype nv_wsqrsumlocal(N_Vector x, N_Vector w) { double r; fail(shud_nv_wsqrsum(WS(x), LEN(x), D(x), D(w), &r), "N_VWSqrSumLocal"); return r; }
-realtype nv_wsqrsummasklocal(N_Vector x, N_Vector w, N_Vector id) {
+// The flat reductions return the LOCAL value, or - when the workspace carries a device allreduce (a distributed vector
+// on the library's own communicator, N_VSetDistributed_ShudB200) - the GLOBAL one.  LocalOnly brackets the *local
+// members of the table; with a host allreduce hook (any other communicator) the global members are local + hook.
+struct LocalOnly {
+    shud_nvws *ws;
+    explicit LocalOnly(shud_nvws *w) : ws(w) { shud_nv_ws_local(ws, 1); }
+    ~LocalOnly() { shud_nv_ws_local(ws, 0); }
+};
+realtype f_dot(N_Vector x, N_Vector y) { double r; fail(shud_nv_dotprod(WS(x), LEN(x), D(x), D(y), &r), "N_VDotProd"); return r; }
+realtype f_maxnorm(N_Vector x) { double r; fail(shud_nv_maxnorm(WS(x), LEN(x), D(x), &r), "N_VMaxNorm"); return r; }
+realtype f_min(N_Vector x) { double r; fail(shud_nv_min(WS(x), LEN(x), D(x), &r), "N_VMin"); return r; }
+realtype f_l1(N_Vector x) { double r; fail(shud_nv_l1norm(WS(x), LEN(x), D(x), &r), "N_VL1Norm"); return r; }
+realtype f_wsqr(N_Vector x, N_Vector w) { double r; fail(shud_nv_wsqrsum(WS(x), LEN(x), D(x), D(w), &r), "N_VWSqrSumLocal"); return r; }
+realtype f_wsqrmask(N_Vector x, N_Vector w, N_Vector id) {
     double r; fail(shud_nv_wsqrsum_mask(WS(x), LEN(x), D(x), D(w), D(id), &r), "N_VWSqrSumMaskLocal"); return r;
 }
-booleantype nv_invtestlocal(N_Vector x, N_Vector z) {
+booleantype f_invtest(N_Vector x, N_Vector z) {
     int ok = 0; fail(shud_nv_invtest(WS(x), LEN(x), D(x), D(z), &ok), "N_VInvTest"); wrote(z); return ok ? SUNTRUE : SUNFALSE;
 }
-booleantype nv_constrmasklocal(N_Vector c, N_Vector x, N_Vector m) {
+booleantype f_constrmask(N_Vector c, N_Vector x, N_Vector m) {
     int ok = 0; fail(shud_nv_constrmask(WS(x), LEN(x), D(c), D(x), D(m), &ok), "N_VConstrMask"); wrote(m); return ok ? SUNTRUE : SUNFALSE;
 }
-realtype nv_minquotientlocal(N_Vector num, N_Vector den) {
+realtype f_minquot(N_Vector num, N_Vector den) {
     double r; fail(shud_nv_minquotient(WS(num), LEN(num), D(num), D(den), &r), "N_VMinQuotient"); return r;
 }
 
-// global reductions: local kernel + the allreduce hook (identity on one GPU)
-realtype nv_dotprod(N_Vector x, N_Vector y) { return allreduce1(x, nv_dotprodlocal(x, y), 0); }
-realtype nv_maxnorm(N_Vector x) { return allreduce1(x, nv_maxnormlocal(x), 1); }
-realtype nv_min(N_Vector x) { return allreduce1(x, nv_minlocal(x), 2); }
-realtype nv_l1norm(N_Vector x) { g_unused_calls++; return allreduce1(x, nv_l1normlocal(x), 0); }
+// local reductions
+realtype nv_dotprodlocal(N_Vector x, N_Vector y) { LocalOnly g(WS(x)); return f_dot(x, y); }
+realtype nv_maxnormlocal(N_Vector x) { LocalOnly g(WS(x)); return f_maxnorm(x); }
+realtype nv_minlocal(N_Vector x) { LocalOnly g(WS(x)); return f_min(x); }
+realtype nv_l1normlocal(N_Vector x) { LocalOnly g(WS(x)); return f_l1(x); }
+realtype nv_wsqrsumlocal(N_Vector x, N_Vector w) { LocalOnly g(WS(x)); return f_wsqr(x, w); }
+realtype nv_wsqrsummasklocal(N_Vector x, N_Vector w, N_Vector id) { LocalOnly g(WS(x)); return f_wsqrmask(x, w, id); }
+booleantype nv_invtestlocal(N_Vector x, N_Vector z) { LocalOnly g(WS(x)); return f_invtest(x, z); }
+booleantype nv_constrmasklocal(N_Vector c, N_Vector x, N_Vector m) { LocalOnly g(WS(x)); return f_constrmask(c, x, m); }
+realtype nv_minquotientlocal(N_Vector num, N_Vector den) { LocalOnly g(WS(num)); return f_minquot(num, den); }
+
+// global reductions
+realtype nv_dotprod(N_Vector x, N_Vector y) { return CT(x)->allreduce ? allreduce1(x, nv_dotprodlocal(x, y), 0) : f_dot(x, y); }
+realtype nv_maxnorm(N_Vector x) { return CT(x)->allreduce ? allreduce1(x, nv_maxnormlocal(x), 1) : f_maxnorm(x); }
+realtype nv_min(N_Vector x) { return CT(x)->allreduce ? allreduce1(x, nv_minlocal(x), 2) : f_min(x); }
+realtype nv_l1norm(N_Vector x) { g_unused_calls++; return CT(x)->allreduce ? allreduce1(x, nv_l1normlocal(x), 0) : f_l1(x); }
 realtype nv_wrmsnorm(N_Vector x, N_Vector w) {
     Content *c = CT(x);
-    if (!c->allreduce) {  // one GPU: the sqrt(sum / N) is done by the reduction kernel's last block
+    if (!c->allreduce) {  // the sqrt(sum / N_global) is done by the reduction kernel's last block (one GPU), or on the
+                          // host behind the device allreduce (distributed vector on the library's communicator)
         double r; fail(shud_nv_wrmsnorm(c->ws, c->length, c->dev, D(w), c->global_length, &r), "N_VWrmsNorm"); return r;
     }
     return sqrt(allreduce1(x, nv_wsqrsumlocal(x, w), 0) / (double)c->global_length);
 }
 realtype nv_wrmsnormmask(N_Vector x, N_Vector w, N_Vector id) {
     g_unused_calls++;
-    return sqrt(allreduce1(x, nv_wsqrsummasklocal(x, w, id), 0) / (double)CT(x)->global_length);
+    const double s = CT(x)->allreduce ? allreduce1(x, nv_wsqrsummasklocal(x, w, id), 0) : f_wsqrmask(x, w, id);
+    return sqrt(s / (double)CT(x)->global_length);
 }
-realtype nv_wl2norm(N_Vector x, N_Vector w) { g_unused_calls++; return sqrt(allreduce1(x, nv_wsqrsumlocal(x, w), 0)); }
+realtype nv_wl2norm(N_Vector x, N_Vector w) {
+    g_unused_calls++;
+    return sqrt(CT(x)->allreduce ? allreduce1(x, nv_wsqrsumlocal(x, w), 0) : f_wsqr(x, w));
+}
 booleantype nv_invtest(N_Vector x, N_Vector z) {
     g_unused_calls++;
+    if (!CT(x)->allreduce) return f_invtest(x, z);
     return allreduce1(x, nv_invtestlocal(x, z) ? 1.0 : 0.0, 2) > 0.5 ? SUNTRUE : SUNFALSE;
 }
 booleantype nv_constrmask(N_Vector c, N_Vector x, N_Vector m) {
     g_unused_calls++;
+    if (!CT(x)->allreduce) return f_constrmask(c, x, m);
     return allreduce1(x, nv_constrmasklocal(c, x, m) ? 1.0 : 0.0, 2) > 0.5 ? SUNTRUE : SUNFALSE;
 }
-realtype nv_minquotient(N_Vector num, N_Vector den) { g_unused_calls++; return allreduce1(num, nv_minquotientlocal(num, den), 2); }
+realtype nv_minquotient(N_Vector num, N_Vector den) {
+    g_unused_calls++;
+    return CT(num)->allreduce ? allreduce1(num, nv_minquotientlocal(num, den), 2) : f_minquot(num, den);
+}
 
 // ---- fused and vector-array operations (nvec <= SHUD_NV_MAXVEC per launch; longer lists in chunks) ----
 int nv_linearcombination(int nvec, realtype *c, N_Vector *X, N_Vector z) {
@@ -243,7 +271,7 @@ int nv_scaleaddmulti(int nvec, realtype *a, N_Vector x, N_Vector *Y, N_Vector *Z
     }
     return 0;
 }
-int nv_dotprodmultilocal(int nvec, N_Vector x, N_Vector *Y, realtype *out) {
+int dotprodmulti_flat(int nvec, N_Vector x, N_Vector *Y, realtype *out) {
     for (int k0 = 0; k0 < nvec; k0 += SHUD_NV_MAXVEC) {
         const int n = nvec - k0 < SHUD_NV_MAXVEC ? nvec - k0 : SHUD_NV_MAXVEC;
         const double *py[SHUD_NV_MAXVEC];
@@ -252,6 +280,10 @@ int nv_dotprodmultilocal(int nvec, N_Vector x, N_Vector *Y, realtype *out) {
     }
     return 0;
 }
+int nv_dotprodmultilocal(int nvec, N_Vector x, N_Vector *Y, realtype *out) {
+    LocalOnly g(WS(x));
+    return dotprodmulti_flat(nvec, x, Y, out);
+}
 int nv_dotprodmultiallreduce(int nvec, N_Vector x, realtype *sum) {
     Content *c = CT(x);
     if (c->allreduce) fail(c->allreduce(c->comm, sum, nvec, 0), "allreduce");
@@ -259,6 +291,7 @@ int nv_dotprodmultiallreduce(int nvec, N_Vector x, realtype *sum) {
 }
 int nv_dotprodmulti(int nvec, N_Vector x, N_Vector *Y, realtype *out) {
     // ONE allreduce for all the dot products of a Gram-Schmidt sweep
+    if (!CT(x)->allreduce) return dotprodmulti_flat(nvec, x, Y, out);  // global already behind a device allreduce
     nv_dotprodmultilocal(nvec, x, Y, out);
     return nv_dotprodmultiallreduce(nvec, x, out);
 }
@@ -377,7 +410,15 @@ N_Vector N_VNew_ShudB200(sunindextype length, shud_nvws *ws, struct shud_ctx *gp
 
 void N_VSetDistributed_ShudB200(N_Vector v, sunindextype global_length, shud_nv_allreduce_fn fn, void *comm) {
     Content *c = CT(v);
-    c->global_length = global_length; c->allreduce = fn; c->comm = comm;
+    c->global_length = global_length; c->comm = comm;
+    if (fn == shud_b200_nv_allreduce) {
+        // the library's own communicator: partial results never leave the device before they are reduced
+        // (ncclAllReduce on the vectors' stream, one host synchronisation per reduction)
+        c->allreduce = nullptr;
+        shud_nv_ws_set_allreduce(c->ws, shud_b200_allreduce_dev, comm);
+    } else {
+        c->allreduce = fn;
+    }
 }
 
 int N_VCopyToDevice_ShudB200(N_Vector v) {

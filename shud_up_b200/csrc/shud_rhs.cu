@@ -1628,6 +1628,18 @@ int shud_b200_allreduce(shud_ctx *c, double *vals, int n, int op) {
     return SHUD_OK;
 }
 
+// the same on values that are already in device memory, enqueued on `stream` (no copy, no synchronisation): the hook of
+// shud_nv_ws_set_allreduce.  `ctx` is the shud_ctx; `stream` must be ordered like the context stream.
+int shud_b200_allreduce_dev(void *ctx, double *dev_vals, int n, int op, void *stream) {
+    shud_ctx *c = (shud_ctx *)ctx;
+    if (!c || !dev_vals || n < 0 || op < 0 || op > 2) return SHUD_ERR_ARG;
+    if (n == 0) return SHUD_OK;
+    if (!c->nccl_comm || !c->nccl_allreduce) return SHUD_ERR_ARG;
+    static const int nccl_op[3] = {0 /*ncclSum*/, 2 /*ncclMax*/, 3 /*ncclMin*/};
+    return c->nccl_allreduce(dev_vals, dev_vals, (size_t)n, 8 /*ncclFloat64*/, nccl_op[op], c->nccl_comm, (cudaStream_t)stream) == 0
+               ? SHUD_OK : SHUD_ERR_CUDA;
+}
+
 int shud_b200_exchange_plan(shud_ctx *c, int npeers, const int32_t *peer_rank, const int32_t *send_count,
                             const int32_t *recv_count, const int32_t *send_cells) {
     if (!c || npeers < 0 || (npeers > 0 && (!peer_rank || !send_count || !recv_count))) return SHUD_ERR_ARG;

@@ -469,11 +469,19 @@ class HaloExchange:
 #   ghost reaches reaches on my cells' banks / up- / downstream of my reaches / flowing into my lakes, owned elsewhere
 #                 (stage)                                                ordinary local reaches, ydot 0
 # ------------------------------------------------------------------------------------------------------------------
-def assign_cells(mesh, nparts):
+def assign_cells(mesh, nparts, reach_weight=0.0):
     """Hilbert-range owner of every cell with only the constraints the cut-river path still has: a lake stays with its
     cells and bank cells, a head-BC cell with its neighbours.  River trees are cut wherever the ranges fall, so the
-    balance no longer depends on the size of the largest tree."""
+    balance no longer depends on the size of the largest tree.
+    reach_weight: work of one reach (its routing, its segments) in units of one cell's work; it is spread over the
+    reach's bank cells - which decide who owns the reach - so that ranges rich in rivers get fewer cells."""
     Ne, Nl = (int(np.asarray(mesh[k]).reshape(-1)[0]) for k in ("Ne", "Nl"))
+    wcell = np.ones(Ne, dtype=np.float64)
+    if reach_weight > 0.0 and int(np.asarray(mesh["Ns"]).reshape(-1)[0]) > 0:
+        se = np.asarray(mesh["seg_iEle"]).astype(np.int64) - 1
+        sr = np.asarray(mesh["seg_iRiv"]).astype(np.int64) - 1
+        per_reach = np.bincount(sr, minlength=int(np.asarray(mesh["Nr"]).reshape(-1)[0])).astype(np.float64)
+        np.add.at(wcell, se, reach_weight / per_reach[sr])
     parent = np.arange(Ne, dtype=np.int64)
 
     def find(a):
@@ -510,13 +518,14 @@ def assign_cells(mesh, nparts):
         else np.arange(Ne, dtype=np.int64)
     atoms, inv = np.unique(root, return_inverse=True)
     size = np.bincount(inv, minlength=atoms.size)
+    work = np.bincount(inv, weights=wcell, minlength=atoms.size)
     x = np.asarray(mesh["ele_x"], dtype=np.float64); y = np.asarray(mesh["ele_y"], dtype=np.float64)
     ax = np.bincount(inv, weights=x, minlength=atoms.size) / size
     ay = np.bincount(inv, weights=y, minlength=atoms.size) / size
     order = np.argsort(_hilbert_key(ax, ay), kind="stable")
-    csum = np.cumsum(size[order]) - 0.5 * size[order]
+    csum = np.cumsum(work[order]) - 0.5 * work[order]
     part_of_atom = np.empty(atoms.size, dtype=np.int32)
-    part_of_atom[order] = np.minimum((csum * nparts / float(Ne)).astype(np.int64), nparts - 1)
+    part_of_atom[order] = np.minimum((csum * nparts / float(work.sum())).astype(np.int64), nparts - 1)
     return part_of_atom[inv].astype(np.int32)
 
 

@@ -87,6 +87,20 @@ def test_mesh_container_round_trip(tmp_path, basin):
     open(bad, "wb").write(b"NOTSHUD!" + raw[8:])
     with pytest.raises(RuntimeError):
         api.LoadedMesh(bad)
+    # crafted headers: an array offset near 2^64 (would wrap in offset + size), a misaligned one, and a payload size
+    # beyond what the file holds must all be refused, not dereferenced
+    import struct
+    hdr = 8 + 4 + 4 + 6 * 4 + 8 + 8                      # Header: magic, version, nfields, 6 ints, nbathy, payload_bytes
+    ent0 = hdr + 24 + 4 + 4 + 8                          # first Entry's `offset` field
+    for off in (2 ** 64 - 64, 8):
+        b = bytearray(raw); b[ent0:ent0 + 8] = struct.pack("<Q", off)
+        open(bad, "wb").write(bytes(b))
+        with pytest.raises(RuntimeError):
+            api.LoadedMesh(bad)
+    b = bytearray(raw); b[hdr - 8:hdr] = struct.pack("<Q", 2 ** 40)
+    open(bad, "wb").write(bytes(b))
+    with pytest.raises(RuntimeError):
+        api.LoadedMesh(bad)
 
 
 def test_mesh_container_ingest_rate(tmp_path):

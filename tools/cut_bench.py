@@ -29,7 +29,8 @@ dev = torch.device(f"cuda:{lrank}")
 dist.init_process_group("nccl", device_id=dev)
 t0 = time.time()
 mesh = synth.make(nx, ny, ntree=max(1, ny // 10), reaches_per_tree=nx)      # every rank builds the whole mesh
-part = partition.assign_cells(mesh, world)
+rw = float(os.environ.get("CUT_REACH_WEIGHT", "0"))
+part = partition.assign_cells(mesh, world, reach_weight=rw)
 closures = [partition._closure_with_lakes(mesh, part, p) for p in range(world)]
 loc, plan = partition.extract_cut(mesh, part, rank, closures)
 t_setup = time.time() - t0
@@ -90,6 +91,6 @@ if rank == 0:
                       "imbalance": float(a[:, 1].max() / a[:, 1].mean() - 1.0),
                       "ghost_cells": a[:, 2].astype(int).tolist(), "ghost_reaches": a[:, 3].astype(int).tolist(),
                       "halo_cells": a[:, 4].astype(int).tolist(), "doubles_sent_per_f": a[:, 5].astype(int).tolist(),
-                      "parity_n_bad": int(a[:, 6].sum()), "ghost_ydot_zero": bool(a[:, 7].min() > 0), "setup_s": t_setup}))
+                      "reach_weight": rw, "parity_n_bad": int(a[:, 6].sum()), "ghost_ydot_zero": bool(a[:, 7].min() > 0), "setup_s": t_setup}))
 rhs.close()
 dist.destroy_process_group()
