@@ -488,10 +488,17 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
                     nsf = t_sf[r]; ygw_n = t_gw[r]; zs_n = t_zs[r]; zb_n = t_zb[r]; kh_n = t_kh[r];
                 } else
 #endif
-                if (!HALO || k < Ne) {
+                if (k < Ne) {
                     nsf = Y[k]; ygw_n = Y[2 * NE + k]; zs_n = __ldg(m.z_surf + k); zb_n = __ldg(m.z_bottom + k);
                     kh_n = m.effKH[k];
                     if (m.has_headbc && (m.flags[k] & F_HEADBC)) ygw_n = m.ele_yBC[k];
+                } else if (!HALO) {
+                    // Never taken: a single domain has no neighbour id >= Ne.  The branch is kept on purpose - with the
+                    // test folded away at compile time ptxas schedules the gathers of the branch above differently and
+                    // the kernel loses 3.5 % (measured on B200, same instruction count: 106.1 vs 102.6 us; the round-1
+                    // kernel had this shape).  It mirrors the halo branch below without its arithmetic.
+                    const int h = k - Ne;
+                    nsf = m.h_state[2 * h]; ygw_n = m.h_state[2 * h + 1]; zs_n = m.h_zs[h]; zb_n = m.h_zb[h]; kh_n = m.h_aqd[h];
                 } else {  // halo cell of a partition: state from the last halo exchange
                     const int h = k - Ne;
                     const double *hs = halo_state(m);
@@ -609,21 +616,23 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
 }
 
 // stage of reach r as the solver sees it: the vector entry of an own reach, the exchanged stage of a ghost reach
+template <bool HALO>
 __device__ __forceinline__ double reach_y(const DevMesh &m, const double *__restrict__ Yr, int r) {
-    if (m.r_gslot) {
+    if (HALO && m.r_gslot) {
         const int gs = m.r_gslot[r];
         if (gs >= 0) return __ldcg(halo_state(m) + m.g_roff + gs);
     }
     return Yr[r];
 }
 // Manning flux of reach r towards its downstream end, everything gathered from global memory
+template <bool HALO>
 __device__ __forceinline__ double reach_down_flux(const DevMesh &m, const double *__restrict__ Yr, int r, int *err) {
-    const double yraw = reach_y(m, Yr, r);
+    const double yraw = reach_y<HALO>(m, Yr, r);
     const double ystg = (m.r_bc[r] > 0) ? m.r_yBC[r] : yraw;
     const int down = m.r_down[r];
     double y_dn = 0., depth_dn = 0., slope_dn = 0.;
     if (down >= 0) {
-        y_dn = (m.r_bc[down] > 0) ? m.r_yBC[down] : reach_y(m, Yr, down);
+        y_dn = (m.r_bc[down] > 0) ? m.r_yBC[down] : reach_y<HALO>(m, Yr, down);
         depth_dn = m.r_depth[down];
         slope_dn = m.r_slope[down];
     }
@@ -654,13 +663,13 @@ __device__ __forceinline__ double block_sum(double v, double *sm) {
 //     (Flux_RiverDown MD_RiverFlux.cpp:5-63, PassValue MD_f.cpp:228-240, f_applyDY MD_f.cpp:157-179);
 //     blocks [nb_riv, nb_riv+Nl) - one block per lake (MD_f.cpp:16-17,44-47,180-191).
 // ---------------------------------------------------------------------------------------------
-template <bool DIAG>
+template <bool DIAG, bool HALO>
 __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag &d, const double *__restrict__ Y,
                                                 double *__restrict__ DY, int nb_riv, double *sm) {
     const size_t NE = (size_t)m.Ne;
     const size_t LD = (size_t)m.ld;
     const double *Yr = Y + 3 * NE;
-    if (m.h_flags && m.r_gslot) {
+    if (HALO && m.h_flags && m.r_gslot) {
         // ghost reaches: this kernel reads exchanged stages too; one lane per neighbour acquires its flag (long set)
         if ((int)threadIdx.x < m.h_nflags) {
             const unsigned long long e = *m.h_epoch + 1ull;
@@ -677,7 +686,7 @@ __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag 
     }
     if ((int)blockIdx.x < nb_riv) {
         const int r = blockIdx.x * blockDim.x + threadIdx.x;
-        if (r >= m.Nr || (m.r_gslot && m.r_gslot[r] >= 0)) {
+        if (r >= m.Nr || (HALO && m.r_gslot && m.r_gslot[r] >= 0)) {
             // past the end, or a ghost reach: its owner integrates it, its entry of ydot is 0 here
             if (r < m.Nr) DY[3 * NE + r] = 0.;
             return;
@@ -689,9 +698,9 @@ __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag 
         const RivGeom g = riv_geom(yraw, w0, bank);
         // Flux_RiverDown of this reach and of its upstream reaches (re-evaluated rather than exchanged: state only)
         int err = 0;
-        const double qdown = reach_down_flux(m, Yr, r, &err);
+        const double qdown = reach_down_flux<HALO>(m, Yr, r, &err);
         double up = 0.;
-        for (int k = u0; k < u1; k++) up += -reach_down_flux(m, Yr, m.r_up_idx[k], &err);
+        for (int k = u0; k < u1; k++) up += -reach_down_flux<HALO>(m, Yr, m.r_up_idx[k], &err);
         if (err) raise_err(m.err, err, r + 1);
         // everything above needs statics and the state only; the segment fluxes come from the cell kernel
         // (programmatic dependent launch: this grid starts in the cell kernel's last wave and waits here)
@@ -730,7 +739,7 @@ __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag 
         qg += edge_sub(ygw, m.z_bottom[i], yl, m.l_yi0[l], m.effKH[i], m.bank_kh[k], m.dist[j * LD + i], B);
     }
     for (int k = m.l_rin_ptr[l] + threadIdx.x; k < m.l_rin_ptr[l + 1]; k += blockDim.x)
-    { int e2 = 0; qin += reach_down_flux(m, Yr, m.l_rin_idx[k], &e2); }
+    { int e2 = 0; qin += reach_down_flux<HALO>(m, Yr, m.l_rin_idx[k], &e2); }
     qs = block_sum<128>(qs, sm);
     qg = block_sum<128>(qg, sm);
     qin = block_sum<128>(qin, sm);
@@ -748,12 +757,12 @@ __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag 
         }
     }
 }
-template <bool DIAG>
+template <bool DIAG, bool HALO>
 __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const double *__restrict__ Y,
                                                     double *__restrict__ DY, int nb_riv) {
     __shared__ double sm[8];
-    river_lake_body<DIAG>(m, d, Y, DY, nb_riv, sm);
-    if (m.h_flags) {
+    river_lake_body<DIAG, HALO>(m, d, Y, DY, nb_riv, sm);
+    if (HALO && m.h_flags) {
         // peer-to-peer exchange: the epoch word advances when the LAST block of this grid is through - every block reads
         // it (parity of the halo buffer) - and the cell kernel, whose halo tiles read it too, has completed
         __syncthreads();
@@ -1406,6 +1415,7 @@ void shud_b200_destroy(shud_ctx *c) {
     if (c->xstream) cudaStreamSynchronize(c->xstream);
     drop_graphs(c);  // the captured exchange graphs hold NCCL nodes: gone before the communicator
     if (c->nccl_comm && c->nccl_comm_destroy) c->nccl_comm_destroy(c->nccl_comm);
+    if (c->nccl_dl) dlclose(c->nccl_dl);
     for (void *q : c->p2p_opened) cudaIpcCloseMemHandle(q);
     if (c->p2p_block) cudaFree(c->p2p_block);
     if (c->xstream) cudaStreamDestroy(c->xstream);
@@ -1934,6 +1944,10 @@ static int ensure_diag(shud_ctx *c) {
 }
 
 }  // extern "C"
+// a context with halo cells or ghosts runs the kernels compiled with the exchange code (HALO = true)
+static inline bool is_partition(const shud_ctx *c) {
+    return c->Nhalo > 0 || c->n_ghost_cells > 0 || c->n_ghost_reaches > 0 || c->use_p2p;
+}
 // the pre-pass; on a partition connected peer-to-peer it carries the send side of the halo exchange, so EVERY f() of such
 // a context exchanges (all ranks make the same calls)
 static void launch_prepass(shud_ctx *c, const double *y) {
@@ -1959,13 +1973,13 @@ static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        const cudaError_t e = c->Nhalo > 0 ? cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, true>, c->m, c->diag, y, ydot, 0)
+        const cudaError_t e = is_partition(c) ? cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, true>, c->m, c->diag, y, ydot, 0)
                                            : cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, false>, c->m, c->diag, y, ydot, 0);
         if (e == cudaSuccess) return;
         cudaGetLastError();
         c->use_pdl = 0;
     }
-    if (c->Nhalo > 0) k_fused<DIAG, 4, true><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
+    if (is_partition(c)) k_fused<DIAG, 4, true><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
     else k_fused<DIAG, 4, false><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
 }
 template <bool DIAG>
@@ -1974,7 +1988,7 @@ static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     launch_fused<DIAG>(c, y, ydot, true);
     const int nb_riv = (c->Nr + 127) / 128;
     if (nb_riv + c->Nl == 0 && c->use_p2p) {  // no reach, no lake: a one-block launch that only advances the epoch word
-        k_river_lake<DIAG><<<1, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, 1);
+        k_river_lake<DIAG, true><<<1, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, 1);
     }
     if (nb_riv + c->Nl > 0) {
         bool done = false;
@@ -1985,10 +1999,11 @@ static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            done = cudaLaunchKernelEx(&cfg, k_river_lake<DIAG>, c->m, c->diag, y, ydot, nb_riv) == cudaSuccess;
+            done = (is_partition(c) ? cudaLaunchKernelEx(&cfg, k_river_lake<DIAG, true>, c->m, c->diag, y, ydot, nb_riv)
+                         : cudaLaunchKernelEx(&cfg, k_river_lake<DIAG, false>, c->m, c->diag, y, ydot, nb_riv)) == cudaSuccess;
             if (!done) { cudaGetLastError(); c->use_pdl = 0; }
         }
-        if (!done) k_river_lake<DIAG><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+        if (!done) k_river_lake<DIAG, true><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
     }
     CK(cudaGetLastError());
     return SHUD_OK;
@@ -2005,6 +2020,8 @@ static void drop_graphs(shud_ctx *c) {
 int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     (void)t;  // f() depends on t only through values uploaded by shud_b200_set_forcing
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    // a partition needs somewhere to read its halo / ghost states from: a registered buffer or the peer-to-peer buffers
+    if ((c->Nhalo > 0 || c->n_ghost_cells > 0 || c->n_ghost_reaches > 0) && !c->m.h_state) return SHUD_ERR_ARG;
     if (!c->use_graph) return launch_rhs<false>(c, y, ydot);
     // the launch sequence is fixed; only the two vector pointers vary between calls (CVODE alternates
     // between a handful of work vectors) -> one instantiated graph per pointer pair, launched as one unit
@@ -2068,7 +2085,7 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
     }
     const int nb_riv = (c->Nr + 127) / 128;
-    if (nb_riv + c->Nl > 0) k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    if (nb_riv + c->Nl > 0) k_river_lake<false, true><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
     CK(cudaGetLastError());
     return SHUD_OK;
 }
@@ -2086,9 +2103,12 @@ int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydo
     const int nb_riv = (c->Nr + 127) / 128;
     if (stage == 0) launch_prepass(c, y);
     else if (stage == 1) launch_fused<false>(c, y, ydot);
-    else if (stage == 2 && nb_riv + c->Nl > 0)
-        k_river_lake<false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
-    else return SHUD_ERR_ARG;
+    else if (stage == 2 && nb_riv + c->Nl > 0) {
+        if (is_partition(c))
+            k_river_lake<false, true><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+        else
+            k_river_lake<false, false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    } else return SHUD_ERR_ARG;
     CK(cudaGetLastError());
     return SHUD_OK;
 }
@@ -2096,6 +2116,7 @@ int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydo
 int shud_b200_rhs_diag_dev(shud_ctx *c, double t, const double *y, double *ydot) {
     (void)t;
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
+    if ((c->Nhalo > 0 || c->n_ghost_cells > 0 || c->n_ghost_reaches > 0) && !c->m.h_state) return SHUD_ERR_ARG;
     int rc = ensure_diag(c);
     if (rc) return rc;
     return launch_rhs<true>(c, y, ydot);
