@@ -651,11 +651,14 @@ def gpu_arm(a):
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": config_for(world),
-               "multi_gpu_detail": (f"halo exchange of {hx.bytes_per_exchange} B per rank and f(), overlapped with the interior "
-                                    f"tiles; step launched as: {step_mode}; per rank [ms/step, interior tiles, boundary "
+               "multi_gpu_detail": (f"halo exchange of {hx.bytes_per_exchange} B per rank and f() "
+                                    + ("inside the three launches of f() (pre-pass stores into the neighbours' buffers, halo "
+                                       "tiles acquire the flags)" if p2p else "overlapped with the interior tiles")
+                                    + f"; step launched as: {step_mode}; per rank [ms/step, interior tiles, boundary "
                                     f"tiles]: {per_rank}") if world > 1 else None,
                "parity": par,
-               "gpu_launches": (nst + ((4 if p2p else 3) if world > 1 else 0)) * steps,
+               # peer-to-peer: the same three kernels as a single domain; NCCL path: + pack, the split cell kernel, halo pre-pass
+               "gpu_launches": (nst + ((0 if p2p else 2) if world > 1 else 0)) * steps,
                "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,

@@ -290,7 +290,7 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 
 // HALO: the context is a partition (halo cells, flag acquire of the peer-to-peer exchange); a single domain compiles
 // neither (the cell kernel is sensitive to its instruction footprint: 106.4 vs 102.6 us with the halo code present)
-template <bool DIAG, int MINB, bool HALO>
+template <bool DIAG, int MINB, int HALO>
 __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, const double *__restrict__ Y,
                                                           double *__restrict__ DY, int tile0) {
     __shared__ double t_sf[TILE], t_gw[TILE], t_zs[TILE], t_zb[TILE], t_kh[TILE], t_dep[TILE], t_fus[TILE], t_area[TILE];
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         // budget would spill it to local memory, i.e. to L2).  Order: soil first - the lateral role needs only its
         // results (P1, G1, ponding) - then the ET partition while the lateral role does the weir and the lateral
         // sums, then the three balance equations of the cell.
-        if (HALO && m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles) {
+        if (HALO == 2 && m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles) {
             // a tile with ghost cells: this role reads exchanged states too - acquire the neighbours' flags (the lateral
             // role does the same for itself), then the ghost cells take (Ysurf, Yunsat, Ygw) from the halo buffer
             if (lane_cell < m.h_nflags) acquire_flag(m, lane_cell);
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
             dgw = SHUD_DIVS(dgw, sy);
             double dus = VIN(15) - v.Eu - v.Tu;
             dus = SHUD_DIVS(dus, sy);
-            if (fl & (HALO ? (F_LAKE | F_GHOST) : F_LAKE)) { dsf = 0.; dus = 0.; dgw = 0.; }  // lake cell; ghost: its owner integrates it
+            if (fl & (HALO == 2 ? (F_LAKE | F_GHOST) : F_LAKE)) { dsf = 0.; dus = 0.; dgw = 0.; }  // lake cell; ghost: its owner integrates it
             DY[i] = dsf;
             DY[NE + i] = dus;
             DY[2 * NE + i] = dgw;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         acquire_flag(m, lane_cell);
     }
     bar_sync(1, TILE);           // the tile's own values are in shared memory (lateral warps)
-    if (HALO && m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles) {
+    if (HALO == 2 && m.h_flags && (int)blockIdx.x + tile0 >= m.n_int_tiles) {
         if (fl & F_GHOST) {
             // ghost cell: state from the exchange, effKH evaluated here (the pre-pass saw its stale vector entry)
             double gsf, gus, ggw, gkh;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         const int q = q0 + lane_cell;
         s_lc = __ldg(m.cs_cell + q) - i0; s_sgm = __ldg(m.cs_seg + q);
         s_yr = m.cs_yr[q];
-        if (HALO && m.cs_g) { const int gs = __ldg(m.cs_g + q); if (gs >= 0) s_yr = __ldcg(halo_state(m) + m.g_roff + gs); }
+        if (HALO == 2 && m.cs_g) { const int gs = __ldg(m.cs_g + q); if (gs >= 0) s_yr = __ldcg(halo_state(m) + m.g_roff + gs); }
         s_zr = __ldg(m.cs_zr + q); s_zbk = __ldg(m.cs_zbk + q); s_cwr = __ldg(m.cs_cwr + q);
         s_len = __ldg(m.cs_len + q);
         const double qg = flux_r2e_gw(s_yr, s_zr, t_gw[s_lc], t_zb[s_lc], t_kh[s_lc], __ldg(m.cs_ksatH + q), s_len,
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
         const int q = q0 + tq;
         const int lc = __ldg(m.cs_cell + q) - i0, sgm = __ldg(m.cs_seg + q);
         double yr = m.cs_yr[q];
-        if (HALO && m.cs_g) { const int gs = __ldg(m.cs_g + q); if (gs >= 0) yr = __ldcg(halo_state(m) + m.g_roff + gs); }
+        if (HALO == 2 && m.cs_g) { const int gs = __ldg(m.cs_g + q); if (gs >= 0) yr = __ldcg(halo_state(m) + m.g_roff + gs); }
         const double zr = __ldg(m.cs_zr + q), len = __ldg(m.cs_len + q);
         const double qs = weir_jtoi(t_zs[lc], x_isf2[lc], zr, yr, __ldg(m.cs_zbk + q), __ldg(m.cs_cwr + q), len, t_dep[lc]);
         const double qg = flux_r2e_gw(yr, zr, t_gw[lc], t_zb[lc], t_kh[lc], __ldg(m.cs_ksatH + q), len,
@@ -625,16 +625,16 @@ __global__ void __launch_bounds__(2 * TILE, MINB) k_fused(DevMesh m, DevDiag d, 
 }
 
 // stage of reach r as the solver sees it: the vector entry of an own reach, the exchanged stage of a ghost reach
-template <bool HALO>
+template <int HALO>
 __device__ __forceinline__ double reach_y(const DevMesh &m, const double *__restrict__ Yr, int r) {
-    if (HALO && m.r_gslot) {
+    if (HALO == 2 && m.r_gslot) {
         const int gs = m.r_gslot[r];
         if (gs >= 0) return __ldcg(halo_state(m) + m.g_roff + gs);
     }
     return Yr[r];
 }
 // Manning flux of reach r towards its downstream end, everything gathered from global memory
-template <bool HALO>
+template <int HALO>
 __device__ __forceinline__ double reach_down_flux(const DevMesh &m, const double *__restrict__ Yr, int r, int *err) {
     const double yraw = reach_y<HALO>(m, Yr, r);
     const double ystg = (m.r_bc[r] > 0) ? m.r_yBC[r] : yraw;
@@ -672,13 +672,13 @@ __device__ __forceinline__ double block_sum(double v, double *sm) {
 //     (Flux_RiverDown MD_RiverFlux.cpp:5-63, PassValue MD_f.cpp:228-240, f_applyDY MD_f.cpp:157-179);
 //     blocks [nb_riv, nb_riv+Nl) - one block per lake (MD_f.cpp:16-17,44-47,180-191).
 // ---------------------------------------------------------------------------------------------
-template <bool DIAG, bool HALO>
+template <bool DIAG, int HALO>
 __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag &d, const double *__restrict__ Y,
                                                 double *__restrict__ DY, int nb_riv, double *sm) {
     const size_t NE = (size_t)m.Ne;
     const size_t LD = (size_t)m.ld;
     const double *Yr = Y + 3 * NE;
-    if (HALO && m.h_flags && m.r_gslot) {
+    if (HALO == 2 && m.h_flags && m.r_gslot) {
         // ghost reaches: this kernel reads exchanged stages too; one lane per neighbour acquires its flag (long set)
         if ((int)threadIdx.x < m.h_nflags) {
             const unsigned long long e = *m.h_epoch + 1ull;
@@ -695,7 +695,7 @@ __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag 
     }
     if ((int)blockIdx.x < nb_riv) {
         const int r = blockIdx.x * blockDim.x + threadIdx.x;
-        if (r >= m.Nr || (HALO && m.r_gslot && m.r_gslot[r] >= 0)) {
+        if (r >= m.Nr || (HALO == 2 && m.r_gslot && m.r_gslot[r] >= 0)) {
             // past the end, or a ghost reach: its owner integrates it, its entry of ydot is 0 here
             if (r < m.Nr) DY[3 * NE + r] = 0.;
             return;
@@ -766,12 +766,18 @@ __device__ __forceinline__ void river_lake_body(const DevMesh &m, const DevDiag 
         }
     }
 }
-template <bool DIAG, bool HALO>
+template <bool DIAG, int HALO>
 __global__ void __launch_bounds__(128) k_river_lake(DevMesh m, DevDiag d, const double *__restrict__ Y,
                                                     double *__restrict__ DY, int nb_riv) {
     __shared__ double sm[8];
     river_lake_body<DIAG, HALO>(m, d, Y, DY, nb_riv, sm);
-    if (HALO && m.h_flags) {
+    if (HALO == 1 && m.h_flags && blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
+        // no ghost reach: no block of this grid reads the epoch word, the last thread advances it once the cell kernel
+        // (whose halo tiles read it) has completed
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        *m.h_epoch = *m.h_epoch + 1ull;
+    }
+    if (HALO == 2 && m.h_flags) {
         // peer-to-peer exchange: the epoch word advances when the LAST block of this grid is through - every block reads
         // it (parity of the halo buffer) - and the cell kernel, whose halo tiles read it too, has completed
         __syncthreads();
@@ -1973,25 +1979,51 @@ static void launch_prepass(shud_ctx *c, const double *y) {
         k_effkh<<<nb, 256, 0, c->stream>>>(c->m, y);
     }
 }
+// which instantiation of the cell / river kernels a context runs: 0 single domain, 1 partition with halo cells only,
+// 2 partition with ghost cells / reaches (cut river trees)
+static inline int halo_level(const shud_ctx *c) {
+    if (c->n_ghost_cells > 0 || c->n_ghost_reaches > 0 || c->force_halo == 2) return 2;
+    return is_partition(c) ? 1 : 0;
+}
+// one launch of the cell kernel over tiles [tile0, tile0 + ntiles) on `stream`, optionally programmatically dependent
+template <bool DIAG>
+static cudaError_t launch_cells(shud_ctx *c, int ntiles, int tile0, cudaStream_t stream, const double *y, double *ydot, bool pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ntiles); cfg.blockDim = dim3(2 * TILE); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    switch (halo_level(c)) {
+        case 0: return cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, 0>, c->m, c->diag, y, ydot, tile0);
+        case 1: return cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, 1>, c->m, c->diag, y, ydot, tile0);
+        default: return cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, 2>, c->m, c->diag, y, ydot, tile0);
+    }
+}
+template <bool DIAG>
+static cudaError_t launch_river(shud_ctx *c, int nblocks, int nb_riv, const double *y, double *ydot, bool pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    switch (halo_level(c)) {
+        case 0: return cudaLaunchKernelEx(&cfg, k_river_lake<DIAG, 0>, c->m, c->diag, y, ydot, nb_riv);
+        case 1: return cudaLaunchKernelEx(&cfg, k_river_lake<DIAG, 1>, c->m, c->diag, y, ydot, nb_riv);
+        default: return cudaLaunchKernelEx(&cfg, k_river_lake<DIAG, 2>, c->m, c->diag, y, ydot, nb_riv);
+    }
+}
 template <bool DIAG>
 static void launch_fused(shud_ctx *c, const double *y, double *ydot, bool pdl = false) {
     const int nb = (c->Ne + TILE - 1) / TILE;
     if (pdl && c->use_pdl) {
         // launched while k_effkh is still running (programmatic stream serialisation)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(nb); cfg.blockDim = dim3(2 * TILE); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        const cudaError_t e = is_partition(c) ? cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, true>, c->m, c->diag, y, ydot, 0)
-                                           : cudaLaunchKernelEx(&cfg, k_fused<DIAG, 4, false>, c->m, c->diag, y, ydot, 0);
-        if (e == cudaSuccess) return;
+        if (launch_cells<DIAG>(c, nb, 0, c->stream, y, ydot, true) == cudaSuccess) return;
         cudaGetLastError();
         c->use_pdl = 0;
     }
-    if (is_partition(c)) k_fused<DIAG, 4, true><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
-    else k_fused<DIAG, 4, false><<<nb, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
+    launch_cells<DIAG>(c, nb, 0, c->stream, y, ydot, false);
 }
 template <bool DIAG>
 static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
@@ -1999,22 +2031,15 @@ static int launch_rhs(shud_ctx *c, const double *y, double *ydot) {
     launch_fused<DIAG>(c, y, ydot, true);
     const int nb_riv = (c->Nr + 127) / 128;
     if (nb_riv + c->Nl == 0 && c->use_p2p) {  // no reach, no lake: a one-block launch that only advances the epoch word
-        k_river_lake<DIAG, true><<<1, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, 1);
+        launch_river<DIAG>(c, 1, 1, y, ydot, false);
     }
     if (nb_riv + c->Nl > 0) {
         bool done = false;
         if (c->use_pdl) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(nb_riv + c->Nl); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            done = (is_partition(c) ? cudaLaunchKernelEx(&cfg, k_river_lake<DIAG, true>, c->m, c->diag, y, ydot, nb_riv)
-                         : cudaLaunchKernelEx(&cfg, k_river_lake<DIAG, false>, c->m, c->diag, y, ydot, nb_riv)) == cudaSuccess;
+            done = launch_river<DIAG>(c, nb_riv + c->Nl, nb_riv, y, ydot, true) == cudaSuccess;
             if (!done) { cudaGetLastError(); c->use_pdl = 0; }
         }
-        if (!done) k_river_lake<DIAG, true><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+        if (!done) launch_river<DIAG>(c, nb_riv + c->Nl, nb_riv, y, ydot, false);
     }
     CK(cudaGetLastError());
     return SHUD_OK;
@@ -2077,7 +2102,7 @@ int shud_b200_rhs_interior_dev(shud_ctx *c, double t, const double *y, double *y
     }
     CK(cudaEventRecord(c->ev_kh, c->stream));
     if (c->n_int_tiles > 0)
-        k_fused<false, 4, true><<<c->n_int_tiles, 2 * TILE, 0, c->stream>>>(c->m, c->diag, y, ydot, 0);
+        launch_cells<false>(c, c->n_int_tiles, 0, c->stream, y, ydot, false);
     CK(cudaGetLastError());
     return SHUD_OK;
 }
@@ -2090,13 +2115,13 @@ int shud_b200_rhs_boundary_dev(shud_ctx *c, double t, const double *y, double *y
     const bool side = hs != c->stream && c->ev_kh;
     if (side) CK(cudaStreamWaitEvent(hs, c->ev_kh, 0));
     if (c->n_bnd_tiles > 0)
-        k_fused<false, 4, true><<<c->n_bnd_tiles, 2 * TILE, 0, hs>>>(c->m, c->diag, y, ydot, c->n_int_tiles);
+        launch_cells<false>(c, c->n_bnd_tiles, c->n_int_tiles, hs, y, ydot, false);
     if (side) {
         CK(cudaEventRecord(c->ev_bnd, hs));
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
     }
     const int nb_riv = (c->Nr + 127) / 128;
-    if (nb_riv + c->Nl > 0) k_river_lake<false, true><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+    if (nb_riv + c->Nl > 0) launch_river<false>(c, nb_riv + c->Nl, nb_riv, y, ydot, false);
     CK(cudaGetLastError());
     return SHUD_OK;
 }
@@ -2115,10 +2140,7 @@ int shud_b200_rhs_stage_dev(shud_ctx *c, int stage, const double *y, double *ydo
     if (stage == 0) launch_prepass(c, y);
     else if (stage == 1) launch_fused<false>(c, y, ydot);
     else if (stage == 2 && nb_riv + c->Nl > 0) {
-        if (is_partition(c))
-            k_river_lake<false, true><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
-        else
-            k_river_lake<false, false><<<nb_riv + c->Nl, 128, 0, c->stream>>>(c->m, c->diag, y, ydot, nb_riv);
+        launch_river<false>(c, nb_riv + c->Nl, nb_riv, y, ydot, false);
     } else return SHUD_ERR_ARG;
     CK(cudaGetLastError());
     return SHUD_OK;
