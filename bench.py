@@ -386,6 +386,11 @@ def gpu_arm(a):
     # ---------------- device-resident timing (value) ----------------
     for _ in range(warm):
         step()
+    # the parity check above kept the GPU idle for seconds while the CPU oracle ran: W steps (< 1 ms) do not bring the
+    # clocks back from their idle state, so the untimed warm-up goes on for half a second of back-to-back steps (the
+    # count is fixed, so every rank issues the same number of exchanges)
+    for _ in range(4000):
+        step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
