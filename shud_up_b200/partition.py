@@ -469,14 +469,20 @@ class HaloExchange:
 #   ghost reaches reaches on my cells' banks / up- / downstream of my reaches / flowing into my lakes, owned elsewhere
 #                 (stage)                                                ordinary local reaches, ydot 0
 # ------------------------------------------------------------------------------------------------------------------
-def assign_cells(mesh, nparts, reach_weight=0.0):
+def assign_cells(mesh, nparts, reach_weight=0.0, lake_cell_weight=0.25, return_work=False):
     """Hilbert-range owner of every cell with only the constraints the cut-river path still has: a lake stays with its
     cells and bank cells, a head-BC cell with its neighbours.  River trees are cut wherever the ranges fall, so the
     balance no longer depends on the size of the largest tree.
     reach_weight: work of one reach (its routing, its segments) in units of one cell's work; it is spread over the
-    reach's bank cells - which decide who owns the reach - so that ranges rich in rivers get fewer cells."""
+    reach's bank cells - which decide who owns the reach - so that ranges rich in rivers get fewer cells.
+    lake_cell_weight: work of a lake cell in the same units - the cell kernel does none of the soil, edge or segment
+    work for it (fun_Ele_lakeVertical / lakeHorizon, MD_ElementFlux.cpp:2-23), so a lake, which has to stay whole,
+    weighs little and the ranges balance WORK rather than cell counts (qhh's lake is 14 % of its cells).
+    return_work: also return the work of every cell (for balance reports)."""
     Ne, Nl = (int(np.asarray(mesh[k]).reshape(-1)[0]) for k in ("Ne", "Nl"))
     wcell = np.ones(Ne, dtype=np.float64)
+    if Nl:
+        wcell[np.asarray(mesh["ele_iLake"]) > 0] = lake_cell_weight
     if reach_weight > 0.0 and int(np.asarray(mesh["Ns"]).reshape(-1)[0]) > 0:
         se = np.asarray(mesh["seg_iEle"]).astype(np.int64) - 1
         sr = np.asarray(mesh["seg_iRiv"]).astype(np.int64) - 1
@@ -526,7 +532,8 @@ def assign_cells(mesh, nparts, reach_weight=0.0):
     csum = np.cumsum(work[order]) - 0.5 * work[order]
     part_of_atom = np.empty(atoms.size, dtype=np.int32)
     part_of_atom[order] = np.minimum((csum * nparts / float(work.sum())).astype(np.int64), nparts - 1)
-    return part_of_atom[inv].astype(np.int32)
+    part = part_of_atom[inv].astype(np.int32)
+    return (part, wcell) if return_work else part
 
 
 def _closure_with_lakes(mesh, part, rank):

@@ -73,13 +73,15 @@ def test_cut_partitions_reproduce_the_single_domain(basin, case, nparts):
 
 
 def test_balance_no_longer_depends_on_the_largest_river_tree():
+    """8 parts: with whole river trees per partition the largest tree sets the balance; with cut rivers the Hilbert
+    ranges balance the WORK to a few per cent (a lake cell, which the cell kernel skips, counts a quarter of a cell:
+    qhh's lake - 14 % of its cells - has to stay whole but weighs little)"""
     for basin, case in (("heihe", "rand3"), ("qhh", "rand4")):
         mesh = oracle_lib.load_case(basin, case)
-        for nparts in (8,):
-            old = np.bincount(partition.assign(mesh, nparts), minlength=nparts)
-            new = np.bincount(partition.assign_cells(mesh, nparts), minlength=nparts)
-            imb = lambda s: s.max() / s.mean() - 1.0
-            print(basin, nparts, "whole trees", imb(old), "cut rivers", imb(new))
-            assert imb(new) <= imb(old) + 1e-12
-            if basin == "heihe":
-                assert imb(new) <= 0.05
+        nparts = 8
+        old = np.bincount(partition.assign(mesh, nparts), minlength=nparts)
+        part, w = partition.assign_cells(mesh, nparts, return_work=True)
+        new = np.bincount(part, weights=w, minlength=nparts)
+        imb = lambda s: s.max() / s.mean() - 1.0
+        print(basin, nparts, "whole trees (cells)", imb(old), "cut rivers (work)", imb(new), "cells", np.bincount(part, minlength=nparts))
+        assert imb(new) <= 0.05 and imb(new) < imb(old)
