@@ -15,11 +15,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     names = []
-    for h in ("shud_b200.h", "shud_nvector.h"):
+    for h in ("shud_b200.h", "shud_nvector.h", "shud_sundials.h", "shud_cvode.h"):
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-        names += re.findall(r"\b(shud_(?:b200|nv)_\w+)\s*\(", txt)
-    return sorted(set(names))
+        names += re.findall(r"\b(shud_(?:b200|nv|cv|spgmr)_\w+)\s*\(", txt)
+        names += re.findall(r"\b(N_V\w+)\s*\(", txt)          # the vector constructors and the generic dispatch
+    # function-pointer typedefs and struct members are not entry points
+    skip = {"shud_nv_allreduce_fn", "shud_nv_allreduce_dev_fn", "shud_cv_rhs_fn", "N_Vector", "N_Vector_ID", "N_Vector_Ops", "N_Vector_S"}
+    return sorted(n for n in set(names) if n not in skip)
 
 
 @pytest.fixture(scope="module")
