@@ -85,3 +85,74 @@ def test_balance_no_longer_depends_on_the_largest_river_tree():
         imb = lambda s: s.max() / s.mean() - 1.0
         print(basin, nparts, "whole trees (cells)", imb(old), "cut rivers (work)", imb(new), "cells", np.bincount(part, minlength=nparts))
         assert imb(new) <= 0.05 and imb(new) < imb(old)
+
+
+def _gloo_cut_worker(rank, world, port, q):
+    """one process per partition: the item lists of extract_cut carried over torch.distributed (gloo) deliver what the
+    halo cells, ghost cells and ghost reaches need; the ordinary RHS on the refreshed local mesh gives the bits of the
+    single domain on everything this rank owns"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mesh = oracle_lib.load_case("heihe", "rand3")
+    Ne, Nr = int(mesh["Ne"][0]), int(mesh["Nr"][0])
+    ref = oracle_lib.oracle_rhs(mesh, want_diag=False)["ydot"]
+    part = partition.assign_cells(mesh, world)
+    loc, plan = partition.extract_cut(mesh, part, rank)
+    nloc, nh = int(loc["Ne"][0]), loc["halo_gid"].size
+    ngc, ngr, nr_loc = int(loc["n_ghost_cells"][0]), int(loc["n_ghost_reaches"][0]), int(loc["Nr"][0])
+    y = np.array(loc["y"], dtype=np.float64, copy=True)
+    truth = y.copy()
+    # forget everything this rank does not own: it must come back through the exchange
+    ghost_c = np.r_[nloc - ngc:nloc, 2 * nloc - ngc:2 * nloc, 3 * nloc - ngc:3 * nloc]
+    ghost_r = np.arange(3 * nloc + nr_loc - ngr, 3 * nloc + nr_loc)
+    y[ghost_c] = -7.0; y[ghost_r] = -7.0
+    sends, recvs, reqs = [], [], []
+    off = 0
+    for j, peer in enumerate(plan["peers"]):
+        n = int(plan["send_counts"][j].sum())
+        sends.append(torch.from_numpy(np.ascontiguousarray(truth[plan["send_items"][off:off + n]])))
+        recvs.append(torch.empty(int(plan["recv_counts"][j].sum()), dtype=torch.float64))
+        off += n
+        reqs.append(dist.isend(sends[-1], int(peer)))
+        reqs.append(dist.irecv(recvs[-1], int(peer)))
+    for r in reqs:
+        r.wait()
+    halo, gc, gr = [], [], []
+    for j in range(len(plan["peers"])):
+        a = recvs[j].numpy(); c = plan["recv_counts"][j]
+        halo.append(a[:c[0]]); gc.append(a[c[0]:c[0] + c[1]]); gr.append(a[c[0] + c[1]:])
+    halo = np.concatenate(halo) if halo else np.zeros(0)
+    ok = np.array_equal(halo, loc["halo_state_expected"])
+    gcv = (np.concatenate(gc) if gc else np.zeros(0)).reshape(-1, 3)
+    y[nloc - ngc:nloc] = gcv[:, 0]; y[2 * nloc - ngc:2 * nloc] = gcv[:, 1]; y[3 * nloc - ngc:3 * nloc] = gcv[:, 2]
+    y[ghost_r] = np.concatenate(gr) if gr else np.zeros(0)
+    ok = ok and np.array_equal(y, truth)
+    loc2 = dict(loc); loc2["y"] = y; loc2["halo_state_expected"] = halo
+    ext, ne, nhh = bench.extended_for_oracle(loc2)
+    o = oracle_lib.oracle_rhs(ext, want_diag=False)["ydot"]
+    NE, nown, nro = ne + nhh, loc["_own_ref"].size, loc["_riv_ref"].size
+    for b in range(3):
+        ok = ok and np.array_equal(o[b * NE:b * NE + nown], ref[b * Ne + loc["_own_ref"]])
+    ok = ok and np.array_equal(o[3 * NE:3 * NE + nro], ref[3 * Ne + loc["_riv_ref"]])
+    q.put((rank, bool(ok), ngc + ngr, nh))
+    dist.destroy_process_group()
+
+
+def test_cut_river_exchange_over_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7
+    ps = [ctx.Process(target=_gloo_cut_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res), res
+    assert sum(g for _, _, g, _ in res) > 0 and all(h > 0 for _, _, _, h in res), res
