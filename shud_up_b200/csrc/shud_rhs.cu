@@ -1791,6 +1791,9 @@ int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
     CK(cudaSetDevice(c->device));
     const char *env = getenv("SHUD_P2P");
     if (env && atoi(env) == 0) return SHUD_OK;  // keep the NCCL path (A/B)
+    for (void *q : c->p2p_opened) cudaIpcCloseMemHandle(q);  // a repeated connect maps afresh
+    c->p2p_opened.clear();
+    c->use_p2p = 0;
     P2PTable T{};
     T.npeers = (int)c->x_peer.size();
     int so = 0;
@@ -1877,6 +1880,7 @@ int shud_b200_rhs_exchange_dev(shud_ctx *c, double t, const double *y, double *y
     if (!c || !y || !ydot) return SHUD_ERR_ARG;
     if (c->use_p2p) return shud_b200_rhs_dev(c, t, y, ydot);  // peer-to-peer: every f() of this context exchanges
     if (!c->nccl_comm || !c->xstream) return SHUD_ERR_ARG;    // shud_b200_comm_init + shud_b200_exchange_plan first
+    if (!c->x_sidx && c->Nhalo > 0) return SHUD_ERR_ARG;      // an item plan (shud_b200_exchange_plan_items) needs the peer-to-peer transport
     if (!c->use_xgraph) return exchange_launch(c, t, y, ydot);
     // as shud_b200_rhs_dev: the sequence (collective included) is fixed, one instantiated graph per pointer pair
     for (auto &g : c->xgraphs)
