@@ -4,7 +4,12 @@
 // Model_Data::ET (MD_ET.cpp:282-342), which the reference runs on the host once per ET step (src/Model/shud.cpp:
 // 106-109), with one kernel that writes the RHS's forcing arrays in place: the 9*Ne doubles of
 // shud_b200_set_forcing never cross PCIe, and the host keeps only O(stations + classes) work per step (time-series
-// lookups, solarPosition()).  One thread per cell, ~200 B/cell of HBM traffic, 2 exp + 4 log per cell: HBM-bound.
+// lookups, solarPosition()).  One thread per cell, ~200 B/cell of HBM traffic.  What depends only on the land-cover
+// class (LAI, the two logarithms of the aerodynamic resistance, the canopy resistance, the soil-heat factor) is
+// evaluated once per class by k_land_classes, same expressions and association, so a cell is left with 1 exp, 1 log
+// and 8 divisions (the first version: 2 exp, 4 log, ~24 divisions = 1540 warp-instructions per 32 cells, issue-bound
+// at 0.33 of the HBM roofline).  With SHUD_RCP (the build's default, shud_phys.cuh) divisors shared by several
+// quotients or uniform over the cells are applied as reciprocals: <= 1.5 ulp per quotient, inside the 1e-12 tolerance.
 // Helper formulas: src/Equations/is_sm_et.hpp / is_sm_et.cpp, Equations.hpp:66-72, functions.hpp:191-201; the
 // constants are those of src/Model/Macros.hpp:43-83.  Parity: tests/test_land_gpu.py against sequences dumped
 // from the reference itself (tests/golden/{ccw,qhh}.land.npz).
@@ -25,28 +30,72 @@ __device__ __forceinline__ double frozen_fraction(double T, double high, double 
     return l_min(1.0, l_max((high - T) / (high - low), 0.0));
 }
 
-__global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, double tsr_den, double DT_min, CryoStep cs) {
-    __shared__ double s_sx[kTsrSmem], s_sy[kTsrSmem], s_sz[kTsrSmem], s_wdt[kTsrSmem];
+#ifdef SHUD_RCP
+#define L_RCP(x, d, rd) ((x) * (rd))  // x / d with the reciprocal of d at hand
+#else
+#define L_RCP(x, d, rd) ((x) / (d))
+#endif
+
+// per land-cover class, once per step: [lai | 0.4 exp(-lai/2) | log(.)log(.) of AerodynamicResistance | 200 / lai]
+__global__ void k_land_classes(DevLand L) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= L.nlc) return;
+    const double *t_lai = L.tab + 5 * L.nforc;
+    const double lai = t_lai[c] * L.cLAItsd;
+    double gfac = 0.1, LL = 0., rs = 0.;
+    if (lai > 0) {
+        gfac = 0.4 * exp(-0.5 * lai);
+        const double hc = lai * 0.5, Zm = hc * 1.3333;
+        const double d = 0.67 * hc, Z_om = 0.123 * hc, Z_ov = 0.0123 * hc;  // AerodynamicResistance(Uz, hc, Zm, Zm)
+        LL = log(fabs(Zm - d) / Z_om) * log(fabs(Zm - d) / (Z_ov));
+        rs = 200. / lai;  // BulkSurfaceResistance(lai)
+    }
+    L.cls[c] = lai; L.cls[L.nlc + c] = gfac; L.cls[2 * L.nlc + c] = LL; L.cls[3 * L.nlc + c] = rs;
+}
+
+#ifndef LAND_MINB
+#define LAND_MINB 8
+#endif
+#ifndef LAND_BLOCK
+#define LAND_BLOCK 128
+#endif
+__global__ void __launch_bounds__(LAND_BLOCK, LAND_MINB) k_land(DevMesh m, DevLand L, int tsr_n, double tsr_den, double DT_min, CryoStep cs) {
+    // sun samples of the step; a sample the reference skips for every cell (weight or cos(zenith) floor) gets weight 0
+    __shared__ double s_sx[kTsrSmem], s_sy[kTsrSmem], s_sz[kTsrSmem], s_wdt[kTsrSmem], s_den[kTsrSmem], s_rden[kTsrSmem];
     const double *t_forc = L.tab, *t_lai = t_forc + 5 * L.nforc, *t_mf = t_lai + L.nlc;
     const double *g_sx = t_mf + L.nmf, *g_sy = g_sx + L.tsr_cap, *g_sz = g_sy + L.tsr_cap, *g_wdt = g_sz + L.tsr_cap;
     const int ns = tsr_n < kTsrSmem ? tsr_n : kTsrSmem;
+    // the cell's own inputs first: their loads are in flight while the block stages the sun samples
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < m.Ne;
+    const int ic = valid ? i : m.Ne - 1;
+    const int idx = __ldg(L.iForc + ic) - 1, lc = __ldg(L.iLC + ic) - 1, imf = __ldg(L.iMF + ic) - 1;
+    const unsigned cflags = __ldg(m.flags + ic);
+    const double Zi = __ldg(m.z_surf + ic), fixP = __ldg(L.fixP + ic), windH = __ldg(L.windH + ic), vgFrac = __ldg(m.vegFrac + ic);
+    const double albedo = L.net ? 0. : __ldg(L.albedo + ic);
+    const double snow0 = L.snow[ic], ics0 = L.ics[ic];
+    double nx = 0., ny = 0., nz = 0.;
+    if (L.tsr && tsr_n > 0 && tsr_den > 0.0) { nx = __ldg(L.nx + ic); ny = __ldg(L.ny + ic); nz = __ldg(L.nz + ic); }
     for (int k = threadIdx.x; k < ns; k += blockDim.x) {
-        s_sx[k] = g_sx[k]; s_sy[k] = g_sy[k]; s_sz[k] = g_sz[k]; s_wdt[k] = g_wdt[k];
+        const double sz = g_sz[k];
+        double denom = sz, wdt = g_wdt[k];
+        if (denom < L.cosz_min) denom = L.cosz_min;
+        if (!(wdt > 0.0) || !(denom > 0.0) || !isfinite(denom)) { wdt = 0.0; denom = 1.0; }
+        s_sx[k] = g_sx[k]; s_sy[k] = g_sy[k]; s_sz[k] = sz; s_wdt[k] = wdt; s_den[k] = denom; s_rden[k] = 1.0 / denom;
     }
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.Ne) return;
+    const double rDT = 1.0 / DT_min, r1440 = 1.0 / 1440., r_tsr_den = 1.0 / tsr_den;
+    if (!valid) return;
     // ---------------- tReadForcing, MD_ET.cpp:21-281 ----------------
-    const int idx = L.iForc[i] - 1;
     const double *row = t_forc + 5 * idx;
     double t_prcp = row[0] * L.cPrep;
-    const double t0 = row[1], Zt = L.forc_z[idx], Zi = m.z_surf[i];
+    const double t0 = row[1], Zt = L.forc_z[idx];
     double t_temp;  // TemperatureOnElevation, Equations.hpp:66-72
     if (fabs(Zi - kL_NA) < kZERO || fabs(Zt - kL_NA) < kZERO) t_temp = t0;
     else t_temp = t0 + (Zt - Zi) * kL_dTdZ;
     t_temp = t_temp + L.cTemp;
-    const double lai = t_lai[L.iLC[i] - 1] * L.cLAItsd;
-    const double mf = t_mf[L.iMF[i] - 1] * L.cMF / 1440.;
+    const double lai = __ldg(L.cls + lc);  // t_lai[lc] * cLAItsd
+    const double mf = L_RCP(t_mf[imf] * L.cMF, 1440., r1440);
     const double dswrf_h = row[4];
     double dswrf_t = dswrf_h, factor = 1.0;
     if (L.tsr) {
@@ -55,13 +104,21 @@ __global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, d
         } else {
             double num = 0.0;
             if (tsr_den > 0.0 && tsr_n > 0) {
-                const double nx = L.nx[i], ny = L.ny[i], nz = L.nz[i];
-                for (int k = 0; k < tsr_n; k++) {
-                    const bool in_s = k < kTsrSmem;
-                    const double wdt = in_s ? s_wdt[k] : g_wdt[k];
+                for (int k = 0; k < ns; k++) {
+                    const double wdt = s_wdt[k];
                     if (!(wdt > 0.0)) continue;
-                    const double sx = in_s ? s_sx[k] : g_sx[k], sy = in_s ? s_sy[k] : g_sy[k], sz = in_s ? s_sz[k] : g_sz[k];
-                    const double cosi = nx * sx + ny * sy + nz * sz;
+                    const double cosi = nx * s_sx[k] + ny * s_sy[k] + nz * s_sz[k];
+                    if (!(cosi > 0.0) || !isfinite(cosi)) continue;
+                    double fk = L_RCP(cosi, s_den[k], s_rden[k]);
+                    if (!isfinite(fk) || !(fk > 0.0)) continue;
+                    if (fk > L.cap) fk = L.cap;
+                    num += wdt * fk;
+                }
+                for (int k = kTsrSmem; k < tsr_n; k++) {  // more samples than the staged ones (rare): global tables
+                    const double wdt = g_wdt[k];
+                    if (!(wdt > 0.0)) continue;
+                    const double sz = g_sz[k];
+                    const double cosi = nx * g_sx[k] + ny * g_sy[k] + nz * sz;
                     if (!(cosi > 0.0) || !isfinite(cosi)) continue;
                     double denom = sz;
                     if (denom < L.cosz_min) denom = L.cosz_min;
@@ -74,7 +131,7 @@ __global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, d
             }
             double feff = 0.0;
             if (tsr_den > 0.0) {
-                feff = num / tsr_den;
+                feff = L_RCP(num, tsr_den, r_tsr_den);
                 if (!isfinite(feff) || !(feff > 0.0)) feff = 0.0;
                 if (feff > L.cap) feff = L.cap;
             }
@@ -82,52 +139,62 @@ __global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, d
         }
         dswrf_t = dswrf_h * factor;
     }
-    double t_rn = L.net ? dswrf_t : dswrf_t * (1 - L.albedo[i]);
+    double t_rn = L.net ? dswrf_t : dswrf_t * (1 - albedo);
     const double Uz = fabs(row[3]) + 0.001;
     double t_rh = row[2];
-    t_prcp = t_prcp * 0.001 / 1440.;
+    t_prcp = L_RCP(t_prcp * 0.001, 1440., r1440);
     t_rn = t_rn * 1.0e-6;
     t_rh = l_min(l_max(t_rh, kL_ConstRH), 1.0);
-    const double fixP = L.fixP[i];
     const double lambda = 2.501 - 0.002361 * t_temp;                    // LatentHeat
-    const double Gamma = 0.0016286 * fixP / lambda;                     // PsychrometricConstant
-    const double es = 0.6108 * exp(17.27 * t_temp / (t_temp + 237.3));  // VaporPressure_Sat
+    const double rlambda = 1.0 / lambda;
+    const double Gamma = L_RCP(0.0016286 * fixP, lambda, rlambda);      // PsychrometricConstant
+    const double tt = t_temp + 237.3;
+#ifdef SHUD_RCP
+    const double rtt = 1.0 / tt;
+    const double es = 0.6108 * exp(17.27 * t_temp * rtt);               // VaporPressure_Sat
+    const double Delta = 4098. * es * (rtt * rtt);                      // SlopeSatVaporPressure
+#else
+    const double es = 0.6108 * exp(17.27 * t_temp / (t_temp + 237.3));
+    const double Delta = 4098. * es / (tt * tt);
+#endif
     const double ea = es * t_rh;
     const double ed = es - ea;
-    const double tt = t_temp + 237.3;
-    const double Delta = 4098. * es / (tt * tt);                        // SlopeSatVaporPressure
     const double rho = 3.486 * fixP / (275. + t_temp);                  // AirDensity
-    const bool lake = (m.flags[i] & F_LAKE) != 0;
+    const bool lake = (cflags & F_LAKE) != 0;
     double G;
     if (lake) G = 0.;
-    else if (lai > 0) G = 0.4 * exp(-0.5 * lai) * t_rn;
-    else G = 0.1 * t_rn;
+    else G = __ldg(L.cls + L.nlc + lc) * t_rn;  // lai > 0: 0.4 exp(-lai/2) t_rn, else 0.1 t_rn
     const double RG = t_rn - G;
     // WindProfile(2.0, Uz, windH, 0., ROUGHNESS_WATER)
-    const double U2 = Uz * log((2.0 - 0.) / kL_RoughWater) / log((L.windH[i] - 0.) / kL_RoughWater);
+    const double U2 = Uz * log((2.0 - 0.) / kL_RoughWater) / log(L_RCP(windH - 0., kL_RoughWater, 1.0 / kL_RoughWater));
     double pm_ow;  // PET_PM_openwater, is_sm_et.cpp:57-64
     {
         double ETp = (Delta * RG * kL_SecADay + Gamma * 6.43 * (1.0 + 0.536 * U2) * ed) / (Delta + Gamma);
-        ETp = ETp / lambda;
-        ETp = ETp * 0.001 / kL_SecADay;
+        ETp = L_RCP(ETp, lambda, rlambda);
+        ETp = L_RCP(ETp * 0.001, kL_SecADay, 1.0 / kL_SecADay);
         pm_ow = ETp;
     }
     const double qPotEvap = L.cETP * pm_ow * 60.;
-    const double vgFrac = m.vegFrac[i];
     double qPotTran, etp;
     int err = 0;
     if (lake || lai <= 0.) {
         qPotTran = L.cETP * 0.;
         etp = qPotEvap;
     } else {
-        const double hc = lai * 0.5, Zm = hc * 1.3333;
-        const double d = 0.67 * hc, Z_om = 0.123 * hc, Z_ov = 0.0123 * hc;  // AerodynamicResistance(Uz, hc, Zm, Zm)
-        const double ra = log(fabs(Zm - d) / Z_om) * log(fabs(Zm - d) / (Z_ov)) / (kL_Karman * kL_Karman * Uz);
-        if (ra <= 0.0 || isnan(ra) || isinf(ra) || fabs(ra - kL_NA) < kZERO) err = 10;  // CheckNonZero -> myexit(ERRNAN)
-        const double rs = 200. / lai;  // BulkSurfaceResistance(lai)
-        const double E_rad = Delta * RG, E_air = rho * kL_Cp * ed / ra, r_sa = rs / ra;  // PET_Penman_Monteith
+        // AerodynamicResistance(Uz, hc, Zm, Zm) = log(.) log(.) / (k^2 Uz), the two logarithms from the class table
+        const double LL = __ldg(L.cls + 2 * L.nlc + lc), rs = __ldg(L.cls + 3 * L.nlc + lc);
+#ifdef SHUD_RCP
+        // ra <= 0, NaN or Inf <=> the same of LL (k^2 Uz is positive and finite): CheckNonZero -> myexit(ERRNAN)
+        if (!(LL > 0.0) || isinf(LL)) err = 10;
+        const double rra = (kL_Karman * kL_Karman * Uz) / LL;
+        const double E_rad = Delta * RG, E_air = rho * kL_Cp * ed * rra, r_sa = rs * rra;  // PET_Penman_Monteith
+#else
+        const double ra = LL / (kL_Karman * kL_Karman * Uz);
+        if (ra <= 0.0 || isnan(ra) || isinf(ra) || fabs(ra - kL_NA) < kZERO) err = 10;
+        const double E_rad = Delta * RG, E_air = rho * kL_Cp * ed / ra, r_sa = rs / ra;
+#endif
         double ETp = (E_rad + E_air) / (Delta + Gamma * (1 + r_sa));
-        ETp = ETp / lambda;
+        ETp = L_RCP(ETp, lambda, rlambda);
         ETp = ETp * 0.001;
         qPotTran = L.cETP * ETp * 60.;
         etp = qPotTran * vgFrac + qPotEvap * (1. - vgFrac);
@@ -140,7 +207,7 @@ __global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, d
         const size_t ld = (size_t)m.ld;
         double tacc = L.tacc[i] + T, as = L.acc_s[i], ab = L.acc_b[i];
         if (cs.do_push) {
-            const double x = tacc / cs.nday;  // mean of the day that just ended
+            const double x = L_RCP(tacc, cs.nday, cs.r_nday);  // mean of the day that just ended
             as += x;
             if (cs.pop_s) as -= L.ring_s[cs.slot_s * ld + i];
             L.ring_s[cs.slot_s * ld + i] = x;
@@ -152,21 +219,21 @@ __global__ void __launch_bounds__(256) k_land(DevMesh m, DevLand L, int tsr_n, d
             L.acc_b[i] = ab;
         }
         L.tacc[i] = tacc;
-        fu_Sub = 1. - frozen_fraction(ab / cs.size_b, L.sub_max, L.sub_min);
-        fu_Surf = 1. - frozen_fraction(as / cs.size_s, L.surf_max, L.surf_min);
+        fu_Sub = 1. - frozen_fraction(L_RCP(ab, cs.size_b, cs.r_size_b), L.sub_max, L.sub_min);
+        fu_Surf = 1. - frozen_fraction(L_RCP(as, cs.size_s, cs.r_size_s), L.surf_max, L.surf_min);
     }
-    double snStg = L.snow[i];
+    double snStg = snow0;
     const double snFrac = frozen_fraction(T, kL_Train, kL_Tsnow);
     const double snAcc = snFrac * prcp;
     double snMelt = (T > kL_To ? (T - kL_To) * mf : 0.);
-    snMelt = l_min(l_max(0., snStg / DT_min), l_max(0., snMelt));
+    snMelt = l_min(l_max(0., L_RCP(snStg, DT_min, rDT)), l_max(0., snMelt));
     snStg += (snAcc - snMelt) * DT_min;
-    double icStg = (vgFrac > kZERO) ? (L.ics[i] / vgFrac) : 0.0;
+    double icStg = (vgFrac > kZERO) ? (ics0 / vgFrac) : 0.0;
     double icAcc, icEvap;
     if (lai > kZERO) {
         const double icMax = L.cISmax * kL_IcMax * lai;
-        icAcc = l_min(prcp - snAcc, l_max(0., (icMax - icStg) / DT_min));
-        icEvap = l_min(l_max(0., icStg / DT_min), qPotEvap);
+        icAcc = l_min(prcp - snAcc, l_max(0., L_RCP(icMax - icStg, DT_min, rDT)));
+        icEvap = l_min(l_max(0., L_RCP(icStg, DT_min, rDT)), qPotEvap);
     } else {
         icAcc = 0.;
         icEvap = 0.;
@@ -259,6 +326,8 @@ int shud_b200_land_create(shud_ctx *c, const shud_land *L) {
     d.tsr_cap = 256;
     const size_t ntab = 5 * (size_t)d.nforc + d.nlc + d.nmf + 4 * (size_t)d.tsr_cap;
     d.tab = dev_alloc<double>(c, ntab);
+    d.cls = dev_alloc<double>(c, 4 * (size_t)d.nlc);
+    if (!d.tab || !d.cls) return SHUD_ERR_CUDA;
     CK(cudaMallocHost((void **)&c->land_stage, sizeof(double) * ntab));
     // lake -> its cells, ascending reference id (c->lake_cells is ascending)
     std::vector<int> ptr(c->Nl + 1, 0), cell;
@@ -321,7 +390,9 @@ int shud_b200_land_step(shud_ctx *c, const shud_land_step *S) {
         }
         cs.size_s = (double)c->cryo_size_s; cs.size_b = (double)c->cryo_size_b;
     }
-    k_land<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, d, S->tsr_n, S->tsr_den, S->dt_min, cs);
+    cs.r_nday = 1. / cs.nday; cs.r_size_s = 1. / cs.size_s; cs.r_size_b = 1. / cs.size_b;
+    k_land_classes<<<(d.nlc + 127) / 128, 128, 0, c->stream>>>(d);
+    k_land<<<(c->Ne + LAND_BLOCK - 1) / LAND_BLOCK, LAND_BLOCK, 0, c->stream>>>(c->m, d, S->tsr_n, S->tsr_den, S->dt_min, cs);
     if (c->Nl > 0) k_lake_means<<<(c->Nl + 63) / 64, 64, 0, c->stream>>>(c->m, d);
     CK(cudaGetLastError());
     return SHUD_OK;

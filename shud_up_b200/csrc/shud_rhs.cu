@@ -103,6 +103,7 @@ struct DevLand {
     int net, tsr;
     double cap, cosz_min;
     double *snow, *ics;                         // yEleSnow, yEleIS (device order)
+    double *cls;                                // per-step, per land-cover class: lai | soil-heat factor | log log | rs (k_land_classes)
     double *tab;                                // per-step tables: forc[5 nforc] | lai[nlc] | mf[nmf] | sx|sy|sz|wdt [tsr_cap each]
     int tsr_cap;
     double *prep, *etp, *temp, *tmf, *factor;   // qElePrep, qEleETP, t_temp, t_mf, terrain factor
@@ -117,6 +118,7 @@ struct DevLand {
 struct CryoStep {  // per-step, uniform over the cells (the day clock of the accumulators lives on the host)
     int do_push, pop_s, pop_b, slot_s, slot_b;
     double nday, size_s, size_b;
+    double r_nday, r_size_s, r_size_b;  // their reciprocals (SHUD_RCP)
 };
 
 // ---------------------------------------------------------------------------------------------
