@@ -60,6 +60,14 @@ typedef struct shud_cv_fused {
      * < 0 error; *nli Krylov iterations, *nfe RHS evaluations spent */
     int (*lsolve)(void *ctx, realtype t, realtype gamma, N_Vector y, N_Vector fy, N_Vector ewt, N_Vector b, realtype delta,
                   N_Vector x, int *nli, int *nfe);
+    /* cvPredict (sgn = +1) / cvRestore (sgn = -1): zn[j-1] += sgn zn[j] for k = 1..q, j = q..k, in place; with
+     * acor != NULL also the start of the Newton iteration: acor = 0, y = zn[0] + acor */
+    int (*predict)(void *ctx, int q, realtype sgn, N_Vector *zn, N_Vector y, N_Vector acor);
+    /* one Newton iteration around y (fy = f(t, y)): solve (I - gamma J) x = -(rl1 zn1 + acor - gamma fy) as lsolve
+     * does, then acor += x, y = zn0 + acor, *del = ||x||_WRMS(ewt); returns lsolve's codes - 3: nothing was written,
+     * the caller runs the iteration through nls_residual / lsolve */
+    int (*newton_step)(void *ctx, realtype t, realtype gamma, realtype rl1, N_Vector zn0, N_Vector zn1, N_Vector acor,
+                       N_Vector y, N_Vector fy, N_Vector ewt, realtype delta, realtype *del, int *nli, int *nfe);
 } shud_cv_fused;
 
 /* CVodeCreate(CV_BDF) + CVodeInit(f, t0, y0) + CVodeSetUserData: work vectors are cloned from y0 */

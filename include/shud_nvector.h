@@ -105,6 +105,17 @@ int shud_spgmr_create(struct shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_g
 void shud_spgmr_destroy(shud_spgmr *s);
 int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, const double *fy, const double *ewt,
                      const double *b, double tol, double *x, int *nli, double *resnorm);
+/* One whole Newton iteration of the BDF corrector around y (fy = f(t, y)): the right-hand side
+ * b = -(rl1 zn1 + acor - gamma fy) is formed, scaled and normed in one pass (never stored), solved as above, and the
+ * correction applied in one pass: acor += x, y = zn0 + acor, *del = ||x||_WRMS(ewt) over n_global entries.  Element by
+ * element the arithmetic of cvNlsResidual, N_VScale(-1), shud_spgmr_solve, N_VLinearSum x 2, N_VWrmsNorm.  Returns
+ * shud_spgmr_solve's codes, or 3 when ||ewt b||_2 <= tol before the first iteration (nothing written). */
+int shud_spgmr_newton_step(shud_spgmr *s, double t, double gamma, double rl1, const double *zn0, const double *zn1,
+                           double *acor, double *y, const double *fy, const double *ewt, double tol, int64_t n_global,
+                           double *del, int *nli, double *resnorm);
+/* cvPredict (sgn = +1) / cvRestore (sgn = -1) of the Nordsieck array zn[0..q] in one pass, the in-place sums in the
+ * order of the reference's N_VLinearSum calls; with acor != NULL also acor = 0, y = zn[0] + acor (start of cvNls). */
+int shud_nv_bdf_predict(shud_nvws *ws, int64_t n, int q, double sgn, double *const *zn, double *y, double *acor);
 
 #ifdef __cplusplus
 }

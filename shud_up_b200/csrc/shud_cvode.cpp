@@ -67,6 +67,7 @@ struct shud_cv {
     long nli, ncfl, nfeLS, nps;
     shud_cv_fused fused;
     int have_fused;
+    int nls_primed;  // the fused predictor has left acor = 0 and y = zn[0] + acor
     double uround;
 };
 
@@ -299,13 +300,8 @@ int ls_solve(shud_cv *cv, N_Vector b, N_Vector ynow, N_Vector fnow) {
 }
 
 // ---------------------------------------------------------------- nonlinear solver: Newton ----
-// cvNlsResidual: res = rl1 zn[1] + ycor - gamma f(tn, zn[0] + ycor)
-int nls_residual(shud_cv *cv, N_Vector ycor, N_Vector res) {
-    N_VLinearSum(1.0, cv->zn[0], 1.0, ycor, cv->y);
-    const int retval = cv->f(cv->tn, cv->y, cv->ftemp, cv->user_data);
-    cv->nfe++;
-    if (retval < 0) return SHUD_CV_RHSFUNC_FAIL;
-    if (retval > 0) return 1;
+// res = rl1 zn[1] + ycor - gamma ftemp
+int residual_of_ftemp(shud_cv *cv, N_Vector ycor, N_Vector res) {
     if (cv->have_fused && cv->fused.nls_residual)
         return cv->fused.nls_residual(cv->fused.ctx, cv->rl1, cv->zn[1], ycor, cv->gamma, cv->ftemp, res) ? SHUD_CV_RHSFUNC_FAIL : 0;
     N_VLinearSum(cv->rl1, cv->zn[1], 1.0, ycor, res);
@@ -313,9 +309,18 @@ int nls_residual(shud_cv *cv, N_Vector ycor, N_Vector res) {
     return 0;
 }
 
-// cvNlsConvTest
-int nls_conv_test(shud_cv *cv, N_Vector ycor, N_Vector delta, double tol) {
-    const double del = N_VWrmsNorm(delta, cv->ewt);
+// cvNlsResidual: res = rl1 zn[1] + ycor - gamma f(tn, zn[0] + ycor); y_current: cv->y already holds zn[0] + ycor
+int nls_residual(shud_cv *cv, N_Vector ycor, N_Vector res, bool y_current = false) {
+    if (!y_current) N_VLinearSum(1.0, cv->zn[0], 1.0, ycor, cv->y);
+    const int retval = cv->f(cv->tn, cv->y, cv->ftemp, cv->user_data);
+    cv->nfe++;
+    if (retval < 0) return SHUD_CV_RHSFUNC_FAIL;
+    if (retval > 0) return 1;
+    return residual_of_ftemp(cv, ycor, res);
+}
+
+// cvNlsConvTest (del = ||delta||_WRMS)
+int nls_conv_test(shud_cv *cv, N_Vector ycor, double del, double tol) {
     const int m = cv->mnewt;
     if (m > 0) cv->crate = rmax(CRDOWN * cv->crate, del / cv->delp);
     const double dcon = del * rmin(1.0, cv->crate) / tol;
@@ -333,11 +338,51 @@ int nls_conv_test(shud_cv *cv, N_Vector ycor, N_Vector delta, double tol) {
 // routine (cvLsInitialize), so crate restarts at 1 on every call and there is no "retry with a fresh Jacobian".
 int nls(shud_cv *cv) {
     cv->crate = 1.0;
-    N_VConst(0.0, cv->acor);
+    const bool primed = cv->nls_primed != 0;  // the fused predictor has already set acor = 0, y = zn[0] + acor
+    cv->nls_primed = 0;
+    if (!primed) N_VConst(0.0, cv->acor);
     cv->acnrmcur = 0;
     N_Vector delta = cv->tempv;
     cv->mnewt = 0;
-    int retval = nls_residual(cv, cv->acor, delta);
+    if (cv->have_fused && cv->fused.newton_step) {
+        // Device route: the residual, the linear solve and the update of one iteration are a single hook; y is
+        // always zn[0] + acor when f is evaluated, as in nls_residual.  Same arithmetic as the route below.
+        if (!primed) N_VLinearSum(1.0, cv->zn[0], 1.0, cv->acor, cv->y);
+        for (;;) {
+            int retval = cv->f(cv->tn, cv->y, cv->ftemp, cv->user_data);
+            cv->nfe++;
+            if (retval < 0) return SHUD_CV_RHSFUNC_FAIL;
+            if (retval > 0) return NLS_CONV_RECVR;
+            cv->nni++;
+            double del = 0.0;
+            int nli = 0, nfe = 0;
+            const int r = cv->fused.newton_step(cv->fused.ctx, cv->tn, cv->gamma, cv->rl1, cv->zn[0], cv->zn[1], cv->acor, cv->y,
+                                                cv->ftemp, cv->ewt, EPLIFAC * cv->tq[4] * cv->nrmfac, &del, &nli, &nfe);
+            cv->nli += nli; cv->nfeLS += nfe;
+            if (r < 0) return SHUD_CV_LSOLVE_FAIL;
+            if (r == 3) {
+                // right-hand side already below the tolerance (cvLsSolve's norm test): delta = b on the first
+                // iteration, 0 later - rare, through the vector operations
+                if (residual_of_ftemp(cv, cv->acor, delta)) return SHUD_CV_RHSFUNC_FAIL;
+                N_VScale(-1.0, delta, delta);
+                if (cv->mnewt > 0) N_VConst(0.0, delta);
+                N_VLinearSum(1.0, cv->acor, 1.0, delta, cv->acor);
+                N_VLinearSum(1.0, cv->zn[0], 1.0, cv->acor, cv->y);
+                del = N_VWrmsNorm(delta, cv->ewt);
+            } else {
+                if (r != 0) cv->ncfl++;
+                if (r == 2 || (r == 1 && cv->mnewt > 0)) return NLS_CONV_RECVR;
+            }
+            retval = nls_conv_test(cv, cv->acor, del, cv->tq[4]);
+            if (retval == NLS_SUCCESS) break;
+            if (retval != NLS_CONTINUE) return retval;
+            cv->mnewt++;
+            if (cv->mnewt >= NLS_MAXCOR) return NLS_CONV_RECVR;
+        }
+        if (!cv->acnrmcur) cv->acnrm = N_VWrmsNorm(cv->acor, cv->ewt);
+        return 0;
+    }
+    int retval = nls_residual(cv, cv->acor, delta, primed);
     if (retval != 0) return retval < 0 ? retval : NLS_CONV_RECVR;
     for (;;) {
         cv->nni++;
@@ -346,7 +391,7 @@ int nls(shud_cv *cv) {
         if (retval < 0) return SHUD_CV_LSOLVE_FAIL;
         if (retval > 0) return NLS_CONV_RECVR;
         N_VLinearSum(1.0, cv->acor, 1.0, delta, cv->acor);
-        retval = nls_conv_test(cv, cv->acor, delta, cv->tq[4]);
+        retval = nls_conv_test(cv, cv->acor, N_VWrmsNorm(delta, cv->ewt), cv->tq[4]);
         if (retval == NLS_SUCCESS) break;
         if (retval != NLS_CONTINUE) return retval;
         cv->mnewt++;
@@ -425,12 +470,17 @@ void predict(shud_cv *cv) {  // cvPredict
     if (cv->tstopset) {
         if ((cv->tn - cv->tstop) * cv->h > 0.0) cv->tn = cv->tstop;
     }
+    if (cv->have_fused && cv->fused.predict) {
+        // one pass over the Nordsieck array; it also leaves acor = 0 and y = zn[0] + acor for the Newton iteration
+        if (cv->fused.predict(cv->fused.ctx, cv->q, 1.0, cv->zn, cv->y, cv->acor) == 0) { cv->nls_primed = 1; return; }
+    }
     for (int k = 1; k <= cv->q; k++)
         for (int j = cv->q; j >= k; j--) N_VLinearSum(1.0, cv->zn[j - 1], 1.0, cv->zn[j], cv->zn[j - 1]);
 }
 
 void restore(shud_cv *cv, double saved_t) {  // cvRestore
     cv->tn = saved_t;
+    if (cv->have_fused && cv->fused.predict && cv->fused.predict(cv->fused.ctx, cv->q, -1.0, cv->zn, nullptr, nullptr) == 0) return;
     for (int k = 1; k <= cv->q; k++)
         for (int j = cv->q; j >= k; j--) N_VLinearSum(1.0, cv->zn[j - 1], -1.0, cv->zn[j], cv->zn[j - 1]);
 }
@@ -756,7 +806,7 @@ int shud_cv_reinit(shud_cv *cv, realtype t0, N_Vector y0) {
     cv->nst = cv->nfe = cv->ncfn = cv->netf = cv->nni = cv->nscon = 0;
     cv->nli = cv->ncfl = cv->nfeLS = cv->nps = 0;
     cv->h0u = 0.0; cv->next_h = 0.0; cv->next_q = 0; cv->h = 0.0;
-    cv->saved_tq5 = 0.0; cv->indx_acor = 0;
+    cv->saved_tq5 = 0.0; cv->indx_acor = 0; cv->nls_primed = 0;
     memset(cv->tau, 0, sizeof(cv->tau)); memset(cv->tq, 0, sizeof(cv->tq)); memset(cv->l, 0, sizeof(cv->l));
     return SHUD_CV_SUCCESS;
 }

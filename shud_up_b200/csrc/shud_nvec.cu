@@ -541,6 +541,55 @@ struct FLinCombDiv {  // x = (sum c_k V_k) ./ ewt
         x[i] = s / ewt[i];
     }
 };
+// Right-hand side of a Newton iteration, scaled, and its squared 2-norm in one pass:
+// b = -((rl1 zn1 + acor) + (-gamma) f) (cvNlsResidual + the sign change of the Newton solver), V0 = ewt b (the first
+// Krylov vector before normalisation); term = V0^2.  Same arithmetic, element by element, as N_VLinearCombination ->
+// N_VScale(-1) -> N_VProd -> N_VDotProd; b itself is never stored.
+struct TNewtonRhs {
+    double rl1, gamma; const double *zn1, *acor, *f, *ewt; double *v0;
+    __device__ double term(int, int64_t i) const {
+        double r = rl1 * zn1[i];
+        r += 1.0 * acor[i];
+        r += (-gamma) * f[i];
+        const double o = ewt[i] * (-1.0 * r);
+        v0[i] = o;
+        return o * o;
+    }
+};
+// End of a Newton iteration in one pass: x = (sum c_k V_k) ./ ewt (FLinCombDiv), acor += x, y = zn0 + acor;
+// term = (x ewt)^2 (the WRMS norm of the correction); x itself is never stored.
+struct TNewtonFinish {
+    int nv; Coef c; Ptrs V; const double *ewt, *zn0; double *acor, *y;
+    __device__ double term(int, int64_t i) const {
+        double s = c.c[0] * V.p[0][i];
+        for (int k = 1; k < nv; k++) s += c.c[k] * V.p[k][i];
+        const double w = ewt[i], x = s / w;
+        const double a = acor[i] + 1.0 * x;
+        acor[i] = a;
+        y[i] = 1.0 * zn0[i] + 1.0 * a;
+        const double t = x * w;
+        return t * t;
+    }
+};
+// cvPredict / cvRestore on the whole Nordsieck array in one pass: the in-place Pascal-triangle sums
+// zn[j-1] += sgn zn[j] (k = 1..q, j = q..k) run on registers, element by element in the order of the N_VLinearSum
+// calls; optionally the start of the Newton iteration as well: acor = 0, y = zn[0] + acor.
+template <int Q>
+struct FPredict {
+    double sgn; MPtrs Z; double *y, *acor;
+    __device__ void operator()(int64_t i) const {
+        double z[Q + 1];
+#pragma unroll
+        for (int j = 0; j <= Q; j++) z[j] = Z.p[j][i];
+#pragma unroll
+        for (int k = 1; k <= Q; k++)
+#pragma unroll
+            for (int j = Q; j >= k; j--) z[j - 1] = z[j - 1] + sgn * z[j];
+#pragma unroll
+        for (int j = 0; j < Q; j++) Z.p[j][i] = z[j];
+        if (acor) { acor[i] = 0.0; y[i] = 1.0 * z[0] + 1.0 * 0.0; }
+    }
+};
 }  // namespace
 
 struct shud_spgmr {
@@ -586,25 +635,15 @@ void shud_spgmr_destroy(shud_spgmr *s) {
     delete s;
 }
 
-int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, const double *fy, const double *ewt,
-                     const double *b, double tol, double *x, int *nli_out, double *res_out) {
-    if (!s || !y || !fy || !ewt || !b || !x) return SHUD_ERR_ARG;
+// Arnoldi / modified Gram-Schmidt iterations from the scaled residual in V[0] (2-norm beta): normalises V[0], runs
+// up to maxl iterations (one RHS call each), solves the small least-squares problem; yk[0..k_used) are the
+// coefficients of the correction in the Krylov basis.
+static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y, const double *fy, const double *ewt,
+                         double beta, double tol, double *yk, int *k_used_out, double *res_out, bool *conv_out) {
     shud_nvws *ws = s->ws;
     const int64_t n = s->n;
     const int maxl = s->maxl;
     int rc;
-    // r0 = S b, beta = ||r0||_2
-    if ((rc = run_map(ws, n, FProdTo{ewt, b, s->V[0]}))) return rc;
-    if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[0], s->V[0]}, s->dH))) return rc;
-    CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
-    CKN(cudaStreamSynchronize(ws->stream));
-    const double beta = sqrt(s->hH[0]);
-    if (nli_out) *nli_out = 0;
-    if (res_out) *res_out = beta;
-    if (beta <= tol) {
-        if ((rc = run_map(ws, n, FConst{0.0, x}))) return rc;
-        return 0;
-    }
     if ((rc = run_map(ws, n, FScaleTo{1.0 / beta, s->V[0], s->V[0]}))) return rc;
     double H[SHUD_NV_MAXVEC + 1][SHUD_NV_MAXVEC] = {{0}};
     double g[SHUD_NV_MAXVEC + 1] = {0}, cs[SHUD_NV_MAXVEC] = {0}, sn[SHUD_NV_MAXVEC] = {0};
@@ -643,19 +682,87 @@ int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, con
         k_used = k + 1;
         if (fabs(g[k + 1]) <= tol) { conv = true; break; }
     }
-    FLinCombDiv f;
-    f.nv = k_used; f.ewt = ewt; f.x = x;
-    double yk[SHUD_NV_MAXVEC] = {0};
+    for (int i = 0; i < SHUD_NV_MAXVEC; i++) yk[i] = 0.0;
     for (int i = k_used - 1; i >= 0; i--) {
         double acc = g[i];
         for (int j = i + 1; j < k_used; j++) acc -= H[i][j] * yk[j];
         yk[i] = acc / H[i][i];
     }
+    *k_used_out = k_used;
+    *res_out = fabs(g[k_used]);
+    *conv_out = conv;
+    return 0;
+}
+
+int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, const double *fy, const double *ewt,
+                     const double *b, double tol, double *x, int *nli_out, double *res_out) {
+    if (!s || !y || !fy || !ewt || !b || !x) return SHUD_ERR_ARG;
+    shud_nvws *ws = s->ws;
+    const int64_t n = s->n;
+    int rc;
+    // r0 = S b, beta = ||r0||_2
+    if ((rc = run_map(ws, n, FProdTo{ewt, b, s->V[0]}))) return rc;
+    if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[0], s->V[0]}, s->dH))) return rc;
+    CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    CKN(cudaStreamSynchronize(ws->stream));
+    const double beta = sqrt(s->hH[0]);
+    if (nli_out) *nli_out = 0;
+    if (res_out) *res_out = beta;
+    if (beta <= tol) {
+        if ((rc = run_map(ws, n, FConst{0.0, x}))) return rc;
+        return 0;
+    }
+    double yk[SHUD_NV_MAXVEC], res = 0.0;
+    int k_used = 0;
+    bool conv = false;
+    if ((rc = spgmr_iterate(s, t, gamma, y, fy, ewt, beta, tol, yk, &k_used, &res, &conv))) return rc;
+    FLinCombDiv f;
+    f.nv = k_used; f.ewt = ewt; f.x = x;
     for (int i = 0; i < k_used; i++) { f.c.c[i] = yk[i]; f.V.p[i] = s->V[i]; }
     if ((rc = run_map(ws, n, f))) return rc;
     if (nli_out) *nli_out = k_used;
-    if (res_out) *res_out = fabs(g[k_used]);
-    return conv ? 0 : (fabs(g[k_used]) < beta ? 1 : 2);
+    if (res_out) *res_out = res;
+    return conv ? 0 : (res < beta ? 1 : 2);
+}
+
+int shud_spgmr_newton_step(shud_spgmr *s, double t, double gamma, double rl1, const double *zn0, const double *zn1,
+                           double *acor, double *y, const double *fy, const double *ewt, double tol, int64_t n_global,
+                           double *del, int *nli_out, double *res_out) {
+    if (!s || !zn0 || !zn1 || !acor || !y || !fy || !ewt || !del) return SHUD_ERR_ARG;
+    shud_nvws *ws = s->ws;
+    const int64_t n = s->n;
+    int rc;
+    if ((rc = run_reduce_dev<R_SUM>(ws, n, TNewtonRhs{rl1, gamma, zn1, acor, fy, ewt, s->V[0]}, s->dH))) return rc;
+    CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    CKN(cudaStreamSynchronize(ws->stream));
+    const double beta = sqrt(s->hH[0]);
+    if (nli_out) *nli_out = 0;
+    if (res_out) *res_out = beta;
+    if (beta <= tol) return 3;  // nothing written: the caller takes the unfused route for this iteration
+    double yk[SHUD_NV_MAXVEC], res = 0.0;
+    int k_used = 0;
+    bool conv = false;
+    if ((rc = spgmr_iterate(s, t, gamma, y, fy, ewt, beta, tol, yk, &k_used, &res, &conv))) return rc;
+    TNewtonFinish f;
+    f.nv = k_used; f.ewt = ewt; f.zn0 = zn0; f.acor = acor; f.y = y;
+    for (int i = 0; i < k_used; i++) { f.c.c[i] = yk[i]; f.V.p[i] = s->V[i]; }
+    if ((rc = run_reduce<R_SUM, 1>(ws, n, f, 1, 1, (double)(n_global > 0 ? n_global : n), del))) return rc;
+    if (nli_out) *nli_out = k_used;
+    if (res_out) *res_out = res;
+    return conv ? 0 : (res < beta ? 1 : 2);
+}
+
+int shud_nv_bdf_predict(shud_nvws *ws, int64_t n, int q, double sgn, double *const *zn, double *y, double *acor) {
+    if (!zn || q < 1 || q > 5 || (acor && !y)) return SHUD_ERR_ARG;
+    MPtrs Z;
+    if (!fill(Z, zn, q + 1)) return SHUD_ERR_ARG;
+    switch (q) {
+        case 1: return run_map(ws, n, FPredict<1>{sgn, Z, y, acor});
+        case 2: return run_map(ws, n, FPredict<2>{sgn, Z, y, acor});
+        case 3: return run_map(ws, n, FPredict<3>{sgn, Z, y, acor});
+        case 4: return run_map(ws, n, FPredict<4>{sgn, Z, y, acor});
+        default: return run_map(ws, n, FPredict<5>{sgn, Z, y, acor});
+    }
 }
 
 }  // extern "C"

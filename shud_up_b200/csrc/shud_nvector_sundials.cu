@@ -524,6 +524,29 @@ static int fused_lsolve(void *ctx, realtype t, realtype gamma, N_Vector y, N_Vec
     return rc;
 }
 
+static int fused_predict(void *ctx, int q, realtype sgn, N_Vector *zn, N_Vector y, N_Vector acor) {
+    cv_fused_ctx *c = (cv_fused_ctx *)ctx;
+    if (q < 1 || q > 5) return -1;
+    double *z[6];
+    for (int j = 0; j <= q; j++) z[j] = D(zn[j]);
+    const int rc = shud_nv_bdf_predict(c->ws, LEN(zn[0]), q, sgn, z, y ? D(y) : nullptr, acor ? D(acor) : nullptr);
+    for (int j = 0; j < q; j++) wrote(zn[j]);
+    if (acor) { wrote(acor); wrote(y); }
+    return rc;
+}
+static int fused_newton_step(void *ctx, realtype t, realtype gamma, realtype rl1, N_Vector zn0, N_Vector zn1, N_Vector acor,
+                             N_Vector y, N_Vector fy, N_Vector ewt, realtype delta, realtype *del, int *nli, int *nfe) {
+    cv_fused_ctx *c = (cv_fused_ctx *)ctx;
+    double res = 0.0;
+    int it = 0;
+    const int rc = shud_spgmr_newton_step(c->spgmr, t, gamma, rl1, D(zn0), D(zn1), D(acor), D(y), D(fy), D(ewt), delta,
+                                          CT(y)->global_length, del, &it, &res);
+    if (nli) *nli = it;
+    if (nfe) *nfe = it;
+    if (rc != 3 && rc >= 0) { wrote(acor); wrote(y); }
+    return rc;
+}
+
 int shud_b200_cv_fused_create(shud_ctx *gpu, shud_nvws *ws, int maxl, shud_cv_fused *out) {
     if (!gpu || !ws || !out) return SHUD_ERR_ARG;
     cv_fused_ctx *c = (cv_fused_ctx *)calloc(1, sizeof(cv_fused_ctx));
@@ -532,6 +555,7 @@ int shud_b200_cv_fused_create(shud_ctx *gpu, shud_nvws *ws, int maxl, shud_cv_fu
     const int rc = shud_spgmr_create(gpu, ws, maxl > 0 ? maxl : 5, shud_b200_ny(gpu), &c->spgmr);
     if (rc) { free(c); return rc; }
     out->ctx = c; out->ewt_set = fused_ewt_set; out->nls_residual = fused_nls_residual; out->lsolve = fused_lsolve;
+    out->predict = fused_predict; out->newton_step = fused_newton_step;
     return SHUD_OK;
 }
 void shud_b200_cv_fused_destroy(shud_cv_fused *f) {
