@@ -510,10 +510,10 @@ def gpu_arm(a):
 
     # ---------------- RHS + SPGMR together (configs[3]): BDF / Newton / SPGMR steps of the library's integrator ------
     # The CVODE-shaped integrator (include/shud_cvode.h) runs in C on SHUD B200 N_Vectors: the time loop, the Newton
-    # iteration, SPGMR and every vector operation are library code; Python only starts each step.  One GPU: the
-    # device-fused Newton-Krylov pieces (shud_b200_cv_fused_create).  N > 1: the generic operations table on distributed
-    # vectors - every reduction is a local kernel + one ncclAllReduce inside the library (all dot products of a
-    # Gram-Schmidt sweep in one call) - and f() = halo exchange + RHS (shud_b200_f_exchange).
+    # iteration, SPGMR and every vector operation are library code; Python only starts each step.  The device-fused
+    # Newton-Krylov pieces (shud_b200_cv_fused_create) at every N; N > 1: distributed vectors - every reduction is a
+    # local kernel + one ncclAllReduce of the scalar on the device inside the library - and f() = halo exchange + RHS
+    # (shud_b200_f_exchange).  SHUD_NK_FUSED=0: the generic operations table instead.
     nk = None
     if world == 1 or native:
         import ctypes as C
@@ -539,7 +539,7 @@ def gpu_arm(a):
         cvi = _cv.CVode(L, _cv.fn_address(L, "shud_b200_f_exchange" if world > 1 else "shud_b200_f"), rhs._h.value, 0.0, yv)
         cvi.configure(rtol=1e-4, atol=1e-4, init_step=1e-3, max_step=10.0)
         fz = None
-        if world == 1:
+        if os.environ.get("SHUD_NK_FUSED", "1") != "0":
             fz = _cv.Fused()
             L.shud_b200_cv_fused_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_cv.Fused)]
             L.shud_b200_cv_fused_destroy.argtypes = [C.POINTER(_cv.Fused)]
@@ -572,9 +572,12 @@ def gpu_arm(a):
               "ms_per_rhs_call_incl_vector_ops": w_nk * 1e3 / max(nrhs, 1),
               "what": ("CVODE-shaped integrator of the library (BDF 1-5, Newton, SPGMR(5), difference-quotient Jv; "
                        "csrc/shud_cvode.cpp) on SHUD B200 N_Vectors, "
-                       + ("device-fused Newton-Krylov pieces (shud_spgmr_solve)" if world == 1 else
-                          f"{world} partitions: distributed vectors, reductions = local kernel + ncclAllReduce in the "
-                          "library, f() = halo exchange + RHS"))}
+                       + ("device-fused Newton-Krylov pieces (one-pass predictor, shud_spgmr_newton_step)" if fz is not None
+                          else "generic operations table")
+                       + ("" if world == 1 else
+                          f"; {world} partitions: distributed vectors, every reduction = local kernel + ncclAllReduce of "
+                          "the scalar on the device inside the library, f() = halo exchange + RHS")),
+              "fused": fz is not None}
         cvi.close()
         if fz is not None:
             L.shud_b200_cv_fused_destroy(C.byref(fz))

@@ -103,6 +103,10 @@ struct shud_ctx;
 typedef struct shud_spgmr shud_spgmr;
 int shud_spgmr_create(struct shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_global, shud_spgmr **out);
 void shud_spgmr_destroy(shud_spgmr *s);
+/* global length of a distributed vector (sigma of the difference quotient is sqrt(N_global)); on a workspace with a
+ * device allreduce (shud_nv_ws_set_allreduce) every dot product of the solve is reduced over the ranks on the device
+ * and f() is shud_b200_rhs_exchange_dev */
+void shud_spgmr_set_nglobal(shud_spgmr *s, int64_t n_global);
 int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, const double *fy, const double *ewt,
                      const double *b, double tol, double *x, int *nli, double *resnorm);
 /* One whole Newton iteration of the BDF corrector around y (fy = f(t, y)): the right-hand side

@@ -311,6 +311,9 @@ int run_reduce_dev(shud_nvws *ws, int64_t n, F f, double *d_result) {
     k_reduce<KIND, 1, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, 1, ws->partial, ws->counter, d_result,
                                                              ws->h_out_dev + (SHUD_NV_MAXVEC - 1), 0, 1.0);
     CKN(cudaGetLastError());
+    // distributed vector: the scalar is reduced over the ranks where it lies, on the same stream, before the next
+    // kernel reads it (every rank runs the same sequence)
+    if (ws->ar_dev && !ws->ar_off && ws->ar_dev(ws->ar_ctx, d_result, 1, KIND, (void *)ws->stream) != 0) return SHUD_ERR_CUDA;
     return SHUD_OK;
 }
 bool fill(Ptrs &P, const double *const *X, int nv) {
@@ -626,6 +629,10 @@ int shud_spgmr_create(shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_global, 
     return SHUD_OK;
 }
 
+void shud_spgmr_set_nglobal(shud_spgmr *s, int64_t n_global) {
+    if (s && n_global > 0) s->sqrtN = sqrt((double)n_global);
+}
+
 void shud_spgmr_destroy(shud_spgmr *s) {
     if (!s) return;
     cudaSetDevice(s->ws->device);
@@ -651,10 +658,11 @@ static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y,
     int k_used = 0;
     bool conv = false;
     const double sig = s->sqrtN;  // 1/||S^-1 v_k||_WRMS: v_k has unit 2-norm (CVLS' sigma without a reduction)
+    const bool dist = ws->ar_dev && !ws->ar_off;  // a partition of a multi-GPU run: f() = halo exchange + RHS
     for (int k = 0; k < maxl; k++) {
         // w = S (I - gamma J) S^-1 v_k, J by difference quotient: 1 RHS call
         if ((rc = shud_nv_dq_perturb(ws, n, sig, s->V[k], ewt, y, s->ytemp))) return rc;
-        if ((rc = shud_b200_rhs_dev(s->gpu, t, s->ytemp, s->ftemp))) return rc;
+        if ((rc = dist ? shud_b200_rhs_exchange_dev(s->gpu, t, s->ytemp, s->ftemp) : shud_b200_rhs_dev(s->gpu, t, s->ytemp, s->ftemp))) return rc;
         // ... fused with the first dot product of the modified Gram-Schmidt sweep; every later pass subtracts the
         // previous projection and forms the next dot product (the last one the squared norm) in one read of w.
         // Coefficients stay on the device: h_i is written by the reduction's last block and read by the next pass.

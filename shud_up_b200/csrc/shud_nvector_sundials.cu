@@ -516,6 +516,7 @@ static int fused_lsolve(void *ctx, realtype t, realtype gamma, N_Vector y, N_Vec
     cv_fused_ctx *c = (cv_fused_ctx *)ctx;
     double res = 0.0;
     int it = 0;
+    shud_spgmr_set_nglobal(c->spgmr, CT(y)->global_length);
     const int rc = shud_spgmr_solve(c->spgmr, t, gamma, D(y), D(fy), D(ewt), D(b), delta, D(x), &it, &res);
     wrote(x);
     if (nli) *nli = it;
@@ -539,6 +540,7 @@ static int fused_newton_step(void *ctx, realtype t, realtype gamma, realtype rl1
     cv_fused_ctx *c = (cv_fused_ctx *)ctx;
     double res = 0.0;
     int it = 0;
+    shud_spgmr_set_nglobal(c->spgmr, CT(y)->global_length);
     const int rc = shud_spgmr_newton_step(c->spgmr, t, gamma, rl1, D(zn0), D(zn1), D(acor), D(y), D(fy), D(ewt), delta,
                                           CT(y)->global_length, del, &it, &res);
     if (nli) *nli = it;
