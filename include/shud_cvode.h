@@ -68,6 +68,8 @@ typedef struct shud_cv_fused {
      * the caller runs the iteration through nls_residual / lsolve */
     int (*newton_step)(void *ctx, realtype t, realtype gamma, realtype rl1, N_Vector zn0, N_Vector zn1, N_Vector acor,
                        N_Vector y, N_Vector fy, N_Vector ewt, realtype delta, realtype *del, int *nli, int *nfe);
+    /* ewt_set and *nrm = ||y||_WRMS(ewt) in one pass (the weights and the tolsf test at the top of CVode's loop) */
+    int (*ewt_set_norm)(void *ctx, realtype rtol, realtype atol, N_Vector y, N_Vector ewt, realtype *nrm);
 } shud_cv_fused;
 
 /* CVodeCreate(CV_BDF) + CVodeInit(f, t0, y0) + CVodeSetUserData: work vectors are cloned from y0 */

@@ -89,6 +89,9 @@ int shud_nv_dq_combine(shud_nvws *ws, int64_t n, double sigma, double gamma, con
  * shud_nv_newton_resid:  r = gamma f + psi - y                        (right-hand side of the Newton system)
  * shud_nv_newton_update: y += x; acor += x; *del = ||x||_WRMS(ewt)    (Newton correction + its convergence norm) */
 int shud_nv_ewt(shud_nvws *ws, int64_t n, double rtol, double atol, const double *y, double *ewt);
+/* ewt = 1 ./ (rtol |y| + atol) and *nrm = ||y||_WRMS(ewt) in one pass (cvEwtSet + the tolsf test of CVode's loop) */
+int shud_nv_ewt_wrms(shud_nvws *ws, int64_t n, double rtol, double atol, const double *y, double *ewt, int64_t n_global,
+                     double *nrm);
 int shud_nv_newton_resid(shud_nvws *ws, int64_t n, double gamma, const double *f, const double *psi, const double *y, double *r);
 int shud_nv_newton_update(shud_nvws *ws, int64_t n, const double *x, const double *ewt, int64_t n_global, double *y,
                           double *acor, double *del);

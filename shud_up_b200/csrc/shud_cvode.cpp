@@ -694,7 +694,9 @@ int step(shud_cv *cv) {  // cvStep
     complete_step(cv);
     prepare_next_step(cv, dsm);
     cv->etamax = (cv->nst <= SMALL_NST) ? ETAMX2 : ETAMX3;
-    N_VScale(cv->tq[2], cv->acor, cv->acor);
+    // acor * tq[2] is the estimated local error (CVodeGetEstLocalErrors); nothing of this integrator reads it and the
+    // next step starts from acor = 0, so the device route leaves the pass out
+    if (!(cv->have_fused && cv->fused.newton_step)) N_VScale(cv->tq[2], cv->acor, cv->acor);
     return 0;
 }
 
@@ -941,8 +943,13 @@ int shud_cv_solve(shud_cv *cv, realtype tout, N_Vector yout, realtype *tret, int
     for (;;) {
         cv->next_h = cv->h;
         cv->next_q = cv->q;
+        double nrm = -1.0;
         if (cv->nst > 0) {
-            if (ewt_set(cv, cv->zn[0], cv->ewt) != 0) {
+            if (cv->have_fused && cv->fused.ewt_set_norm && cv->abstol > 0.0) {
+                // weights and the norm of the tolsf test below in one pass over zn[0]
+                if (cv->fused.ewt_set_norm(cv->fused.ctx, cv->reltol, cv->abstol, cv->zn[0], cv->ewt, &nrm) != 0) nrm = -1.0;
+            }
+            if (nrm < 0.0 && ewt_set(cv, cv->zn[0], cv->ewt) != 0) {
                 istate = SHUD_CV_ILL_INPUT;
                 cv->tretlast = *tret = cv->tn;
                 N_VScale(1.0, cv->zn[0], yout);
@@ -955,7 +962,7 @@ int shud_cv_solve(shud_cv *cv, realtype tout, N_Vector yout, realtype *tret, int
             N_VScale(1.0, cv->zn[0], yout);
             break;
         }
-        const double nrm = N_VWrmsNorm(cv->zn[0], cv->ewt);
+        if (nrm < 0.0) nrm = N_VWrmsNorm(cv->zn[0], cv->ewt);
         if (cv->uround * nrm > 1.0) {
             istate = SHUD_CV_TOO_MUCH_ACC;
             cv->tretlast = *tret = cv->tn;

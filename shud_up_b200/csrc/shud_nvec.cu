@@ -11,6 +11,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <vector>
+#include <atomic>
+#include <cstring>
 
 #include "shud_b200.h"
 #include "shud_nvector.h"
@@ -105,6 +107,15 @@ struct FEwt {
     double rtol, atol; const double *y; double *w;
     __device__ void operator()(int64_t i) const { w[i] = 1.0 / (rtol * fabs(y[i]) + atol); }
 };
+struct TEwtNorm {  // w = 1 / (rtol |y| + atol) (FEwt); term = (y w)^2
+    double rtol, atol; const double *y; double *w;
+    __device__ double term(int, int64_t i) const {
+        const double yi = y[i], wi = 1.0 / (rtol * fabs(yi) + atol);
+        w[i] = wi;
+        const double t = yi * wi;
+        return t * t;
+    }
+};
 struct FNewtonResid {
     double gamma; const double *f, *psi, *y; double *r;
     __device__ void operator()(int64_t i) const { r[i] = (gamma * f[i] + psi[i]) - y[i]; }
@@ -146,7 +157,8 @@ __device__ __forceinline__ double block_reduce(double v, double *sm) {
 // post: 0 none, 1 sqrt(v / nglob), 2 sqrt(v)
 template <int KIND, int NV, class F>
 __global__ void __launch_bounds__(NT) k_reduce(int64_t n, F f, int nv, double *partial, unsigned *counter,
-                                               double *d_out, volatile double *h_out, int post, double nglob) {
+                                               double *d_out, volatile double *h_out, int post, double nglob,
+                                               volatile double *h_ticket = nullptr, double ticket = 0.0) {
     __shared__ double sm[NT / 32];
     __shared__ bool last;
     double acc[NV];
@@ -188,6 +200,9 @@ __global__ void __launch_bounds__(NT) k_reduce(int64_t n, F f, int nv, double *p
             h_out[k] = v;
         }
     }
+    // the host spins on this word instead of synchronising the stream: the results above (mapped host memory) are
+    // ordered ahead of it
+    if (h_ticket && threadIdx.x == 0) { __threadfence_system(); *h_ticket = ticket; }
 }
 
 struct TDot { const double *x, *y; __device__ double term(int, int64_t i) const { return x[i] * y[i]; } };
@@ -248,8 +263,9 @@ struct shud_nvws {
     double *partial;       // [SHUD_NV_MAXVEC][MAXB]
     unsigned *counter;
     double *d_out;         // [SHUD_NV_MAXVEC]
-    double *h_out;         // mapped pinned, [SHUD_NV_MAXVEC]
+    double *h_out;         // mapped pinned, [SHUD_NV_MAXVEC] results + [1] ticket of the last signalled reduction
     double *h_out_dev;     // device alias of h_out
+    double ticket = 0.0;   // last ticket handed out
     // distributed vector: the partial results of a reduction stay on the device, are reduced over the ranks in place
     // (ncclAllReduce on the same stream) and only then copied to the host: one synchronisation per reduction
     shud_nv_allreduce_dev_fn ar_dev = nullptr;
@@ -275,6 +291,20 @@ int run_map(shud_nvws *ws, int64_t n, F f) {
     CKN(cudaGetLastError());
     return SHUD_OK;
 }
+// Wait for the reduction that carries `ticket`: spin on the mapped word (a few microseconds sooner than a stream
+// synchronisation, and kernels queued behind the reduction keep running); the stream is polled now and then, so an
+// error or a lost ticket ends in the ordinary synchronisation.
+int wait_ticket(shud_nvws *ws, double ticket) {
+    volatile double *p = ws->h_out + SHUD_NV_MAXVEC;
+    for (unsigned spin = 1;; spin++) {
+        if (*p == ticket) { std::atomic_thread_fence(std::memory_order_acquire); return SHUD_OK; }
+        if ((spin & 4095u) == 0 && cudaStreamQuery(ws->stream) != cudaErrorNotReady) break;
+    }
+    CKN(cudaStreamSynchronize(ws->stream));
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return *p == ticket ? SHUD_OK : SHUD_ERR_CUDA;
+}
+
 template <int KIND, int NV, class F>
 int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, double *out) {
     if (!ws || !out || nv < 1 || nv > NV) return SHUD_ERR_ARG;
@@ -296,20 +326,25 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
         }
         return SHUD_OK;
     }
+    const double ticket = (ws->ticket += 1.0);
     k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
-                                                              ws->h_out_dev, post, nglob);
+                                                              ws->h_out_dev, post, nglob, ws->h_out_dev + SHUD_NV_MAXVEC, ticket);
     CKN(cudaGetLastError());
-    CKN(cudaStreamSynchronize(ws->stream));
+    const int rc = wait_ticket(ws, ticket);
+    if (rc) return rc;
     for (int k = 0; k < nv; k++) out[k] = ws->h_out[k];
     return SHUD_OK;
 }
 // same reduction, result left in device memory (d_result), no synchronisation: for device-resident
 // solver loops (shud_spgmr_solve) that consume the scalar in a following kernel
+// h_result (device alias of mapped host memory, optional): the scalar lands in host memory as well; ticket > 0: the
+// host may wait_ticket() for it
 template <int KIND, class F>
-int run_reduce_dev(shud_nvws *ws, int64_t n, F f, double *d_result) {
+int run_reduce_dev(shud_nvws *ws, int64_t n, F f, double *d_result, double *h_result = nullptr, double ticket = 0.0) {
     if (!ws || !d_result || n <= 0) return SHUD_ERR_ARG;
     k_reduce<KIND, 1, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, 1, ws->partial, ws->counter, d_result,
-                                                             ws->h_out_dev + (SHUD_NV_MAXVEC - 1), 0, 1.0);
+                                                             h_result ? h_result : ws->h_out_dev + (SHUD_NV_MAXVEC - 1), 0, 1.0,
+                                                             ticket > 0.0 ? ws->h_out_dev + SHUD_NV_MAXVEC : nullptr, ticket);
     CKN(cudaGetLastError());
     // distributed vector: the scalar is reduced over the ranks where it lies, on the same stream, before the next
     // kernel reads it (every rank runs the same sequence)
@@ -342,7 +377,8 @@ int shud_nv_ws_create(int device, void *stream, shud_nvws **out) {
     CKN(cudaMalloc(&ws->counter, sizeof(unsigned)));
     CKN(cudaMemset(ws->counter, 0, sizeof(unsigned)));
     CKN(cudaMalloc(&ws->d_out, sizeof(double) * SHUD_NV_MAXVEC));
-    CKN(cudaHostAlloc(&ws->h_out, sizeof(double) * SHUD_NV_MAXVEC, cudaHostAllocMapped));
+    CKN(cudaHostAlloc(&ws->h_out, sizeof(double) * (SHUD_NV_MAXVEC + 1), cudaHostAllocMapped));
+    memset(ws->h_out, 0, sizeof(double) * (SHUD_NV_MAXVEC + 1));
     CKN(cudaHostGetDevicePointer((void **)&ws->h_out_dev, ws->h_out, 0));
     *out = ws;
     return SHUD_OK;
@@ -460,6 +496,9 @@ int shud_nv_constvectorarray(shud_nvws *ws, int64_t n, int nv, double c, double 
 }
 int shud_nv_ewt(shud_nvws *ws, int64_t n, double rtol, double atol, const double *y, double *ewt) {
     return run_map(ws, n, FEwt{rtol, atol, y, ewt});
+}
+int shud_nv_ewt_wrms(shud_nvws *ws, int64_t n, double rtol, double atol, const double *y, double *ewt, int64_t ng, double *nrm) {
+    return run_reduce<R_SUM, 1>(ws, n, TEwtNorm{rtol, atol, y, ewt}, 1, 1, (double)(ng > 0 ? ng : n), nrm);
 }
 int shud_nv_newton_resid(shud_nvws *ws, int64_t n, double gamma, const double *f, const double *psi, const double *y,
                          double *r) {
@@ -604,8 +643,26 @@ struct shud_spgmr {
     std::vector<double *> V;   // maxl+1 Krylov vectors
     double *ytemp, *ftemp;
     double *dH;                // device scalars: Gram-Schmidt coefficients of the current column + squared norm
-    double *hH;                // pinned host copy
+    double *hH;                // pinned host copy (mapped: the reductions of a single-GPU solve write it directly)
+    double *hH_dev;            // its device alias
 };
+
+// a sum over the (distributed) vector into dH[0] and hH[0]
+template <class F>
+static int reduce_to_host(shud_spgmr *s, F f) {
+    shud_nvws *ws = s->ws;
+    int rc;
+    if (ws->ar_dev && !ws->ar_off) {
+        if ((rc = run_reduce_dev<R_SUM>(ws, s->n, f, s->dH))) return rc;
+        CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+        CKN(cudaStreamSynchronize(ws->stream));
+        return SHUD_OK;
+    }
+    const double ticket = (ws->ticket += 1.0);
+    if ((rc = run_reduce_dev<R_SUM>(ws, s->n, f, s->dH, s->hH_dev, ticket))) return rc;
+    return wait_ticket(ws, ticket);
+}
+
 
 extern "C" {
 
@@ -624,7 +681,8 @@ int shud_spgmr_create(shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_global, 
     CKN(cudaMalloc(&s->ytemp, sizeof(double) * s->n));
     CKN(cudaMalloc(&s->ftemp, sizeof(double) * s->n));
     CKN(cudaMalloc(&s->dH, sizeof(double) * (maxl + 2)));
-    CKN(cudaMallocHost(&s->hH, sizeof(double) * (maxl + 2)));
+    CKN(cudaHostAlloc(&s->hH, sizeof(double) * (maxl + 2), cudaHostAllocMapped));
+    CKN(cudaHostGetDevicePointer((void **)&s->hH_dev, s->hH, 0));
     *out = s;
     return SHUD_OK;
 }
@@ -667,13 +725,20 @@ static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y,
         // previous projection and forms the next dot product (the last one the squared norm) in one read of w.
         // Coefficients stay on the device: h_i is written by the reduction's last block and read by the next pass.
         double *w = s->V[k + 1];
-        if ((rc = run_reduce_dev<R_SUM>(ws, n, TDqCombineDot{sig, gamma, s->V[k], ewt, s->ftemp, fy, w, s->V[0]}, s->dH))) return rc;
+        // one GPU: every scalar also lands in mapped host memory, the last one with a ticket the host spins on (the
+        // normalisation below runs while the host does the Givens rotations); distributed: the allreduced scalars
+        // are copied back and the stream synchronised
+        double *const hd = dist ? nullptr : s->hH_dev;
+        const double ticket = dist ? 0.0 : (ws->ticket += 1.0);
+        if ((rc = run_reduce_dev<R_SUM>(ws, n, TDqCombineDot{sig, gamma, s->V[k], ewt, s->ftemp, fy, w, s->V[0]}, s->dH, hd))) return rc;
         for (int i = 0; i < k; i++)
-            if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegDot{s->dH + i, s->V[i], w, s->V[i + 1]}, s->dH + i + 1))) return rc;
-        if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegSq{s->dH + k, s->V[k], w}, s->dH + k + 1))) return rc;
+            if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegDot{s->dH + i, s->V[i], w, s->V[i + 1]}, s->dH + i + 1, hd ? hd + i + 1 : nullptr))) return rc;
+        if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegSq{s->dH + k, s->V[k], w}, s->dH + k + 1, hd ? hd + k + 1 : nullptr, ticket))) return rc;
         if ((rc = run_map(ws, n, FNormalizeDev{s->dH + k + 1, s->V[k + 1]}))) return rc;
-        CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, ws->stream));
-        CKN(cudaStreamSynchronize(ws->stream));  // the one host synchronisation of this Krylov iteration
+        if (dist) {
+            CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, ws->stream));
+            CKN(cudaStreamSynchronize(ws->stream));  // the one host synchronisation of this Krylov iteration
+        } else if ((rc = wait_ticket(ws, ticket))) return rc;
         for (int i = 0; i <= k; i++) H[i][k] = s->hH[i];
         H[k + 1][k] = sqrt(s->hH[k + 1]);
         for (int i = 0; i < k; i++) {
@@ -710,9 +775,7 @@ int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, con
     int rc;
     // r0 = S b, beta = ||r0||_2
     if ((rc = run_map(ws, n, FProdTo{ewt, b, s->V[0]}))) return rc;
-    if ((rc = run_reduce_dev<R_SUM>(ws, n, TDot{s->V[0], s->V[0]}, s->dH))) return rc;
-    CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
-    CKN(cudaStreamSynchronize(ws->stream));
+    if ((rc = reduce_to_host(s, TDot{s->V[0], s->V[0]}))) return rc;
     const double beta = sqrt(s->hH[0]);
     if (nli_out) *nli_out = 0;
     if (res_out) *res_out = beta;
@@ -740,9 +803,7 @@ int shud_spgmr_newton_step(shud_spgmr *s, double t, double gamma, double rl1, co
     shud_nvws *ws = s->ws;
     const int64_t n = s->n;
     int rc;
-    if ((rc = run_reduce_dev<R_SUM>(ws, n, TNewtonRhs{rl1, gamma, zn1, acor, fy, ewt, s->V[0]}, s->dH))) return rc;
-    CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
-    CKN(cudaStreamSynchronize(ws->stream));
+    if ((rc = reduce_to_host(s, TNewtonRhs{rl1, gamma, zn1, acor, fy, ewt, s->V[0]}))) return rc;
     const double beta = sqrt(s->hH[0]);
     if (nli_out) *nli_out = 0;
     if (res_out) *res_out = beta;

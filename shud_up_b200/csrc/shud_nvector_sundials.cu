@@ -502,6 +502,12 @@ static int fused_ewt_set(void *ctx, realtype rtol, realtype atol, N_Vector y, N_
     wrote(ewt);
     return rc;
 }
+static int fused_ewt_set_norm(void *ctx, realtype rtol, realtype atol, N_Vector y, N_Vector ewt, realtype *nrm) {
+    cv_fused_ctx *c = (cv_fused_ctx *)ctx;
+    const int rc = shud_nv_ewt_wrms(c->ws, LEN(y), rtol, atol, D(y), D(ewt), CT(y)->global_length, nrm);
+    wrote(ewt);
+    return rc;
+}
 static int fused_nls_residual(void *ctx, realtype rl1, N_Vector zn1, N_Vector ycor, realtype gamma, N_Vector f, N_Vector res) {
     cv_fused_ctx *c = (cv_fused_ctx *)ctx;
     // (rl1 zn1 + ycor) + (-gamma f): the two N_VLinearSum calls of cvNlsResidual in one pass, same operation order
@@ -557,7 +563,7 @@ int shud_b200_cv_fused_create(shud_ctx *gpu, shud_nvws *ws, int maxl, shud_cv_fu
     const int rc = shud_spgmr_create(gpu, ws, maxl > 0 ? maxl : 5, shud_b200_ny(gpu), &c->spgmr);
     if (rc) { free(c); return rc; }
     out->ctx = c; out->ewt_set = fused_ewt_set; out->nls_residual = fused_nls_residual; out->lsolve = fused_lsolve;
-    out->predict = fused_predict; out->newton_step = fused_newton_step;
+    out->predict = fused_predict; out->newton_step = fused_newton_step; out->ewt_set_norm = fused_ewt_set_norm;
     return SHUD_OK;
 }
 void shud_b200_cv_fused_destroy(shud_cv_fused *f) {
