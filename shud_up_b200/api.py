@@ -62,6 +62,7 @@ def lib():
         "shud_b200_allreduce": (C.c_int, [vp, _PD, C.c_int, C.c_int]),
         "shud_b200_perm": (C.c_int, [vp, _PI, _PI]),
         "shud_b200_rhs_dev": (C.c_int, [vp, C.c_double, vp, vp]),
+        "shud_b200_rhs_dq_dev": (C.c_int, [vp, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
         "shud_b200_rhs": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_stage_dev": (C.c_int, [vp, C.c_int, vp, vp]),
         "shud_b200_rhs_interior_dev": (C.c_int, [vp, C.c_double, vp, vp]),
@@ -224,6 +225,12 @@ class ShudRHS:
         """asynchronous RHS on device vectors in device order (torch cuda float64 tensors)."""
         fn = lib().shud_b200_rhs_diag_dev if diag else lib().shud_b200_rhs_dev
         _chk(fn(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "shud_b200_rhs_dev")
+
+    def f_dq_dev(self, t, sigma, v_dev, ewt_dev, y0_dev, ytemp_dev, ydot_dev):
+        """ytemp = sigma (v ./ ewt) + y0 formed by the pre-pass, ydot = f(t, ytemp): the difference-quotient evaluation
+        of SPGMR's J v (single domain)"""
+        _chk(lib().shud_b200_rhs_dq_dev(self._h, float(t), float(sigma), _ptr(v_dev), _ptr(ewt_dev), _ptr(y0_dev),
+                                        _ptr(ytemp_dev), _ptr(ydot_dev)), "shud_b200_rhs_dq_dev")
 
     def f_interior_dev(self, t, y_dev, ydot_dev):
         """part of the RHS of a partition that needs no exchanged halo data (overlaps the halo exchange)"""

@@ -13,6 +13,7 @@
 #include <vector>
 #include <atomic>
 #include <cstring>
+#include <cstdlib>
 
 #include "shud_b200.h"
 #include "shud_nvector.h"
@@ -645,6 +646,7 @@ struct shud_spgmr {
     double *dH;                // device scalars: Gram-Schmidt coefficients of the current column + squared norm
     double *hH;                // pinned host copy (mapped: the reductions of a single-GPU solve write it directly)
     double *hH_dev;            // its device alias
+    int fold_dq = 1;           // shud_b200_rhs_dq_dev where the context allows it (SHUD_FOLD_DQ=0: separate perturbation)
 };
 
 // a sum over the (distributed) vector into dH[0] and hH[0]
@@ -671,6 +673,7 @@ int shud_spgmr_create(shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_global, 
     if ((void *)ws->stream != shud_b200_stream(gpu)) return SHUD_ERR_ARG;  // RHS and vector work share one stream
     shud_spgmr *s = new shud_spgmr();
     s->gpu = gpu; s->ws = ws; s->maxl = maxl; s->n = shud_b200_ny(gpu);
+    if (const char *e = getenv("SHUD_FOLD_DQ")) s->fold_dq = atoi(e);
     s->sqrtN = sqrt((double)(n_global > 0 ? n_global : s->n));
     CKN(cudaSetDevice(ws->device));
     for (int k = 0; k <= maxl; k++) {
@@ -719,8 +722,11 @@ static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y,
     const bool dist = ws->ar_dev && !ws->ar_off;  // a partition of a multi-GPU run: f() = halo exchange + RHS
     for (int k = 0; k < maxl; k++) {
         // w = S (I - gamma J) S^-1 v_k, J by difference quotient: 1 RHS call
-        if ((rc = shud_nv_dq_perturb(ws, n, sig, s->V[k], ewt, y, s->ytemp))) return rc;
-        if ((rc = dist ? shud_b200_rhs_exchange_dev(s->gpu, t, s->ytemp, s->ftemp) : shud_b200_rhs_dev(s->gpu, t, s->ytemp, s->ftemp))) return rc;
+        // (single domain: the perturbation is formed by the RHS's own pre-pass)
+        if (dist || !s->fold_dq || shud_b200_rhs_dq_dev(s->gpu, t, sig, s->V[k], ewt, y, s->ytemp, s->ftemp) != 0) {
+            if ((rc = shud_nv_dq_perturb(ws, n, sig, s->V[k], ewt, y, s->ytemp))) return rc;
+            if ((rc = dist ? shud_b200_rhs_exchange_dev(s->gpu, t, s->ytemp, s->ftemp) : shud_b200_rhs_dev(s->gpu, t, s->ytemp, s->ftemp))) return rc;
+        }
         // ... fused with the first dot product of the modified Gram-Schmidt sweep; every later pass subtracts the
         // previous projection and forms the next dot product (the last one the squared norm) in one read of w.
         // Coefficients stay on the device: h_i is written by the reduction's last block and read by the next pass.

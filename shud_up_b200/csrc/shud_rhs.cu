@@ -197,6 +197,38 @@ __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restri
     asm volatile("griddepcontrol.launch_dependents;");
     effkh_body(m, Y);
 }
+// The pre-pass of a difference-quotient evaluation f(y0 + sigma v / ewt) (CVLS' Jv inside SPGMR): it forms the
+// perturbed state - the arithmetic of shud_nv_dq_perturb, element by element - stores it for the cell and river
+// kernels, and evaluates effKH from the value it has just formed: one pass over (v, ewt, y0) instead of a vector
+// kernel followed by a pre-pass that reads the result back.  A reach stage another thread forms is re-formed here.
+struct DqArgs { double sigma; const double *v, *ewt, *y0; double *yt; };
+__device__ __forceinline__ double dq_val(const DqArgs &A, size_t k) { return A.sigma * (A.v[k] / A.ewt[k]) + A.y0[k]; }
+__global__ void __launch_bounds__(256) k_effkh_dq(DevMesh m, DqArgs A) {
+    const size_t NE = (size_t)m.Ne, NE3 = 3 * NE;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < m.Ns; q += gridDim.x * blockDim.x) {
+        const int r = __ldg(m.cs_riv + q);
+        m.cs_yr[q] = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : dq_val(A, NE3 + r);
+    }
+    for (size_t k = NE3 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < NE3 + m.Nr + m.Nl; k += (size_t)gridDim.x * blockDim.x)
+        A.yt[k] = dq_val(A, k);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.Ne) return;
+    A.yt[i] = dq_val(A, i);
+    A.yt[NE + i] = dq_val(A, NE + i);
+    const double ygw_t = dq_val(A, 2 * NE + i);
+    A.yt[2 * NE + i] = ygw_t;
+    const unsigned fl = m.flags[i];
+    double kh;
+    if (fl & F_LAKE) {
+        kh = m.ksatH[i];
+    } else {
+        const double ygw = (fl & F_HEADBC) ? m.ele_yBC[i] : ygw_t;
+        int e = 0;
+        kh = eff_kh(ygw, m.aqd[i], m.macD[i], m.macKsatH[i], m.vAreaF[i], m.ksatH[i], &e);
+        if (e) raise_err(m.err, e, i + 1);
+    }
+    m.effKH[i] = kh;
+}
 // the same with the send side of the peer-to-peer halo exchange in its first blocks
 __global__ void __launch_bounds__(256) k_effkh_pack(DevMesh m, const double *__restrict__ Y, PackArgs P) {
     asm volatile("griddepcontrol.launch_dependents;");
@@ -963,6 +995,9 @@ struct shud_ctx {
     int use_pdl = 1;   // programmatic dependent launch of the cell kernel behind k_effkh (SHUD_PDL)
     struct GraphEntry { const double *y; double *yd; cudaGraphExec_t exec; unsigned long used; };
     std::vector<GraphEntry> graphs, xgraphs;
+    // graphs of shud_b200_rhs_dq_dev: keyed by every pointer of the call and sigma
+    struct DqGraph { DqArgs a; double *yd; cudaGraphExec_t exec; unsigned long used; };
+    std::vector<DqGraph> dqgraphs;
 };
 
 #define CK(call)                                                                                         \
@@ -2057,6 +2092,64 @@ static void drop_graphs(shud_ctx *c) {
     c->graphs.clear();
     for (auto &g : c->xgraphs) cudaGraphExecDestroy(g.exec);
     c->xgraphs.clear();
+    for (auto &g : c->dqgraphs) cudaGraphExecDestroy(g.exec);
+    c->dqgraphs.clear();
+}
+
+// f(t, y0 + sigma v ./ ewt) with the perturbation formed by the pre-pass (k_effkh_dq); ytemp receives the perturbed
+// state.  A single domain only: a partition's pre-pass carries the halo exchange (the caller perturbs with
+// shud_nv_dq_perturb and calls shud_b200_rhs_dev / _rhs_exchange_dev there).
+static int launch_rhs_dq(shud_ctx *c, const DqArgs &A, double *ydot) {
+    k_effkh_dq<<<(c->Ne + 255) / 256, 256, 0, c->stream>>>(c->m, A);
+    // no programmatic launch of the cell kernel here: its vertical role reads ytemp from its first instruction on
+    launch_fused<false>(c, A.yt, ydot, false);
+    const int nb_riv = (c->Nr + 127) / 128;
+    if (nb_riv + c->Nl > 0) {
+        bool done = false;
+        if (c->use_pdl) {
+            done = launch_river<false>(c, nb_riv + c->Nl, nb_riv, A.yt, ydot, true) == cudaSuccess;
+            if (!done) { cudaGetLastError(); c->use_pdl = 0; }
+        }
+        if (!done) launch_river<false>(c, nb_riv + c->Nl, nb_riv, A.yt, ydot, false);
+    }
+    CK(cudaGetLastError());
+    return SHUD_OK;
+}
+int shud_b200_rhs_dq_dev(shud_ctx *c, double t, double sigma, const double *v, const double *ewt, const double *y0,
+                         double *ytemp, double *ydot) {
+    (void)t;
+    if (!c || !v || !ewt || !y0 || !ytemp || !ydot) return SHUD_ERR_ARG;
+    if (halo_level(c) != 0 || c->use_p2p) return SHUD_ERR_ARG;
+    DqArgs A;
+    A.sigma = sigma; A.v = v; A.ewt = ewt; A.y0 = y0; A.yt = ytemp;
+    if (!c->use_graph) return launch_rhs_dq(c, A, ydot);
+    for (auto &g : c->dqgraphs)
+        if (g.a.v == v && g.yd == ydot && g.a.ewt == ewt && g.a.y0 == y0 && g.a.yt == ytemp && g.a.sigma == sigma) {
+            g.used = ++c->graph_clock;
+            CK(cudaGraphLaunch(g.exec, c->stream));
+            return SHUD_OK;
+        }
+    if (c->dqgraphs.size() >= 32) {
+        size_t lru = 0;
+        for (size_t k = 1; k < c->dqgraphs.size(); k++)
+            if (c->dqgraphs[k].used < c->dqgraphs[lru].used) lru = k;
+        cudaGraphExecDestroy(c->dqgraphs[lru].exec);
+        c->dqgraphs.erase(c->dqgraphs.begin() + lru);
+    }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_rhs_dq(c, A, ydot);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == SHUD_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != SHUD_OK || e != cudaSuccess || !exec) {
+        cudaGetLastError();
+        return launch_rhs_dq(c, A, ydot);
+    }
+    c->dqgraphs.push_back({A, ydot, exec, ++c->graph_clock});
+    CK(cudaGraphLaunch(exec, c->stream));
+    return SHUD_OK;
 }
 
 int shud_b200_rhs_dev(shud_ctx *c, double t, const double *y, double *ydot) {

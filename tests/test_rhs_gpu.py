@@ -251,3 +251,47 @@ def test_ragged_and_riverless_meshes(n):
     assert got["ydot"].size == 3 * n
     bad = parity.mismatches(got["ydot"], ref["ydot"], parity.ydot_scale(snap, ref))
     assert bad.size == 0, (n, bad[:5], got["ydot"][bad[:5]], ref["ydot"][bad[:5]])
+
+
+@pytest.mark.parametrize("basin,case", [("ccw", "rand1"), ("qhh", "lakes6"), ("heihe", "ic")])
+def test_difference_quotient_evaluation_folded_into_the_prepass(basin, case):
+    """shud_b200_rhs_dq_dev: ytemp = sigma (v ./ ewt) + y0 formed by the pre-pass and f(ytemp) - bit for bit the perturbed
+    vector of shud_nv_dq_perturb and the ydot of shud_b200_rhs_dev on it (CVLS' difference-quotient J v inside SPGMR,
+    src/Equations/cvode_config.cpp:172-179), on repeated calls (graph replay) and with another direction"""
+    import torch
+    from shud_up_b200.api import ShudRHS
+    from shud_up_b200.nvector import NVectorOps
+    snap = oracle_lib.load_case(basin, case)
+    rhs = ShudRHS(snap)
+
+    def reset():
+        rhs.set_forcing(snap, qEleE_IC=snap["qEleE_IC_in"])
+        rhs.set_carried(snap["ele_u_satn"])
+
+    reset()
+    st = rhs.torch_stream()
+    rng = np.random.default_rng(11)
+    y_ref = np.ascontiguousarray(snap["y"])
+    n = y_ref.size
+    sigma = float(np.sqrt(n))
+    with torch.cuda.stream(st):
+        y0 = torch.empty(n, dtype=torch.float64, device="cuda")
+        rhs.to_device_order(torch.from_numpy(y_ref).cuda(), y0)
+        ewt = 1.0 / (1e-4 * y0.abs() + 1e-4)
+        vs = [torch.from_numpy(rng.normal(0, 1, n) / np.sqrt(n)).cuda() for _ in range(2)]
+        ops = NVectorOps(0, rhs.stream_ptr, owner=rhs)
+        for v in vs:
+            yt_a, yd_a = torch.empty_like(y0), torch.empty_like(y0)
+            yt_b, yd_b = torch.full_like(y0, float("nan")), torch.full_like(y0, float("nan"))
+            ops.DQPerturb(sigma, v, ewt, y0, yt_a)
+            reset()
+            rhs.f_dev(0.0, yt_a, yd_a)
+            st.synchronize()
+            for rep in range(3):
+                reset()  # both arms start from the same carried saturation / interception state
+                rhs.f_dq_dev(0.0, sigma, v, ewt, y0, yt_b, yd_b)
+                st.synchronize()
+                assert torch.equal(yt_a, yt_b), (basin, case, rep)
+                assert torch.equal(yd_a, yd_b), (basin, case, rep, float((yd_a - yd_b).abs().max()))
+        assert rhs.check()[0] == 0
+        ops.close()
