@@ -16,6 +16,7 @@
 
 #include "shud_oracle.h"
 #include "shud_sundials.h"
+#include "shud_cvode.h"
 
 typedef struct { sunindextype length; int own; double *data; long *opcount; } host_content;
 #define HC(v) ((host_content *)(v)->content)
@@ -179,4 +180,63 @@ int host_test_f(realtype t, N_Vector y, N_Vector ydot, void *user_data) {
         fd[i] = -lam[i] * yd[i] + kappa * (left - 2.0 * yd[i] + right) - 0.5 * yd[i] * yd[i] * yd[i];
     }
     return 0;
+}
+
+/* ---- The integrator's optional hooks (shud_cv_fused: predict, newton_step, ewt_set_norm - on the GPU single fused
+ * kernels, shud_up_b200/csrc/shud_nvector_sundials.cu) restated through the generic vector operations, in the order
+ * the unhooked integrator runs them.  Test infrastructure: tests/test_cvode_cpu.py checks that the hooked control
+ * flow of shud_cvode.cpp reproduces the plain one bit for bit. ---- */
+typedef struct host_fused_ctx { shud_cv *cv; N_Vector b, x; long calls[3]; } host_fused_ctx;
+
+static int hf_predict(void *ctx, int q, realtype sgn, N_Vector *zn, N_Vector y, N_Vector acor) {
+    ((host_fused_ctx *)ctx)->calls[0]++;
+    for (int k = 1; k <= q; k++)
+        for (int j = q; j >= k; j--) N_VLinearSum(1.0, zn[j - 1], sgn, zn[j], zn[j - 1]);
+    if (acor) { N_VConst(0.0, acor); N_VLinearSum(1.0, zn[0], 1.0, acor, y); }
+    return 0;
+}
+static int hf_newton_step(void *ctx, realtype t, realtype gamma, realtype rl1, N_Vector zn0, N_Vector zn1, N_Vector acor,
+                          N_Vector y, N_Vector fy, N_Vector ewt, realtype delta, realtype *del, int *nli, int *nfe) {
+    host_fused_ctx *c = (host_fused_ctx *)ctx;
+    c->calls[1]++;
+    N_VLinearSum(rl1, zn1, 1.0, acor, c->b);
+    N_VLinearSum(-gamma, fy, 1.0, c->b, c->b);
+    N_VScale(-1.0, c->b, c->b);
+    int it = 0;
+    const int r = shud_cv_linsolve(c->cv, t, gamma, y, fy, ewt, c->b, delta, c->x, &it);
+    *nli = it; *nfe = 0;  /* the integrator's own difference quotient has counted its RHS calls */
+    if (r < 0 || r == 3) return r;
+    N_VLinearSum(1.0, acor, 1.0, c->x, acor);
+    N_VLinearSum(1.0, zn0, 1.0, acor, y);
+    *del = N_VWrmsNorm(c->x, ewt);
+    return r;
+}
+static int hf_ewt_set_norm(void *ctx, realtype rtol, realtype atol, N_Vector y, N_Vector ewt, realtype *nrm) {
+    host_fused_ctx *c = (host_fused_ctx *)ctx;
+    c->calls[2]++;
+    N_VAbs(y, c->b);
+    N_VScale(rtol, c->b, c->b);
+    N_VAddConst(c->b, atol, c->b);
+    N_VInv(c->b, ewt);
+    *nrm = N_VWrmsNorm(y, ewt);
+    return 0;
+}
+int host_cv_fused_create(shud_cv *cv, N_Vector tmpl, shud_cv_fused *out) {
+    host_fused_ctx *c = (host_fused_ctx *)calloc(1, sizeof(host_fused_ctx));
+    if (!c || !cv || !tmpl || !out) return -1;
+    c->cv = cv; c->b = N_VClone(tmpl); c->x = N_VClone(tmpl);
+    memset(out, 0, sizeof(*out));
+    out->ctx = c; out->predict = hf_predict; out->newton_step = hf_newton_step; out->ewt_set_norm = hf_ewt_set_norm;
+    return 0;
+}
+void host_cv_fused_calls(const shud_cv_fused *f, long *calls3) {
+    const host_fused_ctx *c = (const host_fused_ctx *)f->ctx;
+    for (int k = 0; k < 3; k++) calls3[k] = c->calls[k];
+}
+void host_cv_fused_destroy(shud_cv_fused *f) {
+    host_fused_ctx *c = (host_fused_ctx *)f->ctx;
+    if (!c) return;
+    N_VDestroy(c->b); N_VDestroy(c->x);
+    free(c);
+    f->ctx = NULL;
 }

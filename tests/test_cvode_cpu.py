@@ -161,3 +161,56 @@ def test_oracle_rhs_under_the_integrator_converges_with_the_tolerance():
     wrms = np.sqrt(np.mean(((ya - yb) / (1e-4 * np.abs(yb) + 1e-4)) ** 2))
     assert wrms < 1.0, (wrms, ends[1e-4][1], ends[1e-7][1])
     assert ends[1e-4][1]["nst"] >= 36 and ends[1e-7][1]["nst"] > ends[1e-4][1]["nst"]
+
+
+def _run_steps(hooked, nsteps, rhs="test"):
+    L = host_cv.lib()
+    if rhs == "test":
+        L_, y, cv = _make(1e-6, 1e-8, max_num_steps=100000)
+        keep = None
+    else:
+        import oracle_lib
+        snap = oracle_lib.load_case("ccw", "ic")
+        keep = host_cv.OracleCV(snap)
+        keep.satn[:] = oracle_lib.oracle_prime(snap, snap["y"])
+        y = host_cv.HostVector(snap["y"].size, np.ascontiguousarray(snap["y"]))
+        cv = cvode.CVode(L, keep.f_addr, keep.user_data, 0.0, y.h)
+        cv.configure(rtol=1e-4, atol=1e-4, init_step=1e-3, max_step=10.0)
+    fz, calls = None, None
+    if hooked:
+        fz = cvode.Fused()
+        L.host_cv_fused_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(cvode.Fused)]
+        L.host_cv_fused_calls.argtypes = [C.POINTER(cvode.Fused), C.POINTER(C.c_long)]
+        L.host_cv_fused_destroy.argtypes = [C.POINTER(cvode.Fused)]
+        assert L.host_cv_fused_create(cv._h, y.h, C.byref(fz)) == 0
+        cv.set_fused(fz)
+    traj = []
+    for _ in range(nsteps):
+        cv.solve(1e9, y.h, itask=cvode.CV_ONE_STEP)
+        traj.append((cv.t, y.array.copy()))
+    st = cv.stats()
+    if hooked:
+        c3 = (C.c_long * 3)()
+        L.host_cv_fused_calls(C.byref(fz), c3)
+        calls = list(c3)
+    cv.close()
+    if hooked:
+        L.host_cv_fused_destroy(C.byref(fz))
+    y.close()
+    return traj, st, calls
+
+
+@pytest.mark.parametrize("rhs,nsteps", [("test", 150), ("oracle", 40)])
+def test_hooked_newton_step_and_predictor_reproduce_the_plain_integrator(rhs, nsteps):
+    """shud_cv_fused.predict / newton_step / ewt_set_norm (single fused kernels on the GPU) restated with the generic
+    vector operations (oracle/host_cv.c): the hooked control flow of the integrator - predictor that also primes the
+    Newton iteration, one hook per Newton iteration, weights + norm in one call - takes the same steps and produces the
+    same vectors, bit for bit, as the plain route (cvPredict / cvNls / cvLsSolve / cvEwtSet sequence)"""
+    plain, st0, _ = _run_steps(False, nsteps, rhs)
+    hook, st1, calls = _run_steps(True, nsteps, rhs)
+    assert calls[0] >= nsteps and calls[1] >= nsteps and calls[2] >= nsteps - 1, calls
+    for k in ("nst", "nfe", "nfeLS", "nni", "nli", "ncfn", "netf", "ncfl", "qlast", "hlast"):
+        assert st0[k] == st1[k], (k, st0, st1)
+    for (t0, y0), (t1, y1) in zip(plain, hook):
+        assert t0 == t1
+        assert np.array_equal(y0, y1)
