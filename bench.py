@@ -488,7 +488,7 @@ def gpu_arm(a):
         ms_land = (time.perf_counter() - t0) / 20 * 1e3
         assert rhs.check()[0] == 0
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
-        for a_, b_ in ev:  # device time of one step (table copy + k_land), CUDA events on the context stream
+        for a_, b_ in ev:  # device time of one step (k_land_tables + k_land), CUDA events on the context stream
             a_.record(st); rhs.land_step(S); b_.record(st)
         st.synchronize()
         ms_land_dev = float(np.median([a_.elapsed_time(b_) for a_, b_ in ev]))
@@ -504,7 +504,7 @@ def gpu_arm(a):
                     "roofline_frac": 208 * Ne / (ms_land_dev * 1e-3) / 1e9 / peak_l,
                     "replaces_upload_ms": ms_up,
                     "what": "shud_b200_land_step: tReadForcing + ET per cell on the device (terrain radiation on); ms_per_step = "
-                            "host call to completion, device_ms = table copy + k_land by CUDA events, 208 B/cell "
+                            "host call to completion, device_ms = k_land_tables + k_land by CUDA events around each call (calls back to back), 208 B/cell "
                             "algorithmic (96 read, 112 written); replaces_upload_ms = shud_b200_set_forcing of the 7 per-cell "
                             "arrays the reference's host loop would hand over each ET step"}
 

@@ -6,7 +6,7 @@
 // shud_b200_set_forcing never cross PCIe, and the host keeps only O(stations + classes) work per step (time-series
 // lookups, solarPosition()).  One thread per cell, ~200 B/cell of HBM traffic.  What depends only on the land-cover
 // class (LAI, the two logarithms of the aerodynamic resistance, the canopy resistance, the soil-heat factor) is
-// evaluated once per class by k_land_classes, same expressions and association, so a cell is left with 1 exp, 1 log
+// evaluated once per class by k_land_tables, same expressions and association, so a cell is left with 1 exp, 1 log
 // and 8 divisions (the first version: 2 exp, 4 log, ~24 divisions = 1540 warp-instructions per 32 cells, issue-bound
 // at 0.33 of the HBM roofline).  With SHUD_RCP (the build's default, shud_phys.cuh) divisors shared by several
 // quotients or uniform over the cells are applied as reciprocals: <= 1.5 ulp per quotient, inside the 1e-12 tolerance.
@@ -36,12 +36,16 @@ __device__ __forceinline__ double frozen_fraction(double T, double high, double 
 #define L_RCP(x, d, rd) ((x) / (d))
 #endif
 
-// per land-cover class, once per step: [lai | 0.4 exp(-lai/2) | log(.)log(.) of AerodynamicResistance | 200 / lai]
-__global__ void k_land_classes(DevLand L) {
+// The step's tables, once per step: pulled from the pinned staging buffer (mapped host memory: a few hundred doubles
+// over PCIe, no copy-engine operation on the stream) into L.tab, and per land-cover class
+// [lai | 0.4 exp(-lai/2) | log(.)log(.) of AerodynamicResistance | 200 / lai] into L.cls.  k_land is launched
+// programmatically dependent: its per-cell loads run under this kernel, it waits before its first table read.
+__global__ void k_land_tables(DevLand L, const double *__restrict__ stage, int ntab) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ntab; k += gridDim.x * blockDim.x) L.tab[k] = stage[k];
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= L.nlc) return;
-    const double *t_lai = L.tab + 5 * L.nforc;
-    const double lai = t_lai[c] * L.cLAItsd;
+    const double lai = stage[5 * L.nforc + c] * L.cLAItsd;
     double gfac = 0.1, LL = 0., rs = 0.;
     if (lai > 0) {
         gfac = 0.4 * exp(-0.5 * lai);
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(LAND_BLOCK, LAND_MINB) k_land(DevMesh m, DevLa
     const double snow0 = L.snow[ic], ics0 = L.ics[ic];
     double nx = 0., ny = 0., nz = 0.;
     if (L.tsr && tsr_n > 0 && tsr_den > 0.0) { nx = __ldg(L.nx + ic); ny = __ldg(L.ny + ic); nz = __ldg(L.nz + ic); }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the step's tables are in place (k_land_tables)
     for (int k = threadIdx.x; k < ns; k += blockDim.x) {
         const double sz = g_sz[k];
         double denom = sz, wdt = g_wdt[k];
@@ -328,7 +333,10 @@ int shud_b200_land_create(shud_ctx *c, const shud_land *L) {
     d.tab = dev_alloc<double>(c, ntab);
     d.cls = dev_alloc<double>(c, 4 * (size_t)d.nlc);
     if (!d.tab || !d.cls) return SHUD_ERR_CUDA;
-    CK(cudaMallocHost((void **)&c->land_stage, sizeof(double) * ntab));
+    CK(cudaHostAlloc((void **)&c->land_stage, sizeof(double) * 2 * ntab, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&c->land_stage_dev, c->land_stage, 0));
+    c->land_ntab = ntab;
+    for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&c->land_ev[k], cudaEventDisableTiming));
     // lake -> its cells, ascending reference id (c->lake_cells is ascending)
     std::vector<int> ptr(c->Nl + 1, 0), cell;
     std::vector<double> rn(std::max(c->Nl, 1), 1.0);
@@ -360,8 +368,10 @@ int shud_b200_land_step(shud_ctx *c, const shud_land_step *S) {
     const int n = S->tsr_n > 0 ? S->tsr_n : 0;
     if (n > d.tsr_cap || (n > 0 && (!S->tsr_sx || !S->tsr_sy || !S->tsr_sz || !S->tsr_wdt))) return SHUD_ERR_ARG;
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused
-    double *h = c->land_stage;
+    const int half = c->land_flip;
+    c->land_flip ^= 1;
+    if (c->land_ev_set[half]) CK(cudaEventSynchronize(c->land_ev[half]));  // the step before last has read this half
+    double *h = c->land_stage + half * c->land_ntab;
     size_t o = 0;
     memcpy(h + o, S->forc, sizeof(double) * 5 * d.nforc); o += 5 * (size_t)d.nforc;
     memcpy(h + o, S->lai, sizeof(double) * d.nlc); o += d.nlc;
@@ -371,7 +381,7 @@ int shud_b200_land_step(shud_ctx *c, const shud_land_step *S) {
         if (n > 0) memcpy(h + o, smp[a], sizeof(double) * n);
         o += d.tsr_cap;
     }
-    CK(cudaMemcpyAsync(d.tab, h, sizeof(double) * o, cudaMemcpyHostToDevice, c->stream));
+    const int ntab = (int)o;
     CryoStep cs = {};
     cs.size_s = cs.size_b = 1.;
     if (d.cryo) {
@@ -391,8 +401,22 @@ int shud_b200_land_step(shud_ctx *c, const shud_land_step *S) {
         cs.size_s = (double)c->cryo_size_s; cs.size_b = (double)c->cryo_size_b;
     }
     cs.r_nday = 1. / cs.nday; cs.r_size_s = 1. / cs.size_s; cs.r_size_b = 1. / cs.size_b;
-    k_land_classes<<<(d.nlc + 127) / 128, 128, 0, c->stream>>>(d);
-    k_land<<<(c->Ne + LAND_BLOCK - 1) / LAND_BLOCK, LAND_BLOCK, 0, c->stream>>>(c->m, d, S->tsr_n, S->tsr_den, S->dt_min, cs);
+    k_land_tables<<<(std::max(ntab, d.nlc) + 255) / 256, 256, 0, c->stream>>>(d, c->land_stage_dev + half * c->land_ntab, ntab);
+
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((c->Ne + LAND_BLOCK - 1) / LAND_BLOCK); cfg.blockDim = dim3(LAND_BLOCK); cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = c->use_pdl ? 1 : 0;
+        if (cudaLaunchKernelEx(&cfg, k_land, c->m, d, S->tsr_n, S->tsr_den, S->dt_min, cs) != cudaSuccess) {
+            cudaGetLastError();
+            k_land<<<cfg.gridDim, cfg.blockDim, 0, c->stream>>>(c->m, d, S->tsr_n, S->tsr_den, S->dt_min, cs);
+        }
+    }
+    CK(cudaEventRecord(c->land_ev[half], c->stream));  // (behind k_land: nothing between the two launches of the programmatic pair)
+    c->land_ev_set[half] = 1;
     if (c->Nl > 0) k_lake_means<<<(c->Nl + 63) / 64, 64, 0, c->stream>>>(c->m, d);
     CK(cudaGetLastError());
     return SHUD_OK;

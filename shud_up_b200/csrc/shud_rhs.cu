@@ -103,7 +103,7 @@ struct DevLand {
     int net, tsr;
     double cap, cosz_min;
     double *snow, *ics;                         // yEleSnow, yEleIS (device order)
-    double *cls;                                // per-step, per land-cover class: lai | soil-heat factor | log log | rs (k_land_classes)
+    double *cls;                                // per-step, per land-cover class: lai | soil-heat factor | log log | rs (k_land_tables)
     double *tab;                                // per-step tables: forc[5 nforc] | lai[nlc] | mf[nmf] | sx|sy|sz|wdt [tsr_cap each]
     int tsr_cap;
     double *prep, *etp, *temp, *tmf, *factor;   // qElePrep, qEleETP, t_temp, t_mf, terrain factor
@@ -933,7 +933,14 @@ struct shud_ctx {
     DevDiag diag{};
     DevLand land{};
     bool has_land = false;
-    double *land_stage = nullptr;  // pinned staging of the per-step tables
+    // pinned (mapped) staging of the per-step tables, two halves used alternately: the host fills one while the
+    // device may still read the other (land_ev[k]: the last k_land_tables that read half k)
+    double *land_stage = nullptr;
+    double *land_stage_dev = nullptr;  // its device alias
+    size_t land_ntab = 0;
+    cudaEvent_t land_ev[2] = {nullptr, nullptr};
+    int land_ev_set[2] = {0, 0};
+    int land_flip = 0;
     double cryo_tstart = -9999., cryo_nday = 0.;  // _AccTemp::Time_start, N_of_day (identical for every cell)
     int cryo_size_s = 0, cryo_head_s = 0, cryo_size_b = 0, cryo_head_b = 0;
     bool diag_alloc = false;
@@ -1466,6 +1473,8 @@ void shud_b200_destroy(shud_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->land_stage) cudaFreeHost(c->land_stage);
+    for (int k = 0; k < 2; k++)
+        if (c->land_ev[k]) cudaEventDestroy(c->land_ev[k]);
     if (c->xstream) cudaStreamSynchronize(c->xstream);
     drop_graphs(c);  // the captured exchange graphs hold NCCL nodes: gone before the communicator
     if (c->nccl_comm && c->nccl_comm_destroy) c->nccl_comm_destroy(c->nccl_comm);
