@@ -535,6 +535,11 @@ def gpu_arm(a):
             dist.all_reduce(ng)
             n_glob = int(ng[0])
             L.N_VSetDistributed_ShudB200(yv, n_glob, C.c_void_p(_cv.fn_address(L, "shud_b200_nv_allreduce")), rhs._h)
+            _nr, _rk, _bx = C.c_int(0), C.c_int(0), (C.c_void_p * 16)()
+            L.shud_b200_p2p_mailboxes.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+            L.shud_b200_p2p_mailboxes(rhs._h, C.byref(_nr), C.byref(_rk), _bx)
+            ar_mode = ("inside the reduction kernels: partials stored into every rank's mailbox over NVLink, combined in rank order"
+                       if _nr.value > 1 and os.environ.get("SHUD_P2P_AR", "1") != "0" else "ncclAllReduce of the scalar on the stream")
         rhs.prime(mesh["y"])
         cvi = _cv.CVode(L, _cv.fn_address(L, "shud_b200_f_exchange" if world > 1 else "shud_b200_f"), rhs._h.value, 0.0, yv)
         cvi.configure(rtol=1e-4, atol=1e-4, init_step=1e-3, max_step=10.0)
@@ -575,8 +580,8 @@ def gpu_arm(a):
                        + ("device-fused Newton-Krylov pieces (one-pass predictor, shud_spgmr_newton_step)" if fz is not None
                           else "generic operations table")
                        + ("" if world == 1 else
-                          f"; {world} partitions: distributed vectors, every reduction = local kernel + ncclAllReduce of "
-                          "the scalar on the device inside the library, f() = halo exchange + RHS")),
+                          f"; {world} partitions: distributed vectors, allreduce of every reduction {ar_mode}, "
+                          "f() = halo exchange + RHS")),
               "fused": fz is not None}
         cvi.close()
         if fz is not None:

@@ -218,6 +218,10 @@ int shud_b200_allreduce(shud_ctx *ctx, double *vals, int n, int op);
 /* The same on doubles already in DEVICE memory, enqueued on `stream` without copy or synchronisation (ctx = the shud_ctx):
  * the allreduce hook of a distributed N_Vector workspace (shud_nv_ws_set_allreduce, include/shud_nvector.h). */
 int shud_b200_allreduce_dev(void *ctx, double *dev_vals, int n, int op, void *stream);
+/* After shud_b200_p2p_connect: the mailboxes of all ranks for the in-kernel allreduce of the device vector's reductions
+ * (boxes[0..*nranks), for shud_nv_ws_set_peer_allreduce; *nranks = 0 when a rank's block could not be mapped or the
+ * ranks share a process).  N_VSetDistributed_ShudB200 on the library's communicator installs them by itself. */
+int shud_b200_p2p_mailboxes(shud_ctx *ctx, int *nranks, int *rank, void **boxes);
 /* ---- land-surface step on the device ----
  * Replaces the per-cell loops of Model_Data::updateforcing / tReadForcing (src/ModelData/MD_ET.cpp:14-281:
  * lapse-rate temperature, terrain-radiation factor, Penman-Monteith potential evaporation / transpiration) and

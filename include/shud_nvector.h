@@ -34,6 +34,14 @@ void *shud_nv_ws_stream(const shud_nvws *ws); /* the cudaStream_t the workspace 
  * same reductions.  shud_nv_ws_local(ws, 1) ... shud_nv_ws_local(ws, 0) brackets calls that must stay local. */
 typedef int (*shud_nv_allreduce_dev_fn)(void *ctx, double *dev_vals, int n, int op, void *stream);
 int shud_nv_ws_set_allreduce(shud_nvws *ws, shud_nv_allreduce_dev_fn fn, void *ctx);
+/* Allreduce INSIDE the reduction kernels: boxes[r] = device pointer to rank r's mailbox (SHUD_NV_ARBOX_BYTES of zeroed
+ * device memory, the other ranks' mapped through CUDA IPC - shud_b200_p2p_mailboxes hands them out).  The last block of
+ * every reduction stores the rank's partials into every mailbox over NVLink, waits for the others' and combines them in
+ * rank order: one kernel per global reduction, the same bits on every rank.  Takes precedence over the hook above;
+ * one workspace per set of mailboxes; every rank must issue the same reductions in the same order.  nranks <= 1: off. */
+#define SHUD_NV_MAXRANKS 16
+#define SHUD_NV_ARBOX_BYTES 4096
+int shud_nv_ws_set_peer_allreduce(shud_nvws *ws, int nranks, int rank, void *const *boxes);
 void shud_nv_ws_local(shud_nvws *ws, int on);
 int shud_nv_ws_device(const shud_nvws *ws);
 

@@ -153,13 +153,39 @@ __device__ __forceinline__ double block_reduce(double v, double *sm) {
     return t;  // valid in thread 0
 }
 
+// ---- allreduce over NVLink inside the reduction kernel (one process per GPU, the ranks' mailboxes mapped through
+// CUDA IPC by shud_b200_p2p_connect): the last block of the reduction stores the rank's partial results into every
+// rank's mailbox (peer stores + a release of the sequence number), waits for the other ranks' sequence numbers in its
+// own mailbox, and combines the partials in rank order - the same bits on every rank, no second kernel, no NCCL call.
+// Two slots by the parity of the sequence number: a rank can be at most one reduction ahead of the slowest one.
+struct ArBox {
+    double val[2][SHUD_NV_MAXRANKS][SHUD_NV_MAXVEC];
+    unsigned long long tag[2][SHUD_NV_MAXRANKS];
+};
+static_assert(sizeof(ArBox) <= SHUD_NV_ARBOX_BYTES, "mailbox larger than the region shud_b200_p2p_export reserves");
+struct PeerAR {
+    int nranks, rank;
+    unsigned long long seq;
+    ArBox *box[SHUD_NV_MAXRANKS];
+};
+__device__ __forceinline__ void ar_release(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ar_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // NV accumulators per thread (1 for plain reductions, up to SHUD_NV_MAXVEC for the multi forms);
 // F::term(k, i) is the value element i contributes to accumulator k.
 // post: 0 none, 1 sqrt(v / nglob), 2 sqrt(v)
 template <int KIND, int NV, class F>
 __global__ void __launch_bounds__(NT) k_reduce(int64_t n, F f, int nv, double *partial, unsigned *counter,
                                                double *d_out, volatile double *h_out, int post, double nglob,
-                                               volatile double *h_ticket = nullptr, double ticket = 0.0) {
+                                               volatile double *h_ticket = nullptr, double ticket = 0.0,
+                                               PeerAR P = PeerAR{}) {
+    __shared__ double sv[NV];
     __shared__ double sm[NT / 32];
     __shared__ bool last;
     double acc[NV];
@@ -194,7 +220,37 @@ __global__ void __launch_bounds__(NT) k_reduce(int64_t n, F f, int nv, double *p
         double v = ident<KIND>();
         for (int b = threadIdx.x; b < (int)gridDim.x; b += NT) v = comb<KIND>(v, partial[(size_t)k * MAXB + b]);
         v = block_reduce<KIND>(v, sm);
+        if (threadIdx.x == 0) sv[k] = v;
+    }
+    if (P.nranks > 1) {
+        __syncthreads();
+        const int par = (int)(P.seq & 1ull);
+        ArBox *const me = P.box[P.rank];
+        if ((int)threadIdx.x < P.nranks) {
+            ArBox *const dst = P.box[threadIdx.x];  // thread r serves rank r: send to it, then wait for it
+            for (int k = 0; k < nv; k++) dst->val[par][P.rank][k] = sv[k];
+            __threadfence_system();
+            ar_release(&dst->tag[par][P.rank], P.seq);
+            const long long t0 = clock64();
+            while (ar_acquire(&me->tag[par][threadIdx.x]) < P.seq) {
+                if (clock64() - t0 > 6000000000ll) {  // ~3 s: a rank is missing - poison the result instead of hanging
+                    for (int k = 0; k < nv; k++) ((volatile double *)me->val[par][threadIdx.x])[k] = nan("");
+                    break;
+                }
+            }
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
+            for (int k = 0; k < nv; k++) {
+                double v = ident<KIND>();
+                for (int r = 0; r < P.nranks; r++) v = comb<KIND>(v, ((const volatile double *)me->val[par][r])[k]);
+                sv[k] = v;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < nv; k++) {
+            double v = sv[k];
             if (post == 1) v = sqrt(v / nglob);
             else if (post == 2) v = sqrt(v);
             d_out[k] = v;
@@ -267,6 +323,9 @@ struct shud_nvws {
     double *h_out;         // mapped pinned, [SHUD_NV_MAXVEC] results + [1] ticket of the last signalled reduction
     double *h_out_dev;     // device alias of h_out
     double ticket = 0.0;   // last ticket handed out
+    // allreduce inside the reduction kernels over the ranks' mailboxes (shud_nv_ws_set_peer_allreduce); preferred to ar_dev
+    PeerAR peer{};
+    unsigned long long peer_seq = 0;
     // distributed vector: the partial results of a reduction stay on the device, are reduced over the ranks in place
     // (ncclAllReduce on the same stream) and only then copied to the host: one synchronisation per reduction
     shud_nv_allreduce_dev_fn ar_dev = nullptr;
@@ -313,6 +372,19 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
         for (int k = 0; k < nv; k++) out[k] = (KIND == R_MIN) ? DBL_MAX : 0.0;
         return SHUD_OK;
     }
+    if (ws->peer.nranks > 1 && !ws->ar_off) {
+        // every rank calls this with the same nv (SPMD): the kernel itself combines the ranks' partials over NVLink
+        PeerAR P = ws->peer;
+        P.seq = ++ws->peer_seq;
+        const double ticket = (ws->ticket += 1.0);
+        k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out, ws->h_out_dev,
+                                                                  post, nglob, ws->h_out_dev + SHUD_NV_MAXVEC, ticket, P);
+        CKN(cudaGetLastError());
+        const int rc = wait_ticket(ws, ticket);
+        if (rc) return rc;
+        for (int k = 0; k < nv; k++) out[k] = ws->h_out[k];
+        return SHUD_OK;
+    }
     if (ws->ar_dev && !ws->ar_off) {
         // every rank calls this with the same nv (SPMD): raw partials -> allreduce on the device -> host, post on the host
         k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
@@ -343,10 +415,13 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
 template <int KIND, class F>
 int run_reduce_dev(shud_nvws *ws, int64_t n, F f, double *d_result, double *h_result = nullptr, double ticket = 0.0) {
     if (!ws || !d_result || n <= 0) return SHUD_ERR_ARG;
+    PeerAR P{};
+    if (ws->peer.nranks > 1 && !ws->ar_off) { P = ws->peer; P.seq = ++ws->peer_seq; }
     k_reduce<KIND, 1, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, 1, ws->partial, ws->counter, d_result,
                                                              h_result ? h_result : ws->h_out_dev + (SHUD_NV_MAXVEC - 1), 0, 1.0,
-                                                             ticket > 0.0 ? ws->h_out_dev + SHUD_NV_MAXVEC : nullptr, ticket);
+                                                             ticket > 0.0 ? ws->h_out_dev + SHUD_NV_MAXVEC : nullptr, ticket, P);
     CKN(cudaGetLastError());
+    if (P.nranks > 1) return SHUD_OK;  // reduced over the ranks by the kernel itself
     // distributed vector: the scalar is reduced over the ranks where it lies, on the same stream, before the next
     // kernel reads it (every rank runs the same sequence)
     if (ws->ar_dev && !ws->ar_off && ws->ar_dev(ws->ar_ctx, d_result, 1, KIND, (void *)ws->stream) != 0) return SHUD_ERR_CUDA;
@@ -395,6 +470,14 @@ void shud_nv_ws_destroy(shud_nvws *ws) {
 int shud_nv_ws_set_allreduce(shud_nvws *ws, shud_nv_allreduce_dev_fn fn, void *ctx) {
     if (!ws) return SHUD_ERR_ARG;
     ws->ar_dev = fn; ws->ar_ctx = ctx; ws->ar_off = 0;
+    return SHUD_OK;
+}
+int shud_nv_ws_set_peer_allreduce(shud_nvws *ws, int nranks, int rank, void *const *boxes) {
+    if (!ws || nranks < 0 || nranks > SHUD_NV_MAXRANKS || rank < 0 || (nranks > 0 && (rank >= nranks || !boxes))) return SHUD_ERR_ARG;
+    ws->peer = PeerAR{};
+    ws->peer.nranks = nranks; ws->peer.rank = rank;
+    for (int r = 0; r < nranks; r++) ws->peer.box[r] = (ArBox *)boxes[r];
+    ws->peer_seq = 0;
     return SHUD_OK;
 }
 void shud_nv_ws_local(shud_nvws *ws, int on) { if (ws) ws->ar_off += on ? 1 : -1; }
@@ -654,7 +737,7 @@ template <class F>
 static int reduce_to_host(shud_spgmr *s, F f) {
     shud_nvws *ws = s->ws;
     int rc;
-    if (ws->ar_dev && !ws->ar_off) {
+    if (ws->ar_dev && !ws->ar_off && ws->peer.nranks <= 1) {
         if ((rc = run_reduce_dev<R_SUM>(ws, s->n, f, s->dH))) return rc;
         CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
         CKN(cudaStreamSynchronize(ws->stream));
@@ -734,14 +817,15 @@ static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y,
         // one GPU: every scalar also lands in mapped host memory, the last one with a ticket the host spins on (the
         // normalisation below runs while the host does the Givens rotations); distributed: the allreduced scalars
         // are copied back and the stream synchronised
-        double *const hd = dist ? nullptr : s->hH_dev;
-        const double ticket = dist ? 0.0 : (ws->ticket += 1.0);
+        const bool via_copy = dist && ws->peer.nranks <= 1;  // scalars allreduced by NCCL behind the kernels
+        double *const hd = via_copy ? nullptr : s->hH_dev;
+        const double ticket = via_copy ? 0.0 : (ws->ticket += 1.0);
         if ((rc = run_reduce_dev<R_SUM>(ws, n, TDqCombineDot{sig, gamma, s->V[k], ewt, s->ftemp, fy, w, s->V[0]}, s->dH, hd))) return rc;
         for (int i = 0; i < k; i++)
             if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegDot{s->dH + i, s->V[i], w, s->V[i + 1]}, s->dH + i + 1, hd ? hd + i + 1 : nullptr))) return rc;
         if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegSq{s->dH + k, s->V[k], w}, s->dH + k + 1, hd ? hd + k + 1 : nullptr, ticket))) return rc;
         if ((rc = run_map(ws, n, FNormalizeDev{s->dH + k + 1, s->V[k + 1]}))) return rc;
-        if (dist) {
+        if (via_copy) {
             CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, ws->stream));
             CKN(cudaStreamSynchronize(ws->stream));  // the one host synchronisation of this Krylov iteration
         } else if ((rc = wait_ticket(ws, ticket))) return rc;

@@ -416,6 +416,15 @@ void N_VSetDistributed_ShudB200(N_Vector v, sunindextype global_length, shud_nv_
         // (ncclAllReduce on the vectors' stream, one host synchronisation per reduction)
         c->allreduce = nullptr;
         shud_nv_ws_set_allreduce(c->ws, shud_b200_allreduce_dev, comm);
+        // ... and, when the ranks' peer-to-peer blocks are mapped (shud_b200_p2p_connect), not even a second kernel:
+        // the reduction kernels combine the ranks' partials themselves over NVLink (SHUD_P2P_AR=0: NCCL as above)
+        int nr = 0, rk = 0;
+        void *boxes[SHUD_NV_MAXRANKS] = {nullptr};
+        const char *env = getenv("SHUD_P2P_AR");
+        if (!(env && atoi(env) == 0) && shud_b200_p2p_mailboxes((shud_ctx *)comm, &nr, &rk, boxes) == 0 && nr > 1)
+            shud_nv_ws_set_peer_allreduce(c->ws, nr, rk, boxes);
+        else
+            shud_nv_ws_set_peer_allreduce(c->ws, 0, 0, nullptr);
     } else {
         c->allreduce = fn;
     }

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "shud_b200.h"
+#include "shud_nvector.h"  // SHUD_NV_ARBOX_BYTES, SHUD_NV_MAXRANKS: the mailbox region of the in-kernel allreduce
 #include "shud_phys.cuh"
 
 namespace {
@@ -991,6 +992,8 @@ struct shud_ctx {
     int *x_items = nullptr;                  // flat device-order indices into the state vector of what I send
     int x_nitems = 0;
     // peer-to-peer exchange (shud_b200_p2p_export / _connect)
+    int ar_nranks = 0, ar_rank = 0;       // mailboxes of the vector reductions' in-kernel allreduce, one per rank
+    void *ar_box[16] = {nullptr};
     void *p2p_block = nullptr;            // [flags: P2P_MAXPEER u64 | epoch | count | pad to 256 B][buffer 0][buffer 1]
     size_t p2p_stride = 0;                // bytes of one halo buffer (multiple of 256)
     std::vector<void *> p2p_opened;       // neighbours' blocks mapped through CUDA IPC
@@ -1813,8 +1816,10 @@ int shud_b200_p2p_export(shud_ctx *c, int rank, void *blob) {
     const size_t ndbl = (size_t)2 * c->Nhalo + 3 * (size_t)c->n_ghost_cells + (size_t)c->n_ghost_reaches;
     if (!c->p2p_block) {
         c->p2p_stride = (std::max<size_t>(ndbl, 1) * sizeof(double) + 255) / 256 * 256;
-        CK(cudaMalloc(&c->p2p_block, P2P_HDR + 2 * c->p2p_stride));  // its own allocation: one IPC handle, nothing else exposed
-        CK(cudaMemset(c->p2p_block, 0, P2P_HDR + 2 * c->p2p_stride));
+        // its own allocation: one IPC handle, nothing else exposed; behind the two halo buffers the mailbox of the
+        // in-kernel allreduce of the distributed vector's reductions (shud_nv_ws_set_peer_allreduce)
+        CK(cudaMalloc(&c->p2p_block, P2P_HDR + 2 * c->p2p_stride + SHUD_NV_ARBOX_BYTES));
+        CK(cudaMemset(c->p2p_block, 0, P2P_HDR + 2 * c->p2p_stride + SHUD_NV_ARBOX_BYTES));
     }
     P2PBlob b;
     memset(&b, 0, sizeof(b));
@@ -1832,6 +1837,13 @@ int shud_b200_p2p_export(shud_ctx *c, int rank, void *blob) {
     return SHUD_OK;
 }
 
+int shud_b200_p2p_mailboxes(shud_ctx *c, int *nranks, int *rank, void **boxes) {
+    if (!c || !nranks || !rank || !boxes) return SHUD_ERR_ARG;
+    *nranks = c->ar_nranks; *rank = c->ar_rank;
+    for (int r = 0; r < c->ar_nranks; r++) boxes[r] = c->ar_box[r];
+    return SHUD_OK;
+}
+
 int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
     if (!c || !blobs || !c->p2p_block || rank < 0 || rank >= world) return SHUD_ERR_ARG;
     CK(cudaSetDevice(c->device));
@@ -1843,6 +1855,9 @@ int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
     P2PTable T{};
     T.npeers = (int)c->x_peer.size();
     int so = 0;
+    c->ar_nranks = 0;
+    std::vector<char *> mapped(world, nullptr);  // block of rank r as this process sees it
+    mapped[rank] = (char *)c->p2p_block;
     for (int p = 0; p < T.npeers; p++) {
         const int r = c->x_peer[p];
         if (r < 0 || r >= world) return SHUD_ERR_ARG;
@@ -1852,7 +1867,9 @@ int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
         for (int j = 0; j < b.npeers; j++) if (b.peer[j] == rank) slot = j;
         if (b.rank != r || slot < 0) return SHUD_ERR_ARG;
         char *base = nullptr;
-        if (b.pid == (long long)getpid()) {
+        if (r == rank) {
+            base = (char *)c->p2p_block;
+        } else if (b.pid == (long long)getpid()) {
             base = (char *)b.base;  // same process: the pointer itself (IPC handles cannot be opened by their creator)
             int dev_peer = -1;
             cudaPointerAttributes pa;
@@ -1871,6 +1888,7 @@ int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
             }
             c->p2p_opened.push_back(base);
         }
+        mapped[r] = base;
         T.buf[0][p] = (double *)(base + P2P_HDR);
         T.buf[1][p] = (double *)(base + P2P_HDR + b.stride);
         T.flag[p] = (unsigned long long *)base + slot;
@@ -1893,6 +1911,29 @@ int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
     c->m.h_done = (unsigned int *)((unsigned long long *)mine + P2P_MAXPEER + 1) + 1;  // beside the pack counter
     c->m.h_nflags = T.npeers;
     c->m.n_int_tiles = c->n_int_tiles;
+    // mailboxes of the in-kernel allreduce: every rank's block, not only the neighbours' (other processes only; a rank
+    // that cannot be mapped leaves the allreduce to NCCL)
+    if (world >= 2 && world <= SHUD_NV_MAXRANKS) {
+        bool ok = true;
+        for (int r = 0; r < world && ok; r++) {
+            P2PBlob b;
+            memcpy(&b, (const char *)blobs + (size_t)r * SHUD_P2P_BLOB_BYTES, sizeof(b));
+            if (b.rank != r) { ok = false; break; }
+            if (!mapped[r]) {
+                if (b.pid == (long long)getpid()) { ok = false; break; }  // several contexts of one process: no mailbox allreduce
+                char *base = nullptr;
+                if (cudaIpcOpenMemHandle((void **)&base, b.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = false;
+                    break;
+                }
+                c->p2p_opened.push_back(base);
+                mapped[r] = base;
+            }
+            c->ar_box[r] = mapped[r] + P2P_HDR + 2 * b.stride;
+        }
+        if (ok) { c->ar_nranks = world; c->ar_rank = rank; }
+    }
     drop_graphs(c);
     c->use_p2p = 1;
     return SHUD_OK;
