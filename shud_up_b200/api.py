@@ -317,6 +317,14 @@ class ShudRHS:
         _chk(rc, "p2p_connect")
         return True
 
+    def p2p_mailboxes(self):
+        """(nranks, rank, [device pointers]) of the in-kernel allreduce mailboxes mapped by p2p_connect (nranks 0: none)"""
+        nr, rk, bx = C.c_int(0), C.c_int(0), (C.c_void_p * 16)()
+        fn = lib().shud_b200_p2p_mailboxes
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        _chk(fn(self._h, C.byref(nr), C.byref(rk), bx), "p2p_mailboxes")
+        return nr.value, rk.value, [bx[k] for k in range(nr.value)]
+
     def p2p_connect(self, dist, device):
         """collective: exchange the halo-buffer descriptors of all ranks, map the neighbours' buffers (CUDA IPC over
         NVLink), barrier.  After it f_exchange_dev moves the halo with peer stores + flags instead of NCCL."""

@@ -23,6 +23,8 @@ def _lib():
         PP = C.POINTER(C.c_void_p)
         sig = {
             "shud_nv_ws_create": [ci, vp, C.POINTER(vp)],
+            "shud_nv_ws_set_peer_allreduce": [vp, ci, ci, C.POINTER(vp)],
+            "shud_nv_ws_local": [vp, ci],
             "shud_nv_linearsum": [vp, i64, dbl, vp, dbl, vp, vp],
             "shud_nv_const": [vp, i64, dbl, vp],
             "shud_nv_prod": [vp, i64, vp, vp, vp],
@@ -64,6 +66,7 @@ def _lib():
             fn.restype = C.c_int
             fn.argtypes = args
         L.shud_nv_ws_destroy.restype = None
+        L.shud_nv_ws_local.restype = None
         L.shud_nv_ws_destroy.argtypes = [vp]
         L.shud_spgmr_destroy.restype = None
         L.shud_spgmr_destroy.argtypes = [vp]
@@ -110,6 +113,16 @@ class NVectorOps:
 
     def _c(self, rc, what):
         api._chk(rc, what)
+
+    def set_peer_allreduce(self, nranks, rank, boxes):
+        """every reduction of this table becomes a global one: the reduction kernels combine the ranks' partial results
+        through the mailboxes `boxes` (ShudRHS.p2p_mailboxes) over NVLink; nranks <= 1 switches it off"""
+        arr = (C.c_void_p * 16)(*([b for b in boxes] + [None] * (16 - len(boxes))))
+        self._c(self._L.shud_nv_ws_set_peer_allreduce(self._h, int(nranks), int(rank), arr), "set_peer_allreduce")
+
+    def local(self, on):
+        """reductions stay local while on (the *local members of the operations table)"""
+        self._L.shud_nv_ws_local(self._h, 1 if on else 0)
 
     # ---- streaming ----
     def N_VLinearSum(self, a, x, b, y, z):
