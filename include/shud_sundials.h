@@ -148,7 +148,11 @@ typedef struct shud_nv_content {
 N_Vector N_VNew_ShudB200(sunindextype length, shud_nvws *ws, struct shud_ctx *gpu, SUNContext sunctx);
 /* wrap existing device storage (not owned) */
 N_Vector N_VMake_ShudB200(sunindextype length, double *dev, shud_nvws *ws, struct shud_ctx *gpu, SUNContext sunctx);
-/* distributed vector: global length + allreduce hook (inherited by clones) */
+/* distributed vector: global length + allreduce hook (inherited by clones).  global_length = the number of OWNED
+ * entries over all ranks: a partition whose rivers are cut carries ghost entries in its local vector (ydot = 0, state
+ * from the exchange); they are zero in every correction, residual and Krylov vector, add nothing to a sum and must not
+ * add to N.  fn == shud_b200_nv_allreduce with comm = the shud_ctx: the library reduces on the device - inside the
+ * reduction kernels over NVLink mailboxes after shud_b200_p2p_connect, else ncclAllReduce on the stream. */
 void N_VSetDistributed_ShudB200(N_Vector v, sunindextype global_length, shud_nv_allreduce_fn fn, void *comm);
 /* host mirror -> device (after SetIC2Y-style writes through N_VGetArrayPointer); device -> host mirror (what
  * N_VGetArrayPointer does implicitly).  With a context the mirror is in the reference's order, the device vector in

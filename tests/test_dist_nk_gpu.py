@@ -1,0 +1,55 @@
+"""The whole multi-GPU solver path on one GPU: two ranks as two processes on cuda:0, ccw cut into two Hilbert ranges
+(rivers cut: ghost cells / reaches), the library's integrator with the device-fused Newton-Krylov hooks on distributed
+vectors - halo exchange by peer stores + flags into the other process's block (CUDA IPC), every global reduction combined
+inside the reduction kernel through the mailboxes, f() = shud_b200_f_exchange - against the single domain under the same
+integrator.  (bench.py --gpus N runs the same code one rank per GPU over NVLink.)"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+T_END = 15.0  # minutes (max_step 0.5: at least 30 steps)
+
+
+def _launch(world, d, mode="cut"):
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_nk_worker.py"), str(r), str(world), str(d), str(T_END), mode],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=600)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, outs[r][-3000:]
+    return [dict(np.load(os.path.join(d, f"nk{r}.npz"))) for r in range(world)]
+
+
+@pytest.mark.parametrize("mode", ["trees", "cut"])
+def test_two_process_newton_krylov_run_tracks_the_single_domain(tmp_path, mode):
+    one = tmp_path / "one"; two = tmp_path / "two"
+    one.mkdir(); two.mkdir()
+    ref = _launch(1, one)[0]
+    res = _launch(2, two, mode)
+    y_ref = np.empty(ref["gid"].size); y_ref[ref["gid"]] = ref["val"]
+    # the two ranks own every entry exactly once
+    gid = np.concatenate([r["gid"] for r in res])
+    assert np.array_equal(np.sort(gid), np.arange(y_ref.size))
+    y = np.empty_like(y_ref); y[gid] = np.concatenate([r["val"] for r in res])
+    # both ranks took the same steps (every decision of the integrator rests on globally reduced scalars)
+    for k in ("nst", "nfe", "nfeLS", "nni", "nli", "ncfn", "netf", "qlast"):
+        assert res[0][k][0] == res[1][k][0], (k, res[0][k], res[1][k])
+    assert int(res[0]["nst"][0]) == int(ref["nst"][0]), (res[0]["nst"], ref["nst"])
+    # end state: the single domain's up to the order of the sums (ghost entries are zero in every vector a norm or a
+    # dot product is taken of, and the global length counts owned entries only)
+    ewt = 1e-4 * np.abs(y_ref) + 1e-4
+    wrms = float(np.sqrt(np.mean(((y - y_ref) / ewt) ** 2)))
+    print(mode, "ny", int(res[0]["ny"]), int(res[1]["ny"]), "of", y_ref.size, "steps", int(res[0]["nst"][0]), "single", int(ref["nst"][0]), "wrms", wrms, "wall", float(res[0]["wall"]), float(ref["wall"]))
+    assert int(ref["nst"][0]) >= 30
+    assert wrms < 1e-3, wrms
