@@ -164,9 +164,14 @@ int shud_b200_rhs(shud_ctx *ctx, double t, const double *y_host, double *ydot_ho
 /* The difference-quotient evaluation of CVLS' Jv (cvLsDQJtimes, inside SUNLinSol_SPGMR), the perturbation folded into
  * the pre-pass of the RHS: ytemp = sigma (v ./ ewt) + y0 - the arithmetic of shud_nv_dq_perturb - and
  * ydot = f(t, ytemp), without a vector kernel of its own and without reading ytemp back for effKH.  Single domain
- * (a partition's pre-pass carries the halo exchange: SHUD_ERR_ARG there; perturb, then shud_b200_rhs_dev). */
+ * (a partition's pre-pass carries the halo exchange: SHUD_ERR_ARG there; perturb, then shud_b200_rhs_dev).
+ * ss_dev != NULL: v is an unnormalised Krylov vector with squared 2-norm *ss_dev (device memory, e.g. the result of
+ * the Gram-Schmidt sweep's last reduction); the direction is (1 / sqrt(ss)) v, stored to vnorm_dev (!= v_dev) when
+ * that is not NULL - the solver's normalisation pass done on the way. */
+int shud_b200_dq_foldable(const shud_ctx *ctx); /* 1: shud_b200_rhs_dq_dev serves this context (single domain) */
 int shud_b200_rhs_dq_dev(shud_ctx *ctx, double t, double sigma, const double *v_dev, const double *ewt_dev,
-                         const double *y0_dev, double *ytemp_dev, double *ydot_dev);
+                         const double *y0_dev, double *ytemp_dev, double *ydot_dev, const double *ss_dev,
+                         double *vnorm_dev);
 /* The RHS of a partition in two parts, so that the halo exchange overlaps the bulk of the work: _interior needs no
  * exchanged data (effKH of the owned cells + every tile of cells that sees no halo cell); _boundary (after the
  * exchange has landed in the halo state buffer) does the halo effKH, the remaining tiles and the river/lake kernel.

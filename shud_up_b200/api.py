@@ -62,7 +62,7 @@ def lib():
         "shud_b200_allreduce": (C.c_int, [vp, _PD, C.c_int, C.c_int]),
         "shud_b200_perm": (C.c_int, [vp, _PI, _PI]),
         "shud_b200_rhs_dev": (C.c_int, [vp, C.c_double, vp, vp]),
-        "shud_b200_rhs_dq_dev": (C.c_int, [vp, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
+        "shud_b200_rhs_dq_dev": (C.c_int, [vp, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp]),
         "shud_b200_rhs": (C.c_int, [vp, C.c_double, vp, vp]),
         "shud_b200_rhs_stage_dev": (C.c_int, [vp, C.c_int, vp, vp]),
         "shud_b200_rhs_interior_dev": (C.c_int, [vp, C.c_double, vp, vp]),
@@ -226,11 +226,13 @@ class ShudRHS:
         fn = lib().shud_b200_rhs_diag_dev if diag else lib().shud_b200_rhs_dev
         _chk(fn(self._h, float(t), _ptr(y_dev), _ptr(ydot_dev)), "shud_b200_rhs_dev")
 
-    def f_dq_dev(self, t, sigma, v_dev, ewt_dev, y0_dev, ytemp_dev, ydot_dev):
+    def f_dq_dev(self, t, sigma, v_dev, ewt_dev, y0_dev, ytemp_dev, ydot_dev, ss_dev=None, vnorm_dev=None):
         """ytemp = sigma (v ./ ewt) + y0 formed by the pre-pass, ydot = f(t, ytemp): the difference-quotient evaluation
-        of SPGMR's J v (single domain)"""
+        of SPGMR's J v (single domain).  ss_dev: v is unnormalised, its squared 2-norm lies in ss_dev[0]; the
+        normalised direction goes to vnorm_dev"""
         _chk(lib().shud_b200_rhs_dq_dev(self._h, float(t), float(sigma), _ptr(v_dev), _ptr(ewt_dev), _ptr(y0_dev),
-                                        _ptr(ytemp_dev), _ptr(ydot_dev)), "shud_b200_rhs_dq_dev")
+                                        _ptr(ytemp_dev), _ptr(ydot_dev), _ptr(ss_dev) if ss_dev is not None else None,
+                                        _ptr(vnorm_dev) if vnorm_dev is not None else None), "shud_b200_rhs_dq_dev")
 
     def f_interior_dev(self, t, y_dev, ydot_dev):
         """part of the RHS of a partition that needs no exchanged halo data (overlaps the halo exchange)"""

@@ -730,7 +730,15 @@ struct shud_spgmr {
     double *hH;                // pinned host copy (mapped: the reductions of a single-GPU solve write it directly)
     double *hH_dev;            // its device alias
     int fold_dq = 1;           // shud_b200_rhs_dq_dev where the context allows it (SHUD_FOLD_DQ=0: separate perturbation)
+    double *wraw = nullptr;    // folded route: the unnormalised Krylov vector in the making (r0, then each w); the RHS
+                               // pre-pass of the next iteration normalises it into V[k] on the way
 };
+
+// the folded route: a single domain whose RHS pre-pass perturbs and normalises (shud_b200_rhs_dq_dev)
+static bool spgmr_folds(const shud_spgmr *s) {
+    const shud_nvws *ws = s->ws;
+    return s->fold_dq && s->wraw && !(ws->ar_dev && !ws->ar_off) && shud_b200_dq_foldable(s->gpu);
+}
 
 // a sum over the (distributed) vector into dH[0] and hH[0]
 template <class F>
@@ -764,6 +772,7 @@ int shud_spgmr_create(shud_ctx *gpu, shud_nvws *ws, int maxl, int64_t n_global, 
         CKN(cudaMalloc(&p, sizeof(double) * s->n));
         s->V.push_back(p);
     }
+    CKN(cudaMalloc(&s->wraw, sizeof(double) * s->n));
     CKN(cudaMalloc(&s->ytemp, sizeof(double) * s->n));
     CKN(cudaMalloc(&s->ftemp, sizeof(double) * s->n));
     CKN(cudaMalloc(&s->dH, sizeof(double) * (maxl + 2)));
@@ -782,7 +791,7 @@ void shud_spgmr_destroy(shud_spgmr *s) {
     cudaSetDevice(s->ws->device);
     cudaDeviceSynchronize();
     for (double *p : s->V) cudaFree(p);
-    cudaFree(s->ytemp); cudaFree(s->ftemp); cudaFree(s->dH); cudaFreeHost(s->hH);
+    cudaFree(s->wraw); cudaFree(s->ytemp); cudaFree(s->ftemp); cudaFree(s->dH); cudaFreeHost(s->hH);
     delete s;
 }
 
@@ -795,7 +804,10 @@ static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y,
     const int64_t n = s->n;
     const int maxl = s->maxl;
     int rc;
-    if ((rc = run_map(ws, n, FScaleTo{1.0 / beta, s->V[0], s->V[0]}))) return rc;
+    // folded route (single domain): r0 lies unnormalised in wraw with its squared norm in dH[0]; the pre-pass of each
+    // RHS call normalises the vector of the iteration into V[k] while it perturbs with it
+    const bool fold = spgmr_folds(s);
+    if (!fold && (rc = run_map(ws, n, FScaleTo{1.0 / beta, s->V[0], s->V[0]}))) return rc;
     double H[SHUD_NV_MAXVEC + 1][SHUD_NV_MAXVEC] = {{0}};
     double g[SHUD_NV_MAXVEC + 1] = {0}, cs[SHUD_NV_MAXVEC] = {0}, sn[SHUD_NV_MAXVEC] = {0};
     g[0] = beta;
@@ -806,14 +818,16 @@ static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y,
     for (int k = 0; k < maxl; k++) {
         // w = S (I - gamma J) S^-1 v_k, J by difference quotient: 1 RHS call
         // (single domain: the perturbation is formed by the RHS's own pre-pass)
-        if (dist || !s->fold_dq || shud_b200_rhs_dq_dev(s->gpu, t, sig, s->V[k], ewt, y, s->ytemp, s->ftemp) != 0) {
+        if (fold) {
+            if ((rc = shud_b200_rhs_dq_dev(s->gpu, t, sig, s->wraw, ewt, y, s->ytemp, s->ftemp, s->dH + k, s->V[k]))) return rc;
+        } else {
             if ((rc = shud_nv_dq_perturb(ws, n, sig, s->V[k], ewt, y, s->ytemp))) return rc;
             if ((rc = dist ? shud_b200_rhs_exchange_dev(s->gpu, t, s->ytemp, s->ftemp) : shud_b200_rhs_dev(s->gpu, t, s->ytemp, s->ftemp))) return rc;
         }
         // ... fused with the first dot product of the modified Gram-Schmidt sweep; every later pass subtracts the
         // previous projection and forms the next dot product (the last one the squared norm) in one read of w.
         // Coefficients stay on the device: h_i is written by the reduction's last block and read by the next pass.
-        double *w = s->V[k + 1];
+        double *w = fold ? s->wraw : s->V[k + 1];
         // one GPU: every scalar also lands in mapped host memory, the last one with a ticket the host spins on (the
         // normalisation below runs while the host does the Givens rotations); distributed: the allreduced scalars
         // are copied back and the stream synchronised
@@ -824,7 +838,7 @@ static int spgmr_iterate(shud_spgmr *s, double t, double gamma, const double *y,
         for (int i = 0; i < k; i++)
             if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegDot{s->dH + i, s->V[i], w, s->V[i + 1]}, s->dH + i + 1, hd ? hd + i + 1 : nullptr))) return rc;
         if ((rc = run_reduce_dev<R_SUM>(ws, n, TAxpyNegSq{s->dH + k, s->V[k], w}, s->dH + k + 1, hd ? hd + k + 1 : nullptr, ticket))) return rc;
-        if ((rc = run_map(ws, n, FNormalizeDev{s->dH + k + 1, s->V[k + 1]}))) return rc;
+        if (!fold && (rc = run_map(ws, n, FNormalizeDev{s->dH + k + 1, s->V[k + 1]}))) return rc;
         if (via_copy) {
             CKN(cudaMemcpyAsync(s->hH, s->dH, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, ws->stream));
             CKN(cudaStreamSynchronize(ws->stream));  // the one host synchronisation of this Krylov iteration
@@ -864,8 +878,9 @@ int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, con
     const int64_t n = s->n;
     int rc;
     // r0 = S b, beta = ||r0||_2
-    if ((rc = run_map(ws, n, FProdTo{ewt, b, s->V[0]}))) return rc;
-    if ((rc = reduce_to_host(s, TDot{s->V[0], s->V[0]}))) return rc;
+    double *const r0 = spgmr_folds(s) ? s->wraw : s->V[0];
+    if ((rc = run_map(ws, n, FProdTo{ewt, b, r0}))) return rc;
+    if ((rc = reduce_to_host(s, TDot{r0, r0}))) return rc;
     const double beta = sqrt(s->hH[0]);
     if (nli_out) *nli_out = 0;
     if (res_out) *res_out = beta;
@@ -893,7 +908,7 @@ int shud_spgmr_newton_step(shud_spgmr *s, double t, double gamma, double rl1, co
     shud_nvws *ws = s->ws;
     const int64_t n = s->n;
     int rc;
-    if ((rc = reduce_to_host(s, TNewtonRhs{rl1, gamma, zn1, acor, fy, ewt, s->V[0]}))) return rc;
+    if ((rc = reduce_to_host(s, TNewtonRhs{rl1, gamma, zn1, acor, fy, ewt, spgmr_folds(s) ? s->wraw : s->V[0]}))) return rc;
     const double beta = sqrt(s->hH[0]);
     if (nli_out) *nli_out = 0;
     if (res_out) *res_out = beta;

@@ -202,22 +202,33 @@ __global__ void __launch_bounds__(256) k_effkh(DevMesh m, const double *__restri
 // perturbed state - the arithmetic of shud_nv_dq_perturb, element by element - stores it for the cell and river
 // kernels, and evaluates effKH from the value it has just formed: one pass over (v, ewt, y0) instead of a vector
 // kernel followed by a pre-pass that reads the result back.  A reach stage another thread forms is re-formed here.
-struct DqArgs { double sigma; const double *v, *ewt, *y0; double *yt; };
-__device__ __forceinline__ double dq_val(const DqArgs &A, size_t k) { return A.sigma * (A.v[k] / A.ewt[k]) + A.y0[k]; }
+// With ss != NULL the direction is given unnormalised: v[k] / sqrt(*ss) is what is perturbed with - the arithmetic of the
+// Krylov solver's normalisation kernel, (1 / sqrt(ss)) * v - and the normalised direction is stored to v_out (a buffer
+// other than v: another thread may still re-form a reach stage from v).  It saves the solver a pass per Krylov vector.
+struct DqArgs { double sigma; const double *v, *ewt, *y0; double *yt; const double *ss; double *v_out; };
+__device__ __forceinline__ double dq_dir(const DqArgs &A, size_t k, double rs) { return A.ss ? rs * A.v[k] : A.v[k]; }
+__device__ __forceinline__ double dq_entry(const DqArgs &A, size_t k, double rs) {  // an entry this thread owns
+    const double v = dq_dir(A, k, rs);
+    if (A.v_out) A.v_out[k] = v;
+    const double yt = A.sigma * (v / A.ewt[k]) + A.y0[k];
+    A.yt[k] = yt;
+    return yt;
+}
 __global__ void __launch_bounds__(256) k_effkh_dq(DevMesh m, DqArgs A) {
     const size_t NE = (size_t)m.Ne, NE3 = 3 * NE;
+    double rs = 1.0;
+    if (A.ss) { const double s = sqrt(*A.ss); rs = s != 0.0 ? 1.0 / s : 1.0; }
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < m.Ns; q += gridDim.x * blockDim.x) {
         const int r = __ldg(m.cs_riv + q);
-        m.cs_yr[q] = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : dq_val(A, NE3 + r);
+        m.cs_yr[q] = (__ldg(m.cs_bc + q) > 0) ? m.r_yBC[r] : A.sigma * (dq_dir(A, NE3 + r, rs) / A.ewt[NE3 + r]) + A.y0[NE3 + r];
     }
     for (size_t k = NE3 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < NE3 + m.Nr + m.Nl; k += (size_t)gridDim.x * blockDim.x)
-        A.yt[k] = dq_val(A, k);
+        dq_entry(A, k, rs);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.Ne) return;
-    A.yt[i] = dq_val(A, i);
-    A.yt[NE + i] = dq_val(A, NE + i);
-    const double ygw_t = dq_val(A, 2 * NE + i);
-    A.yt[2 * NE + i] = ygw_t;
+    dq_entry(A, i, rs);
+    dq_entry(A, NE + i, rs);
+    const double ygw_t = dq_entry(A, 2 * NE + i, rs);
     const unsigned fl = m.flags[i];
     double kh;
     if (fl & F_LAKE) {
@@ -2165,16 +2176,19 @@ static int launch_rhs_dq(shud_ctx *c, const DqArgs &A, double *ydot) {
     CK(cudaGetLastError());
     return SHUD_OK;
 }
+int shud_b200_dq_foldable(const shud_ctx *c) { return c && halo_level(c) == 0 && !c->use_p2p ? 1 : 0; }
+
 int shud_b200_rhs_dq_dev(shud_ctx *c, double t, double sigma, const double *v, const double *ewt, const double *y0,
-                         double *ytemp, double *ydot) {
+                         double *ytemp, double *ydot, const double *ss, double *v_out) {
     (void)t;
-    if (!c || !v || !ewt || !y0 || !ytemp || !ydot) return SHUD_ERR_ARG;
+    if (!c || !v || !ewt || !y0 || !ytemp || !ydot || (v_out && v_out == v)) return SHUD_ERR_ARG;
     if (halo_level(c) != 0 || c->use_p2p) return SHUD_ERR_ARG;
     DqArgs A;
-    A.sigma = sigma; A.v = v; A.ewt = ewt; A.y0 = y0; A.yt = ytemp;
+    A.sigma = sigma; A.v = v; A.ewt = ewt; A.y0 = y0; A.yt = ytemp; A.ss = ss; A.v_out = v_out;
     if (!c->use_graph) return launch_rhs_dq(c, A, ydot);
     for (auto &g : c->dqgraphs)
-        if (g.a.v == v && g.yd == ydot && g.a.ewt == ewt && g.a.y0 == y0 && g.a.yt == ytemp && g.a.sigma == sigma) {
+        if (g.a.v == v && g.yd == ydot && g.a.ewt == ewt && g.a.y0 == y0 && g.a.yt == ytemp && g.a.sigma == sigma &&
+            g.a.ss == ss && g.a.v_out == v_out) {
             g.used = ++c->graph_clock;
             CK(cudaGraphLaunch(g.exec, c->stream));
             return SHUD_OK;

@@ -293,5 +293,21 @@ def test_difference_quotient_evaluation_folded_into_the_prepass(basin, case):
                 st.synchronize()
                 assert torch.equal(yt_a, yt_b), (basin, case, rep)
                 assert torch.equal(yd_a, yd_b), (basin, case, rep, float((yd_a - yd_b).abs().max()))
+        # the unnormalised form: direction (1 / sqrt(ss)) v, normalised vector handed back - the solver's normalisation
+        # pass done by the pre-pass
+        raw = vs[0] * 3.7
+        ss = (raw * raw).sum().reshape(1)
+        vn_a = (1.0 / torch.sqrt(ss)) * raw
+        yt_a, yd_a = torch.empty_like(y0), torch.empty_like(y0)
+        ops.DQPerturb(sigma, vn_a, ewt, y0, yt_a)
+        reset()
+        rhs.f_dev(0.0, yt_a, yd_a)
+        st.synchronize()
+        vn_b, yt_b, yd_b = (torch.full_like(y0, float("nan")) for _ in range(3))
+        for rep in range(2):
+            reset()
+            rhs.f_dq_dev(0.0, sigma, raw, ewt, y0, yt_b, yd_b, ss_dev=ss, vnorm_dev=vn_b)
+            st.synchronize()
+            assert torch.equal(vn_a, vn_b) and torch.equal(yt_a, yt_b) and torch.equal(yd_a, yd_b), (basin, case, rep)
         assert rhs.check()[0] == 0
         ops.close()
