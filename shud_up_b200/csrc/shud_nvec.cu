@@ -69,13 +69,23 @@ struct FAbs { const double *x; double *z; __device__ void operator()(int64_t i) 
 struct FInv { const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = 1.0 / x[i]; } };
 struct FAddConst { const double *x; double b; double *z; __device__ void operator()(int64_t i) const { z[i] = x[i] + b; } };
 struct FCompare { double c; const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = (fabs(x[i]) >= c) ? 1.0 : 0.0; } };
+// The linear combinations are instantiated per vector count: with the count known the loads of all addends are
+// issued before the first multiply-add (with a run-time loop each load waited for the sum of the ones before it and the
+// kernels ran at 2.9 TB/s); the sum itself keeps its left-to-right order.
+template <int NV>
+__device__ __forceinline__ double lincomb_at(const Coef &c, const Ptrs &X, int64_t i) {
+    double x[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) x[k] = X.p[k][i];
+    double s = c.c[0] * x[0];
+#pragma unroll
+    for (int k = 1; k < NV; k++) s += c.c[k] * x[k];
+    return s;
+}
+template <int NV>
 struct FLinComb {
-    int nv; Coef c; Ptrs X; double *z;
-    __device__ void operator()(int64_t i) const {
-        double s = c.c[0] * X.p[0][i];
-        for (int k = 1; k < nv; k++) s += c.c[k] * X.p[k][i];
-        z[i] = s;
-    }
+    Coef c; Ptrs X; double *z;
+    __device__ void operator()(int64_t i) const { z[i] = lincomb_at<NV>(c, X, i); }
 };
 struct FScaleAddMulti {
     int nv; Coef a; const double *x; Ptrs Y; MPtrs Z;
@@ -543,10 +553,19 @@ int shud_nv_minquotient(shud_nvws *ws, int64_t n, const double *num, const doubl
 }
 
 int shud_nv_linearcombination(shud_nvws *ws, int64_t n, int nv, const double *c, const double *const *X, double *z) {
-    FLinComb f; f.nv = nv; f.z = z;
-    if (!c || !fill(f.X, X, nv)) return SHUD_ERR_ARG;
-    for (int k = 0; k < nv; k++) f.c.c[k] = c[k];
-    return run_map(ws, n, f);
+    Coef cf; Ptrs P;
+    if (!c || !fill(P, X, nv)) return SHUD_ERR_ARG;
+    for (int k = 0; k < nv; k++) cf.c[k] = c[k];
+    switch (nv) {
+        case 1: return run_map(ws, n, FLinComb<1>{cf, P, z});
+        case 2: return run_map(ws, n, FLinComb<2>{cf, P, z});
+        case 3: return run_map(ws, n, FLinComb<3>{cf, P, z});
+        case 4: return run_map(ws, n, FLinComb<4>{cf, P, z});
+        case 5: return run_map(ws, n, FLinComb<5>{cf, P, z});
+        case 6: return run_map(ws, n, FLinComb<6>{cf, P, z});
+        case 7: return run_map(ws, n, FLinComb<7>{cf, P, z});
+        default: return run_map(ws, n, FLinComb<8>{cf, P, z});
+    }
 }
 int shud_nv_scaleaddmulti(shud_nvws *ws, int64_t n, int nv, const double *a, const double *x, const double *const *Y,
                           double *const *Z) {
@@ -659,13 +678,10 @@ struct FNormalizeDev {  // w /= sqrt(n2[0])  (left untouched when the norm is 0)
     }
 };
 struct FScaleTo { double c; const double *x; double *z; __device__ void operator()(int64_t i) const { z[i] = c * x[i]; } };
+template <int NV>
 struct FLinCombDiv {  // x = (sum c_k V_k) ./ ewt
-    int nv; Coef c; Ptrs V; const double *ewt; double *x;
-    __device__ void operator()(int64_t i) const {
-        double s = c.c[0] * V.p[0][i];
-        for (int k = 1; k < nv; k++) s += c.c[k] * V.p[k][i];
-        x[i] = s / ewt[i];
-    }
+    Coef c; Ptrs V; const double *ewt; double *x;
+    __device__ void operator()(int64_t i) const { x[i] = lincomb_at<NV>(c, V, i) / ewt[i]; }
 };
 // Right-hand side of a Newton iteration, scaled, and its squared 2-norm in one pass:
 // b = -((rl1 zn1 + acor) + (-gamma) f) (cvNlsResidual + the sign change of the Newton solver), V0 = ewt b (the first
@@ -684,15 +700,16 @@ struct TNewtonRhs {
 };
 // End of a Newton iteration in one pass: x = (sum c_k V_k) ./ ewt (FLinCombDiv), acor += x, y = zn0 + acor;
 // term = (x ewt)^2 (the WRMS norm of the correction); x itself is never stored.
+template <int NV>
 struct TNewtonFinish {
-    int nv; Coef c; Ptrs V; const double *ewt, *zn0; double *acor, *y;
+    Coef c; Ptrs V; const double *ewt, *zn0; double *acor, *y;
     __device__ double term(int, int64_t i) const {
-        double s = c.c[0] * V.p[0][i];
-        for (int k = 1; k < nv; k++) s += c.c[k] * V.p[k][i];
-        const double w = ewt[i], x = s / w;
-        const double a = acor[i] + 1.0 * x;
+        const double w = ewt[i], a0 = acor[i], z0 = zn0[i];
+        const double s = lincomb_at<NV>(c, V, i);
+        const double x = s / w;
+        const double a = a0 + 1.0 * x;
         acor[i] = a;
-        y[i] = 1.0 * zn0[i] + 1.0 * a;
+        y[i] = 1.0 * z0 + 1.0 * a;
         const double t = x * w;
         return t * t;
     }
@@ -892,10 +909,18 @@ int shud_spgmr_solve(shud_spgmr *s, double t, double gamma, const double *y, con
     int k_used = 0;
     bool conv = false;
     if ((rc = spgmr_iterate(s, t, gamma, y, fy, ewt, beta, tol, yk, &k_used, &res, &conv))) return rc;
-    FLinCombDiv f;
-    f.nv = k_used; f.ewt = ewt; f.x = x;
-    for (int i = 0; i < k_used; i++) { f.c.c[i] = yk[i]; f.V.p[i] = s->V[i]; }
-    if ((rc = run_map(ws, n, f))) return rc;
+    Coef cf; Ptrs P;
+    for (int i = 0; i < k_used; i++) { cf.c[i] = yk[i]; P.p[i] = s->V[i]; }
+    switch (k_used) {
+        case 1: rc = run_map(ws, n, FLinCombDiv<1>{cf, P, ewt, x}); break;
+        case 2: rc = run_map(ws, n, FLinCombDiv<2>{cf, P, ewt, x}); break;
+        case 3: rc = run_map(ws, n, FLinCombDiv<3>{cf, P, ewt, x}); break;
+        case 4: rc = run_map(ws, n, FLinCombDiv<4>{cf, P, ewt, x}); break;
+        case 5: rc = run_map(ws, n, FLinCombDiv<5>{cf, P, ewt, x}); break;
+        case 6: rc = run_map(ws, n, FLinCombDiv<6>{cf, P, ewt, x}); break;
+        default: rc = run_map(ws, n, FLinCombDiv<7>{cf, P, ewt, x}); break;
+    }
+    if (rc) return rc;
     if (nli_out) *nli_out = k_used;
     if (res_out) *res_out = res;
     return conv ? 0 : (res < beta ? 1 : 2);
@@ -917,10 +942,19 @@ int shud_spgmr_newton_step(shud_spgmr *s, double t, double gamma, double rl1, co
     int k_used = 0;
     bool conv = false;
     if ((rc = spgmr_iterate(s, t, gamma, y, fy, ewt, beta, tol, yk, &k_used, &res, &conv))) return rc;
-    TNewtonFinish f;
-    f.nv = k_used; f.ewt = ewt; f.zn0 = zn0; f.acor = acor; f.y = y;
-    for (int i = 0; i < k_used; i++) { f.c.c[i] = yk[i]; f.V.p[i] = s->V[i]; }
-    if ((rc = run_reduce<R_SUM, 1>(ws, n, f, 1, 1, (double)(n_global > 0 ? n_global : n), del))) return rc;
+    Coef cf; Ptrs P;
+    for (int i = 0; i < k_used; i++) { cf.c[i] = yk[i]; P.p[i] = s->V[i]; }
+    const double ng = (double)(n_global > 0 ? n_global : n);
+    switch (k_used) {
+        case 1: rc = run_reduce<R_SUM, 1>(ws, n, TNewtonFinish<1>{cf, P, ewt, zn0, acor, y}, 1, 1, ng, del); break;
+        case 2: rc = run_reduce<R_SUM, 1>(ws, n, TNewtonFinish<2>{cf, P, ewt, zn0, acor, y}, 1, 1, ng, del); break;
+        case 3: rc = run_reduce<R_SUM, 1>(ws, n, TNewtonFinish<3>{cf, P, ewt, zn0, acor, y}, 1, 1, ng, del); break;
+        case 4: rc = run_reduce<R_SUM, 1>(ws, n, TNewtonFinish<4>{cf, P, ewt, zn0, acor, y}, 1, 1, ng, del); break;
+        case 5: rc = run_reduce<R_SUM, 1>(ws, n, TNewtonFinish<5>{cf, P, ewt, zn0, acor, y}, 1, 1, ng, del); break;
+        case 6: rc = run_reduce<R_SUM, 1>(ws, n, TNewtonFinish<6>{cf, P, ewt, zn0, acor, y}, 1, 1, ng, del); break;
+        default: rc = run_reduce<R_SUM, 1>(ws, n, TNewtonFinish<7>{cf, P, ewt, zn0, acor, y}, 1, 1, ng, del); break;
+    }
+    if (rc) return rc;
     if (nli_out) *nli_out = k_used;
     if (res_out) *res_out = res;
     return conv ? 0 : (res < beta ? 1 : 2);
