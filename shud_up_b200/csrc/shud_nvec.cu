@@ -34,11 +34,21 @@ struct Coef {
     double c[SHUD_NV_MAXVEC];
 };
 
-inline int grid_for(int64_t n) {
+inline int grid_for(int64_t n, int cap = MAXB) {
     int64_t b = (n + (int64_t)NT * UNROLL - 1) / ((int64_t)NT * UNROLL);
     if (b < 1) b = 1;
-    if (b > MAXB) b = MAXB;
+    if (b > cap) b = cap;
     return (int)b;
+}
+// blocks of a reduction: 4 per SM (half as many partial sums, atomics and fences in the kernel's tail as with 8; measured
+// on the Newton-Krylov step: 8 -> 0.755, 4 -> 0.736, 2 -> 0.829 ms); A/B knobs SHUD_NV_RBLOCKS / SHUD_NV_MBLOCKS
+inline int rgrid_for(int64_t n) {
+    static const int per_sm = [] { const char *e = getenv("SHUD_NV_RBLOCKS"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+    return grid_for(n, 148 * per_sm);
+}
+inline int mgrid_for(int64_t n) {
+    static const int per_sm = [] { const char *e = getenv("SHUD_NV_MBLOCKS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+    return grid_for(n, 148 * per_sm);
 }
 
 // ---------------- streaming ----------------
@@ -357,7 +367,7 @@ template <class F>
 int run_map(shud_nvws *ws, int64_t n, F f) {
     if (!ws) return SHUD_ERR_ARG;
     if (n <= 0) return SHUD_OK;
-    k_map<<<grid_for(n), NT, 0, ws->stream>>>(n, f);
+    k_map<<<mgrid_for(n), NT, 0, ws->stream>>>(n, f);
     CKN(cudaGetLastError());
     return SHUD_OK;
 }
@@ -387,7 +397,7 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
         PeerAR P = ws->peer;
         P.seq = ++ws->peer_seq;
         const double ticket = (ws->ticket += 1.0);
-        k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out, ws->h_out_dev,
+        k_reduce<KIND, NV, F><<<rgrid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out, ws->h_out_dev,
                                                                   post, nglob, ws->h_out_dev + SHUD_NV_MAXVEC, ticket, P);
         CKN(cudaGetLastError());
         const int rc = wait_ticket(ws, ticket);
@@ -397,7 +407,7 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
     }
     if (ws->ar_dev && !ws->ar_off) {
         // every rank calls this with the same nv (SPMD): raw partials -> allreduce on the device -> host, post on the host
-        k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
+        k_reduce<KIND, NV, F><<<rgrid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
                                                                   ws->h_out_dev, 0, 1.0);
         CKN(cudaGetLastError());
         if (ws->ar_dev(ws->ar_ctx, ws->d_out, nv, KIND, (void *)ws->stream) != 0) return SHUD_ERR_CUDA;
@@ -410,7 +420,7 @@ int run_reduce(shud_nvws *ws, int64_t n, F f, int nv, int post, double nglob, do
         return SHUD_OK;
     }
     const double ticket = (ws->ticket += 1.0);
-    k_reduce<KIND, NV, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
+    k_reduce<KIND, NV, F><<<rgrid_for(n), NT, 0, ws->stream>>>(n, f, nv, ws->partial, ws->counter, ws->d_out,
                                                               ws->h_out_dev, post, nglob, ws->h_out_dev + SHUD_NV_MAXVEC, ticket);
     CKN(cudaGetLastError());
     const int rc = wait_ticket(ws, ticket);
@@ -427,7 +437,7 @@ int run_reduce_dev(shud_nvws *ws, int64_t n, F f, double *d_result, double *h_re
     if (!ws || !d_result || n <= 0) return SHUD_ERR_ARG;
     PeerAR P{};
     if (ws->peer.nranks > 1 && !ws->ar_off) { P = ws->peer; P.seq = ++ws->peer_seq; }
-    k_reduce<KIND, 1, F><<<grid_for(n), NT, 0, ws->stream>>>(n, f, 1, ws->partial, ws->counter, d_result,
+    k_reduce<KIND, 1, F><<<rgrid_for(n), NT, 0, ws->stream>>>(n, f, 1, ws->partial, ws->counter, d_result,
                                                              h_result ? h_result : ws->h_out_dev + (SHUD_NV_MAXVEC - 1), 0, 1.0,
                                                              ticket > 0.0 ? ws->h_out_dev + SHUD_NV_MAXVEC : nullptr, ticket, P);
     CKN(cudaGetLastError());
