@@ -70,6 +70,12 @@ typedef struct shud_cv_fused {
                        N_Vector y, N_Vector fy, N_Vector ewt, realtype delta, realtype *del, int *nli, int *nfe);
     /* ewt_set and *nrm = ||y||_WRMS(ewt) in one pass (the weights and the tolsf test at the top of CVode's loop) */
     int (*ewt_set_norm)(void *ctx, realtype rtol, realtype atol, N_Vector y, N_Vector ewt, realtype *nrm);
+    /* cvCompleteStep's zn[j] += l[j] acor (j = 0..q) together with what the top of CVode()'s loop does next with the
+     * new zn[0]: ewt_next = 1 ./ (rtol |zn0| + atol), *nrm = ||zn0||_WRMS(ewt_next), and yout = zn0 when yout != NULL
+     * (CV_ONE_STEP's copy).  ewt_next is a second weight vector: the step's own weights stay valid for the order
+     * selection that follows (cvPrepareNextStep). */
+    int (*complete_step)(void *ctx, int q, realtype *l, N_Vector acor, N_Vector *zn, realtype rtol, realtype atol,
+                         N_Vector ewt_next, N_Vector yout, realtype *nrm);
 } shud_cv_fused;
 
 /* CVodeCreate(CV_BDF) + CVodeInit(f, t0, y0) + CVodeSetUserData: work vectors are cloned from y0 */

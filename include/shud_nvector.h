@@ -130,6 +130,10 @@ int shud_spgmr_newton_step(shud_spgmr *s, double t, double gamma, double rl1, co
                            double *del, int *nli, double *resnorm);
 /* cvPredict (sgn = +1) / cvRestore (sgn = -1) of the Nordsieck array zn[0..q] in one pass, the in-place sums in the
  * order of the reference's N_VLinearSum calls; with acor != NULL also acor = 0, y = zn[0] + acor (start of cvNls). */
+/* cvCompleteStep's zn[j] += l[j] acor (j = 0..q), the next step's weights ewt = 1 ./ (rtol |zn0| + atol), *nrm =
+ * ||zn0||_WRMS(ewt) over n_global entries and, with yout != NULL, yout = zn0 - one pass. */
+int shud_nv_bdf_complete(shud_nvws *ws, int64_t n, int q, const double *l, const double *acor, double *const *zn,
+                         double rtol, double atol, double *ewt, double *yout, int64_t n_global, double *nrm);
 int shud_nv_bdf_predict(shud_nvws *ws, int64_t n, int q, double sgn, double *const *zn, double *y, double *acor);
 
 #ifdef __cplusplus

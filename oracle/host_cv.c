@@ -186,7 +186,7 @@ int host_test_f(realtype t, N_Vector y, N_Vector ydot, void *user_data) {
  * kernels, shud_up_b200/csrc/shud_nvector_sundials.cu) restated through the generic vector operations, in the order
  * the unhooked integrator runs them.  Test infrastructure: tests/test_cvode_cpu.py checks that the hooked control
  * flow of shud_cvode.cpp reproduces the plain one bit for bit. ---- */
-typedef struct host_fused_ctx { shud_cv *cv; N_Vector b, x; long calls[3]; } host_fused_ctx;
+typedef struct host_fused_ctx { shud_cv *cv; N_Vector b, x; long calls[4]; } host_fused_ctx;
 
 static int hf_predict(void *ctx, int q, realtype sgn, N_Vector *zn, N_Vector y, N_Vector acor) {
     ((host_fused_ctx *)ctx)->calls[0]++;
@@ -221,17 +221,31 @@ static int hf_ewt_set_norm(void *ctx, realtype rtol, realtype atol, N_Vector y, 
     *nrm = N_VWrmsNorm(y, ewt);
     return 0;
 }
+static int hf_complete_step(void *ctx, int q, realtype *l, N_Vector acor, N_Vector *zn, realtype rtol, realtype atol,
+                            N_Vector ewt_next, N_Vector yout, realtype *nrm) {
+    host_fused_ctx *c = (host_fused_ctx *)ctx;
+    c->calls[3]++;
+    N_VScaleAddMulti(q + 1, l, acor, zn, zn);
+    N_VAbs(zn[0], c->b);
+    N_VScale(rtol, c->b, c->b);
+    N_VAddConst(c->b, atol, c->b);
+    N_VInv(c->b, ewt_next);
+    *nrm = N_VWrmsNorm(zn[0], ewt_next);
+    if (yout) N_VScale(1.0, zn[0], yout);
+    return 0;
+}
 int host_cv_fused_create(shud_cv *cv, N_Vector tmpl, shud_cv_fused *out) {
     host_fused_ctx *c = (host_fused_ctx *)calloc(1, sizeof(host_fused_ctx));
     if (!c || !cv || !tmpl || !out) return -1;
     c->cv = cv; c->b = N_VClone(tmpl); c->x = N_VClone(tmpl);
     memset(out, 0, sizeof(*out));
     out->ctx = c; out->predict = hf_predict; out->newton_step = hf_newton_step; out->ewt_set_norm = hf_ewt_set_norm;
+    out->complete_step = hf_complete_step;
     return 0;
 }
-void host_cv_fused_calls(const shud_cv_fused *f, long *calls3) {
+void host_cv_fused_calls(const shud_cv_fused *f, long *calls4) {
     const host_fused_ctx *c = (const host_fused_ctx *)f->ctx;
-    for (int k = 0; k < 3; k++) calls3[k] = c->calls[k];
+    for (int k = 0; k < 4; k++) calls4[k] = c->calls[k];
 }
 void host_cv_fused_destroy(shud_cv_fused *f) {
     host_fused_ctx *c = (host_fused_ctx *)f->ctx;

@@ -68,6 +68,13 @@ struct shud_cv {
     shud_cv_fused fused;
     int have_fused;
     int nls_primed;  // the fused predictor has left acor = 0 and y = zn[0] + acor
+    // fused cvCompleteStep: the weights and the tolsf norm of the NEXT step are formed with the update of zn (the step's
+    // own weights stay in ewt for cvPrepareNextStep); the top of CVode()'s loop swaps them in
+    N_Vector ewt_next;
+    int ewt_next_valid;
+    double nrm_next;
+    N_Vector yout_hint;  // CV_ONE_STEP: the caller's vector, filled by the same pass
+    int yout_done;
     double uround;
 };
 
@@ -604,7 +611,14 @@ void complete_step(shud_cv *cv) {  // cvCompleteStep
     for (int i = cv->q; i >= 2; i--) cv->tau[i] = cv->tau[i - 1];
     if (cv->q == 1 && cv->nst > 1) cv->tau[2] = cv->tau[1];
     cv->tau[1] = cv->h;
-    N_VScaleAddMulti(cv->q + 1, cv->l, cv->acor, cv->zn, cv->zn);
+    if (cv->have_fused && cv->fused.complete_step && cv->abstol > 0.0 && cv->ewt_next &&
+        cv->fused.complete_step(cv->fused.ctx, cv->q, cv->l, cv->acor, cv->zn, cv->reltol, cv->abstol, cv->ewt_next,
+                                cv->yout_hint, &cv->nrm_next) == 0) {
+        cv->ewt_next_valid = 1;
+        cv->yout_done = cv->yout_hint != nullptr;
+    } else {
+        N_VScaleAddMulti(cv->q + 1, cv->l, cv->acor, cv->zn, cv->zn);
+    }
     cv->qwait--;
     if (cv->qwait == 1 && cv->q != cv->qmax) {
         N_VScale(1.0, cv->acor, cv->zn[cv->qmax]);
@@ -780,6 +794,7 @@ int shud_cv_create(shud_cv_rhs_fn f, void *user_data, realtype t0, N_Vector y0, 
     cv->hmin = 0.0; cv->hmax_inv = 0.0; cv->hin = 0.0;
     bool ok = true;
     for (int j = 0; j <= L_MAX; j++) ok = ok && (cv->zn[j] = N_VClone(y0));
+    ok = ok && (cv->ewt_next = N_VClone(y0));
     ok = ok && (cv->ewt = N_VClone(y0)) && (cv->y = N_VClone(y0)) && (cv->acor = N_VClone(y0)) &&
          (cv->tempv = N_VClone(y0)) && (cv->ftemp = N_VClone(y0)) && (cv->vtemp1 = N_VClone(y0));
     for (int k = 0; k <= SPGMR_MAXL_DEFAULT; k++) ok = ok && (cv->V[k] = N_VClone(y0));
@@ -793,6 +808,7 @@ int shud_cv_create(shud_cv_rhs_fn f, void *user_data, realtype t0, N_Vector y0, 
 void shud_cv_free(shud_cv *cv) {
     if (!cv) return;
     for (int j = 0; j <= L_MAX; j++) free_vec(&cv->zn[j]);
+    free_vec(&cv->ewt_next);
     free_vec(&cv->ewt); free_vec(&cv->y); free_vec(&cv->acor); free_vec(&cv->tempv); free_vec(&cv->ftemp); free_vec(&cv->vtemp1);
     for (int k = 0; k <= SPGMR_MAXL_DEFAULT; k++) free_vec(&cv->V[k]);
     free_vec(&cv->xcor); free_vec(&cv->ls_x); free_vec(&cv->ls_vtemp);
@@ -808,7 +824,7 @@ int shud_cv_reinit(shud_cv *cv, realtype t0, N_Vector y0) {
     cv->nst = cv->nfe = cv->ncfn = cv->netf = cv->nni = cv->nscon = 0;
     cv->nli = cv->ncfl = cv->nfeLS = cv->nps = 0;
     cv->h0u = 0.0; cv->next_h = 0.0; cv->next_q = 0; cv->h = 0.0;
-    cv->saved_tq5 = 0.0; cv->indx_acor = 0; cv->nls_primed = 0;
+    cv->saved_tq5 = 0.0; cv->indx_acor = 0; cv->nls_primed = 0; cv->ewt_next_valid = 0; cv->yout_done = 0;
     memset(cv->tau, 0, sizeof(cv->tau)); memset(cv->tq, 0, sizeof(cv->tq)); memset(cv->l, 0, sizeof(cv->l));
     return SHUD_CV_SUCCESS;
 }
@@ -940,12 +956,19 @@ int shud_cv_solve(shud_cv *cv, realtype tout, N_Vector yout, realtype *tret, int
     }
     long nstloc = 0;
     int istate = SHUD_CV_SUCCESS;
+    cv->yout_hint = itask == SHUD_CV_ONE_STEP ? yout : nullptr;
+    cv->yout_done = 0;
     for (;;) {
         cv->next_h = cv->h;
         cv->next_q = cv->q;
         double nrm = -1.0;
         if (cv->nst > 0) {
-            if (cv->have_fused && cv->fused.ewt_set_norm && cv->abstol > 0.0) {
+            if (cv->ewt_next_valid) {
+                // formed by the fused cvCompleteStep of the step before, from the zn[0] that is still there
+                N_Vector tmp = cv->ewt; cv->ewt = cv->ewt_next; cv->ewt_next = tmp;
+                nrm = cv->nrm_next;
+                cv->ewt_next_valid = 0;
+            } else if (cv->have_fused && cv->fused.ewt_set_norm && cv->abstol > 0.0) {
                 // weights and the norm of the tolsf test below in one pass over zn[0]
                 if (cv->fused.ewt_set_norm(cv->fused.ctx, cv->reltol, cv->abstol, cv->zn[0], cv->ewt, &nrm) != 0) nrm = -1.0;
             }
@@ -1001,7 +1024,7 @@ int shud_cv_solve(shud_cv *cv, realtype tout, N_Vector yout, realtype *tret, int
         if (itask == SHUD_CV_ONE_STEP) {
             istate = SHUD_CV_SUCCESS;
             cv->tretlast = *tret = cv->tn;
-            N_VScale(1.0, cv->zn[0], yout);
+            if (!cv->yout_done) N_VScale(1.0, cv->zn[0], yout);
             cv->next_q = cv->qprime; cv->next_h = cv->hprime;
             break;
         }

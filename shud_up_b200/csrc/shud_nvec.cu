@@ -724,6 +724,26 @@ struct TNewtonFinish {
         return t * t;
     }
 };
+// cvCompleteStep's update of the Nordsieck array, the weights of the next step and the norm of its tolsf test, and
+// (CV_ONE_STEP) the copy of the solution to the caller's vector in one pass: zn[j] = l[j] acor + zn[j]
+// (FScaleAddMulti), w = 1 / (rtol |zn0| + atol) (FEwt), term = (zn0 w)^2 (TWSqr), yout = zn0.
+template <int Q>
+struct TCompleteStep {
+    Coef l; const double *acor; MPtrs Z; double rtol, atol; double *ewt, *yout;
+    __device__ double term(int, int64_t i) const {
+        const double xi = acor[i];
+        double z[Q + 1];
+#pragma unroll
+        for (int j = 0; j <= Q; j++) z[j] = Z.p[j][i];
+#pragma unroll
+        for (int j = 0; j <= Q; j++) { z[j] = l.c[j] * xi + z[j]; Z.p[j][i] = z[j]; }
+        const double z0 = z[0], w = 1.0 / (rtol * fabs(z0) + atol);
+        ewt[i] = w;
+        if (yout) yout[i] = 1.0 * z0;
+        const double t = z0 * w;
+        return t * t;
+    }
+};
 // cvPredict / cvRestore on the whole Nordsieck array in one pass: the in-place Pascal-triangle sums
 // zn[j-1] += sgn zn[j] (k = 1..q, j = q..k) run on registers, element by element in the order of the N_VLinearSum
 // calls; optionally the start of the Newton iteration as well: acor = 0, y = zn[0] + acor.
@@ -968,6 +988,22 @@ int shud_spgmr_newton_step(shud_spgmr *s, double t, double gamma, double rl1, co
     if (nli_out) *nli_out = k_used;
     if (res_out) *res_out = res;
     return conv ? 0 : (res < beta ? 1 : 2);
+}
+
+int shud_nv_bdf_complete(shud_nvws *ws, int64_t n, int q, const double *l, const double *acor, double *const *zn, double rtol,
+                         double atol, double *ewt, double *yout, int64_t ng, double *nrm) {
+    if (!l || !acor || !zn || !ewt || !nrm || q < 1 || q > 5) return SHUD_ERR_ARG;
+    MPtrs Z; Coef c;
+    if (!fill(Z, zn, q + 1)) return SHUD_ERR_ARG;
+    for (int j = 0; j <= q; j++) c.c[j] = l[j];
+    const double g = (double)(ng > 0 ? ng : n);
+    switch (q) {
+        case 1: return run_reduce<R_SUM, 1>(ws, n, TCompleteStep<1>{c, acor, Z, rtol, atol, ewt, yout}, 1, 1, g, nrm);
+        case 2: return run_reduce<R_SUM, 1>(ws, n, TCompleteStep<2>{c, acor, Z, rtol, atol, ewt, yout}, 1, 1, g, nrm);
+        case 3: return run_reduce<R_SUM, 1>(ws, n, TCompleteStep<3>{c, acor, Z, rtol, atol, ewt, yout}, 1, 1, g, nrm);
+        case 4: return run_reduce<R_SUM, 1>(ws, n, TCompleteStep<4>{c, acor, Z, rtol, atol, ewt, yout}, 1, 1, g, nrm);
+        default: return run_reduce<R_SUM, 1>(ws, n, TCompleteStep<5>{c, acor, Z, rtol, atol, ewt, yout}, 1, 1, g, nrm);
+    }
 }
 
 int shud_nv_bdf_predict(shud_nvws *ws, int64_t n, int q, double sgn, double *const *zn, double *y, double *acor) {

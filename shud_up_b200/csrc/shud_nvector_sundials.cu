@@ -517,6 +517,19 @@ static int fused_ewt_set_norm(void *ctx, realtype rtol, realtype atol, N_Vector 
     wrote(ewt);
     return rc;
 }
+static int fused_complete_step(void *ctx, int q, realtype *l, N_Vector acor, N_Vector *zn, realtype rtol, realtype atol,
+                               N_Vector ewt_next, N_Vector yout, realtype *nrm) {
+    cv_fused_ctx *c = (cv_fused_ctx *)ctx;
+    if (q < 1 || q > 5) return -1;
+    double *z[6];
+    for (int j = 0; j <= q; j++) z[j] = D(zn[j]);
+    const int rc = shud_nv_bdf_complete(c->ws, LEN(acor), q, l, D(acor), z, rtol, atol, D(ewt_next), yout ? D(yout) : nullptr,
+                                        CT(acor)->global_length, nrm);
+    for (int j = 0; j <= q; j++) wrote(zn[j]);
+    wrote(ewt_next);
+    if (yout) wrote(yout);
+    return rc;
+}
 static int fused_nls_residual(void *ctx, realtype rl1, N_Vector zn1, N_Vector ycor, realtype gamma, N_Vector f, N_Vector res) {
     cv_fused_ctx *c = (cv_fused_ctx *)ctx;
     // (rl1 zn1 + ycor) + (-gamma f): the two N_VLinearSum calls of cvNlsResidual in one pass, same operation order
@@ -573,6 +586,7 @@ int shud_b200_cv_fused_create(shud_ctx *gpu, shud_nvws *ws, int maxl, shud_cv_fu
     if (rc) { free(c); return rc; }
     out->ctx = c; out->ewt_set = fused_ewt_set; out->nls_residual = fused_nls_residual; out->lsolve = fused_lsolve;
     out->predict = fused_predict; out->newton_step = fused_newton_step; out->ewt_set_norm = fused_ewt_set_norm;
+    out->complete_step = fused_complete_step;
     return SHUD_OK;
 }
 void shud_b200_cv_fused_destroy(shud_cv_fused *f) {

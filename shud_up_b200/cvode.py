@@ -21,7 +21,8 @@ class Stats(C.Structure):
 
 class Fused(C.Structure):
     _fields_ = [("ctx", C.c_void_p), ("ewt_set", C.c_void_p), ("nls_residual", C.c_void_p), ("lsolve", C.c_void_p),
-                ("predict", C.c_void_p), ("newton_step", C.c_void_p), ("ewt_set_norm", C.c_void_p)]
+                ("predict", C.c_void_p), ("newton_step", C.c_void_p), ("ewt_set_norm", C.c_void_p),
+                ("complete_step", C.c_void_p)]
 
 
 def bind(lib):
