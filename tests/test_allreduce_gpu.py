@@ -27,6 +27,8 @@ def test_reduction_kernels_combine_the_ranks_partials_through_the_mailboxes(tmp_
         for p in procs:
             if p.poll() is None:
                 p.kill()
+    if any(p.returncode == 77 for p in procs):
+        pytest.skip("this GPU admits one context at a time (exclusive-process mode): no second rank on it")
     for r, p in enumerate(procs):
         assert p.returncode == 0, outs[r][-2000:]
     res = [dict(np.load(os.path.join(tmp_path, f"result{r}.npz"))) for r in range(world)]

@@ -26,6 +26,8 @@ def _launch(world, d, mode="cut"):
         for p in procs:
             if p.poll() is None:
                 p.kill()
+    if any(p.returncode == 77 for p in procs):
+        pytest.skip("this GPU admits one context at a time (exclusive-process mode): no second rank on it")
     for r, p in enumerate(procs):
         assert p.returncode == 0, outs[r][-3000:]
     return [dict(np.load(os.path.join(d, f"nk{r}.npz"))) for r in range(world)]
