@@ -494,10 +494,15 @@ int shud_nv_ws_set_allreduce(shud_nvws *ws, shud_nv_allreduce_dev_fn fn, void *c
 }
 int shud_nv_ws_set_peer_allreduce(shud_nvws *ws, int nranks, int rank, void *const *boxes) {
     if (!ws || nranks < 0 || nranks > SHUD_NV_MAXRANKS || rank < 0 || (nranks > 0 && (rank >= nranks || !boxes))) return SHUD_ERR_ARG;
+    // the same mailboxes again (every vector of a run is made distributed on the one workspace): the sequence numbers
+    // run on - the tags in the mailboxes do
+    bool same = nranks > 0 && ws->peer.nranks == nranks && ws->peer.rank == rank;
+    for (int r = 0; r < nranks && same; r++) same = ws->peer.box[r] == (ArBox *)boxes[r];
+    if (same) return SHUD_OK;
     ws->peer = PeerAR{};
     ws->peer.nranks = nranks; ws->peer.rank = rank;
     for (int r = 0; r < nranks; r++) ws->peer.box[r] = (ArBox *)boxes[r];
-    ws->peer_seq = 0;
+    ws->peer_seq = 0;  // fresh mailboxes are zeroed (shud_b200_p2p_export / _connect)
     return SHUD_OK;
 }
 void shud_nv_ws_local(shud_nvws *ws, int on) { if (ws) ws->ar_off += on ? 1 : -1; }

@@ -1867,6 +1867,9 @@ int shud_b200_p2p_connect(shud_ctx *c, int rank, int world, const void *blobs) {
     T.npeers = (int)c->x_peer.size();
     int so = 0;
     c->ar_nranks = 0;
+    // my mailbox starts from zero tags with every (re)connect: a workspace that installs these mailboxes counts from 1
+    // (no peer stores into it before its own connect and the barrier the callers hold after this call)
+    CK(cudaMemset((char *)c->p2p_block + P2P_HDR + 2 * c->p2p_stride, 0, SHUD_NV_ARBOX_BYTES));
     std::vector<char *> mapped(world, nullptr);  // block of rank r as this process sees it
     mapped[rank] = (char *)c->p2p_block;
     for (int p = 0; p < T.npeers; p++) {

@@ -75,6 +75,12 @@ with torch.cuda.stream(st):
         glo["dot"].append(ops.N_VDotProd(x, y)); glo["wrms"].append(ops.N_VWrmsNorm(x, w))
         glo["max"].append(ops.N_VMaxNorm(x)); glo["min"].append(ops.N_VMin(x)); glo["multi"].append(ops.N_VDotProdMulti(x, Y))
         x.mul_(1.0 + 0.25 * (k + 1)); st.synchronize()
+    # the same mailboxes installed again (a second vector made distributed on this workspace): the sequence goes on
+    ops.local(True)
+    out["loc_again"] = np.array([ops.N_VDotProd(y, y)])
+    ops.local(False)
+    ops.set_peer_allreduce(nr, rk, boxes)
+    out["glo_again"] = np.array([ops.N_VDotProd(y, y), ops.N_VDotProd(y, y)])
 for k_, v_ in loc.items():
     out["loc_" + k_] = np.array(v_, dtype=np.float64)
 for k_, v_ in glo.items():

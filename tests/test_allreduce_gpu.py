@@ -42,4 +42,6 @@ def test_reduction_kernels_combine_the_ranks_partials_through_the_mailboxes(tmp_
     assert np.array_equal(res[0]["glo_max"], np.maximum(res[0]["loc_max"], res[1]["loc_max"]))
     assert np.array_equal(res[0]["glo_min"], np.minimum(res[0]["loc_min"], res[1]["loc_min"]))
     assert np.array_equal(res[0]["glo_wrms"], np.sqrt(((0.0 + res[0]["loc_wsq"]) + res[1]["loc_wsq"]) / n_global))
+    again = (0.0 + res[0]["loc_again"][0]) + res[1]["loc_again"][0]
+    assert np.array_equal(res[0]["glo_again"], [again, again]) and np.array_equal(res[1]["glo_again"], [again, again])
     assert not np.array_equal(res[0]["loc_dot"], res[1]["loc_dot"])                  # the ranks did hold different data
