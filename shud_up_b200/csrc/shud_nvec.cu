@@ -653,10 +653,6 @@ int shud_nv_wrmsnormvectorarray(shud_nvws *ws, int64_t n, int nv, const double *
 // =============================================================================================
 namespace {
 struct FProdTo { const double *a, *b; double *z; __device__ void operator()(int64_t i) const { z[i] = a[i] * b[i]; } };
-struct FAxpyDevNeg {  // w -= h[0] * v
-    const double *h, *v; double *w;
-    __device__ void operator()(int64_t i) const { w[i] = w[i] + (-h[0]) * v[i]; }
-};
 // fused passes of the modified Gram-Schmidt sweep (same arithmetic and the same reduction tree as the separate
 // kernels: results are bit-identical; one read of w and one launch less per Krylov basis vector)
 struct TDqCombineDot {  // out = S (I - gamma J) S^-1 v (FDqCombine);  term = out * u
@@ -669,7 +665,7 @@ struct TDqCombineDot {  // out = S (I - gamma J) S^-1 v (FDqCombine);  term = ou
         return o * u[i];
     }
 };
-struct TAxpyNegDot {  // w -= h[0] * v (FAxpyDevNeg);  term = w_new * u
+struct TAxpyNegDot {  // w -= h[0] * v;  term = w_new * u
     const double *h, *v; double *w; const double *u;
     __device__ double term(int, int64_t i) const {
         const double wn = w[i] + (-h[0]) * v[i];
