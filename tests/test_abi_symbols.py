@@ -100,3 +100,27 @@ def test_headers_are_plain_c_and_cxx(tmp_path):
     r = subprocess.run(["g++", "-std=c++14", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src_cc)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_new_entry_points_reject_bad_arguments_before_touching_a_device(lib):
+    """argument checks of the entry points added for the fused Newton-Krylov step and the in-kernel allreduce: a NULL
+    context / workspace / vector or an order outside 1..5 is SHUD_ERR_ARG (-2), with or without a GPU"""
+    vp, d, i64 = ctypes.c_void_p, ctypes.c_double, ctypes.c_int64
+    ERR_ARG = -2
+    lib.shud_b200_rhs_dq_dev.argtypes = [vp, d, d, vp, vp, vp, vp, vp, vp, vp]
+    assert lib.shud_b200_rhs_dq_dev(None, 0.0, 1.0, None, None, None, None, None, None, None) == ERR_ARG
+    lib.shud_b200_dq_foldable.argtypes = [vp]
+    assert lib.shud_b200_dq_foldable(None) == 0
+    lib.shud_b200_p2p_mailboxes.argtypes = [vp, vp, vp, vp]
+    assert lib.shud_b200_p2p_mailboxes(None, None, None, None) == ERR_ARG
+    lib.shud_nv_ws_set_peer_allreduce.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    assert lib.shud_nv_ws_set_peer_allreduce(None, 2, 0, None) == ERR_ARG
+    lib.shud_nv_bdf_predict.argtypes = [vp, i64, ctypes.c_int, d, vp, vp, vp]
+    assert lib.shud_nv_bdf_predict(None, 10, 0, 1.0, None, None, None) == ERR_ARG          # order 0
+    assert lib.shud_nv_bdf_predict(None, 10, 6, 1.0, None, None, None) == ERR_ARG          # order 6
+    lib.shud_nv_bdf_complete.argtypes = [vp, i64, ctypes.c_int, vp, vp, vp, d, d, vp, vp, i64, vp]
+    assert lib.shud_nv_bdf_complete(None, 10, 2, None, None, None, 1e-4, 1e-4, None, None, 0, None) == ERR_ARG
+    lib.shud_spgmr_newton_step.argtypes = [vp, d, d, d, vp, vp, vp, vp, vp, vp, d, i64, vp, vp, vp]
+    assert lib.shud_spgmr_newton_step(None, 0.0, 1.0, 1.0, None, None, None, None, None, None, 1.0, 0, None, None, None) == ERR_ARG
+    lib.shud_nv_ewt_wrms.argtypes = [vp, i64, d, d, vp, vp, i64, vp]
+    assert lib.shud_nv_ewt_wrms(None, 10, 1e-4, 1e-4, None, None, 0, None) == ERR_ARG
